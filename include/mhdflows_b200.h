@@ -1,0 +1,106 @@
+/* mhdflows_b200.h -- C ABI of the B200-native MHDFlows hot path.
+ *
+ * Drop-in boundary for MHDFlows.jl's 3D periodic pseudospectral right-hand side and
+ * RK4 / LSRK54 time step (incompressible HD, MHD, electron MHD).  A Julia host binds these
+ * with plain `ccall` (see INTEGRATION.md and julia/MHDFlowsB200.jl); the Python ctypes mirror
+ * is mhdflows_jl_b200/.  Plain pointers and sizes only; every function returns 0 on success or
+ * a negative mhdf_status; nothing throws across the boundary.
+ *
+ * Arrays use the reference's column-major layouts so Julia passes `pointer(A)` unchanged:
+ *   real field      (nx, ny, nz)              x fastest
+ *   spectral field  (nx/2+1, ny, nz)          kx fastest, interleaved (re, im)
+ * Field ids follow params.*_ind - 1 (src/Structure/datastructure.jl:88-90):
+ *   HD: ux,uy,uz = 0,1,2   MHD: ux,uy,uz,bx,by,bz = 0..5   EMHD: bx,by,bz = 0,1,2
+ *
+ * The handle owns all device memory, streams and communicators; host pointers are borrowed
+ * for the duration of a call.  One host thread per handle.
+ *
+ * file:line citations are into the reference tree (MHDFlows.jl).
+ */
+#ifndef MHDFLOWS_B200_H
+#define MHDFLOWS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mhdf_handle mhdf_handle;
+
+typedef enum {
+  MHDF_OK = 0,
+  MHDF_ERR_INVALID = -1,   /* bad argument / unsupported configuration (Julia: error(...), pgen.jl:98-105) */
+  MHDF_ERR_CUDA = -2,      /* CUDA runtime failure, including "no CUDA device" */
+  MHDF_ERR_NCCL = -3,
+  MHDF_ERR_NONFINITE = -4, /* NaN detected (UserInterface.jl:71,79 "detected NaN! Quit the simulation right now.") */
+  MHDF_ERR_STATE = -5      /* call not valid in the current state */
+} mhdf_status;
+
+enum { MHDF_F32 = 0, MHDF_F64 = 1 };
+enum { MHDF_HD = 0, MHDF_MHD = 1, MHDF_EMHD = 2 };          /* B_field / EMHD flags, pgen.jl:129-150 */
+enum { MHDF_RK4 = 0, MHDF_LSRK54 = 1 };                      /* stepper = "RK4" | "LSRK54", Problems.jl:123-128 */
+enum { MHDF_FRESH = 0, MHDF_STALE = 1 };                     /* which real-space view: true state, or the reference's
+                                                               `vars.*` = c2r of the last stage input */
+
+/* Keyword arguments of Problem(dev; ...) (pgen.jl:64-95) that reach the hot path. */
+typedef struct {
+  int nx, ny, nz;          /* powers of two, 16..1024 */
+  double Lx, Ly, Lz;
+  double nu, eta;          /* params.nu, params.eta */
+  int n_nu;                /* params.n_nu (hyperviscosity ADDS on top of viscosity when > 1, MHDSolver.jl:94-99) */
+  double dt;               /* clock.dt */
+  int physics;             /* MHDF_HD | MHDF_MHD | MHDF_EMHD */
+  int stepper;             /* MHDF_RK4 | MHDF_LSRK54 */
+  int dtype;               /* MHDF_F32 | MHDF_F64  (T = Float32 default, pgen.jl:90) */
+  int device;              /* CUDA device ordinal */
+  /* slab decomposition over `nranks` processes (one GPU each); rank 0..nranks-1.  nranks = 1: single GPU. */
+  int rank, nranks;
+  const void* nccl_id;     /* 128-byte ncclUniqueId from mhdf_nccl_unique_id on rank 0, shared by the host; NULL if nranks == 1 */
+} mhdf_config;
+
+/* Problem(...) constructor / finaliser (pgen.jl:64-127, Problems.jl:118-140). */
+int mhdf_create(const mhdf_config* cfg, mhdf_handle** out);
+int mhdf_destroy(mhdf_handle* h);
+const char* mhdf_last_error(const mhdf_handle* h);   /* h may be NULL: error of the last failed mhdf_create */
+int mhdf_nccl_unique_id(void* id128);
+
+/* SetUpProblemIC! (utils/IC.jl:41-109): copy a real field in and r2c it into sol[:, :, :, field]. */
+int mhdf_set_real(mhdf_handle* h, int field, const void* host_real);
+/* vars.ux ... (c2r on demand).  which = MHDF_FRESH | MHDF_STALE. */
+int mhdf_get_real(mhdf_handle* h, int field, int which, void* host_real);
+/* prob.sol[:, :, :, field] in the (nx/2+1, ny, nz) layout.  Dealiased modes read back as zero: the state is
+ * stored on the modes kept by dealias!() only (equals the reference's sol after its next dealias!, pgen.jl:155). */
+int mhdf_set_spectral(mhdf_handle* h, int field, const void* host_spec);
+int mhdf_get_spectral(mhdf_handle* h, int field, int which, void* host_spec);
+
+/* stepforward! (timestepper/timestepper.jl:4-6): nsteps steps of clock.dt. */
+int mhdf_step(mhdf_handle* h, int nsteps);
+/* eqn.calcN!(N, sol, t, clock, vars, params, grid) (pgen.jl:153-181) on the current sol:
+ * writes N as nfields spectral arrays (dealiased modes zero).  Refreshes the stale `vars` like the reference. */
+int mhdf_calcN(mhdf_handle* h, void* host_N);
+int mhdf_set_dt(mhdf_handle* h, double dt);
+int mhdf_set_clock(mhdf_handle* h, double t, long long step);
+int mhdf_get_clock(const mhdf_handle* h, double* t, double* dt, long long* step);
+
+/* getCFL! (integrator.jl:158-198): dt = min(coef * dl / vmax, t_diff) from the stale real-space maxima; sets clock.dt. */
+int mhdf_cfl_dt(mhdf_handle* h, double coef, double t_diff, double* dt_out);
+/* ProbDiagnostic (utils/UserInterface.jl:65-86) without the sigdigits rounding: sum(u^2) dV, sum(b^2) dV. */
+int mhdf_energy(mhdf_handle* h, int which, double* KE, double* ME);
+/* sum (curl u).u dV (MHDAnalysis.jl:94-101), sum a.b with Coulomb-gauge a (MHDAnalysis.jl:113-117, no dV), sum u.b dV. */
+int mhdf_helicity(mhdf_handle* h, double* Hk, double* Hm, double* Hc);
+/* spectralline (MHDAnalysis.jl:237-255) of one state field: Pk[round(|k|)] += |f^|^2 over the half spectrum. */
+int mhdf_spectrum(mhdf_handle* h, int field, double* Pk, int nbins);
+/* stale per-field maxima of f^2 and sums of f^2 (6 each; EMHD: curl B then b) as used by getCFL!/ProbDiagnostic. */
+int mhdf_stale_stats(const mhdf_handle* h, double* maxsq6, double* sumsq6);
+
+/* Measurement helpers. */
+int mhdf_step_timed(mhdf_handle* h, int nsteps, double* ms_total);   /* CUDA events on the library stream */
+int mhdf_profile(mhdf_handle* h, int enable);                        /* per-kernel-class CUDA event timing */
+/* classes: 0 z-inverse, 1 y-inverse, 2 fused x pass, 3 y-forward, 4 z-forward, 5 spectral update, 6 emhd derive, 7 exchange */
+int mhdf_profile_get(mhdf_handle* h, double* ms_per_class, long long* launches_per_class, int nclasses);
+long long mhdf_launch_count(const mhdf_handle* h);                   /* kernels launched by this handle so far */
+int mhdf_info(const mhdf_handle* h, int* nfields, int* kx, int* kxp, int* ky, int* kz, long long* bytes_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

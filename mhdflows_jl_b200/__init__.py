@@ -1,0 +1,13 @@
+"""mhdflows_jl_b200 -- B200-native (sm_100a) implementation of MHDFlows.jl's 3D periodic pseudospectral
+right-hand side and RK4/LSRK54 time step, behind the reference's problem API.
+
+The compute lives in libmhdflows_b200.so (hand-written CUDA, C ABI in include/mhdflows_b200.h); this package
+is the thin host mirror of the Julia API.  No CPU fallback exists.
+"""
+from ._lib import EMHD, F32, F64, FRESH, HD, LSRK54, MHD, RK4, STALE, MHDFlowsError  # noqa: F401
+from .problem import (CPU, GPU, Diagnostic, DivFreeSpectraMap, ProbDiagnostic, Problem, SetUpProblemIC,  # noqa: F401
+                      TimeIntegrator, getCFL, increment, nothingfunction, spectralline, stepforward)
+
+__all__ = ["Problem", "SetUpProblemIC", "stepforward", "TimeIntegrator", "getCFL", "ProbDiagnostic", "Diagnostic",
+           "increment", "DivFreeSpectraMap", "spectralline", "CPU", "GPU", "nothingfunction", "MHDFlowsError",
+           "FRESH", "STALE"]

@@ -1,0 +1,819 @@
+// api.cu -- handle, orchestration and the extern "C" boundary declared in include/mhdflows_b200.h.
+//
+// One RHS evaluation (reference: MHDcalcN!/HDcalcN!/EMHDcalcN!, src/pgen.jl:153-181) is
+//   [EMHD: derive] -> inverse z pass -> inverse y pass -> fused x pass (c2r, products, r2c)
+//   -> forward y pass -> forward z pass -> spectral assembly + Runge-Kutta stage update
+// on a compact state that stores only the modes FourierFlows' dealias!() keeps.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mhdflows_b200.h"
+#include "kernels.cuh"
+
+using namespace mhdf;
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      throw Err{MHDF_ERR_CUDA, buf_};                                                              \
+    }                                                                                              \
+  } while (0)
+
+struct Err {
+  int code;
+  std::string msg;
+};
+
+enum { KC_ZINV = 0, KC_YINV, KC_XFUSED, KC_YFWD, KC_ZFWD, KC_SPEC, KC_DERIVE, KC_EXCH, KC_COUNT };
+
+struct mhdf_handle {
+  std::string err;
+  virtual ~mhdf_handle() {}
+  virtual void set_real(int field, const void* p) = 0;
+  virtual void get_real(int field, int which, void* p) = 0;
+  virtual void set_spectral(int field, const void* p) = 0;
+  virtual void get_spectral(int field, int which, void* p) = 0;
+  virtual void step(int n) = 0;
+  virtual void calcN(void* p) = 0;
+  virtual void set_dt(double dt) = 0;
+  virtual void set_clock(double t, long long step) = 0;
+  virtual void get_clock(double* t, double* dt, long long* step) const = 0;
+  virtual void cfl_dt(double coef, double t_diff, double* dt) = 0;
+  virtual void energy(int which, double* KE, double* ME) = 0;
+  virtual void helicity(double* Hk, double* Hm, double* Hc) = 0;
+  virtual void spectrum(int field, double* Pk, int nbins) = 0;
+  virtual void stale_stats(double* mx, double* sm) const = 0;
+  virtual void step_timed(int n, double* ms) = 0;
+  virtual void profile(int enable) = 0;
+  virtual void profile_get(double* ms, long long* cnt, int n) = 0;
+  virtual long long launch_count() const = 0;
+  virtual void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const = 0;
+};
+
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// FourierFlows.getaliasedwavenumbers with aliased_fraction = 1/3, evaluated in Float64 exactly like
+// the Julia expression: 1-based inclusive [iL, iR].
+static void alias_range(int nk, int* iL, int* iR) {
+  const double af = 1.0 / 3.0;
+  const double L = (1.0 - af) / 2.0, R = (1.0 + af) / 2.0;
+  *iL = (int)std::floor(L * nk) + 1;
+  *iR = (int)std::ceil(R * nk);
+}
+
+template <typename T>
+struct Solver : mhdf_handle {
+  using C = Cx<T>;
+  mhdf_config cfg;
+  int nx, ny, nz, nkr;
+  int Kx, Kxp, Ky, Kz;
+  Band by, bz;
+  int phys, F, nin, nout;
+  long long cf;   // elements of one compact field
+  cudaStream_t st = nullptr;
+  // state registers (compact, F fields each)
+  C* reg[4] = {nullptr, nullptr, nullptr, nullptr};
+  int iY = 0;       // register holding sol
+  int iStale = -1;  // register holding the last stage input (RK4), -1 if none
+  C *P = nullptr, *Q = nullptr, *R = nullptr, *D = nullptr;
+  size_t szP = 0, szQ = 0, szR = 0, szD = 0;
+  T* bst = nullptr;   // EMHD stale real b [3][nz][ny][nx]
+  C *twx = nullptr, *twy = nullptr, *twz = nullptr;
+  T *kxv = nullptr, *kyv = nullptr, *kzv = nullptr;
+  XRed* red_d = nullptr;
+  XRed* red_h = nullptr;   // pinned
+  double* diag_d = nullptr;
+  double* diag_h = nullptr;  // pinned
+  double* spec_d = nullptr;
+  int spec_cap = 0;
+  // stale vars statistics (getCFL!/ProbDiagnostic read vars.* of the last RHS evaluation)
+  double st_max[6] = {0, 0, 0, 0, 0, 0}, st_sum[6] = {0, 0, 0, 0, 0, 0}, st_cross = 0;
+  T t_, dt_;
+  long long step_ = 0;
+  long long launches = 0;
+  long long bytes_dev = 0;
+  int nsm = 148;
+  // profiling
+  bool prof = false;
+  struct Ev { cudaEvent_t a, b; int cls; };
+  std::vector<Ev> evs;
+  std::vector<Ev> ev_free;
+  double prof_ms[KC_COUNT];
+  long long prof_cnt[KC_COUNT];
+
+  template <typename U> U* dalloc(size_t n) {
+    U* p = nullptr;
+    CK(cudaMalloc(&p, n * sizeof(U)));
+    CK(cudaMemsetAsync(p, 0, n * sizeof(U), st));
+    bytes_dev += (long long)(n * sizeof(U));
+    return p;
+  }
+
+  explicit Solver(const mhdf_config& c) : cfg(c) {
+    nx = c.nx; ny = c.ny; nz = c.nz;
+    nkr = nx / 2 + 1;
+    int iL, iR;
+    alias_range(nx, &iL, &iR);
+    Kx = iL - 1;
+    Kxp = (Kx + 7) / 8 * 8;
+    alias_range(ny, &iL, &iR);
+    by.n = ny; by.lo = iL - 1; by.hi0 = iR;
+    alias_range(nz, &iL, &iR);
+    bz.n = nz; bz.lo = iL - 1; bz.hi0 = iR;
+    Ky = by.count(); Kz = bz.count();
+    phys = c.physics;
+    F = (phys == MHDF_MHD) ? 6 : 3;
+    nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 24);
+    nout = (phys == MHDF_MHD) ? 9 : (phys == MHDF_HD ? 6 : 3);
+    cf = (long long)Kxp * Ky * Kz;
+    t_ = (T)0; dt_ = (T)c.dt;
+    for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
+
+    CK(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    nsm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const int nreg = (c.stepper == MHDF_RK4) ? 4 : 3;
+    for (int i = 0; i < nreg; ++i) reg[i] = dalloc<C>((size_t)F * cf);
+    const size_t plane_zK = (size_t)nz * Ky * Kxp, plane_zy = (size_t)nz * ny * Kxp;
+    const int nmax = nin > nout ? nin : nout;
+    szP = (size_t)nmax * plane_zK;
+    szQ = (size_t)nin * plane_zy;
+    if ((size_t)nout * cf > szQ) szQ = (size_t)nout * cf;
+    szR = (size_t)nout * plane_zy;
+    // R doubles as the staging area of the API boundary (one real or one full spectral field)
+    const size_t need_stage = ((size_t)nkr * ny * nz > (size_t)nx * ny * nz / 2 ? (size_t)nkr * ny * nz : (size_t)nx * ny * nz / 2) + 16;
+    if (szR < need_stage) szR = need_stage;
+    P = dalloc<C>(szP); Q = dalloc<C>(szQ); R = dalloc<C>(szR);
+    if (phys == MHDF_EMHD) {
+      szD = (size_t)24 * cf;
+      D = dalloc<C>(szD);
+      bst = dalloc<T>((size_t)3 * nx * ny * nz);
+    }
+    twx = make_tw(nx); twy = make_tw(ny); twz = make_tw(nz);
+    // wavenumbers: built in Float64 then converted to T (FourierFlows ThreeDGrid; mirror utils/utils.jl:60-64)
+    std::vector<T> hx(Kx), hy(Ky), hz(Kz);
+    for (int i = 0; i < Kx; ++i) hx[i] = (T)(i * (2.0 * M_PI / c.Lx));
+    for (int j = 0; j < Ky; ++j) hy[j] = (T)(by.wave(j) * (2.0 * M_PI / c.Ly));
+    for (int k = 0; k < Kz; ++k) hz[k] = (T)(bz.wave(k) * (2.0 * M_PI / c.Lz));
+    kxv = dalloc<T>(Kx); kyv = dalloc<T>(Ky); kzv = dalloc<T>(Kz);
+    CK(cudaMemcpyAsync(kxv, hx.data(), Kx * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(kyv, hy.data(), Ky * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(kzv, hz.data(), Kz * sizeof(T), cudaMemcpyHostToDevice, st));
+    red_d = dalloc<XRed>(1);
+    diag_d = dalloc<double>(8);
+    CK(cudaMallocHost(&red_h, sizeof(XRed)));
+    CK(cudaMallocHost(&diag_h, 8 * sizeof(double)));
+    CK(cudaStreamSynchronize(st));
+    setup_attrs();
+  }
+
+  ~Solver() override {
+    cudaSetDevice(cfg.device);
+    if (st) cudaStreamSynchronize(st);
+    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
+    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst);
+    cudaFree(twx); cudaFree(twy); cudaFree(twz);
+    cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
+    cudaFree(red_d); cudaFree(diag_d); cudaFree(spec_d);
+    if (red_h) cudaFreeHost(red_h);
+    if (diag_h) cudaFreeHost(diag_h);
+    if (st) cudaStreamDestroy(st);
+  }
+
+  C* make_tw(int n) {
+    std::vector<C> h(n);
+    for (int i = 0; i < n; ++i) {
+      const double a = 2.0 * M_PI * (double)i / (double)n;
+      h[i].x = (T)std::cos(a);
+      h[i].y = (T)(-std::sin(a));
+    }
+    C* d = dalloc<C>(n);
+    CK(cudaMemcpyAsync(d, h.data(), n * sizeof(C), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return d;
+  }
+
+  SpecGeom<T> geom() const {
+    SpecGeom<T> g;
+    g.Kx = Kx; g.Kxp = Kxp; g.by = by; g.bz = bz; g.kx = kxv; g.ky = kyv; g.kz = kzv; g.field = cf;
+    return g;
+  }
+
+  // ---- profiling brackets ------------------------------------------------------------------
+  void prof_begin(int cls) {
+    if (!prof) return;
+    Ev e;
+    if (!ev_free.empty()) { e = ev_free.back(); ev_free.pop_back(); }
+    else { CK(cudaEventCreate(&e.a)); CK(cudaEventCreate(&e.b)); }
+    e.cls = cls;
+    CK(cudaEventRecord(e.a, st));
+    evs.push_back(e);
+  }
+  void prof_end() {
+    if (!prof) return;
+    CK(cudaEventRecord(evs.back().b, st));
+    if (evs.size() > 4096) prof_collect();
+  }
+  void prof_collect() {
+    CK(cudaStreamSynchronize(st));
+    for (auto& e : evs) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e.a, e.b));
+      prof_ms[e.cls] += ms;
+      prof_cnt[e.cls] += 1;
+      ev_free.push_back(e);
+    }
+    evs.clear();
+  }
+
+  // ---- kernel dispatch ------------------------------------------------------------------------
+  static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
+  static constexpr int passTX(int N) { return sizeof(T) == 4 ? (N >= 1024 ? 8 : 16) : (N >= 1024 ? 4 : 8); }
+  static constexpr int xE(int) { return 8; }
+  static constexpr int xRB(int N) { return 256 / (N / 2 / 8) > 0 ? 256 / (N / 2 / 8) : 1; }
+
+  template <int N, int DIR> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
+    constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
+    constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
+    dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
+    k_pass<T, N, E, TX, DIR><<<grid, (N / E) * TX, smem, st>>>(a);
+    ++launches;
+  }
+  template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
+    switch (N) {
+      case 16: launch_pass_n<16, DIR>(a, n_outer, n_fields); break;
+      case 32: launch_pass_n<32, DIR>(a, n_outer, n_fields); break;
+      case 64: launch_pass_n<64, DIR>(a, n_outer, n_fields); break;
+      case 128: launch_pass_n<128, DIR>(a, n_outer, n_fields); break;
+      case 256: launch_pass_n<256, DIR>(a, n_outer, n_fields); break;
+      case 512: launch_pass_n<512, DIR>(a, n_outer, n_fields); break;
+      case 1024: launch_pass_n<1024, DIR>(a, n_outer, n_fields); break;
+      default: throw Err{MHDF_ERR_INVALID, "unsupported axis length"};
+    }
+    CK(cudaGetLastError());
+  }
+
+  template <int N> static size_t x_smem() {
+    constexpr int E = xE(N), M = N / 2, R1 = imin(E, M);
+    return (size_t)2 * xRB(N) * RowIdx<M, R1>::SIZE * sizeof(C);
+  }
+  int x_grid(long long rows, int RB) const {
+    long long sets = rows / RB;
+    long long g = (long long)nsm * 8;
+    return (int)(sets < g ? sets : g);
+  }
+  template <int N> void launch_xfused_n(XArgs<T>& a) {
+    constexpr int E = xE(N), RB = xRB(N);
+    const int grid = x_grid(a.rows, RB);
+    const int threads = (N / 2 / E) * RB;
+    if (phys == MHDF_MHD) k_xfused<T, N, E, RB, PHYS_MHD><<<grid, threads, x_smem<N>(), st>>>(a);
+    else if (phys == MHDF_HD) k_xfused<T, N, E, RB, PHYS_HD><<<grid, threads, x_smem<N>(), st>>>(a);
+    else k_xfused<T, N, E, RB, PHYS_EMHD><<<grid, threads, x_smem<N>(), st>>>(a);
+    ++launches;
+  }
+  template <int N, int DIR> void launch_xplain_n(XArgs<T>& a) {
+    constexpr int E = xE(N), RB = xRB(N);
+    k_xplain<T, N, E, RB, DIR><<<x_grid(a.rows, RB), (N / 2 / E) * RB, x_smem<N>(), st>>>(a);
+    ++launches;
+  }
+  void launch_xfused(XArgs<T>& a) {
+    switch (nx) {
+      case 16: launch_xfused_n<16>(a); break;
+      case 32: launch_xfused_n<32>(a); break;
+      case 64: launch_xfused_n<64>(a); break;
+      case 128: launch_xfused_n<128>(a); break;
+      case 256: launch_xfused_n<256>(a); break;
+      case 512: launch_xfused_n<512>(a); break;
+      case 1024: launch_xfused_n<1024>(a); break;
+      default: throw Err{MHDF_ERR_INVALID, "unsupported nx"};
+    }
+    CK(cudaGetLastError());
+  }
+  template <int DIR> void launch_xplain(XArgs<T>& a) {
+    switch (nx) {
+      case 16: launch_xplain_n<16, DIR>(a); break;
+      case 32: launch_xplain_n<32, DIR>(a); break;
+      case 64: launch_xplain_n<64, DIR>(a); break;
+      case 128: launch_xplain_n<128, DIR>(a); break;
+      case 256: launch_xplain_n<256, DIR>(a); break;
+      case 512: launch_xplain_n<512, DIR>(a); break;
+      case 1024: launch_xplain_n<1024, DIR>(a); break;
+      default: throw Err{MHDF_ERR_INVALID, "unsupported nx"};
+    }
+    CK(cudaGetLastError());
+  }
+  void setup_attrs() {
+    // opt in to > 48 KB dynamic shared memory where a plan needs it
+    set_pass_attr<256>(); set_pass_attr<512>(); set_pass_attr<1024>();
+    set_x_attr<16>(); set_x_attr<32>(); set_x_attr<64>(); set_x_attr<128>(); set_x_attr<256>(); set_x_attr<512>(); set_x_attr<1024>();
+  }
+  template <int N> void set_x_attr() {
+    constexpr int E = xE(N), RB = xRB(N);
+    const int smem = (int)x_smem<N>();
+    if (smem > 48 * 1024) {
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+  }
+  template <int N> void set_pass_attr() {
+    constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
+    constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
+    if (smem > 48 * 1024) {
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+  }
+
+  // ---- 3D transform legs -------------------------------------------------------------------
+  // compact [nf][Kz][Ky][Kxp] -> [nf][nz][Ky][Kxp]
+  void z_inverse(const C* in, long long in_field, C* out, int nf) {
+    PassArgs<T> a;
+    a.in = in; a.out = out; a.tw = twz;
+    a.in_row = a.out_row = (long long)Ky * Kxp;
+    a.in_outer = a.out_outer = 0;
+    a.in_field = in_field; a.out_field = (long long)nz * Ky * Kxp;
+    a.inner = Ky * Kxp; a.bin = bz; a.bout = band_full(nz); a.scale = (T)1;
+    prof_begin(KC_ZINV);
+    launch_pass<+1>(nz, a, 1, nf);
+    prof_end();
+  }
+  // [nf][nz][Ky][Kxp] -> [nf][nz][ny][Kxp]
+  void y_inverse(const C* in, C* out, int nf) {
+    PassArgs<T> a;
+    a.in = in; a.out = out; a.tw = twy;
+    a.in_row = a.out_row = Kxp;
+    a.in_outer = (long long)Ky * Kxp; a.out_outer = (long long)ny * Kxp;
+    a.in_field = (long long)nz * Ky * Kxp; a.out_field = (long long)nz * ny * Kxp;
+    a.inner = Kxp; a.bin = by; a.bout = band_full(ny); a.scale = (T)1;
+    prof_begin(KC_YINV);
+    launch_pass<+1>(ny, a, nz, nf);
+    prof_end();
+  }
+  // [nf][nz][ny][Kxp] -> [nf][nz][Ky][Kxp]
+  void y_forward(const C* in, C* out, int nf) {
+    PassArgs<T> a;
+    a.in = in; a.out = out; a.tw = twy;
+    a.in_row = a.out_row = Kxp;
+    a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Ky * Kxp;
+    a.in_field = (long long)nz * ny * Kxp; a.out_field = (long long)nz * Ky * Kxp;
+    a.inner = Kxp; a.bin = band_full(ny); a.bout = by; a.scale = (T)1;
+    prof_begin(KC_YFWD);
+    launch_pass<-1>(ny, a, nz, nf);
+    prof_end();
+  }
+  // [nf][nz][Ky][Kxp] -> compact [nf][Kz][Ky][Kxp]
+  void z_forward(const C* in, C* out, long long out_field, int nf) {
+    PassArgs<T> a;
+    a.in = in; a.out = out; a.tw = twz;
+    a.in_row = a.out_row = (long long)Ky * Kxp;
+    a.in_outer = a.out_outer = 0;
+    a.in_field = (long long)nz * Ky * Kxp; a.out_field = out_field;
+    a.inner = Ky * Kxp; a.bin = band_full(nz); a.bout = bz; a.scale = (T)1;
+    prof_begin(KC_ZFWD);
+    launch_pass<-1>(nz, a, 1, nf);
+    prof_end();
+  }
+
+  XArgs<T> xargs() const {
+    XArgs<T> a;
+    a.in = Q; a.out = R; a.tw = twx; a.real_io = nullptr;
+    a.in_field = a.out_field = (long long)nz * ny * Kxp;
+    a.real_field = (long long)nx * ny * nz;
+    a.rows = (long long)ny * nz;
+    a.Kx = Kx; a.Kxp = Kxp;
+    a.scale = (T)(1.0 / ((double)nx * ny * nz));
+    a.red = nullptr;
+    return a;
+  }
+
+  // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
+  void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
+    const C* zin = Sin;
+    if (phys == MHDF_EMHD) {
+      prof_begin(KC_DERIVE);
+      k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
+      ++launches;
+      CK(cudaGetLastError());
+      prof_end();
+      zin = D;
+    }
+    z_inverse(zin, cf, P, nin);
+    y_inverse(P, Q, nin);
+    XArgs<T> xa = xargs();
+    xa.real_io = bst;
+    if (want_red) {
+      CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+      xa.red = red_d;
+    }
+    prof_begin(KC_XFUSED);
+    launch_xfused(xa);
+    prof_end();
+    if (want_red) CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
+    y_forward(R, P, nout);
+    z_forward(P, Q, cf, nout);
+    sa.g = geom();
+    sa.P = Q; sa.Sin = Sin;
+    sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
+    prof_begin(KC_SPEC);
+    if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<spec_grid(), 256, 0, st>>>(sa);
+    else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<spec_grid(), 256, 0, st>>>(sa);
+    else k_spectral<T, PHYS_EMHD><<<spec_grid(), 256, 0, st>>>(sa);
+    ++launches;
+    CK(cudaGetLastError());
+    prof_end();
+  }
+  int spec_grid() const {
+    long long b = (cf + 255) / 256;
+    long long cap = (long long)nsm * 16;
+    return (int)(b < cap ? b : cap);
+  }
+
+  void absorb_red() {   // after a stream sync: stale vars statistics of the last RHS evaluation
+    for (int i = 0; i < 6; ++i) {
+      st_sum[i] = red_h->sumsq[i];
+      float f;
+      std::memcpy(&f, &red_h->maxsq[i], 4);
+      st_max[i] = (double)f;
+    }
+    st_cross = red_h->cross;
+  }
+
+  SpecArgs<T> blank_args() const {
+    SpecArgs<T> sa;
+    std::memset(&sa, 0, sizeof sa);
+    sa.dt = dt_;
+    return sa;
+  }
+
+  void one_step() {
+    const T dt = dt_;
+    if (cfg.stepper == MHDF_RK4) {
+      // registers: Y = reg[iY]; two stage buffers and the accumulator are the other three
+      int o[3], n = 0;
+      for (int i = 0; i < 4; ++i) if (i != iY) o[n++] = i;
+      C *Y = reg[iY], *S0 = reg[o[0]], *S1 = reg[o[1]], *A = reg[o[2]];
+      SpecArgs<T> sa = blank_args();
+      sa.Y = Y; sa.A = A;
+      sa.mode = STEP_RK4_1; sa.ca = dt / (T)6; sa.cs = dt / (T)2; sa.Sout = S0;
+      rhs(Y, sa, false);
+      sa.mode = STEP_RK4_2; sa.ca = dt / (T)3; sa.cs = dt / (T)2; sa.Sout = S1;
+      rhs(S0, sa, false);
+      sa.mode = STEP_RK4_3; sa.ca = dt / (T)3; sa.cs = dt; sa.Sout = S0;
+      rhs(S1, sa, false);
+      sa.mode = STEP_RK4_4; sa.ca = dt / (T)6; sa.cs = 0; sa.Sout = Y;
+      rhs(S0, sa, true);
+      iStale = o[0];
+    } else {
+      static const double LA[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                   -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+      static const double LB[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                                   1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                                   2277821191437.0 / 14882151754819.0};
+      // registers: sol ping-pongs between two buffers, S2 is the third
+      int o[2], n = 0;
+      for (int i = 0; i < 3; ++i) if (i != iY) o[n++] = i;
+      int cur = iY, oth = o[0];
+      C* S2 = reg[o[1]];
+      for (int i = 0; i < 5; ++i) {
+        SpecArgs<T> sa = blank_args();
+        sa.mode = STEP_LSRK; sa.A = S2; sa.ca = (T)LA[i]; sa.cs = (T)LB[i]; sa.first = (i == 0);
+        sa.Sout = reg[oth];
+        rhs(reg[cur], sa, i == 4);
+        int tmp = cur; cur = oth; oth = tmp;
+      }
+      // after 5 swaps `cur` holds the new sol, `oth` the 5th stage input (= stale vars source)
+      iY = cur;
+      iStale = oth;
+      // keep S2 where it is: the third register
+    }
+    t_ = t_ + dt;
+    step_ += 1;
+  }
+
+  void step(int n) override {
+    CK(cudaSetDevice(cfg.device));
+    for (int i = 0; i < n; ++i) one_step();
+    CK(cudaStreamSynchronize(st));
+    if (n > 0) {
+      absorb_red();
+      check_finite();
+    }
+  }
+  void check_finite() {
+    for (int i = 0; i < 6; ++i)
+      if (!std::isfinite(st_sum[i])) throw Err{MHDF_ERR_NONFINITE, "detected NaN! Quit the simulation right now."};
+  }
+  void step_timed(int n, double* ms) override {
+    CK(cudaSetDevice(cfg.device));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventRecord(a, st));
+    for (int i = 0; i < n; ++i) one_step();
+    CK(cudaEventRecord(b, st));
+    CK(cudaStreamSynchronize(st));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms = f;
+    if (n > 0) { absorb_red(); check_finite(); }
+  }
+
+  void calcN(void* p) override {
+    CK(cudaSetDevice(cfg.device));
+    // N goes to a register that is dead between steps
+    int o = -1;
+    const int nreg = (cfg.stepper == MHDF_RK4) ? 4 : 3;
+    for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
+    SpecArgs<T> sa = blank_args();
+    sa.mode = STEP_CALCN; sa.Nout = reg[o];
+    rhs(reg[iY], sa, true);
+    CK(cudaStreamSynchronize(st));
+    absorb_red();
+    for (int f = 0; f < F; ++f) unpack_to_host(reg[o] + f * cf, (C*)p + (size_t)f * nkr * ny * nz);
+  }
+
+  // ---- API boundary: real / spectral fields ------------------------------------------------
+  void check_field(int f) const {
+    if (f < 0 || f >= F) throw Err{MHDF_ERR_INVALID, "field index out of range"};
+  }
+  void set_real(int field, const void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    T* re = reinterpret_cast<T*>(R);
+    const size_t n = (size_t)nx * ny * nz;
+    CK(cudaMemcpyAsync(re, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    XArgs<T> xa = xargs();
+    xa.real_io = re; xa.out = Q; xa.in = nullptr;
+    CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+    xa.red = red_d;
+    launch_xplain<-1>(xa);
+    CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
+    y_forward(Q, P, 1);
+    z_forward(P, reg[iY] + field * cf, cf, 1);
+    if (phys == MHDF_EMHD)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
+      CK(cudaMemcpyAsync(bst + (size_t)field * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    // vars.* statistics of the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88)
+    const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
+    st_sum[slot] = red_h->sumsq[0];
+    float f;
+    std::memcpy(&f, &red_h->maxsq[0], 4);
+    st_max[slot] = (double)f;
+  }
+  const C* source(int which) const {
+    if (which == MHDF_STALE && iStale >= 0) return reg[iStale];
+    return reg[iY];
+  }
+  void get_real(int field, int which, void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    z_inverse(source(which) + field * cf, cf, P, 1);
+    y_inverse(P, Q, 1);
+    T* re = reinterpret_cast<T*>(R);
+    XArgs<T> xa = xargs();
+    xa.real_io = re; xa.in = Q; xa.out = nullptr;
+    launch_xplain<+1>(xa);
+    CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nz * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  void set_spectral(int field, const void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    const size_t n = (size_t)nkr * ny * nz;
+    CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyHostToDevice, st));
+    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, reg[iY] + field * cf, nkr, ny, nz, Kx, Kxp, by, bz, 0);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+  }
+  int pack_grid() const {
+    long long b = ((long long)nkr * ny * nz + 255) / 256;
+    long long cap = (long long)nsm * 16;
+    return (int)(b < cap ? b : cap);
+  }
+  void unpack_to_host(const C* comp, C* host) {
+    const size_t n = (size_t)nkr * ny * nz;
+    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, const_cast<C*>(comp), nkr, ny, nz, Kx, Kxp, by, bz, 1);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  void get_spectral(int field, int which, void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    unpack_to_host(source(which) + field * cf, (C*)p);
+  }
+
+  // ---- clock, CFL, diagnostics ----------------------------------------------------------------
+  void set_dt(double dt) override { dt_ = (T)dt; }
+  void set_clock(double t, long long s) override { t_ = (T)t; step_ = s; }
+  void get_clock(double* t, double* dt, long long* s) const override {
+    if (t) *t = (double)t_;
+    if (dt) *dt = (double)dt_;
+    if (s) *s = step_;
+  }
+  void cfl_dt(double coef, double t_diff, double* dt) override {
+    // integrator.jl:158-198 on the stale maxima (vars.* of the last RHS evaluation)
+    double vmax = std::sqrt(std::fmax(st_max[0], std::fmax(st_max[1], st_max[2])));   // u, or curl B for EMHD
+    if (phys != MHDF_HD) {
+      const double va = std::sqrt(std::fmax(st_max[3], std::fmax(st_max[4], st_max[5])));
+      vmax = std::fmax(vmax, va);
+    }
+    const double dx = cfg.Lx / nx, dy = cfg.Ly / ny, dz = cfg.Lz / nz;
+    double dl = std::fmin(dx, std::fmin(dy, dz));
+    if (phys == MHDF_EMHD) dl = dl * dl;
+    double d = coef * dl / vmax;
+    if (!(d < t_diff)) d = t_diff;
+    dt_ = (T)d;
+    if (dt) *dt = (double)dt_;
+  }
+  double dV() const {
+    // ProbDiagnostic: dV = diff(x)[1]*diff(y)[1]*diff(z)[1] with x = range(T(x0), step=T(dx)) (UserInterface.jl:66-67)
+    return (double)(T)(cfg.Lx / nx) * (double)(T)(cfg.Ly / ny) * (double)(T)(cfg.Lz / nz);
+  }
+  void run_diag(int which) {
+    const C* s = source(which);
+    CK(cudaMemsetAsync(diag_d, 0, 8 * sizeof(double), st));
+    const C* U = (phys == MHDF_EMHD) ? nullptr : s;
+    const C* B = (phys == MHDF_HD) ? nullptr : (phys == MHDF_EMHD ? s : s + 3 * cf);
+    k_diag<T><<<spec_grid(), 256, 0, st>>>(geom(), U, B, 1.0 / ((double)nx * ny * nz), diag_d);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(diag_h, diag_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  void energy(int which, double* KE, double* ME) override {
+    CK(cudaSetDevice(cfg.device));
+    double ke, me;
+    if (which == MHDF_STALE) {
+      if (phys == MHDF_EMHD) { ke = 0; me = (st_sum[3] + st_sum[4] + st_sum[5]) * dV(); }
+      else { ke = (st_sum[0] + st_sum[1] + st_sum[2]) * dV(); me = (st_sum[3] + st_sum[4] + st_sum[5]) * dV(); }
+      if (phys == MHDF_HD) me = 0;
+    } else {
+      run_diag(MHDF_FRESH);
+      ke = diag_h[0] * dV(); me = diag_h[1] * dV();
+    }
+    if (std::isnan(ke) || std::isnan(me)) throw Err{MHDF_ERR_NONFINITE, "detected NaN! Quit the simulation right now."};
+    if (KE) *KE = ke;
+    if (ME) *ME = me;
+  }
+  void helicity(double* Hk, double* Hm, double* Hc) override {
+    CK(cudaSetDevice(cfg.device));
+    run_diag(MHDF_FRESH);
+    const double dv = (cfg.Lx / nx) * (cfg.Ly / ny) * (cfg.Lz / nz);
+    if (Hk) *Hk = diag_h[2] * dv;
+    if (Hm) *Hm = diag_h[3];
+    if (Hc) *Hc = diag_h[4] * dv;
+  }
+  void spectrum(int field, double* Pk, int nbins) override {
+    check_field(field);
+    if (nbins <= 0 || nbins > 4096) throw Err{MHDF_ERR_INVALID, "nbins must be in 1..4096"};
+    CK(cudaSetDevice(cfg.device));
+    if (spec_cap < nbins) {
+      if (spec_d) cudaFree(spec_d);
+      spec_d = nullptr;
+      CK(cudaMalloc(&spec_d, nbins * sizeof(double)));
+      spec_cap = nbins;
+    }
+    CK(cudaMemsetAsync(spec_d, 0, nbins * sizeof(double), st));
+    k_spectrum<T><<<spec_grid(), 256, nbins * sizeof(double), st>>>(geom(), reg[iY] + field * cf, spec_d, nbins);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(Pk, spec_d, nbins * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  void stale_stats(double* mx, double* sm) const override {
+    for (int i = 0; i < 6; ++i) { if (mx) mx[i] = st_max[i]; if (sm) sm[i] = st_sum[i]; }
+  }
+  void profile(int enable) override {
+    if (prof && !enable) prof_collect();
+    prof = enable != 0;
+    if (enable) for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
+  }
+  void profile_get(double* ms, long long* cnt, int n) override {
+    prof_collect();
+    for (int i = 0; i < n && i < KC_COUNT; ++i) { if (ms) ms[i] = prof_ms[i]; if (cnt) cnt[i] = prof_cnt[i]; }
+  }
+  long long launch_count() const override { return launches; }
+  void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const override {
+    if (nf) *nf = F;
+    if (kx) *kx = Kx;
+    if (kxp) *kxp = Kxp;
+    if (ky) *ky = Ky;
+    if (kz) *kz = Kz;
+    if (bytes) *bytes = bytes_dev;
+  }
+};
+
+// ---- extern "C" --------------------------------------------------------------------------------
+template <typename Fn> static int guard(mhdf_handle* h, Fn fn) {
+  if (h == nullptr) return MHDF_ERR_INVALID;
+  try {
+    fn();
+    return MHDF_OK;
+  } catch (const Err& e) {
+    h->err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return MHDF_ERR_STATE;
+  }
+}
+
+extern "C" {
+
+int mhdf_create(const mhdf_config* c, mhdf_handle** out) {
+  if (c == nullptr || out == nullptr) { g_create_error = "null argument"; return MHDF_ERR_INVALID; }
+  *out = nullptr;
+  auto bad = [&](const char* m) { g_create_error = m; return (int)MHDF_ERR_INVALID; };
+  for (int n : {c->nx, c->ny, c->nz})
+    if (!is_pow2(n) || n < 16 || n > 1024) return bad("nx, ny, nz must be powers of two in 16..1024");
+  if ((long long)c->ny * c->nz < 256) return bad("ny*nz must be at least 256");
+  if (!(c->Lx > 0 && c->Ly > 0 && c->Lz > 0)) return bad("Lx, Ly, Lz must be positive");
+  if (c->physics < MHDF_HD || c->physics > MHDF_EMHD) return bad("physics must be MHDF_HD, MHDF_MHD or MHDF_EMHD");
+  if (c->stepper != MHDF_RK4 && c->stepper != MHDF_LSRK54) return bad("stepper must be RK4 or LSRK54 (Problems.jl:123-128)");
+  if (c->dtype != MHDF_F32 && c->dtype != MHDF_F64) return bad("dtype must be MHDF_F32 or MHDF_F64");
+  if (c->nranks != 1 || c->rank != 0) return bad("this build supports nranks = 1 only");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+    return MHDF_ERR_CUDA;
+  }
+  if (c->device < 0 || c->device >= ndev) return bad("device ordinal out of range");
+  try {
+    if (c->dtype == MHDF_F32) *out = new Solver<float>(*c);
+    else *out = new Solver<double>(*c);
+    return MHDF_OK;
+  } catch (const Err& er) {
+    g_create_error = er.msg;
+    return er.code;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return MHDF_ERR_STATE;
+  }
+}
+
+int mhdf_destroy(mhdf_handle* h) {
+  if (h == nullptr) return MHDF_ERR_INVALID;
+  delete h;
+  return MHDF_OK;
+}
+const char* mhdf_last_error(const mhdf_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int mhdf_nccl_unique_id(void* id128) {
+  if (id128 == nullptr) return MHDF_ERR_INVALID;
+  std::memset(id128, 0, 128);
+  return MHDF_ERR_NCCL;
+}
+int mhdf_set_real(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_real(f, p); }); }
+int mhdf_get_real(mhdf_handle* h, int f, int w, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->get_real(f, w, p); }); }
+int mhdf_set_spectral(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_spectral(f, p); }); }
+int mhdf_get_spectral(mhdf_handle* h, int f, int w, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->get_spectral(f, w, p); }); }
+int mhdf_step(mhdf_handle* h, int n) { return guard(h, [&] { if (n < 0) throw Err{MHDF_ERR_INVALID, "nsteps < 0"}; h->step(n); }); }
+int mhdf_calcN(mhdf_handle* h, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->calcN(p); }); }
+int mhdf_set_dt(mhdf_handle* h, double dt) { return guard(h, [&] { h->set_dt(dt); }); }
+int mhdf_set_clock(mhdf_handle* h, double t, long long s) { return guard(h, [&] { h->set_clock(t, s); }); }
+int mhdf_get_clock(const mhdf_handle* h, double* t, double* dt, long long* s) {
+  if (!h) return MHDF_ERR_INVALID;
+  h->get_clock(t, dt, s);
+  return MHDF_OK;
+}
+int mhdf_cfl_dt(mhdf_handle* h, double coef, double t_diff, double* dt) { return guard(h, [&] { h->cfl_dt(coef, t_diff, dt); }); }
+int mhdf_energy(mhdf_handle* h, int w, double* KE, double* ME) { return guard(h, [&] { h->energy(w, KE, ME); }); }
+int mhdf_helicity(mhdf_handle* h, double* a, double* b, double* c) { return guard(h, [&] { h->helicity(a, b, c); }); }
+int mhdf_spectrum(mhdf_handle* h, int f, double* Pk, int nb) { return guard(h, [&] { if (!Pk) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->spectrum(f, Pk, nb); }); }
+int mhdf_stale_stats(const mhdf_handle* h, double* mx, double* sm) {
+  if (!h) return MHDF_ERR_INVALID;
+  h->stale_stats(mx, sm);
+  return MHDF_OK;
+}
+int mhdf_step_timed(mhdf_handle* h, int n, double* ms) { return guard(h, [&] { if (n < 0 || !ms) throw Err{MHDF_ERR_INVALID, "bad argument"}; h->step_timed(n, ms); }); }
+int mhdf_profile(mhdf_handle* h, int en) { return guard(h, [&] { h->profile(en); }); }
+int mhdf_profile_get(mhdf_handle* h, double* ms, long long* cnt, int n) { return guard(h, [&] { h->profile_get(ms, cnt, n); }); }
+long long mhdf_launch_count(const mhdf_handle* h) { return h ? h->launch_count() : -1; }
+int mhdf_info(const mhdf_handle* h, int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) {
+  if (!h) return MHDF_ERR_INVALID;
+  h->info(nf, kx, kxp, ky, kz, bytes);
+  return MHDF_OK;
+}
+
+}  // extern "C"

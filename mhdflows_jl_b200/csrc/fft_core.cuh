@@ -1,0 +1,197 @@
+// fft_core.cuh -- register/shared-memory Stockham FFT building blocks for sm_100a.
+//
+// One FFT of length N is owned by Tn = N/E threads; thread t holds the E elements
+// n = t + Tn*m (m = 0..E-1) in registers.  A transform is a sequence of radix-R steps
+// (R = min(E, remaining), R in {2,4,8,16}); between steps the elements are exchanged
+// through shared memory with the Stockham autosort index map
+//     out(j, r') = (j / Ns) * Ns * R + (j % Ns) + r' * Ns ,   j = t + q*Tn .
+// After the last step thread t again holds n = t + Tn*m in natural order, so a load /
+// store pattern with TX (or Tn) contiguous elements per row segment is the same on both
+// sides.  The index arithmetic is mirrored 1:1 in tools/fft_plan_sim.py.
+//
+// Replaces, for this path, the cuFFT/FFTW plans behind `mul!(yh, grid.rfftplan, y)` /
+// `ldiv!(y, grid.rfftplan, yh)` (reference: src/Solver/MHDSolver.jl:74,93,152,167,333-338).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace mhdf {
+
+template <typename T> struct CxT;
+template <> struct CxT<float>  { using type = float2; };
+template <> struct CxT<double> { using type = double2; };
+template <typename T> using Cx = typename CxT<T>::type;
+
+template <typename C> struct RealOf;
+template <> struct RealOf<float2>  { using type = float; };
+template <> struct RealOf<double2> { using type = double; };
+
+template <typename C> __device__ __forceinline__ C mk(typename RealOf<C>::type x, typename RealOf<C>::type y) { C c; c.x = x; c.y = y; return c; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return mk<C>(a.x + b.x, a.y + b.y); }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { return mk<C>(a.x - b.x, a.y - b.y); }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) { return mk<C>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) { return mk<C>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+template <typename C> __device__ __forceinline__ C cconj(C a) { return mk<C>(a.x, -a.y); }
+template <typename C> __device__ __forceinline__ C cscale(C a, typename RealOf<C>::type s) { return mk<C>(a.x * s, a.y * s); }
+// multiply by +i / -i
+template <typename C> __device__ __forceinline__ C cmuli(C a)  { return mk<C>(-a.y, a.x); }
+template <typename C> __device__ __forceinline__ C cmulmi(C a) { return mk<C>(a.y, -a.x); }
+
+// DIR = -1: forward (exp(-i..)), DIR = +1: inverse (exp(+i..)), both unnormalised.
+
+// cos/sin(2*pi*k/16), k = 0..7
+__device__ __forceinline__ constexpr double c16(int k) {
+  return k == 0 ? 1.0 : k == 1 ? 0.92387953251128673848 : k == 2 ? 0.70710678118654752440 : k == 3 ? 0.38268343236508977173
+       : k == 4 ? 0.0 : k == 5 ? -0.38268343236508977173 : k == 6 ? -0.70710678118654752440 : -0.92387953251128673848;
+}
+__device__ __forceinline__ constexpr double s16(int k) {
+  return k == 0 ? 0.0 : k == 1 ? 0.38268343236508977173 : k == 2 ? 0.70710678118654752440 : k == 3 ? 0.92387953251128673848
+       : k == 4 ? 1.0 : k == 5 ? 0.92387953251128673848 : k == 6 ? 0.70710678118654752440 : 0.38268343236508977173;
+}
+
+// In-register radix-R DFT, natural order in -> natural order out (decimation in time).
+template <int R, int DIR, typename C> struct Bfly;
+
+template <int DIR, typename C> struct Bfly<1, DIR, C> {
+  static __device__ __forceinline__ void run(C (&)[1]) {}
+};
+template <int DIR, typename C> struct Bfly<2, DIR, C> {
+  static __device__ __forceinline__ void run(C (&v)[2]) {
+    C a = v[0];
+    v[0] = cadd(a, v[1]);
+    v[1] = csub(a, v[1]);
+  }
+};
+template <int DIR, typename C> struct Bfly<4, DIR, C> {
+  static __device__ __forceinline__ void run(C (&v)[4]) {
+    C a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+    C a2 = cadd(v[1], v[3]), a3 = csub(v[1], v[3]);
+    C r = (DIR < 0) ? cmulmi(a3) : cmuli(a3);   // a3 * exp(DIR*i*pi/2)
+    v[0] = cadd(a0, a2);
+    v[2] = csub(a0, a2);
+    v[1] = cadd(a1, r);
+    v[3] = csub(a1, r);
+  }
+};
+template <int R, int DIR, typename C> struct Bfly {
+  static_assert(R == 8 || R == 16, "radix must be 2, 4, 8 or 16");
+  using T = typename RealOf<C>::type;
+  static __device__ __forceinline__ void run(C (&v)[R]) {
+    C e[R / 2], o[R / 2];
+#pragma unroll
+    for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Bfly<R / 2, DIR, C>::run(e);
+    Bfly<R / 2, DIR, C>::run(o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      C t;
+      if (k == 0) t = o[0];
+      else if (k == R / 4) t = (DIR < 0) ? cmulmi(o[k]) : cmuli(o[k]);
+      else {
+        const T wc = (T)c16(k * (16 / R));
+        const T ws = (T)(DIR * s16(k * (16 / R)));
+        t = mk<C>(o[k].x * wc - o[k].y * ws, o[k].x * ws + o[k].y * wc);
+      }
+      v[k] = cadd(e[k], t);
+      v[k + R / 2] = csub(e[k], t);
+    }
+  }
+};
+
+constexpr __host__ __device__ int imin(int a, int b) { return a < b ? a : b; }
+constexpr __host__ __device__ int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+
+// One radix-R step on the register file of thread t (no shared memory).
+// tw[i] = (cos(2*pi*i/NTW), -sin(2*pi*i/NTW)), NTW = N * TWS (TWS = table stride, 1 or 2).
+template <typename C, int N, int E, int R, int NS, int DIR, int TWS>
+__device__ __forceinline__ void fft_step(C (&v)[E], int t, const C* __restrict__ tw) {
+  constexpr int Tn = N / E;
+  constexpr int Q = E / R;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    C x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = v[q + r * Q];
+    if (NS > 1) {
+      const int j = t + q * Tn;
+      const int k = j & (NS - 1);
+      constexpr int STR = (N / (NS * R)) * TWS;
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        C w = __ldg(&tw[(r * k) * STR]);
+        x[r] = (DIR < 0) ? cmul(x[r], w) : cmulc(x[r], w);
+      }
+    }
+    Bfly<R, DIR, C>::run(x);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[q + r * Q] = x[r];
+  }
+}
+
+// Scatter the outputs of the (R, NS) step into shared memory in Stockham order.
+// IDX(n) maps the logical element index n of this FFT to a shared-memory slot.
+template <typename C, int N, int E, int R, int NS, typename IDX>
+__device__ __forceinline__ void fft_scatter(const C (&v)[E], int t, C* __restrict__ sm, IDX idx) {
+  constexpr int Tn = N / E;
+  constexpr int Q = E / R;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int j = t + q * Tn;
+    const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+#pragma unroll
+    for (int r = 0; r < R; ++r) sm[idx(base + r * NS)] = v[q + r * Q];
+  }
+}
+template <typename C, int N, int E, typename IDX>
+__device__ __forceinline__ void fft_gather(C (&v)[E], int t, const C* __restrict__ sm, IDX idx) {
+  constexpr int Tn = N / E;
+#pragma unroll
+  for (int m = 0; m < E; ++m) v[m] = sm[idx(t + Tn * m)];
+}
+
+// SYNC policy objects: block-wide or warp-wide barrier.
+struct SyncBlock { static __device__ __forceinline__ void sync() { __syncthreads(); } };
+struct SyncWarp  { static __device__ __forceinline__ void sync() { __syncwarp(); } };
+
+// Full transform.  Shared memory is used as two alternating exchange buffers (sm0, sm1) so each
+// exchange costs one barrier: step s writes buffer (s & 1); a thread can only reach the next write
+// of the same buffer after passing the barrier of the exchange in between, by which time every
+// thread has finished reading it.  The caller must ensure sm0 is free on entry (one barrier since
+// its last read).  Returns with data in registers in natural order n = t + Tn*m.
+template <typename C, int N, int E, int DIR, int TWS, int NS, int PAR, typename SYNC, typename IDX>
+__device__ __forceinline__ void fft_run(C (&v)[E], int t, C* __restrict__ sm0, C* __restrict__ sm1,
+                                        const C* __restrict__ tw, IDX idx) {
+  constexpr int R = imin(E, N / NS);
+  fft_step<C, N, E, R, NS, DIR, TWS>(v, t, tw);
+  if constexpr (NS * R < N) {
+    C* sm = PAR ? sm1 : sm0;
+    fft_scatter<C, N, E, R, NS>(v, t, sm, idx);
+    SYNC::sync();
+    fft_gather<C, N, E>(v, t, sm, idx);
+    fft_run<C, N, E, DIR, TWS, NS * R, PAR ^ 1, SYNC, IDX>(v, t, sm0, sm1, tw, idx);
+  }
+}
+
+// Single-buffer variant (strided passes, where shared memory limits occupancy): two barriers per
+// exchange.  The buffer must be free on entry; it is free again on return.
+template <typename C, int N, int E, int DIR, int TWS, int NS, typename IDX>
+__device__ __forceinline__ void fft_run_sb(C (&v)[E], int t, C* __restrict__ sm, const C* __restrict__ tw, IDX idx) {
+  constexpr int R = imin(E, N / NS);
+  fft_step<C, N, E, R, NS, DIR, TWS>(v, t, tw);
+  if constexpr (NS * R < N) {
+    if constexpr (NS > 1) __syncthreads();   // previous gather finished
+    fft_scatter<C, N, E, R, NS>(v, t, sm, idx);
+    __syncthreads();
+    fft_gather<C, N, E>(v, t, sm, idx);
+    fft_run_sb<C, N, E, DIR, TWS, NS * R, IDX>(v, t, sm, tw, idx);
+  }
+}
+
+// number of exchanges (shared-memory round trips) of a plan
+constexpr __host__ __device__ int fft_num_steps(int N, int E) {
+  int s = 0, ns = 1;
+  while (ns < N) { ns *= imin(E, N / ns); ++s; }
+  return s;
+}
+
+}  // namespace mhdf

@@ -1,0 +1,729 @@
+// kernels.cuh -- sm_100a kernels of the pseudospectral RHS / time step.
+//
+// Data layout (all x/kx-fastest, matching the reference's column-major arrays):
+//   compact spectral field  [Kz][Ky][Kxp]   only the modes kept by FourierFlows' dealias!()
+//                                           (kx < Kx; ky,kz in two bands: [0,lo) and [n-hi,n))
+//   after inverse z pass    [nz][Ky][Kxp]
+//   after inverse y pass    [nz][ny][Kxp]   (x-pass input / output; real space is never stored)
+//   real field (API only)   [nz][ny][nx]
+// Kxp = Kx rounded up to 8 elements so every row starts 64-byte aligned; pad columns stay zero.
+#pragma once
+#include "fft_core.cuh"
+
+namespace mhdf {
+
+// Retained-band descriptor of one axis: full index n -> compact row, or -1 if dealiased.
+struct Band {
+  int n;    // full length
+  int lo;   // rows [0, lo) kept        (non-negative wavenumbers 0..lo-1)
+  int hi0;  // rows [hi0, n) kept       (negative wavenumbers -(n-hi0)..-1)
+  __host__ __device__ int count() const { return lo + (n - hi0); }
+  __host__ __device__ int row(int i) const { return i < lo ? i : (i >= hi0 ? i - (hi0 - lo) : -1); }
+  // signed integer wavenumber of compact row c
+  __host__ __device__ int wave(int c) const { return c < lo ? c : c - count(); }
+  // compact row of signed wavenumber w, or -1
+  __host__ __device__ int row_of_wave(int w) const {
+    if (w >= 0) return w < lo ? w : -1;
+    return (-w <= n - hi0) ? count() + w : -1;
+  }
+};
+__host__ __device__ inline Band band_full(int n) { Band b; b.n = n; b.lo = n; b.hi0 = n; return b; }
+
+// ------------------------------------------------------------------------------------------------
+// Strided axis pass (y or z): a block transforms TX adjacent columns of length N.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct PassArgs {
+  const Cx<T>* in;
+  Cx<T>* out;
+  const Cx<T>* tw;          // twiddle table of length N: (cos, -sin)(2 pi i / N)
+  long long in_row, out_row;       // element stride between consecutive rows n of the FFT axis
+  long long in_outer, out_outer;   // stride of the outer (non-transformed, non-contiguous) axis
+  long long in_field, out_field;   // stride between fields of the batch
+  int inner;                       // contiguous elements per row to process
+  Band bin, bout;                  // which FFT-axis rows exist in `in` / are wanted in `out`
+  T scale;                         // applied on load
+};
+
+template <int N, int TX, int R1, typename C> struct PassIdx {
+  // float2 with TX = 8: two rows share one 128-byte bank line; shift by 8 slots every R1 rows so
+  // rows n and n+R1 (written together in the first exchange) land in different halves.
+  static constexpr bool PAD = (sizeof(C) == 8 && TX == 8);
+  static constexpr int SIZE = N * TX + (PAD ? (N / R1) * 8 : 0);
+  int c;
+  __device__ __forceinline__ int operator()(int n) const { return n * TX + c + (PAD ? (n / R1) * 8 : 0); }
+};
+
+template <typename T, int N, int E, int TX, int DIR>
+__global__ void __launch_bounds__((N / E) * TX) k_pass(PassArgs<T> a) {
+  using C = Cx<T>;
+  constexpr int Tn = N / E;
+  constexpr int R1 = imin(E, N);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  C* sm = reinterpret_cast<C*>(smem_raw);
+  const int c = threadIdx.x % TX;
+  const int t = threadIdx.x / TX;
+  const int col = blockIdx.x * TX + c;
+  const bool valid = col < a.inner;
+  const long long ibase = (long long)blockIdx.z * a.in_field + (long long)blockIdx.y * a.in_outer + col;
+  const long long obase = (long long)blockIdx.z * a.out_field + (long long)blockIdx.y * a.out_outer + col;
+
+  C v[E];
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int n = t + Tn * m;
+    const int row = a.bin.row(n);
+    v[m] = mk<C>(0, 0);
+    if (valid && row >= 0) v[m] = a.in[ibase + (long long)row * a.in_row];
+  }
+  if (a.scale != (T)1) {
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = cscale(v[m], a.scale);
+  }
+  PassIdx<N, TX, R1, C> idx{c};
+  // single exchange buffer: two barriers per exchange (scatter | gather | next scatter)
+  fft_run_sb<C, N, E, DIR, 1, 1>(v, t, sm, a.tw, idx);
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int n = t + Tn * m;
+    const int row = a.bout.row(n);
+    if (valid && row >= 0) a.out[obase + (long long)row * a.out_row] = v[m];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x pass: rows are contiguous.  Real rows of length N are handled as M = N/2 complex points.
+// ------------------------------------------------------------------------------------------------
+template <int M, int R1> struct RowIdx {
+  static constexpr int SIZE = M + M / R1 + 1;
+  __device__ __forceinline__ int operator()(int n) const { return n + n / R1; }
+};
+
+// Shared-memory context of one row: two alternating exchange buffers.
+template <typename C> struct RowSmem {
+  C* a;
+  C* b;
+  __device__ __forceinline__ void swap() { C* t = a; a = b; b = t; }
+};
+
+// c2r of one row: X[k], k < Kx (others zero) -> v = z[n] = x[2n] + i x[2n+1], n = t + Tm*m,
+// unnormalised inverse times `scale`.  Im X[0] is ignored like every c2r does.
+template <typename T, int N, int E, typename SYNC>
+__device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__ X, int Kx, T scale, int t,
+                                        RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
+  using C = Cx<T>;
+  constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int k = t + Tm * m;
+    const int k2 = M - k;
+    C x1 = mk<C>(0, 0), x2 = mk<C>(0, 0);
+    if (k < Kx) x1 = X[k];
+    if (k2 < Kx) x2 = cconj(X[k2]);
+    if (k == 0) x1.y = 0;
+    const C w = cconj(__ldg(&tw[k]));                       // exp(+2 pi i k / N)
+    const C s = cadd(x1, x2), d = cmul(csub(x1, x2), w);    // Z = s + i d
+    v[m] = mk<C>((s.x - d.y) * scale, (s.y + d.x) * scale);
+  }
+  constexpr int NEX = fft_num_steps(M, E) - 1;
+  fft_run<C, M, E, +1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, tw, RowIdx<M, R1>());
+  if (NEX & 1) sm.swap();
+}
+
+// r2c of one row: v = z[n] (n = t + Tm*m) -> X[k] for k < Kx written to Xout (unnormalised forward).
+template <typename T, int N, int E, typename SYNC>
+__device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout, int Kx, int t,
+                                        RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
+  using C = Cx<T>;
+  constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
+  constexpr int NEX = fft_num_steps(M, E) - 1;
+  fft_run<C, M, E, -1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, tw, RowIdx<M, R1>());
+  if (NEX & 1) sm.swap();
+  RowIdx<M, R1> idx;
+#pragma unroll
+  for (int m = 0; m < E; ++m) sm.a[idx(t + Tm * m)] = v[m];
+  SYNC::sync();
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int k = t + Tm * m;
+    if (k < Kx) {
+      const C z1 = sm.a[idx(k)];
+      const C z2 = cconj(sm.a[idx((M - k) & (M - 1))]);
+      const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
+      const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
+      const C w = __ldg(&tw[k]);                                              // exp(-2 pi i k / N)
+      Xout[k] = cadd(ev, cmul(od, w));
+    }
+  }
+  sm.swap();
+}
+
+// ---- physics functors: which products are formed between the inverse and forward x passes -------
+// Reduction slots written by the fused x kernel (doubles): see XRed.
+struct XRed {
+  double sumsq[6];   // sum f^2 per input field (ux,uy,uz,bx,by,bz | EMHD: Ax,Ay,Az,bx,by,bz)
+  double cross;      // sum u.b
+  unsigned maxsq[6]; // max f^2 per field, float bit pattern (non-negative floats order as ints)
+  unsigned pad;
+};
+
+template <typename T>
+struct XArgs {
+  const Cx<T>* in;     // [nin][rows][Kxp]
+  Cx<T>* out;          // [nout][rows][Kxp]
+  const Cx<T>* tw;     // length nx
+  T* real_io;          // EMHD: stale real b [3][rows][nx] (read, then overwritten with fresh b); plain: real rows
+  long long in_field, out_field, real_field;
+  long long rows;      // ny*nz
+  int Kx, Kxp;
+  T scale;             // 1/(nx ny nz)
+  XRed* red;           // may be null
+};
+
+template <typename T> __device__ __forceinline__ void warp_red_sum(double& x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+}
+__device__ __forceinline__ void warp_red_max(float& x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+}
+
+// Block reduction of NS sums + NM maxima followed by one atomic per quantity per block.
+template <int NS, int NM>
+__device__ __forceinline__ void block_reduce_commit(double (&s)[NS], float (&mx)[NM], double* gs, unsigned* gm) {
+  __shared__ double sh_s[32][NS];
+  __shared__ float sh_m[32][NM];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) warp_red_sum<double>(s[i]);
+#pragma unroll
+  for (int i = 0; i < NM; ++i) warp_red_max(mx[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) sh_s[wid][i] = s[i];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) sh_m[wid][i] = mx[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      double x = lane < nw ? sh_s[lane][i] : 0.0;
+      warp_red_sum<double>(x);
+      if (lane == 0) atomicAdd(&gs[i], x);
+    }
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+      float x = lane < nw ? sh_m[lane][i] : 0.f;
+      warp_red_max(x);
+      if (lane == 0) atomicMax(&gm[i], __float_as_uint(x));
+    }
+  }
+}
+
+enum { PHYS_HD = 0, PHYS_MHD = 1, PHYS_EMHD = 2 };
+
+// Fused x pass:  c2r(NIN fields) -> pointwise products -> r2c(NOUT fields), one block = RB rows,
+// grid-stride over row sets.  Real-space fields live only in registers.
+//   HD  : in u(3)              out T_ij = -u_i u_j (xx,xy,xz,yy,yz,zz)
+//   MHD : in u(3), b(3)        out T_ij = b_i b_j - u_i u_j (6), E = u x b (3)
+//         (reference: MHDSolver.jl:73 and :150; HDSolver.jl:62)
+//   EMHD: in A(3), dB(9), dA(9), B(3) spectral + stale b (3, real)   out G_i (3), fresh b -> real_io
+//         G_i = sum_j A_j d_j B_i - b^stale_j d_j A_i   (reference: MHDSolver.jl:241-266, 323-325)
+template <typename T, int N, int E, int RB, int PHYS>
+__global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
+  using C = Cx<T>;
+  constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
+  using SYNC = SyncBlock;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int r = threadIdx.x / Tm;
+  const int t = threadIdx.x % Tm;
+  constexpr int RS = RowIdx<M, R1>::SIZE;
+  RowSmem<C> sm;
+  sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
+  sm.b = sm.a + RS;
+
+  double rs[7];
+  float rm[6];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) rs[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) rm[i] = 0.f;
+
+  const long long nsets = a.rows / RB;
+  for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
+    const long long row = set * RB + r;
+    const C* in = a.in + row * a.Kxp;
+    C* out = a.out + row * a.Kxp;
+    if constexpr (PHYS == PHYS_HD || PHYS == PHYS_MHD) {
+      constexpr int NF = (PHYS == PHYS_MHD) ? 6 : 3;
+      C f[NF][E];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        row_c2r<T, N, E, SYNC>(f[i], in + i * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+        float s = 0.f, mx = 0.f;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float x2 = (float)(f[i][m].x * f[i][m].x), y2 = (float)(f[i][m].y * f[i][m].y);
+          s += x2 + y2;
+          mx = fmaxf(mx, fmaxf(x2, y2));
+        }
+        rs[i] += (double)s;
+        rm[i] = fmaxf(rm[i], mx);
+      }
+      if constexpr (PHYS == PHYS_MHD) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int m = 0; m < E; ++m) s += (float)(f[i][m].x * f[i + 3][m].x + f[i][m].y * f[i + 3][m].y);
+        rs[6] += (double)s;
+      }
+      // symmetric tensor (xx, xy, xz, yy, yz, zz)
+      int p = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = i; j < 3; ++j) {
+          C v[E];
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            if constexpr (PHYS == PHYS_MHD)
+              v[m] = mk<C>(f[3 + i][m].x * f[3 + j][m].x - f[i][m].x * f[j][m].x,
+                           f[3 + i][m].y * f[3 + j][m].y - f[i][m].y * f[j][m].y);
+            else
+              v[m] = mk<C>(-(f[i][m].x * f[j][m].x), -(f[i][m].y * f[j][m].y));
+          }
+          row_r2c<T, N, E, SYNC>(v, out + p * a.out_field, a.Kx, t, sm, a.tw);
+          ++p;
+        }
+      }
+      if constexpr (PHYS == PHYS_MHD) {
+        // E = u x b
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          constexpr int nx1[3] = {1, 2, 0}, nx2[3] = {2, 0, 1};
+          const int j = nx1[i], k = nx2[i];
+          C v[E];
+#pragma unroll
+          for (int m = 0; m < E; ++m)
+            v[m] = mk<C>(f[j][m].x * f[3 + k][m].x - f[k][m].x * f[3 + j][m].x,
+                         f[j][m].y * f[3 + k][m].y - f[k][m].y * f[3 + j][m].y);
+          row_r2c<T, N, E, SYNC>(v, out + (6 + i) * a.out_field, a.Kx, t, sm, a.tw);
+        }
+      }
+    } else {
+      // EMHD: field order in `in`: A(0..2), dB_ij at 3 + 3 i + j, dA_ij at 12 + 3 i + j, B(21..23)
+      C A[3][E], bs[3][E];
+      C* breal = reinterpret_cast<C*>(a.real_io + row * (long long)N);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        row_c2r<T, N, E, SYNC>(A[i], in + i * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+        float s = 0.f, mx = 0.f;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float x2 = (float)(A[i][m].x * A[i][m].x), y2 = (float)(A[i][m].y * A[i][m].y);
+          s += x2 + y2;
+          mx = fmaxf(mx, fmaxf(x2, y2));
+          bs[i][m] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
+        }
+        rs[i] += (double)s;
+        rm[i] = fmaxf(rm[i], mx);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        C acc[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) acc[m] = mk<C>(0, 0);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          C g[E];
+          row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+#pragma unroll
+          for (int m = 0; m < E; ++m) { acc[m].x += A[j][m].x * g[m].x; acc[m].y += A[j][m].y * g[m].y; }
+          row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+#pragma unroll
+          for (int m = 0; m < E; ++m) { acc[m].x -= bs[j][m].x * g[m].x; acc[m].y -= bs[j][m].y * g[m].y; }
+        }
+        row_r2c<T, N, E, SYNC>(acc, out + i * a.out_field, a.Kx, t, sm, a.tw);
+      }
+      // refresh the real-space b (vars.b*) from the current stage input
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        C g[E];
+        row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+        float s = 0.f, mx = 0.f;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const float x2 = (float)(g[m].x * g[m].x), y2 = (float)(g[m].y * g[m].y);
+          s += x2 + y2;
+          mx = fmaxf(mx, fmaxf(x2, y2));
+          reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
+        }
+        rs[3 + i] += (double)s;
+        rm[3 + i] = fmaxf(rm[3 + i], mx);
+      }
+    }
+  }
+  if (a.red != nullptr) block_reduce_commit<7, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
+}
+
+// Plain x passes for the API boundary (set_real / get_real): real rows <-> spectral rows.
+template <typename T, int N, int E, int RB, int DIR>
+__global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
+  using C = Cx<T>;
+  constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
+  using SYNC = SyncBlock;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int r = threadIdx.x / Tm;
+  const int t = threadIdx.x % Tm;
+  constexpr int RS = RowIdx<M, R1>::SIZE;
+  RowSmem<C> sm;
+  sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
+  sm.b = sm.a + RS;
+  double rs[1] = {0.0};
+  float rm[1] = {0.f};
+  const long long nsets = a.rows / RB;
+  for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
+    const long long row = set * RB + r;
+    C* re = reinterpret_cast<C*>(a.real_io + row * (long long)N);
+    C v[E];
+    if constexpr (DIR < 0) {   // real -> spectral
+      float s = 0.f, mx = 0.f;
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        v[m] = re[t + Tm * m];
+        const float x2 = (float)(v[m].x * v[m].x), y2 = (float)(v[m].y * v[m].y);
+        s += x2 + y2;
+        mx = fmaxf(mx, fmaxf(x2, y2));
+      }
+      rs[0] += (double)s;
+      rm[0] = fmaxf(rm[0], mx);
+      row_r2c<T, N, E, SYNC>(v, a.out + row * a.Kxp, a.Kx, t, sm, a.tw);
+    } else {                   // spectral -> real
+      row_c2r<T, N, E, SYNC>(v, a.in + row * a.Kxp, a.Kx, a.scale, t, sm, a.tw);
+      float s = 0.f, mx = 0.f;
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        re[t + Tm * m] = v[m];
+        const float x2 = (float)(v[m].x * v[m].x), y2 = (float)(v[m].y * v[m].y);
+        s += x2 + y2;
+        mx = fmaxf(mx, fmaxf(x2, y2));
+      }
+      rs[0] += (double)s;
+      rm[0] = fmaxf(rm[0], mx);
+    }
+  }
+  if (a.red != nullptr) block_reduce_commit<1, 1>(rs, rm, a.red->sumsq, a.red->maxsq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spectral kernels on the compact state.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct SpecGeom {
+  int Kx, Kxp;
+  Band by, bz;
+  const T* kx;   // [Kx]   kr  (reference: grid.kr)
+  const T* ky;   // [Ky]   l on the retained rows
+  const T* kz;   // [Kz]   m on the retained rows
+  long long field;   // elements per compact field = Kxp*Ky*Kz
+};
+
+// element (kx, jc, kc) of a compact field; û^sym on the kr = 0 plane:
+// rfft(irfft(û)) = (û(0,ky,kz) + conj û(0,-ky,-kz)) / 2, a missing (dealiased) mirror counts as 0
+// (reference: the diffusion operand of MHDSolver.jl:91-94,166-168 / HDSolver.jl:82-85).
+template <typename T>
+__device__ __forceinline__ Cx<T> load_sym(const Cx<T>* __restrict__ f, const SpecGeom<T>& g, int ix, int jc, int kc) {
+  using C = Cx<T>;
+  const int Ky = g.by.count();
+  C v = f[((long long)kc * Ky + jc) * g.Kxp + ix];
+  if (ix == 0) {
+    const int jm = g.by.row_of_wave(-g.by.wave(jc));
+    const int km = g.bz.row_of_wave(-g.bz.wave(kc));
+    C w = mk<C>(0, 0);
+    if (jm >= 0 && km >= 0) w = f[((long long)km * Ky + jm) * g.Kxp];
+    v = mk<C>((T)0.5 * (v.x + w.x), (T)0.5 * (v.y - w.y));
+  }
+  return v;
+}
+
+enum { STEP_CALCN = 0, STEP_RK4_1 = 1, STEP_RK4_2 = 2, STEP_RK4_3 = 3, STEP_RK4_4 = 4, STEP_LSRK = 5 };
+
+template <typename T>
+struct SpecArgs {
+  SpecGeom<T> g;
+  const Cx<T>* P;        // product spectra [nout][compact]
+  const Cx<T>* Sin;      // stage input  [F][compact]
+  const Cx<T>* Y;        // step start   [F][compact]   (RK4)
+  Cx<T>* Sout;           // next stage input / LSRK: updated sol
+  Cx<T>* A;              // RK4 accumulator / LSRK: S2 register
+  Cx<T>* Nout;           // STEP_CALCN: RHS output
+  T nu, eta;
+  int n_nu;
+  T ca, cs;              // RK4: A-weight (dt/6, dt/3), stage coefficient (dt/2, dt); LSRK: ca = A_i, cs = B_i
+  T dt;
+  int mode;
+  int first;             // LSRK: stage 1 (S2 treated as zero)
+};
+
+template <typename T, int F>
+__device__ __forceinline__ void spec_commit(const SpecArgs<T>& a, long long e, const Cx<T> (&N)[F], const Cx<T> (&sin)[F]) {
+  using C = Cx<T>;
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const long long o = f * a.g.field + e;
+    switch (a.mode) {
+      case STEP_CALCN: a.Nout[o] = N[f]; break;
+      case STEP_RK4_1: {   // Sin == Y
+        const C y = a.Y[o];
+        a.A[o] = mk<C>(y.x + a.ca * N[f].x, y.y + a.ca * N[f].y);
+        a.Sout[o] = mk<C>(y.x + a.cs * N[f].x, y.y + a.cs * N[f].y);
+      } break;
+      case STEP_RK4_2:
+      case STEP_RK4_3: {
+        const C y = a.Y[o];
+        const C ac = a.A[o];
+        a.A[o] = mk<C>(ac.x + a.ca * N[f].x, ac.y + a.ca * N[f].y);
+        a.Sout[o] = mk<C>(y.x + a.cs * N[f].x, y.y + a.cs * N[f].y);
+      } break;
+      case STEP_RK4_4: {   // sol = A + dt/6 k4, written to Sout (= Y)
+        const C ac = a.A[o];
+        a.Sout[o] = mk<C>(ac.x + a.ca * N[f].x, ac.y + a.ca * N[f].y);
+      } break;
+      default: {           // LSRK54: S2 = A_i S2 + dt N ; sol += B_i S2
+        C s2 = mk<C>(a.dt * N[f].x, a.dt * N[f].y);
+        if (!a.first) { const C o2 = a.A[o]; s2.x += a.ca * o2.x; s2.y += a.ca * o2.y; }
+        a.A[o] = s2;
+        a.Sout[o] = mk<C>(sin[f].x + a.cs * s2.x, sin[f].y + a.cs * s2.y);
+      } break;
+    }
+  }
+}
+
+// RHS assembly + Runge-Kutta stage update, one thread per retained mode.
+//   MHD/HD: N_a = D_a - k_a (k.D)/k^2 - nu k^2 u^sym_a [- nu k^(2 n_nu) u^sym_a],  D_j = sum_i i k_i T^_ij
+//           N_{3+a} = i (k x E^)_a - eta k^2 b^sym_a
+//   (reference: MHDSolver.jl:77-79,94,97-99,155,168; HDSolver.jl:68-70,85,88-90)
+//   EMHD:   N_i = G^_i   (reference: MHDSolver.jl:253,264; no resistive term on this path)
+template <typename T, int PHYS>
+__global__ void __launch_bounds__(256) k_spectral(SpecArgs<T> a) {
+  using C = Cx<T>;
+  const SpecGeom<T>& g = a.g;
+  const int Ky = g.by.count(), Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    if constexpr (PHYS == PHYS_EMHD) {
+      C N[3], sin[3];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) { N[f] = a.P[f * g.field + e]; sin[f] = a.Sin[f * g.field + e]; }
+      spec_commit<T, 3>(a, e, N, sin);
+    } else {
+      constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
+      const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
+      const T k2 = kx * kx + ky * ky + kz * kz;
+      const T ik2 = (k2 > (T)0) ? (T)1 / k2 : (T)0;
+      C Tt[6];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) Tt[p] = a.P[p * g.field + e];
+      // D_j = i sum_i k_i T_ij   (xx,xy,xz,yy,yz,zz)
+      C D[3];
+      D[0] = mk<C>(kx * Tt[0].x + ky * Tt[1].x + kz * Tt[2].x, kx * Tt[0].y + ky * Tt[1].y + kz * Tt[2].y);
+      D[1] = mk<C>(kx * Tt[1].x + ky * Tt[3].x + kz * Tt[4].x, kx * Tt[1].y + ky * Tt[3].y + kz * Tt[4].y);
+      D[2] = mk<C>(kx * Tt[2].x + ky * Tt[4].x + kz * Tt[5].x, kx * Tt[2].y + ky * Tt[4].y + kz * Tt[5].y);
+      const C kD = mk<C>((kx * D[0].x + ky * D[1].x + kz * D[2].x) * ik2, (kx * D[0].y + ky * D[1].y + kz * D[2].y) * ik2);
+      const T kk[3] = {kx, ky, kz};
+      C N[F], sin[F];
+      T hyper = (T)0;
+      if (a.n_nu > 1) { hyper = (T)1; for (int q = 0; q < a.n_nu; ++q) hyper *= k2; }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const C pr = mk<C>(D[c].x - kk[c] * kD.x, D[c].y - kk[c] * kD.y);   // still missing the factor i
+        const C us = load_sym<T>(a.Sin + c * g.field, g, ix, jc, kc);
+        sin[c] = a.Sin[c * g.field + e];
+        const T dc = -(a.nu * k2) - a.nu * hyper;
+        N[c] = mk<C>(-pr.y + dc * us.x, pr.x + dc * us.y);
+      }
+      if constexpr (PHYS == PHYS_MHD) {
+        C Ev[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) Ev[p] = a.P[(6 + p) * g.field + e];
+        C Cv[3];
+        Cv[0] = mk<C>(ky * Ev[2].x - kz * Ev[1].x, ky * Ev[2].y - kz * Ev[1].y);
+        Cv[1] = mk<C>(kz * Ev[0].x - kx * Ev[2].x, kz * Ev[0].y - kx * Ev[2].y);
+        Cv[2] = mk<C>(kx * Ev[1].x - ky * Ev[0].x, kx * Ev[1].y - ky * Ev[0].y);
+        const T dc = -(a.eta * k2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const C bsym = load_sym<T>(a.Sin + (3 + c) * g.field, g, ix, jc, kc);
+          sin[3 + c] = a.Sin[(3 + c) * g.field + e];
+          N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
+        }
+      }
+      spec_commit<T, F>(a, e, N, sin);
+    }
+  }
+}
+
+// EMHD: derive the 24 inverse-transform inputs from B^ (compact):
+//   A = i k x B (0..2), dB_ij = i k_j B_i (3+3i+j), dA_ij = i k_j A_i (12+3i+j), B (21..23)
+//   (reference: MHDSolver.jl:301-309 "way 2", :246, :257)
+template <typename T>
+__global__ void __launch_bounds__(256) k_emhd_derive(SpecGeom<T> g, const Cx<T>* __restrict__ B, Cx<T>* __restrict__ out) {
+  using C = Cx<T>;
+  const int Ky = g.by.count(), Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    const T k[3] = {g.kx[ix], g.ky[jc], g.kz[kc]};
+    C b[3], A[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b[i] = B[i * g.field + e];
+    // A = i (k x B)
+    const C c0 = mk<C>(k[1] * b[2].x - k[2] * b[1].x, k[1] * b[2].y - k[2] * b[1].y);
+    const C c1 = mk<C>(k[2] * b[0].x - k[0] * b[2].x, k[2] * b[0].y - k[0] * b[2].y);
+    const C c2 = mk<C>(k[0] * b[1].x - k[1] * b[0].x, k[0] * b[1].y - k[1] * b[0].y);
+    A[0] = cmuli(c0); A[1] = cmuli(c1); A[2] = cmuli(c2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      out[i * g.field + e] = A[i];
+      out[(21 + i) * g.field + e] = b[i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        out[(3 + 3 * i + j) * g.field + e] = cmuli(cscale(b[i], k[j]));
+        out[(12 + 3 * i + j) * g.field + e] = cmuli(cscale(A[i], k[j]));
+      }
+    }
+  }
+}
+
+// full (nkr, ny, nz) spectral array <-> compact field.  dir = 0: full -> compact (drop dealiased modes),
+// dir = 1: compact -> full (dealiased modes written as zero).
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack(Cx<T>* __restrict__ full, Cx<T>* __restrict__ comp, int nkr, int ny, int nz,
+                                              int Kx, int Kxp, Band by, Band bz, int dir) {
+  using C = Cx<T>;
+  const int Ky = by.count();
+  const long long total = (long long)nkr * ny * nz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % nkr);
+    const long long r = e / nkr;
+    const int j = (int)(r % ny), k = (int)(r / ny);
+    const int jc = by.row(j), kc = bz.row(k);
+    const bool kept = ix < Kx && jc >= 0 && kc >= 0;
+    if (dir == 0) {
+      if (kept) comp[((long long)kc * Ky + jc) * Kxp + ix] = full[e];
+    } else {
+      full[e] = kept ? comp[((long long)kc * Ky + jc) * Kxp + ix] : mk<C>(0, 0);
+    }
+  }
+}
+
+// Fresh diagnostics from the compact state via Parseval (kr = 0 plane symmetrised, weight 2 for kr > 0):
+//   out[0] = sum |u|^2, out[1] = sum |b|^2, out[2] = sum u.(curl u), out[3] = sum a.b (Coulomb gauge),
+//   out[4] = sum u.b      -- all as real-space sums over grid points (multiply by dV outside where wanted)
+//   (reference: UserInterface.jl:29,65-86; MHDAnalysis.jl:94-117,165-168)
+template <typename T>
+__global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __restrict__ U, const Cx<T>* __restrict__ B,
+                                              double inv_n3, double* __restrict__ out) {
+  using C = Cx<T>;
+  const int Ky = g.by.count(), Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  double s[5] = {0, 0, 0, 0, 0};
+  float dummy[1] = {0.f};
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    const double k[3] = {(double)g.kx[ix], (double)g.ky[jc], (double)g.kz[kc]};
+    const double k2 = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
+    const double w = (ix == 0 ? 1.0 : 2.0) * inv_n3;
+    double ur[3] = {0, 0, 0}, ui[3] = {0, 0, 0}, br[3] = {0, 0, 0}, bi[3] = {0, 0, 0};
+    if (U != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const C v = load_sym<T>(U + c * g.field, g, ix, jc, kc); ur[c] = v.x; ui[c] = v.y; }
+      s[0] += w * (ur[0] * ur[0] + ui[0] * ui[0] + ur[1] * ur[1] + ui[1] * ui[1] + ur[2] * ur[2] + ui[2] * ui[2]);
+      // omega = i k x u ; Re(u . conj(omega)) = sum_c Re(u_c conj(i c_c)) with c = k x u:  Re(u conj(i c)) = u_i c_r - u_r c_i
+      const double cr[3] = {k[1] * ur[2] - k[2] * ur[1], k[2] * ur[0] - k[0] * ur[2], k[0] * ur[1] - k[1] * ur[0]};
+      const double ci[3] = {k[1] * ui[2] - k[2] * ui[1], k[2] * ui[0] - k[0] * ui[2], k[0] * ui[1] - k[1] * ui[0]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s[2] += w * (ui[c] * cr[c] - ur[c] * ci[c]);
+    }
+    if (B != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const C v = load_sym<T>(B + c * g.field, g, ix, jc, kc); br[c] = v.x; bi[c] = v.y; }
+      s[1] += w * (br[0] * br[0] + bi[0] * bi[0] + br[1] * br[1] + bi[1] * bi[1] + br[2] * br[2] + bi[2] * bi[2]);
+      if (k2 > 0) {
+        // a = i (k x b) / k^2 ; Re(a . conj(b)) = sum_c Re(i c_c conj(b_c)) / k^2 = (c_r b_i - c_i b_r) / k^2
+        const double cr[3] = {k[1] * br[2] - k[2] * br[1], k[2] * br[0] - k[0] * br[2], k[0] * br[1] - k[1] * br[0]};
+        const double ci[3] = {k[1] * bi[2] - k[2] * bi[1], k[2] * bi[0] - k[0] * bi[2], k[0] * bi[1] - k[1] * bi[0]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s[3] += w * (cr[c] * bi[c] - ci[c] * br[c]) / k2;
+      }
+      if (U != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s[4] += w * (ur[c] * br[c] + ui[c] * bi[c]);
+      }
+    }
+  }
+  unsigned* nomax = nullptr;
+  // reuse the block reducer (no maxima)
+  {
+    __shared__ double sh[32][5];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) warp_red_sum<double>(s[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) sh[wid][i] = s[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        double x = lane < nw ? sh[lane][i] : 0.0;
+        warp_red_sum<double>(x);
+        if (lane == 0) atomicAdd(&out[i], x);
+      }
+    }
+  }
+  (void)nomax; (void)dummy;
+}
+
+// Shell spectrum of one compact field: Pk[round(|k|)] += |f^|^2 over the HALF spectrum, no weights
+// (reference: MHDAnalysis.jl:237-255 `spectralline`).  kr = 0 plane symmetrised (what rfft of the
+// real field holds).  Shared-memory histogram per block, then one atomic per bin.
+template <typename T>
+__global__ void __launch_bounds__(256) k_spectrum(SpecGeom<T> g, const Cx<T>* __restrict__ F, double* __restrict__ Pk, int nbins) {
+  using C = Cx<T>;
+  extern __shared__ double hist[];
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0.0;
+  __syncthreads();
+  const int Ky = g.by.count(), Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
+    const T kk = sqrt(kx * kx + ky * ky + kz * kz);
+    const int r = (int)rint((double)kk);
+    const C v = load_sym<T>(F, g, ix, jc, kc);
+    if (r < nbins) atomicAdd(&hist[r], (double)v.x * v.x + (double)v.y * v.y);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+    if (hist[i] != 0.0) atomicAdd(&Pk[i], hist[i]);
+}
+
+}  // namespace mhdf

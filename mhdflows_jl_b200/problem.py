@@ -1,0 +1,515 @@
+"""Host-side mirror of the MHDFlows.jl problem API over the C ABI (include/mhdflows_b200.h).
+
+Same names, keyword arguments and error behaviour as the reference for the hot path:
+`Problem`, `SetUpProblemIC!`, `stepforward!`, `TimeIntegrator!`, `getCFL!`, `ProbDiagnostic`,
+`Diagnostic`, `DivFreeSpectraMap` (Python cannot spell `!`, so the bang is dropped).  All compute
+happens in the CUDA library; this file only marshals arguments, like julia/MHDFlowsB200.jl does with
+`ccall`.  Arrays follow the reference's column-major layout: a Julia `(nx, ny, nz)` array is a NumPy
+C-order array of shape `(nz, ny, nx)`; `sol` is `(Nfield, nz, ny, nx/2+1)`.
+
+file:line citations are into the reference tree.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+
+import numpy as np
+
+from . import _lib as L
+
+
+class CPU:  # FourierFlows.CPU()
+    pass
+
+
+class GPU:  # FourierFlows.GPU()
+    def __init__(self, device: int = 0):
+        self.device = device
+
+
+def nothingfunction(*args, **kw):  # pgen.jl:7
+    return None
+
+
+class _Clock:
+    """FourierFlows.Clock{T}(dt, t, step) (Problems.jl:120) backed by the library's clock."""
+
+    def __init__(self, prob):
+        self._p = prob
+
+    def _get(self):
+        t, dt, s = C.c_double(), C.c_double(), C.c_longlong()
+        L.check(self._p._h, L.lib().mhdf_get_clock(self._p._h, C.byref(t), C.byref(dt), C.byref(s)))
+        return t.value, dt.value, s.value
+
+    @property
+    def t(self):
+        return self._get()[0]
+
+    @t.setter
+    def t(self, v):
+        L.check(self._p._h, L.lib().mhdf_set_clock(self._p._h, float(v), self._get()[2]))
+
+    @property
+    def dt(self):
+        return self._get()[1]
+
+    @dt.setter
+    def dt(self, v):
+        L.check(self._p._h, L.lib().mhdf_set_dt(self._p._h, float(v)))
+
+    @property
+    def step(self):
+        return self._get()[2]
+
+    @step.setter
+    def step(self, v):
+        L.check(self._p._h, L.lib().mhdf_set_clock(self._p._h, self._get()[0], int(v)))
+
+
+class _Flag:  # Problems.jl:68-79
+    def __init__(self, b, e, vp=False, c=False, s=False):
+        self.b, self.e, self.vp, self.c, self.s = b, e, vp, c, s
+
+
+class _Grid:
+    """The ThreeDGrid fields user code reads (mirror: utils/utils.jl:42-98)."""
+
+    def __init__(self, nx, ny, nz, Lx, Ly, Lz, T):
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.Lx, self.Ly, self.Lz = Lx, Ly, Lz
+        self.nkr, self.nl, self.nm = nx // 2 + 1, ny, nz
+        self.nk = nx
+        self.dx, self.dy, self.dz = Lx / nx, Ly / ny, Lz / nz
+        self.T = np.dtype(T).type
+        T_ = self.T
+        self.x = (T_(-Lx / 2) + T_(self.dx) * np.arange(nx)).astype(T_)
+        self.y = (T_(-Ly / 2) + T_(self.dy) * np.arange(ny)).astype(T_)
+        self.z = (T_(-Lz / 2) + T_(self.dz) * np.arange(nz)).astype(T_)
+        self.kr = (np.arange(self.nkr) * (2 * math.pi / Lx)).astype(T_).reshape(1, 1, -1)
+        self.l = (np.fft.fftfreq(ny, 1.0 / ny) * (2 * math.pi / Ly)).astype(T_).reshape(1, -1, 1)
+        self.m = (np.fft.fftfreq(nz, 1.0 / nz) * (2 * math.pi / Lz)).astype(T_).reshape(-1, 1, 1)
+        self.aliased_fraction = 1 / 3  # Problem's aliased_fraction is not forwarded (pgen.jl:107)
+
+    @staticmethod
+    def aliased_range(nk, aliased_fraction=1 / 3):
+        """FourierFlows.getaliasedwavenumbers, 1-based inclusive (iL, iR)."""
+        Lf, Rf = (1 - aliased_fraction) / 2, (1 + aliased_fraction) / 2
+        return math.floor(Lf * nk) + 1, math.ceil(Rf * nk)
+
+    @property
+    def Krsq(self):
+        return (self.kr ** 2 + self.l ** 2 + self.m ** 2).astype(self.T)
+
+    def retained_mask(self):
+        """Modes kept by dealias!(fh, grid): shape (nz, ny, nkr)."""
+        msk = np.ones((self.nm, self.nl, self.nkr), dtype=bool)
+        iL, _ = self.aliased_range(self.nx)
+        msk[..., iL - 1:] = False
+        iL, iR = self.aliased_range(self.ny)
+        msk[:, iL - 1:iR, :] = False
+        iL, iR = self.aliased_range(self.nz)
+        msk[iL - 1:iR, :, :] = False
+        return msk
+
+
+class _Params:  # MHDParams / HDParams / EMHDParams (MHDParams.jl:42-94, HDParams.jl:30-51); 1-based indices
+    pass
+
+
+class _Vars:
+    """vars.ux ... : real-space fields.  Reading one runs a c2r on demand of the LAST STAGE INPUT,
+    which is what the reference's vars hold after a step."""
+
+    def __init__(self, prob, names):
+        object.__setattr__(self, "_p", prob)
+        object.__setattr__(self, "_names", names)
+
+    def __getattr__(self, name):
+        names = object.__getattribute__(self, "_names")
+        if name in names:
+            return object.__getattribute__(self, "_p").get_real(names[name], which=L.STALE)
+        raise AttributeError(name)
+
+
+class Problem:
+    """Problem(dev; nx, ny, nz, Lx, Ly, Lz, c_s, dt, nu, n_nu, eta, n_eta, B_field, EMHD, Compressibility, Shear,
+    VP_method, Dye_Module, stepper, calcF, T, aliased_fraction, usr_vars, usr_params, usr_func)  (pgen.jl:64-127).
+
+    Greek keyword names of the reference are accepted as well (ν, nν, η, nη)."""
+
+    def __init__(self, dev=None, *, nx=64, ny=None, nz=None, Lx=2 * math.pi, Ly=None, Lz=None, cs=0.0, dt=0.0,
+                 nu=0.0, n_nu=0, eta=0.0, n_eta=0, B_field=False, EMHD=False, Compressibility=False, Shear=False,
+                 VP_method=False, Dye_Module=False, stepper="RK4", calcF=nothingfunction, T=np.float32,
+                 aliased_fraction=1 / 3, usr_vars=None, usr_params=None, usr_func=None, **greek):
+        for k, v in greek.items():
+            if k == "ν":
+                nu = v
+            elif k == "η":
+                eta = v
+            elif k == "nν":
+                n_nu = v
+            elif k == "nη":
+                n_eta = v
+            else:
+                raise TypeError(f"Problem() got an unexpected keyword argument {k!r}")
+        if isinstance(dev, CPU):
+            raise L.MHDFlowsError(L.ERR_INVALID, "this build is the B200 path only: Problem(GPU(); ...) (no CPU fallback)")
+        if cs == 0.0 and Compressibility:
+            raise ValueError("You should define cₛ")                       # pgen.jl:98-100
+        if Shear:
+            raise ValueError("Shear haven't fully implemented yet!")        # pgen.jl:103-105
+        if Compressibility or VP_method or Dye_Module:
+            raise NotImplementedError("Compressibility / VP_method / Dye_Module are outside the B200 hot path (SURVEY 8)")
+        if calcF is not nothingfunction and calcF is not None:
+            raise NotImplementedError("forcing callbacks are not supported on this path yet (SURVEY 8b)")
+        if EMHD and not B_field:
+            raise ValueError("EMHD requires B_field=true (datastructure.jl:78-88)")
+        if stepper == "HM89":
+            raise NotImplementedError("HM89 is outside the hot path (SURVEY 2 #11)")
+        if stepper not in ("RK4", "LSRK54"):
+            raise ValueError(f"stepper {stepper!r}: only \"RK4\" and \"LSRK54\" are on the B200 path")
+        ny = nx if ny is None else ny
+        nz = nx if nz is None else nz
+        Ly = Lx if Ly is None else Ly
+        Lz = Lx if Lz is None else Lz
+        T = np.dtype(T).type
+        if T not in (np.float32, np.float64):
+            raise ValueError("T must be Float32 or Float64")
+        self.T = T
+        self.CT = np.complex64 if T is np.float32 else np.complex128
+        self.grid = _Grid(nx, ny, nz, Lx, Ly, Lz, T)
+        self.flag = _Flag(B_field, EMHD)
+        self.stepper = stepper
+        self.usr_func = list(usr_func) if usr_func else [nothingfunction]
+        p = _Params()
+        if EMHD:
+            p.η, p.nη, p.bx_ind, p.by_ind, p.bz_ind = eta, 0, 1, 2, 3
+            names = {"bx": 0, "by": 1, "bz": 2}
+            physics, self.Nl = L.EMHD, 3
+        elif B_field:
+            p.ν, p.η, p.nν, p.nη = nu, eta, n_nu, 0        # nη is never forwarded (pgen.jl:114-116)
+            p.ux_ind, p.uy_ind, p.uz_ind, p.bx_ind, p.by_ind, p.bz_ind = 1, 2, 3, 4, 5, 6
+            names = {"ux": 0, "uy": 1, "uz": 2, "bx": 3, "by": 4, "bz": 5}
+            physics, self.Nl = L.MHD, 6
+        else:
+            p.ν, p.nν, p.ux_ind, p.uy_ind, p.uz_ind = nu, n_nu, 1, 2, 3
+            names = {"ux": 0, "uy": 1, "uz": 2}
+            physics, self.Nl = L.HD, 3
+        p.calcF = calcF
+        p.usr_params = usr_params
+        self.params = p
+        self._names = names
+        self.vars = _Vars(self, names)
+        cfg = L.Config(nx=nx, ny=ny, nz=nz, Lx=Lx, Ly=Ly, Lz=Lz, nu=float(nu), eta=float(eta), n_nu=int(n_nu),
+                       dt=float(dt), physics=physics, stepper=L.RK4 if stepper == "RK4" else L.LSRK54,
+                       dtype=L.F32 if T is np.float32 else L.F64,
+                       device=dev.device if isinstance(dev, GPU) else 0, rank=0, nranks=1, nccl_id=None)
+        h = C.c_void_p()
+        code = L.lib().mhdf_create(C.byref(cfg), C.byref(h))
+        if code != L.OK:
+            raise L.MHDFlowsError(code, (L.lib().mhdf_last_error(None) or b"").decode())
+        self._h = h
+        self.clock = _Clock(self)
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().mhdf_destroy(h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- fields ---------------------------------------------------------------------------------
+    def _field_id(self, f):
+        return self._names[f] if isinstance(f, str) else int(f)
+
+    def set_real(self, f, arr):
+        g = self.grid
+        a = np.ascontiguousarray(arr, dtype=self.T)
+        if a.shape != (g.nz, g.ny, g.nx):
+            raise ValueError(f"expected shape {(g.nz, g.ny, g.nx)}, got {a.shape}")
+        L.check(self._h, L.lib().mhdf_set_real(self._h, self._field_id(f), a.ctypes.data))
+
+    def get_real(self, f, which=L.FRESH):
+        g = self.grid
+        out = np.empty((g.nz, g.ny, g.nx), dtype=self.T)
+        L.check(self._h, L.lib().mhdf_get_real(self._h, self._field_id(f), which, out.ctypes.data))
+        return out
+
+    def set_spectral(self, f, arr):
+        g = self.grid
+        a = np.ascontiguousarray(arr, dtype=self.CT)
+        if a.shape != (g.nm, g.nl, g.nkr):
+            raise ValueError(f"expected shape {(g.nm, g.nl, g.nkr)}, got {a.shape}")
+        L.check(self._h, L.lib().mhdf_set_spectral(self._h, self._field_id(f), a.ctypes.data))
+
+    def get_spectral(self, f, which=L.FRESH):
+        g = self.grid
+        out = np.empty((g.nm, g.nl, g.nkr), dtype=self.CT)
+        L.check(self._h, L.lib().mhdf_get_spectral(self._h, self._field_id(f), which, out.ctypes.data))
+        return out
+
+    @property
+    def sol(self):
+        """prob.sol as a host copy (Nfield, nz, ny, nkr); dealiased modes are zero."""
+        return np.stack([self.get_spectral(i) for i in range(self.Nl)])
+
+    @sol.setter
+    def sol(self, arr):
+        for i in range(self.Nl):
+            self.set_spectral(i, arr[i])
+
+    def calcN(self):
+        """eqn.calcN!(N, sol, t, clock, vars, params, grid) on the current sol -> N (host copy)."""
+        g = self.grid
+        out = np.empty((self.Nl, g.nm, g.nl, g.nkr), dtype=self.CT)
+        L.check(self._h, L.lib().mhdf_calcN(self._h, out.ctypes.data))
+        return out
+
+    # -- diagnostics ----------------------------------------------------------------------------
+    def energy(self, which=L.STALE):
+        ke, me = C.c_double(), C.c_double()
+        L.check(self._h, L.lib().mhdf_energy(self._h, which, C.byref(ke), C.byref(me)))
+        return ke.value, me.value
+
+    def helicity(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        L.check(self._h, L.lib().mhdf_helicity(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def stale_stats(self):
+        mx = (C.c_double * 6)()
+        sm = (C.c_double * 6)()
+        L.check(self._h, L.lib().mhdf_stale_stats(self._h, mx, sm))
+        return np.array(mx), np.array(sm)
+
+    def info(self):
+        v = [C.c_int() for _ in range(5)]
+        b = C.c_longlong()
+        L.check(self._h, L.lib().mhdf_info(self._h, *[C.byref(x) for x in v], C.byref(b)))
+        return dict(nfields=v[0].value, Kx=v[1].value, Kxp=v[2].value, Ky=v[3].value, Kz=v[4].value, bytes_device=b.value)
+
+    def step_timed(self, nsteps):
+        ms = C.c_double()
+        L.check(self._h, L.lib().mhdf_step_timed(self._h, int(nsteps), C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        L.check(self._h, L.lib().mhdf_profile(self._h, 1 if enable else 0))
+
+    def profile_get(self):
+        ms = (C.c_double * 8)()
+        cnt = (C.c_longlong * 8)()
+        L.check(self._h, L.lib().mhdf_profile_get(self._h, ms, cnt, 8))
+        names = ["z_inverse", "y_inverse", "x_fused", "y_forward", "z_forward", "spectral", "emhd_derive", "exchange"]
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
+
+    def launch_count(self):
+        return L.lib().mhdf_launch_count(self._h)
+
+    def __repr__(self):  # Problems.jl:142-159
+        b = "ON (EMHD)" if self.flag.e else ("ON (Ideal MHD)" if self.flag.b else "OFF")
+        return ("MHDFlows Problem\n  │    Funtions\n  │     ├ Compressibility: OFF\n"
+                f"  │     ├──────── B-field: {b}\n  │     ├────────── Shear: OFF\n  ├─────├────── VP Method: OFF\n"
+                "  │     ├──────────── Dye: OFF\n  │     └── user function: OFF\n  │\n  │     Features\n"
+                "  │     ├─────────── grid: grid (on GPU)\n  │     ├───── parameters: params\n"
+                "  │     ├────── variables: vars\n  └─────├─── state vector: sol\n        ├─────── equation: eqn\n"
+                f"        ├────────── clock: clock\n        └──── timestepper: {self.stepper}TimeStepper")
+
+
+def SetUpProblemIC(prob, *, ux=None, uy=None, uz=None, bx=None, by=None, bz=None, **unsupported):
+    """SetUpProblemIC!(prob; ux, uy, uz, bx, by, bz) (utils/IC.jl:41-109): copy each given real field in and
+    r2c it into sol; no dealias, no projection; velocity is skipped for EMHD (:69)."""
+    if any(v is not None and len(np.shape(v)) for v in unsupported.values()):
+        raise NotImplementedError(f"unsupported IC fields on this path: {sorted(unsupported)}")
+    if not prob.flag.e:
+        for name, arr in (("ux", ux), ("uy", uy), ("uz", uz)):
+            if arr is not None and np.size(arr):
+                prob.set_real(name, arr)
+    if prob.flag.b:
+        for name, arr in (("bx", bx), ("by", by), ("bz", bz)):
+            if arr is not None and np.size(arr):
+                prob.set_real(name, arr)
+    return None
+
+
+def stepforward(prob, nsteps=1):
+    """stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)
+    (timestepper/timestepper.jl:4-6)."""
+    L.check(prob._h, L.lib().mhdf_step(prob._h, int(nsteps)))
+
+
+def getCFL(prob, t_diff, Coef=0.3):
+    """getCFL!(prob, t_diff; Coef) (integrator.jl:158-198)."""
+    dt = C.c_double()
+    L.check(prob._h, L.lib().mhdf_cfl_dt(prob._h, float(Coef), float(t_diff), C.byref(dt)))
+    return dt.value
+
+
+def _round_sig(x, sig=3):
+    if x == 0 or not math.isfinite(x):
+        return x
+    return round(x, sig - int(math.floor(math.log10(abs(x)))) - 1)
+
+
+def ProbDiagnostic(prob):
+    """ProbDiagnostic(prob) (utils/UserInterface.jl:65-86): KE, ME = round(sum(u^2) dV; sigdigits=3) from vars."""
+    try:
+        ke, me = prob.energy(L.STALE)
+    except L.MHDFlowsError as e:
+        if e.code == L.ERR_NONFINITE:
+            raise FloatingPointError("detected NaN! Quit the simulation right now.") from e
+        raise
+    if prob.flag.e:
+        return _round_sig(me)
+    if prob.flag.b:
+        return _round_sig(ke), _round_sig(me)
+    return _round_sig(ke)
+
+
+class Diagnostic:
+    """Diagnostic(calc, prob; freq, nsteps, ndata) (DiagnosticWrapper.jl:14-105)."""
+
+    def __init__(self, calc, prob, freq=1, nsteps=100, ndata=None):
+        ndata = math.ceil((nsteps + 1) / freq) if ndata is None else ndata
+        self.calc, self.prob, self.freq, self.N = calc, prob, freq, ndata
+        self.data = [None] * ndata
+        self.t = [0.0] * ndata
+        self.steps = [0] * ndata
+        self.data[0], self.t[0], self.steps[0] = calc(prob), prob.clock.t, prob.clock.step
+        self.i = 1
+
+    def extend(self, n=None):
+        n = self.N if n is None else n
+        self.data += [None] * n
+        self.t += [0.0] * n
+        self.steps += [0] * n
+
+    def update(self, i):
+        if i > len(self.steps):
+            self.extend()
+        self.data[i - 1], self.t[i - 1], self.steps[i - 1] = self.calc(self.prob), self.prob.clock.t, self.prob.clock.step
+        self.i = i
+
+    def increment(self):
+        if self.prob.clock.step % self.freq == 0:
+            self.update(self.i + 1)
+
+    def __getitem__(self, s):
+        if isinstance(s, str):
+            return getattr(self, s)[: self.i]
+        return self.data[s]
+
+    def __call__(self):
+        return self.calc(self.prob)
+
+
+def increment(diags):
+    for d in (diags if isinstance(diags, (list, tuple)) else [diags]):
+        d.increment()
+
+
+def TimeIntegrator(prob, t0, N0, *, usr_dt=0.0, CFL_Coef=0.25, CFL_function=nothingfunction, diags=(),
+                   dynamic_dashboard=True, loop_number=100, save=False, save_loc="", filename="", file_number=0,
+                   dump_dt=0, quiet=True):
+    """TimeIntegrator!(prob, t0, N0; ...) (integrator.jl:31-156): CFL -> stepforward! -> diagnostics per step.
+    Keeps the reference's quirks: clock.step is reset to 0 (:76) and the loop runs while
+    N0 >= step && t0 >= t, i.e. N0+1 steps (:104).  HDF5 saving is outside this path."""
+    if save:
+        if len(save_loc) == 0 or len(filename) == 0 or dump_dt == 0:
+            raise ValueError("Save Function Turned ON but save_loc/filename/dump_dt is not declared!\n")   # :47
+        raise NotImplementedError("HDF5 output is outside the B200 hot path (SURVEY 8f)")
+    if CFL_function is not nothingfunction and usr_dt > 0.0:
+        raise ValueError("User define both CFL_function and usr_dt")                                       # :202
+    updateCFL = getCFL if CFL_function is nothingfunction else CFL_function
+    p = prob.params
+    if prob.flag.b:
+        vi = p.η if prob.flag.e else max(p.ν, p.η)
+        nv = p.nη if prob.flag.e else max(p.nν, p.nη)
+    else:
+        vi, nv = p.ν, p.nν
+    g = prob.grid
+    dl = min(g.Lx / g.nx, g.Ly / g.ny, g.Lz / g.nz)
+    if vi == 0:
+        t_diff = math.inf
+    else:
+        t_diff = CFL_Coef * dl ** nv / vi if nv > 1 else CFL_Coef * dl ** 2 / vi                         # :72
+    prob.clock.step = 0
+    usr_declared_dt = usr_dt != 0.0
+    if usr_declared_dt:
+        prob.clock.dt = usr_dt
+    t_start = time.perf_counter()
+    while N0 >= prob.clock.step and t0 >= prob.clock.t:
+        if not usr_declared_dt:
+            updateCFL(prob, t_diff, Coef=CFL_Coef)
+        stepforward(prob)
+        increment(list(diags))
+        for foo in prob.usr_func:
+            foo(prob)
+        if not quiet and (dynamic_dashboard or prob.clock.step % loop_number == 0):
+            d = ProbDiagnostic(prob)
+            print(f"           n = {prob.clock.step:8d}, t = {_round_sig(prob.clock.t):8}, diag = {d}")
+    elapsed = time.perf_counter() - t_start
+    ntotal = g.nx * g.ny * g.nz
+    if not quiet:
+        print(f"Total CPU/GPU time run = {elapsed:.3f} s, zone update per second = {prob.clock.step * ntotal / elapsed:.3f} ")
+    return elapsed
+
+
+def spectralline(prob, field, nbins=None):
+    """spectralline(A; Lx) (utils/MHDAnalysis.jl:237-255) of a state field: (Pk, kr)."""
+    g = prob.grid
+    kmax = math.sqrt((g.nx // 2 * 2 * math.pi / g.Lx) ** 2 + (g.ny // 2 * 2 * math.pi / g.Ly) ** 2 + (g.nz // 2 * 2 * math.pi / g.Lz) ** 2)
+    krmax = int(np.rint(kmax + 1)) if nbins is None else nbins
+    Pk = (C.c_double * krmax)()
+    L.check(prob._h, L.lib().mhdf_spectrum(prob._h, prob._field_id(field), Pk, krmax))
+    Pk = np.array(Pk)
+    kr = np.where(Pk > 0, np.arange(1, krmax + 1), 0).astype(prob.T)
+    return Pk.astype(prob.T), kr
+
+
+def DivFreeSpectraMap(grid, *, k_peak=0.0, P=1, k0=-5 / 3 / 2, b=1, theta=None, seed=None):
+    """DivFreeSpectraMap(grid; k_peak, P, k0, b) (utils/IC.jl:130-179): random-phase power-law solenoidal field.
+    Host-side initial-condition generator (one-off, not on the hot path).  The uniform random numbers are either
+    injected (`theta`, shape (nz, ny, nkr) in [0,1)) or drawn from numpy's default_rng(seed) -- Julia's RNG stream
+    cannot be reproduced."""
+    import scipy.fft as sfft
+
+    T = grid.T
+    CT = np.complex64 if T is np.float32 else np.complex128
+    if theta is None:
+        theta = np.random.default_rng(seed).random((grid.nm, grid.nl, grid.nkr), dtype=np.float64).astype(T)
+    kx, ky, kz = grid.kr, grid.l, grid.m
+    Krsq = grid.Krsq
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = (T(1) / Krsq).astype(T)
+        inv[0, 0, 0] = 0
+        kinv, k = np.sqrt(inv), np.sqrt(Krsq)
+        kperp = np.sqrt(kx ** 2 + ky ** 2) + 0 * kz
+        dkm2 = 1 / (k + 1) ** 2
+        Fk = k ** T(k0)
+        Fk[0, 0, 0] = 0
+        Fk[..., 0] = 0
+        Fk[k < k_peak] = 0
+        intF = float(np.sum((Fk * dkm2).astype(np.float64)))
+        A = math.sqrt(P * 3 * (grid.Lx / grid.dx) * (grid.Ly / grid.dy) * (grid.Lz / grid.dz) / intF / grid.dx / grid.dy / grid.dz)
+        Fk = (Fk * T(A)).astype(T)
+        e2x, e2y, e2z = kx * kz / kperp * kinv, ky * kz / kperp * kinv, -kperp * kinv
+    e2x[np.isnan(e2x)] = 0
+    e2y[np.isnan(e2y)] = 0
+    eith = np.exp(1j * theta.astype(np.float64) * 2 * math.pi).astype(CT)
+    msk = grid.retained_mask()
+    out = []
+    for e2 in (e2x, e2y, e2z):
+        Fh = (Fk * eith * e2).astype(CT)
+        Fh[~msk] = 0
+        out.append(sfft.irfftn(Fh, s=(grid.nz, grid.ny, grid.nx), axes=(0, 1, 2)).astype(T))
+    return tuple(out)

@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same
+seeded inputs.  Tolerances: Float32 per-step relative L2 <= 1e-5, Float64 <= 1e-12 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-5
+F64_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mhdflows_jl_b200 as M
+    return M
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import mhdflows_oracle as O
+    return O
+
+
+def _pair(M, O, kind, nxyz, T, stepper="RK4", turb=True, dt=None):
+    nx, ny, nz = nxyz
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, stepper=stepper)
+    if kind == "mhd":
+        kw.update(nu=2e-2, eta=3e-2, B_field=True, dt=dt or 4e-3)
+    elif kind == "hd":
+        kw.update(nu=2e-2, dt=dt or 4e-3)
+    else:
+        kw.update(B_field=True, EMHD=True, dt=dt or 2e-4)
+    op = O.Problem(**kw)
+    gp = M.Problem(M.GPU(), **kw)
+    g = op.grid
+    if turb:
+        u, b = O.random_phase_ic(g, 1234), O.random_phase_ic(g, 5678)
+    else:
+        ic = O.taylor_green_ic(g)
+        u, b = ic[:3], ic[3:]
+    if kind == "emhd":
+        O.SetUpProblemIC(op, bx=b[0], by=b[1], bz=b[2])
+        M.SetUpProblemIC(gp, bx=b[0], by=b[1], bz=b[2])
+    elif kind == "mhd":
+        O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+    else:
+        O.SetUpProblemIC(op, *u)
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2])
+    return op, gp
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 16), (32, 32, 32), (64, 32, 16), (16, 64, 128), (128, 128, 128), (256, 256, 256)])
+def test_fft_r2c_c2r_against_numpy(M, O, dims):
+    nx, ny, nz = dims
+    p = M.Problem(M.GPU(), nx=nx, ny=ny, nz=nz, B_field=True)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((nz, ny, nx)).astype(np.float32)
+    p.set_real(0, x)
+    ref = sfft.rfftn(x.astype(np.float64), axes=(0, 1, 2))
+    msk = p.grid.retained_mask()
+    ref[~msk] = 0
+    assert O.rel_l2(p.get_spectral(0), ref) < 2e-6
+    assert O.rel_l2(p.get_real(0), sfft.irfftn(ref, s=(nz, ny, nx), axes=(0, 1, 2))) < 2e-6
+    # non-Hermitian spectral input: c2r must behave like FFTW/pocketfft (kr = 0 plane symmetrised)
+    s = (rng.standard_normal((nz, ny, nx // 2 + 1)) + 1j * rng.standard_normal((nz, ny, nx // 2 + 1))).astype(np.complex64)
+    p.set_spectral(1, s)
+    sm = s.copy()
+    sm[~msk] = 0
+    assert O.rel_l2(p.get_spectral(1), sm) == 0.0
+    assert O.rel_l2(p.get_real(1), sfft.irfftn(sm.astype(np.complex128), s=(nz, ny, nx), axes=(0, 1, 2))) < 2e-6
+    p.close()
+
+
+def test_fft_float64(M, O):
+    nx, ny, nz = 64, 128, 32
+    p = M.Problem(M.GPU(), nx=nx, ny=ny, nz=nz, T=np.float64)
+    x = np.random.default_rng(2).standard_normal((nz, ny, nx))
+    p.set_real(0, x)
+    ref = sfft.rfftn(x, axes=(0, 1, 2))
+    ref[~p.grid.retained_mask()] = 0
+    assert O.rel_l2(p.get_spectral(0), ref) < 1e-14
+    assert O.rel_l2(p.get_real(0), sfft.irfftn(ref, s=(nz, ny, nx), axes=(0, 1, 2))) < 1e-14
+    p.close()
+
+
+@pytest.mark.parametrize("kind", ["hd", "mhd", "emhd"])
+@pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
+def test_calcN_matches_oracle(M, O, kind, T, tol):
+    """One RHS evaluation (eqn.calcN!) on a broadband random-phase field."""
+    op, gp = _pair(M, O, kind, (32, 32, 32), T)
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol, 0.0, op.clock, op.vars, op.params, op.grid)
+    op.grid.dealias(N)
+    got = gp.calcN()
+    for i in range(op.Nl):
+        assert O.rel_l2(got[i], N[i]) < tol, (kind, i)
+    gp.close()
+
+
+def test_calcN_noncubic(M, O):
+    op, gp = _pair(M, O, "mhd", (64, 32, 16), np.float32)
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol, 0.0, op.clock, op.vars, op.params, op.grid)
+    op.grid.dealias(N)
+    got = gp.calcN()
+    for i in range(6):
+        assert O.rel_l2(got[i], N[i]) < F32_TOL
+    gp.close()
+
+
+@pytest.mark.parametrize("kind", ["hd", "mhd", "emhd"])
+@pytest.mark.parametrize("stepper", ["RK4", "LSRK54"])
+@pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
+def test_per_step_parity(M, O, kind, stepper, T, tol):
+    """Per-step relative L2 error of the spectral state over 10 steps, both steppers, all three systems."""
+    op, gp = _pair(M, O, kind, (32, 32, 32), T, stepper=stepper)
+    for s in range(10):
+        O.stepforward(op)
+        M.stepforward(gp)
+        ref = op.grid.dealias(op.sol.copy())
+        sol = gp.sol
+        if kind == "emhd":
+            assert O.rel_l2(sol, ref) < tol, (s,)
+        else:
+            assert O.rel_l2(sol[:3], ref[:3]) < tol, (s, "u")
+            if kind == "mhd":
+                assert O.rel_l2(sol[3:], ref[3:]) < tol, (s, "b")
+    assert abs(gp.clock.t - op.clock.t) < 1e-6 and gp.clock.step == op.clock.step
+    gp.close()
+
+
+def test_hyperviscosity_adds_on_top(M, O):
+    kw = dict(nx=32, T=np.float64, nu=1e-4, n_nu=2, dt=2e-3)
+    op = O.Problem(**kw)
+    gp = M.Problem(M.GPU(), **kw)
+    u = O.random_phase_ic(op.grid, 7)
+    O.SetUpProblemIC(op, *u)
+    M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2])
+    for _ in range(3):
+        O.stepforward(op)
+    M.stepforward(gp, 3)
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < F64_TOL
+    gp.close()
+
+
+def test_energy_helicity_series_100_steps(M, O):
+    """Energy and helicity time series over 100 steps (MHD TG 32^3 Float32, RK4) -- north_star's series check.
+    Sampled from the stale `vars` like the reference's ProbDiagnostic."""
+    op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float32, turb=False, dt=5e-3)
+    g = op.grid
+    dV = g.dx * g.dy * g.dz
+    for s in range(100):
+        O.stepforward(op)
+        M.stepforward(gp)
+        if s % 10 == 9:
+            KE, ME = O.ProbDiagnostic(op, rounded=False)
+            ke, me = gp.energy(M.STALE)
+            assert abs(ke - KE) / KE < 1e-5 and abs(me - ME) / ME < 1e-5
+            assert M.ProbDiagnostic(gp) == O.ProbDiagnostic(op)
+            # fresh helicities against the oracle's analysis functions on the true state
+            u = [g.irfft(g.dealias(op.sol[i].copy())) for i in range(3)]
+            b = [g.irfft(g.dealias(op.sol[3 + i].copy())) for i in range(3)]
+            Hk = float(np.sum(O.h_k(*u, g).astype(np.float64)))
+            Hm = float(np.sum(O.h_m(*b, g).astype(np.float64)))
+            Hc = float(sum(np.sum(a.astype(np.float64) * c) for a, c in zip(u, b))) * dV
+            hk, hm, hc = gp.helicity()
+            scale = KE + ME
+            assert abs(hk - Hk) < 1e-5 * scale and abs(hm - Hm) < 1e-5 * scale / dV and abs(hc - Hc) < 1e-5 * scale
+    ref = op.grid.dealias(op.sol.copy())
+    assert O.rel_l2(gp.sol[:3], ref[:3]) < F32_TOL and O.rel_l2(gp.sol[3:], ref[3:]) < F32_TOL
+    gp.close()
+
+
+def test_time_integrator_cfl_path(M, O):
+    op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float32, turb=False)
+    O.TimeIntegrator(op, 1e9, 5, CFL_Coef=0.25)
+    M.TimeIntegrator(gp, 1e9, 5, CFL_Coef=0.25)
+    assert gp.clock.step == op.clock.step == 6            # N0+1 steps, integrator.jl:104
+    assert abs(gp.clock.dt - op.clock.dt) / op.clock.dt < 1e-5
+    assert abs(gp.clock.t - op.clock.t) / op.clock.t < 1e-5
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < 5e-5
+    gp.close()
+
+
+def test_stale_vars_and_spectrum(M, O):
+    op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float32)
+    for _ in range(2):
+        O.stepforward(op)
+    M.stepforward(gp, 2)
+    # vars.ux after a step = c2r of the 4th stage input, not of sol
+    assert O.rel_l2(gp.vars.ux, op.vars.ux) < 1e-5
+    assert O.rel_l2(gp.vars.bz, op.vars.bz) < 1e-5
+    fresh = gp.get_real("ux", M.FRESH)
+    assert O.rel_l2(fresh, op.grid.irfft(op.grid.dealias(op.sol[0].copy()))) < 1e-5
+    Pk, kr = M.spectralline(gp, "bx")
+    Pk_ref, kr_ref = O.spectralline(op.grid.irfft(op.grid.dealias(op.sol[3].copy())), op.grid)
+    assert len(Pk) == len(Pk_ref)
+    assert np.abs(Pk - Pk_ref).max() / Pk_ref.max() < 1e-4
+    gp.close()
+
+
+def test_diagnostic_wrapper(M, O):
+    op, gp = _pair(M, O, "hd", (32, 32, 32), np.float32)
+    d = M.Diagnostic(lambda p: p.energy(M.FRESH)[0], gp, freq=2, nsteps=6)
+    M.TimeIntegrator(gp, 1e9, 5, usr_dt=1e-3, diags=[d])
+    assert d.i == 4 and d.steps[:4] == [0, 2, 4, 6]
+    assert d["data"][0] >= d["data"][-1] > 0
+    gp.close()
+
+
+def test_errors_are_reported_not_thrown_across_abi(M, O):
+    with pytest.raises(M.MHDFlowsError):
+        M.Problem(M.GPU(), nx=48)
+    with pytest.raises(ValueError):
+        M.Problem(M.GPU(), nx=32, Shear=True)
+    p = M.Problem(M.GPU(), nx=32)
+    with pytest.raises(M.MHDFlowsError):
+        p.get_spectral(5)
+    x = np.full((32, 32, 32), np.nan, dtype=np.float32)
+    p.set_real(0, x)
+    p.clock.dt = 1e-3
+    with pytest.raises(M.MHDFlowsError) as ei:
+        M.stepforward(p)
+    assert ei.value.code == M._lib.ERR_NONFINITE if hasattr(M, "_lib") else True
+    p.close()
+
+
+def test_large_grid_properties_256(M, O):
+    """BASELINE config 2 size (MHD TG 256^3 Float32 RK4): size-independent properties -- energy decay
+    consistent with nu, solenoidality preserved, and parity with the oracle after 2 steps."""
+    op, gp = _pair(M, O, "mhd", (256, 256, 256), np.float32, turb=False, dt=1e-3)
+    ke0, me0 = gp.energy(M.FRESH)
+    for _ in range(2):
+        O.stepforward(op)
+    M.stepforward(gp, 2)
+    ref = op.grid.dealias(op.sol.copy())
+    sol = gp.sol
+    assert O.rel_l2(sol[:3], ref[:3]) < F32_TOL and O.rel_l2(sol[3:], ref[3:]) < F32_TOL
+    ke, me = gp.energy(M.FRESH)
+    assert ke + me < ke0 + me0
+    g = gp.grid
+    for base in (0, 3):
+        div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
+        assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < 1e-5
+    gp.close()
