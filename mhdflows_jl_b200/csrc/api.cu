@@ -244,13 +244,14 @@ struct Solver : mhdf_handle {
   static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
   static constexpr int passTX(int N) { return sizeof(T) == 4 ? (N >= 1024 ? 8 : 16) : (N >= 1024 ? 4 : 8); }
   static constexpr int xE(int) { return 8; }
-  static constexpr int xRB(int N) { return 256 / (N / 2 / 8) > 0 ? 256 / (N / 2 / 8) : 1; }
+  static constexpr int XNT = 64;   // threads per block of the x kernels: small blocks, rows decoupled per warp
+  static constexpr int xRB(int N) { return XNT / (N / 2 / 8) > 0 ? XNT / (N / 2 / 8) : 1; }
 
   template <int N, int DIR> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
     constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
     constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
     dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
-    k_pass<T, N, E, TX, DIR><<<grid, (N / E) * TX, smem, st>>>(a);
+    k_pass<T, N, E, TX, DIR, (DIR > 0)><<<grid, (N / E) * TX, smem, st>>>(a);
     ++launches;
   }
   template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
@@ -273,7 +274,7 @@ struct Solver : mhdf_handle {
   }
   int x_grid(long long rows, int RB) const {
     long long sets = rows / RB;
-    long long g = (long long)nsm * 8;
+    long long g = (long long)nsm * 16;
     return (int)(sets < g ? sets : g);
   }
   template <int N> void launch_xfused_n(XArgs<T>& a) {
@@ -336,8 +337,8 @@ struct Solver : mhdf_handle {
     constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
     constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
     if (smem > 48 * 1024) {
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
   }
 
@@ -346,10 +347,10 @@ struct Solver : mhdf_handle {
   void z_inverse(const C* in, long long in_field, C* out, int nf) {
     PassArgs<T> a;
     a.in = in; a.out = out; a.tw = twz;
-    a.in_row = a.out_row = (long long)Ky * Kxp;
+    a.in_row = a.out_row = Ky * Kxp;
     a.in_outer = a.out_outer = 0;
     a.in_field = in_field; a.out_field = (long long)nz * Ky * Kxp;
-    a.inner = Ky * Kxp; a.bin = bz; a.bout = band_full(nz); a.scale = (T)1;
+    a.inner = Ky * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
     prof_begin(KC_ZINV);
     launch_pass<+1>(nz, a, 1, nf);
     prof_end();
@@ -361,7 +362,7 @@ struct Solver : mhdf_handle {
     a.in_row = a.out_row = Kxp;
     a.in_outer = (long long)Ky * Kxp; a.out_outer = (long long)ny * Kxp;
     a.in_field = (long long)nz * Ky * Kxp; a.out_field = (long long)nz * ny * Kxp;
-    a.inner = Kxp; a.bin = by; a.bout = band_full(ny); a.scale = (T)1;
+    a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
     prof_begin(KC_YINV);
     launch_pass<+1>(ny, a, nz, nf);
     prof_end();
@@ -373,7 +374,7 @@ struct Solver : mhdf_handle {
     a.in_row = a.out_row = Kxp;
     a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Ky * Kxp;
     a.in_field = (long long)nz * ny * Kxp; a.out_field = (long long)nz * Ky * Kxp;
-    a.inner = Kxp; a.bin = band_full(ny); a.bout = by; a.scale = (T)1;
+    a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
     prof_begin(KC_YFWD);
     launch_pass<-1>(ny, a, nz, nf);
     prof_end();
@@ -382,10 +383,10 @@ struct Solver : mhdf_handle {
   void z_forward(const C* in, C* out, long long out_field, int nf) {
     PassArgs<T> a;
     a.in = in; a.out = out; a.tw = twz;
-    a.in_row = a.out_row = (long long)Ky * Kxp;
+    a.in_row = a.out_row = Ky * Kxp;
     a.in_outer = a.out_outer = 0;
     a.in_field = (long long)nz * Ky * Kxp; a.out_field = out_field;
-    a.inner = Ky * Kxp; a.bin = band_full(nz); a.bout = bz; a.scale = (T)1;
+    a.inner = Ky * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
     prof_begin(KC_ZFWD);
     launch_pass<-1>(nz, a, 1, nf);
     prof_end();

@@ -37,13 +37,37 @@ struct PassArgs {
   const Cx<T>* in;
   Cx<T>* out;
   const Cx<T>* tw;          // twiddle table of length N: (cos, -sin)(2 pi i / N)
-  long long in_row, out_row;       // element stride between consecutive rows n of the FFT axis
+  int in_row, out_row;             // element stride between consecutive rows n of the FFT axis (< 2^31 within a field)
   long long in_outer, out_outer;   // stride of the outer (non-transformed, non-contiguous) axis
   long long in_field, out_field;   // stride between fields of the batch
   int inner;                       // contiguous elements per row to process
-  Band bin, bout;                  // which FFT-axis rows exist in `in` / are wanted in `out`
-  T scale;                         // applied on load
+  // retained band of the pruned side: rows [0, lo) and [hi0, N) exist, stored contiguously (shift = hi0 - lo)
+  int lo, hi0, shift;
 };
+
+// predicated 8/16-byte global accesses (no branches, no speculative address use)
+__device__ __forceinline__ float2 ldg_pred(const float2* p, bool ok) {
+  float2 v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+               "@p ld.global.nc.v2.f32 {%0, %1}, [%2];\n\t}"
+               : "=f"(v.x), "=f"(v.y) : "l"(p), "r"((int)ok));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_pred(const double2* p, bool ok) {
+  double2 v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+               "@p ld.global.nc.v2.f64 {%0, %1}, [%2];\n\t}"
+               : "=d"(v.x), "=d"(v.y) : "l"(p), "r"((int)ok));
+  return v;
+}
+__device__ __forceinline__ void stg_pred(float2* p, float2 v, bool ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f32 [%0], {%1, %2};\n\t}"
+               :: "l"(p), "f"(v.x), "f"(v.y), "r"((int)ok) : "memory");
+}
+__device__ __forceinline__ void stg_pred(double2* p, double2 v, bool ok) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}"
+               :: "l"(p), "d"(v.x), "d"(v.y), "r"((int)ok) : "memory");
+}
 
 template <int N, int TX, int R1, typename C> struct PassIdx {
   // float2 with TX = 8: two rows share one 128-byte bank line; shift by 8 slots every R1 rows so
@@ -54,8 +78,9 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
   __device__ __forceinline__ int operator()(int n) const { return n * TX + c + (PAD ? (n / R1) * 8 : 0); }
 };
 
-template <typename T, int N, int E, int TX, int DIR>
-__global__ void __launch_bounds__((N / E) * TX) k_pass(PassArgs<T> a) {
+// PIN: the input side is the pruned (band) side (inverse passes); otherwise the output side is (forward passes).
+template <typename T, int N, int E, int TX, int DIR, bool PIN>
+__global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 2 : 1) k_pass(PassArgs<T> a) {
   using C = Cx<T>;
   constexpr int Tn = N / E;
   constexpr int R1 = imin(E, N);
@@ -65,20 +90,20 @@ __global__ void __launch_bounds__((N / E) * TX) k_pass(PassArgs<T> a) {
   const int t = threadIdx.x / TX;
   const int col = blockIdx.x * TX + c;
   const bool valid = col < a.inner;
-  const long long ibase = (long long)blockIdx.z * a.in_field + (long long)blockIdx.y * a.in_outer + col;
-  const long long obase = (long long)blockIdx.z * a.out_field + (long long)blockIdx.y * a.out_outer + col;
+  const C* ip = a.in + ((long long)blockIdx.z * a.in_field + (long long)blockIdx.y * a.in_outer + col);
+  C* op = a.out + ((long long)blockIdx.z * a.out_field + (long long)blockIdx.y * a.out_outer + col);
 
   C v[E];
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int n = t + Tn * m;
-    const int row = a.bin.row(n);
-    v[m] = mk<C>(0, 0);
-    if (valid && row >= 0) v[m] = a.in[ibase + (long long)row * a.in_row];
-  }
-  if (a.scale != (T)1) {
-#pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = cscale(v[m], a.scale);
+    if (PIN) {
+      const bool ok = valid && (n < a.lo || n >= a.hi0);
+      const int r = n - (n >= a.hi0 ? a.shift : 0);
+      v[m] = ldg_pred(ip + r * a.in_row, ok);
+    } else {
+      v[m] = ldg_pred(ip + n * a.in_row, valid);
+    }
   }
   PassIdx<N, TX, R1, C> idx{c};
   // single exchange buffer: two barriers per exchange (scatter | gather | next scatter)
@@ -86,17 +111,24 @@ __global__ void __launch_bounds__((N / E) * TX) k_pass(PassArgs<T> a) {
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int n = t + Tn * m;
-    const int row = a.bout.row(n);
-    if (valid && row >= 0) a.out[obase + (long long)row * a.out_row] = v[m];
+    if (!PIN) {
+      const bool ok = valid && (n < a.lo || n >= a.hi0);
+      const int r = n - (n >= a.hi0 ? a.shift : 0);
+      stg_pred(op + r * a.out_row, v[m], ok);
+    } else {
+      stg_pred(op + n * a.out_row, v[m], valid);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // x pass: rows are contiguous.  Real rows of length N are handled as M = N/2 complex points.
 // ------------------------------------------------------------------------------------------------
+// One pad slot per 16 elements: 16 consecutive elements (gathers, natural-order accesses, mirrored reads) and the
+// first radix-8/16 scatter are bank-conflict free; offsets r*NS still fold into immediate operands.
 template <int M, int R1> struct RowIdx {
-  static constexpr int SIZE = M + M / R1 + 1;
-  __device__ __forceinline__ int operator()(int n) const { return n + n / R1; }
+  static constexpr int SIZE = M + M / 16 + 1;
+  __device__ __forceinline__ int operator()(int n) const { return n + (n >> 4); }
 };
 
 // Shared-memory context of one row: two alternating exchange buffers.
@@ -157,6 +189,10 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
   }
   sm.swap();
 }
+
+// rows owned by <= 32 threads: warp barrier; otherwise the block must hold exactly one row
+template <bool WARP, int RB> struct XSync { using type = SyncWarp; };
+template <> struct XSync<false, 1> { using type = SyncBlock; };
 
 // ---- physics functors: which products are formed between the inverse and forward x passes -------
 // Reduction slots written by the fused x kernel (doubles): see XRed.
@@ -235,7 +271,8 @@ template <typename T, int N, int E, int RB, int PHYS>
 __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
-  using SYNC = SyncBlock;
+  // a row owned by at most one warp synchronises with __syncwarp only: rows are fully decoupled
+  using SYNC = typename XSync<(Tm <= 32), RB>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int r = threadIdx.x / Tm;
   const int t = threadIdx.x % Tm;
@@ -252,10 +289,22 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   for (int i = 0; i < 6; ++i) rm[i] = 0.f;
 
   const long long nsets = a.rows / RB;
+  constexpr int NINF = (PHYS == PHYS_MHD) ? 6 : (PHYS == PHYS_HD ? 3 : 24);
   for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
     const long long row = set * RB + r;
     const C* in = a.in + row * a.Kxp;
     C* out = a.out + row * a.Kxp;
+    {
+      // pull the next row set of this block towards L2 while this one is being transformed
+      const long long nset = set + gridDim.x;
+      if (nset < nsets) {
+        const char* nb = reinterpret_cast<const char*>(a.in + (nset * RB + r) * a.Kxp);
+        const int bytes = a.Kx * (int)sizeof(C);
+        for (int f = 0; f < NINF; ++f)
+          for (int o = t * 128; o < bytes; o += Tm * 128)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nb + (long long)f * a.in_field * (long long)sizeof(C) + o));
+      }
+    }
     if constexpr (PHYS == PHYS_HD || PHYS == PHYS_MHD) {
       constexpr int NF = (PHYS == PHYS_MHD) ? 6 : 3;
       C f[NF][E];
@@ -374,7 +423,7 @@ template <typename T, int N, int E, int RB, int DIR>
 __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
-  using SYNC = SyncBlock;
+  using SYNC = typename XSync<(Tm <= 32), RB>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int r = threadIdx.x / Tm;
   const int t = threadIdx.x % Tm;
