@@ -1,0 +1,86 @@
+"""The C-ABI library loads and exports every symbol include/mhdflows_b200.h declares; without a GPU it fails
+loudly (no CPU fallback).  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "mhdflows_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mhdf_[a-z_A-Z0-9]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mhdflows_jl_b200 import build
+    return ctypes.CDLL(build.build(verbose=False))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = _header_symbols()
+    for s in ("mhdf_create", "mhdf_destroy", "mhdf_step", "mhdf_calcN", "mhdf_set_real", "mhdf_get_real", "mhdf_set_spectral",
+              "mhdf_get_spectral", "mhdf_cfl_dt", "mhdf_energy", "mhdf_helicity", "mhdf_spectrum", "mhdf_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in _header_symbols():
+        assert hasattr(lib, s), f"libmhdflows_b200.so does not export {s}"
+
+
+def test_python_binding_lists_the_same_symbols():
+    from mhdflows_jl_b200 import _lib
+    assert sorted(_lib.SYMBOLS) == _header_symbols()
+
+
+def test_config_struct_layout_matches_header():
+    from mhdflows_jl_b200 import _lib
+    names = [f[0] for f in _lib.Config._fields_]
+    src = open(os.path.join(ROOT, "include", "mhdflows_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} mhdf_config;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    decl = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        stmt = re.sub(r"^(const\s+)?(int|double|void\s*\*)\s*", "", stmt)
+        decl += [x.strip().lstrip("*").strip() for x in stmt.split(",")]
+    assert names == decl
+    assert ctypes.sizeof(_lib.Config) == 104
+
+
+def test_invalid_arguments_are_status_codes_not_crashes(lib):
+    from mhdflows_jl_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.mhdf_create(None, ctypes.byref(h)) == _lib.ERR_INVALID
+    cfg = _lib.Config(nx=48, ny=32, nz=32, Lx=1.0, Ly=1.0, Lz=1.0, physics=_lib.MHD, stepper=_lib.RK4, dtype=_lib.F32, nranks=1)
+    assert L.mhdf_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.ERR_INVALID
+    assert b"powers of two" in L.mhdf_last_error(None)
+    assert L.mhdf_destroy(None) == _lib.ERR_INVALID
+    assert L.mhdf_step(None, 1) == _lib.ERR_INVALID
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import mhdflows_jl_b200 as M
+    with pytest.raises(M.MHDFlowsError) as ei:
+        M.Problem(M.GPU(), nx=32)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mhdflows_jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), f"{f} references the oracle"

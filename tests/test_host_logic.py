@@ -1,0 +1,79 @@
+"""Host-side mirror of the reference API (mhdflows_jl_b200/problem.py): argument checking, grid formulas, the Diagnostic
+recorder and the IC generator -- everything that does not need the device."""
+import math
+
+import numpy as np
+import pytest
+
+import mhdflows_jl_b200 as M
+from mhdflows_jl_b200 import problem as P
+from oracle import mhdflows_oracle as O
+
+
+def test_problem_rejects_what_the_reference_rejects_before_touching_the_device():
+    with pytest.raises(ValueError, match="Shear"):
+        M.Problem(M.GPU(), nx=32, Shear=True)                       # pgen.jl:103-105
+    with pytest.raises(ValueError, match="c"):
+        M.Problem(M.GPU(), nx=32, Compressibility=True)             # pgen.jl:98-100
+    with pytest.raises(ValueError, match="EMHD requires"):
+        M.Problem(M.GPU(), nx=32, EMHD=True)
+    with pytest.raises(NotImplementedError):
+        M.Problem(M.GPU(), nx=32, stepper="HM89")
+    with pytest.raises(ValueError):
+        M.Problem(M.GPU(), nx=32, stepper="ETDRK4")
+    with pytest.raises(M.MHDFlowsError):
+        M.Problem(M.CPU(), nx=32)
+    with pytest.raises(TypeError):
+        M.Problem(M.GPU(), nx=32, bogus=1)
+
+
+@pytest.mark.parametrize("dims", [(32, 32, 32), (64, 32, 16), (96, 48, 24)])
+def test_grid_matches_oracle_grid(dims):
+    nx, ny, nz = dims
+    g = P._Grid(nx, ny, nz, 2 * math.pi, 3.0, 5.0, np.float32)
+    o = O.Grid(nx, ny, nz, 2 * math.pi, 3.0, 5.0, np.float32)
+    for a in ("x", "y", "z", "kr", "l", "m", "Krsq"):
+        assert np.array_equal(getattr(g, a), getattr(o, a)), a
+    assert np.array_equal(g.retained_mask(), o.retained_mask())
+    for n in (16, 32, 96, 256, 512, 1024):
+        assert g.aliased_range(n) == O.aliased_range(n)
+
+
+def test_divfree_spectra_map_matches_oracle():
+    g = P._Grid(24, 24, 24, 2 * math.pi, 2 * math.pi, 2 * math.pi, np.float64)
+    o = O.Grid(24, T=np.float64)
+    theta = np.random.default_rng(3).random((24, 24, 13))
+    a = M.DivFreeSpectraMap(g, theta=theta, k0=-5 / 6)
+    b = O.DivFreeSpectraMap(o, theta, k0=-5 / 6)
+    for x, y in zip(a, b):
+        assert O.rel_l2(x, y) < 1e-12
+    c = M.DivFreeSpectraMap(g, seed=1234, k0=-5 / 6)
+    d = O.random_phase_ic(o, 1234)
+    assert O.rel_l2(c[0], d[0]) < 1e-12
+
+
+class _FakeClock:
+    def __init__(self):
+        self.t, self.step, self.dt = 0.0, 0, 0.1
+
+
+class _FakeProb:
+    def __init__(self):
+        self.clock = _FakeClock()
+
+
+def test_diagnostic_recorder_semantics():
+    """DiagnosticWrapper.jl:40-105: first value at construction, update every `freq` steps, auto-extend."""
+    p = _FakeProb()
+    d = M.Diagnostic(lambda q: q.clock.step * 10, p, freq=2, nsteps=4)
+    assert d.N == 3 and d.i == 1 and d.data[0] == 0
+    for s in range(1, 11):
+        p.clock.step, p.clock.t = s, 0.1 * s
+        M.increment([d])
+    assert d.i == 6 and d["steps"] == [0, 2, 4, 6, 8, 10] and d["data"][-1] == 100
+    assert len(d.data) >= 6 and d() == 100 and d[1] == 20
+
+
+def test_round_sig_matches_julia_round_sigdigits():
+    assert P._round_sig(42.8134) == 42.8 and P._round_sig(0.0123456) == 0.0123 and P._round_sig(123456.0) == 123000.0
+    assert P._round_sig(0.0) == 0.0 and math.isnan(P._round_sig(float("nan")))
