@@ -1,0 +1,210 @@
+# MHDFlowsB200.jl -- Julia host shim over libmhdflows_b200.so (pure `ccall`; no CUDA.jl, no kernels here).
+#
+# Same exported names and keyword arguments as MHDFlows.jl for the hot path, so a user script changes
+# `using MHDFlows` to `using MHDFlowsB200` (reference: src/MHDFlows.jl:65-88, src/pgen.jl:64-127,
+# src/utils/IC.jl:41-109, src/integrator.jl:31-198, src/utils/UserInterface.jl:65-86,
+# src/DiagnosticWrapper.jl:14-105).  NOT EXECUTED in the build environment (Julia is not installed there);
+# the Python ctypes mirror mhdflows_jl_b200/ is the tested twin of this file -- keep them line-for-line.
+module MHDFlowsB200
+
+export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDiagnostic, Diagnostic,
+       increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum
+
+const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
+
+struct CPU end
+struct GPU; device::Int; end
+GPU() = GPU(0)
+nothingfunction(args...) = nothing
+
+# mirrors `mhdf_config` in include/mhdflows_b200.h field by field
+struct MhdfConfig
+  nx::Cint; ny::Cint; nz::Cint
+  Lx::Cdouble; Ly::Cdouble; Lz::Cdouble
+  nu::Cdouble; eta::Cdouble
+  n_nu::Cint
+  dt::Cdouble
+  physics::Cint; stepper::Cint; dtype::Cint; device::Cint
+  rank::Cint; nranks::Cint
+  nccl_id::Ptr{Cvoid}
+end
+
+const MHDF_HD, MHDF_MHD, MHDF_EMHD = 0, 1, 2
+const MHDF_FRESH, MHDF_STALE = 0, 1
+
+mutable struct Clock{T}          # FourierFlows.Clock, read through the library
+  h::Ptr{Cvoid}
+end
+function _clock(c::Clock)
+  t = Ref{Cdouble}(); dt = Ref{Cdouble}(); s = Ref{Clonglong}()
+  ccall((:mhdf_get_clock, lib), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ref{Clonglong}), c.h, t, dt, s)
+  (t = t[], dt = dt[], step = Int(s[]))
+end
+Base.getproperty(c::Clock, s::Symbol) = s === :h ? getfield(c, :h) : getproperty(_clock(c), s)
+function Base.setproperty!(c::Clock, s::Symbol, v)
+  h = getfield(c, :h)
+  if s === :dt
+    check(h, ccall((:mhdf_set_dt, lib), Cint, (Ptr{Cvoid}, Cdouble), h, v))
+  elseif s === :t
+    check(h, ccall((:mhdf_set_clock, lib), Cint, (Ptr{Cvoid}, Cdouble, Clonglong), h, v, _clock(c).step))
+  elseif s === :step
+    check(h, ccall((:mhdf_set_clock, lib), Cint, (Ptr{Cvoid}, Cdouble, Clonglong), h, _clock(c).t, v))
+  end
+end
+
+struct Flag; b::Bool; e::Bool; vp::Bool; c::Bool; s::Bool; end
+struct Grid{T}; nx::Int; ny::Int; nz::Int; Lx::Float64; Ly::Float64; Lz::Float64; dx::Float64; dy::Float64; dz::Float64; end
+struct Params; ν::Float64; η::Float64; nν::Int; nη::Int; end
+
+mutable struct MHDFlowsProblem{T}
+  h::Ptr{Cvoid}
+  clock::Clock{T}
+  grid::Grid{T}
+  params::Params
+  flag::Flag
+  Nl::Int
+  usr_func::Vector{Any}
+end
+
+function check(h, code)
+  code == 0 && return nothing
+  msg = unsafe_string(ccall((:mhdf_last_error, lib), Cstring, (Ptr{Cvoid},), h))
+  error("mhdflows_b200 error $code: $msg")       # the reference reports through error(...), pgen.jl:99,104
+end
+
+"""
+    Problem(dev; nx, ny, nz, Lx, Ly, Lz, dt, ν, nν, η, nη, B_field, EMHD, stepper, T, ...)   (pgen.jl:64-127)
+"""
+function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2π, Ly = Lx, Lz = Lx, cₛ = 0.0, dt = 0.0,
+                 ν = 0.0, nν = 0, η = 0.0, nη = 0, B_field = false, EMHD = false, Compressibility = false,
+                 Shear = false, VP_method = false, Dye_Module = false, stepper = "RK4", calcF = nothingfunction,
+                 T = Float32, aliased_fraction = 1/3, usr_vars = [], usr_params = [], usr_func = [])
+  dev isa CPU && error("this build is the B200 path only: Problem(GPU(); ...)")
+  cₛ == 0.0 && Compressibility && error("You should define cₛ")
+  Shear && error("Shear haven't fully implemented yet!")
+  (Compressibility || VP_method || Dye_Module) && error("outside the B200 hot path")
+  calcF === nothingfunction || error("forcing callbacks are not supported on this path yet")
+  stepper in ("RK4", "LSRK54") || error("stepper must be \"RK4\" or \"LSRK54\" on the B200 path")
+  physics = EMHD ? MHDF_EMHD : (B_field ? MHDF_MHD : MHDF_HD)
+  cfg = MhdfConfig(nx, ny, nz, Lx, Ly, Lz, ν, η, nν, dt, physics, stepper == "RK4" ? 0 : 1,
+                   T === Float32 ? 0 : 1, dev.device, 0, 1, C_NULL)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  code = ccall((:mhdf_create, lib), Cint, (Ref{MhdfConfig}, Ref{Ptr{Cvoid}}), cfg, h)
+  code == 0 || check(C_NULL, code)
+  prob = MHDFlowsProblem{T}(h[], Clock{T}(h[]), Grid{T}(nx, ny, nz, Lx, Ly, Lz, Lx/nx, Ly/ny, Lz/nz),
+                            Params(ν, η, nν, 0), Flag(B_field, EMHD, false, false, false),
+                            physics == MHDF_MHD ? 6 : 3, isempty(usr_func) ? Any[nothingfunction] : collect(Any, usr_func))
+  finalizer(p -> ccall((:mhdf_destroy, lib), Cint, (Ptr{Cvoid},), p.h), prob)
+  return prob
+end
+
+fieldid(prob, s::Symbol) = prob.flag.e ? Dict(:bx=>0, :by=>1, :bz=>2)[s] :
+                           Dict(:ux=>0, :uy=>1, :uz=>2, :bx=>3, :by=>4, :bz=>5)[s]
+
+"SetUpProblemIC!(prob; ux, uy, uz, bx, by, bz)   (utils/IC.jl:41-109)"
+function SetUpProblemIC!(prob; ux = [], uy = [], uz = [], bx = [], by = [], bz = [])
+  T = typeof(prob).parameters[1]
+  put(s, A) = A == [] ? nothing :
+    check(prob.h, ccall((:mhdf_set_real, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, fieldid(prob, s), Array{T,3}(A)))
+  if !prob.flag.e; put(:ux, ux); put(:uy, uy); put(:uz, uz); end
+  if prob.flag.b;  put(:bx, bx); put(:by, by); put(:bz, bz); end
+  return nothing
+end
+
+"vars.ux etc.: real-space view; `stale = true` reproduces the reference's vars (c2r of the last stage input)"
+function realfield(prob, s::Symbol; stale = true)
+  T = typeof(prob).parameters[1]; g = prob.grid
+  A = Array{T,3}(undef, g.nx, g.ny, g.nz)
+  check(prob.h, ccall((:mhdf_get_real, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), prob.h, fieldid(prob, s), stale ? 1 : 0, A))
+  A
+end
+"prob.sol[:, :, :, i] (dealiased modes read back as zero)"
+function sol(prob, i::Int)
+  T = typeof(prob).parameters[1]; g = prob.grid
+  A = Array{Complex{T},3}(undef, g.nx ÷ 2 + 1, g.ny, g.nz)
+  check(prob.h, ccall((:mhdf_get_spectral, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), prob.h, i - 1, 0, A))
+  A
+end
+
+"stepforward!(prob) == stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)"
+stepforward!(prob, n::Int = 1) = check(prob.h, ccall((:mhdf_step, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, n))
+
+"getCFL!(prob, t_diff; Coef)   (integrator.jl:158-198)"
+function getCFL!(prob, t_diff; Coef = 0.3)
+  dt = Ref{Cdouble}()
+  check(prob.h, ccall((:mhdf_cfl_dt, lib), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ref{Cdouble}), prob.h, Coef, t_diff, dt))
+  dt[]
+end
+
+"ProbDiagnostic(prob)   (utils/UserInterface.jl:65-86)"
+function ProbDiagnostic(prob)
+  KE = Ref{Cdouble}(); ME = Ref{Cdouble}()
+  code = ccall((:mhdf_energy, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Cdouble}, Ref{Cdouble}), prob.h, MHDF_STALE, KE, ME)
+  code == -4 && error("detected NaN! Quit the simulation right now.")
+  check(prob.h, code)
+  ke, me = round(KE[], sigdigits = 3), round(ME[], sigdigits = 3)
+  prob.flag.e ? me : (prob.flag.b ? (ke, me) : ke)
+end
+
+# Diagnostic (DiagnosticWrapper.jl:14-105)
+mutable struct Diagnostic{T}
+  calc::Function; prob; data::Vector{T}; t::Vector{Float64}; steps::Vector{Int}; freq::Int; i::Int
+end
+function Diagnostic(calc, prob; freq = 1, nsteps = 100, ndata = ceil(Int, (nsteps + 1) / freq))
+  v = calc(prob)
+  d = Diagnostic{typeof(v)}(calc, prob, Vector{typeof(v)}(undef, ndata), zeros(ndata), zeros(Int, ndata), freq, 1)
+  d.data[1] = v; d.t[1] = prob.clock.t; d.steps[1] = prob.clock.step
+  d
+end
+function update!(d::Diagnostic, i)
+  if i > length(d.steps)
+    n = length(d.steps); resize!(d.data, 2n); resize!(d.t, 2n); resize!(d.steps, 2n)
+  end
+  d.data[i] = d.calc(d.prob); d.t[i] = d.prob.clock.t; d.steps[i] = d.prob.clock.step; d.i = i
+  nothing
+end
+increment!(d::Diagnostic) = (d.prob.clock.step % d.freq == 0 && update!(d, d.i + 1); nothing)
+increment!(ds::AbstractVector) = (foreach(increment!, ds); nothing)
+
+"TimeIntegrator!(prob, t₀, N₀; usr_dt, CFL_Coef, diags, ...)   (integrator.jl:31-156, loop + CFL; HDF5 output not on this path)"
+function TimeIntegrator!(prob, t₀::Number, N₀::Int; usr_dt = 0.0, CFL_Coef = 0.25, CFL_function = nothingfunction,
+                         diags = [], dynamic_dashboard = true, loop_number = 100, save = false, kwargs...)
+  save && error("HDF5 output is outside the B200 hot path")
+  updateCFL! = CFL_function === nothingfunction ? getCFL! : CFL_function
+  p = prob.params
+  vi = prob.flag.b ? (prob.flag.e ? p.η : max(p.ν, p.η)) : p.ν
+  nv = prob.flag.b ? (prob.flag.e ? p.nη : max(p.nν, p.nη)) : p.nν
+  dl = min(prob.grid.dx, prob.grid.dy, prob.grid.dz)
+  t_diff = nv > 1 ? CFL_Coef * dl^nv / vi : CFL_Coef * dl^2 / vi
+  prob.clock.step = 0
+  usr_dt != 0.0 && (prob.clock.dt = usr_dt)
+  time = @elapsed while (N₀ >= prob.clock.step) && (t₀ >= prob.clock.t)
+    usr_dt == 0.0 && updateCFL!(prob, t_diff; Coef = CFL_Coef)
+    stepforward!(prob)
+    increment!(diags)
+    for foo! in prob.usr_func; foo!(prob); end
+  end
+  n = prob.grid.nx * prob.grid.ny * prob.grid.nz
+  print("Total CPU/GPU time run = $(round(time, digits = 3)) s, zone update per second = $(round(prob.clock.step * n / time, digits = 3)) \n")
+  nothing
+end
+
+"spectralline of a state field (utils/MHDAnalysis.jl:237-255)"
+function spectralline(prob, s::Symbol)
+  g = prob.grid
+  krmax = round(Int, sqrt((g.nx ÷ 2 * 2π / g.Lx)^2 + (g.ny ÷ 2 * 2π / g.Ly)^2 + (g.nz ÷ 2 * 2π / g.Lz)^2) + 1)
+  Pk = zeros(Cdouble, krmax)
+  check(prob.h, ccall((:mhdf_spectrum, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint), prob.h, fieldid(prob, s), Pk, krmax))
+  Pk, [Pk[r] > 0 ? r : 0 for r in 1:krmax]
+end
+
+function _hel(prob)
+  a = Ref{Cdouble}(); b = Ref{Cdouble}(); c = Ref{Cdouble}()
+  check(prob.h, ccall((:mhdf_helicity, lib), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cdouble}), prob.h, a, b, c))
+  a[], b[], c[]
+end
+"sum(h_k(ux,uy,uz)) and sum(h_m(bx,by,bz)) of the current state (utils/MHDAnalysis.jl:94-117)"
+h_k_sum(prob) = _hel(prob)[1]
+h_m_sum(prob) = _hel(prob)[2]
+
+end # module
