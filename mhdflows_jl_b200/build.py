@@ -14,8 +14,8 @@ SOURCES = [os.path.join(CSRC, "api.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "fft_core.cuh"),
                   os.path.join(ROOT, "include", "mhdflows_b200.h")]
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-I/usr/include", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-ldl"]
 
 
 def nvcc_path() -> str:

@@ -5,6 +5,8 @@
 //   -> forward y pass -> forward z pass -> spectral assembly + Runge-Kutta stage update
 // on a compact state that stores only the modes FourierFlows' dealias!() keeps.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdio>
@@ -33,6 +35,44 @@ struct Err {
   int code;
   std::string msg;
 };
+
+// NCCL is bound at run time (dlopen) so the library has no link-time dependency on a particular libnccl; when
+// the host process already loaded one (e.g. PyTorch's) that copy is used.
+struct NcclApi {
+  void* so = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& why) {
+    if (so) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { so = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (so) break; }
+    if (!so) { why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define LD(f) f = reinterpret_cast<decltype(f)>(dlsym(so, "nccl" #f)); if (!f) { why = "libnccl lacks nccl" #f; return false; }
+    LD(GetUniqueId) LD(CommInitRank) LD(CommDestroy) LD(Send) LD(Recv) LD(GroupStart) LD(GroupEnd) LD(AllReduce) LD(AllGather)
+    LD(GetErrorString)
+#undef LD
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess) {                                                                       \
+      char buf_[512];                                                                              \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+      throw Err{MHDF_ERR_NCCL, buf_};                                                              \
+    }                                                                                              \
+  } while (0)
 
 enum { KC_ZINV = 0, KC_YINV, KC_XFUSED, KC_YFWD, KC_ZFWD, KC_SPEC, KC_DERIVE, KC_EXCH, KC_COUNT };
 
@@ -78,6 +118,14 @@ struct Solver : mhdf_handle {
   int nx, ny, nz, nkr;
   int Kx, Kxp, Ky, Kz;
   Band by, bz;
+  // slab decomposition: P_ ranks; real space split along z (nzl planes each), spectral space along compact ky rows
+  // (Kyl rows each, the last slab zero-padded).  One GPU: P_ = 1, nzl = nz, Kyl = Ky.
+  int P_ = 1, rank_ = 0, nzl, Kyl, ky0;
+  ncclComm_t comm = nullptr;
+  int *tab_zfull_in = nullptr, *tab_zfull_out = nullptr, *tab_kz = nullptr;   // z passes
+  int *tab_ky_in = nullptr, *tab_ky_out = nullptr, *tab_yfull = nullptr;      // y passes
+  Cx<T>* plane_loc = nullptr;   // kr = 0 plane of the stage input, local  [F][Kz][Kyl]
+  Cx<T>* plane_all = nullptr;   // gathered                                  [P][F][Kz][Kyl]
   int phys, F, nin, nout;
   long long cf;   // elements of one compact field
   cudaStream_t st = nullptr;
@@ -131,11 +179,17 @@ struct Solver : mhdf_handle {
     alias_range(nz, &iL, &iR);
     bz.n = nz; bz.lo = iL - 1; bz.hi0 = iR;
     Ky = by.count(); Kz = bz.count();
+    P_ = c.nranks; rank_ = c.rank;
+    nzl = nz / P_;
+    Kyl = (Ky + P_ - 1) / P_;
+    ky0 = rank_ * Kyl;
+    if (P_ > 1 && (nz % P_ != 0 || (P_ - 1) * Kyl >= Ky))
+      throw Err{MHDF_ERR_INVALID, "grid too small for this many ranks (need nz % nranks == 0 and a non-empty ky slab per rank)"};
     phys = c.physics;
     F = (phys == MHDF_MHD) ? 6 : 3;
     nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 24);
     nout = (phys == MHDF_MHD) ? 9 : (phys == MHDF_HD ? 6 : 3);
-    cf = (long long)Kxp * Ky * Kz;
+    cf = (long long)Kxp * Kyl * Kz;
     t_ = (T)0; dt_ = (T)c.dt;
     for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
 
@@ -144,39 +198,82 @@ struct Solver : mhdf_handle {
     CK(cudaGetDeviceProperties(&prop, c.device));
     nsm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (P_ > 1) {
+      std::string why;
+      if (!g_nccl.load(why)) throw Err{MHDF_ERR_NCCL, why};
+      if (c.nccl_id == nullptr) throw Err{MHDF_ERR_INVALID, "nranks > 1 needs nccl_id (mhdf_nccl_unique_id on rank 0)"};
+      ncclUniqueId id;
+      std::memcpy(&id, c.nccl_id, sizeof id);
+      NK(g_nccl.CommInitRank(&comm, P_, id, rank_));
+    }
     const int nreg = (c.stepper == MHDF_RK4) ? 4 : 3;
     for (int i = 0; i < nreg; ++i) reg[i] = dalloc<C>((size_t)F * cf);
-    const size_t plane_zK = (size_t)nz * Ky * Kxp, plane_zy = (size_t)nz * ny * Kxp;
-    const int nmax = nin > nout ? nin : nout;
-    szP = (size_t)nmax * plane_zK;
-    szQ = (size_t)nin * plane_zy;
-    if ((size_t)nout * cf > szQ) szQ = (size_t)nout * cf;
-    szR = (size_t)nout * plane_zy;
-    // R doubles as the staging area of the API boundary (one real or one full spectral field)
-    const size_t need_stage = ((size_t)nkr * ny * nz > (size_t)nx * ny * nz / 2 ? (size_t)nkr * ny * nz : (size_t)nx * ny * nz / 2) + 16;
-    if (szR < need_stage) szR = need_stage;
+    // work buffers (elements).  P: inverse-z output / forward-y output (send layouts);  Q: inverse-y output (x input)
+    // / second exchange target;  R: first exchange target / x output / forward-z output / API staging.
+    const size_t e_zK = (size_t)nz * Kyl * Kxp;          // one field after a z pass      [nz][Kyl][Kxp]  (== P_ blocks)
+    const size_t e_zy = (size_t)nzl * ny * Kxp;          // one field in x-pass layout    [nzl][ny][Kxp]
+    const size_t need_stage = ((size_t)nkr * Kyl * nz > (size_t)nx * ny * nzl / 2 ? (size_t)nkr * Kyl * nz : (size_t)nx * ny * nzl / 2) + 16;
+    auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+    szP = mx((size_t)nin * e_zK, (size_t)nout * e_zK);
+    szQ = mx((size_t)nin * e_zy, (size_t)nout * e_zK);
+    szR = mx(mx((size_t)nin * e_zK, (size_t)nout * e_zy), mx((size_t)nout * (size_t)cf, need_stage));
+    if (P_ == 1) szQ = mx(szQ, (size_t)nout * (size_t)cf);
     P = dalloc<C>(szP); Q = dalloc<C>(szQ); R = dalloc<C>(szR);
     if (phys == MHDF_EMHD) {
       szD = (size_t)24 * cf;
       D = dalloc<C>(szD);
-      bst = dalloc<T>((size_t)3 * nx * ny * nz);
+      bst = dalloc<T>((size_t)3 * nx * ny * nzl);
     }
     twx = make_tw(nx); twy = make_tw(ny); twz = make_tw(nz);
     // wavenumbers: built in Float64 then converted to T (FourierFlows ThreeDGrid; mirror utils/utils.jl:60-64)
-    std::vector<T> hx(Kx), hy(Ky), hz(Kz);
+    std::vector<T> hx(Kx), hy(Kyl), hz(Kz);
     for (int i = 0; i < Kx; ++i) hx[i] = (T)(i * (2.0 * M_PI / c.Lx));
-    for (int j = 0; j < Ky; ++j) hy[j] = (T)(by.wave(j) * (2.0 * M_PI / c.Ly));
+    for (int j = 0; j < Kyl; ++j) hy[j] = (ky0 + j < Ky) ? (T)(by.wave(ky0 + j) * (2.0 * M_PI / c.Ly)) : (T)0;
     for (int k = 0; k < Kz; ++k) hz[k] = (T)(bz.wave(k) * (2.0 * M_PI / c.Lz));
-    kxv = dalloc<T>(Kx); kyv = dalloc<T>(Ky); kzv = dalloc<T>(Kz);
+    kxv = dalloc<T>(Kx); kyv = dalloc<T>(Kyl); kzv = dalloc<T>(Kz);
     CK(cudaMemcpyAsync(kxv, hx.data(), Kx * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(kyv, hy.data(), Ky * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(kyv, hy.data(), Kyl * sizeof(T), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(kzv, hz.data(), Kz * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (P_ > 1) build_tables();
     red_d = dalloc<XRed>(1);
     diag_d = dalloc<double>(8);
     CK(cudaMallocHost(&red_h, sizeof(XRed)));
     CK(cudaMallocHost(&diag_h, 8 * sizeof(double)));
+    std::memset(red_h, 0, sizeof(XRed));
     CK(cudaStreamSynchronize(st));
     setup_attrs();
+  }
+
+  int* upload_tab(const std::vector<int>& h) {
+    int* d = dalloc<int>(h.size());
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return d;
+  }
+  // Row-offset tables of the slab layout.  Exchange buffers are [peer][field][z'][ky'][kx]: the piece for / from one
+  // peer is contiguous, `blk(n)` elements for an n-field batch.
+  size_t blk(int nf) const { return (size_t)nf * nzl * Kyl * Kxp; }
+  void build_tables() {
+    // the block size depends on the batch (nin / nout / 1): tables hold offsets for a 1-field batch split as
+    // (peer part, in-block part); kernels need a single int per row, so tables are rebuilt per batch size lazily.
+    plane_loc = dalloc<C>((size_t)F * Kz * Kyl);
+    plane_all = dalloc<C>((size_t)P_ * F * Kz * Kyl);
+  }
+  struct Tabs { int *zfull = nullptr, *kz = nullptr, *ky = nullptr, *yfull = nullptr; };
+  std::vector<std::pair<int, Tabs>> tab_cache;
+  const Tabs& tabs_for(int nf) {
+    for (auto& e : tab_cache) if (e.first == nf) return e.second;
+    const long long B = (long long)blk(nf);
+    if ((long long)P_ * B >= (1LL << 31)) throw Err{MHDF_ERR_INVALID, "slab exchange buffer exceeds 2^31 elements per batch"};
+    std::vector<int> zfull(nz), kz(Kz), ky(Ky), yfull(ny);
+    for (int z = 0; z < nz; ++z) zfull[z] = (int)((z / nzl) * B + (long long)(z % nzl) * Kyl * Kxp);
+    for (int k = 0; k < Kz; ++k) kz[k] = k * Kyl * Kxp;
+    for (int j = 0; j < Ky; ++j) ky[j] = (int)((j / Kyl) * B + (long long)(j % Kyl) * Kxp);
+    for (int y = 0; y < ny; ++y) yfull[y] = y * Kxp;
+    Tabs t;
+    t.zfull = upload_tab(zfull); t.kz = upload_tab(kz); t.ky = upload_tab(ky); t.yfull = upload_tab(yfull);
+    tab_cache.push_back({nf, t});
+    return tab_cache.back().second;
   }
 
   ~Solver() override {
@@ -188,6 +285,9 @@ struct Solver : mhdf_handle {
     cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
+    for (auto& e : tab_cache) { cudaFree(e.second.zfull); cudaFree(e.second.kz); cudaFree(e.second.ky); cudaFree(e.second.yfull); }
+    cudaFree(plane_loc); cudaFree(plane_all);
+    if (comm) g_nccl.CommDestroy(comm);
     cudaFree(red_d); cudaFree(diag_d); cudaFree(spec_d);
     if (red_h) cudaFreeHost(red_h);
     if (diag_h) cudaFreeHost(diag_h);
@@ -209,7 +309,9 @@ struct Solver : mhdf_handle {
 
   SpecGeom<T> geom() const {
     SpecGeom<T> g;
-    g.Kx = Kx; g.Kxp = Kxp; g.by = by; g.bz = bz; g.kx = kxv; g.ky = kyv; g.kz = kzv; g.field = cf;
+    g.Kx = Kx; g.Kxp = Kxp; g.by = by; g.bz = bz; g.Kyl = Kyl; g.ky0 = ky0; g.F = F;
+    g.kx = kxv; g.ky = kyv; g.kz = kzv; g.field = cf;
+    g.mirror = (P_ > 1) ? plane_all : nullptr;
     return g;
   }
 
@@ -251,7 +353,8 @@ struct Solver : mhdf_handle {
     constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
     constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
     dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
-    k_pass<T, N, E, TX, DIR, (DIR > 0)><<<grid, (N / E) * TX, smem, st>>>(a);
+    if (a.in_tab != nullptr) k_pass<T, N, E, TX, DIR, (DIR > 0), true><<<grid, (N / E) * TX, smem, st>>>(a);
+    else k_pass<T, N, E, TX, DIR, (DIR > 0), false><<<grid, (N / E) * TX, smem, st>>>(a);
     ++launches;
   }
   template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
@@ -337,67 +440,117 @@ struct Solver : mhdf_handle {
     constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
     constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
     if (smem > 48 * 1024) {
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
   }
 
   // ---- 3D transform legs -------------------------------------------------------------------
-  // compact [nf][Kz][Ky][Kxp] -> [nf][nz][Ky][Kxp]
+  // One GPU:  compact [nf][Kz][Ky][Kxp] <-> [nf][nz][Ky][Kxp] <-> [nf][nz][ny][Kxp].
+  // Slabs:    the [nz][Kyl][Kxp] side of the z passes and the ky side of the y passes live in the blocked exchange
+  //           layout [peer][nf][nzl][Kyl][Kxp]; the all-to-all in between swaps "all z, my ky" for "my z, all ky".
   void z_inverse(const C* in, long long in_field, C* out, int nf) {
     PassArgs<T> a;
     a.in = in; a.out = out; a.tw = twz;
-    a.in_row = a.out_row = Ky * Kxp;
+    a.in_row = a.out_row = Kyl * Kxp;
     a.in_outer = a.out_outer = 0;
-    a.in_field = in_field; a.out_field = (long long)nz * Ky * Kxp;
-    a.inner = Ky * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+    a.in_field = in_field; a.out_field = (long long)nzl * Kyl * Kxp * (P_ > 1 ? 1 : P_);
+    if (P_ == 1) a.out_field = (long long)nz * Kyl * Kxp;
+    a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+    a.in_tab = a.out_tab = nullptr;
+    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.kz; a.out_tab = t.zfull; }
     prof_begin(KC_ZINV);
     launch_pass<+1>(nz, a, 1, nf);
     prof_end();
   }
-  // [nf][nz][Ky][Kxp] -> [nf][nz][ny][Kxp]
   void y_inverse(const C* in, C* out, int nf) {
     PassArgs<T> a;
     a.in = in; a.out = out; a.tw = twy;
     a.in_row = a.out_row = Kxp;
-    a.in_outer = (long long)Ky * Kxp; a.out_outer = (long long)ny * Kxp;
-    a.in_field = (long long)nz * Ky * Kxp; a.out_field = (long long)nz * ny * Kxp;
+    a.in_outer = (long long)Kyl * Kxp; a.out_outer = (long long)ny * Kxp;
+    a.in_field = (long long)nzl * Kyl * Kxp; a.out_field = (long long)nzl * ny * Kxp;
     a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
+    a.in_tab = a.out_tab = nullptr;
+    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.ky; a.out_tab = t.yfull; }
     prof_begin(KC_YINV);
-    launch_pass<+1>(ny, a, nz, nf);
+    launch_pass<+1>(ny, a, nzl, nf);
     prof_end();
   }
-  // [nf][nz][ny][Kxp] -> [nf][nz][Ky][Kxp]
   void y_forward(const C* in, C* out, int nf) {
     PassArgs<T> a;
     a.in = in; a.out = out; a.tw = twy;
     a.in_row = a.out_row = Kxp;
-    a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Ky * Kxp;
-    a.in_field = (long long)nz * ny * Kxp; a.out_field = (long long)nz * Ky * Kxp;
+    a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
+    a.in_field = (long long)nzl * ny * Kxp; a.out_field = (long long)nzl * Kyl * Kxp;
     a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
+    a.in_tab = a.out_tab = nullptr;
+    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.yfull; a.out_tab = t.ky; }
     prof_begin(KC_YFWD);
-    launch_pass<-1>(ny, a, nz, nf);
+    launch_pass<-1>(ny, a, nzl, nf);
     prof_end();
   }
-  // [nf][nz][Ky][Kxp] -> compact [nf][Kz][Ky][Kxp]
   void z_forward(const C* in, C* out, long long out_field, int nf) {
     PassArgs<T> a;
     a.in = in; a.out = out; a.tw = twz;
-    a.in_row = a.out_row = Ky * Kxp;
+    a.in_row = a.out_row = Kyl * Kxp;
     a.in_outer = a.out_outer = 0;
-    a.in_field = (long long)nz * Ky * Kxp; a.out_field = out_field;
-    a.inner = Ky * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+    a.in_field = (P_ == 1) ? (long long)nz * Kyl * Kxp : (long long)nzl * Kyl * Kxp;
+    a.out_field = out_field;
+    a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+    a.in_tab = a.out_tab = nullptr;
+    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.zfull; a.out_tab = t.kz; }
     prof_begin(KC_ZFWD);
     launch_pass<-1>(nz, a, 1, nf);
     prof_end();
+  }
+  // all-to-all of the blocked layout: piece q (blk(nf) elements) goes to / comes from rank q
+  void exchange(const C* send, C* recv, int nf) {
+    const size_t B = blk(nf);
+    const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat32 : ncclFloat64;
+    prof_begin(KC_EXCH);
+    NK(g_nccl.GroupStart());
+    for (int q = 0; q < P_; ++q) {
+      NK(g_nccl.Send(send + (size_t)q * B, 2 * B, dt, q, comm, st));
+      NK(g_nccl.Recv(recv + (size_t)q * B, 2 * B, dt, q, comm, st));
+    }
+    NK(g_nccl.GroupEnd());
+    prof_end();
+  }
+  // spectral compact (src, field stride cf) -> x-pass layout in Q.  Uses P (and R when exchanging).
+  void to_xlayout(const C* src, int nf) {
+    z_inverse(src, cf, P, nf);
+    if (P_ > 1) { exchange(P, R, nf); y_inverse(R, Q, nf); }
+    else y_inverse(P, Q, nf);
+  }
+  // x-pass layout in `src` (R or Q) -> compact spectral in dst (field stride cf).  Uses P and, when exchanging, `via`.
+  void from_xlayout(const C* src, C* via, C* dst, int nf) {
+    y_forward(src, P, nf);
+    if (P_ > 1) { exchange(P, via, nf); z_forward(via, dst, cf, nf); }
+    else z_forward(P, dst, cf, nf);
+  }
+  // kr = 0 plane of the stage input from every rank (the symmetrised diffusion operand needs the mirror mode)
+  void gather_mirror(const C* S) {
+    if (P_ == 1) return;
+    const long long n = (long long)F * Kz * Kyl;
+    k_plane<T><<<(int)((n + 255) / 256), 256, 0, st>>>(geom(), S, plane_loc);
+    ++launches;
+    CK(cudaGetLastError());
+    NK(g_nccl.AllGather(plane_loc, plane_all, 2 * (size_t)n, sizeof(T) == 4 ? ncclFloat32 : ncclFloat64, comm, st));
+  }
+  void allreduce_red() {
+    if (P_ == 1) return;
+    NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, st));
+    NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint32, ncclMax, comm, st));
   }
 
   XArgs<T> xargs() const {
     XArgs<T> a;
     a.in = Q; a.out = R; a.tw = twx; a.real_io = nullptr;
-    a.in_field = a.out_field = (long long)nz * ny * Kxp;
-    a.real_field = (long long)nx * ny * nz;
-    a.rows = (long long)ny * nz;
+    a.in_field = a.out_field = (long long)nzl * ny * Kxp;
+    a.real_field = (long long)nx * ny * nzl;
+    a.rows = (long long)ny * nzl;
     a.Kx = Kx; a.Kxp = Kxp;
     a.scale = (T)(1.0 / ((double)nx * ny * nz));
     a.red = nullptr;
@@ -407,6 +560,7 @@ struct Solver : mhdf_handle {
   // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
   void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
     const C* zin = Sin;
+    if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {
       prof_begin(KC_DERIVE);
       k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
@@ -415,8 +569,7 @@ struct Solver : mhdf_handle {
       prof_end();
       zin = D;
     }
-    z_inverse(zin, cf, P, nin);
-    y_inverse(P, Q, nin);
+    to_xlayout(zin, nin);
     XArgs<T> xa = xargs();
     xa.real_io = bst;
     if (want_red) {
@@ -426,11 +579,14 @@ struct Solver : mhdf_handle {
     prof_begin(KC_XFUSED);
     launch_xfused(xa);
     prof_end();
-    if (want_red) CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
-    y_forward(R, P, nout);
-    z_forward(P, Q, cf, nout);
+    if (want_red) {
+      allreduce_red();
+      CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
+    }
+    C* spec = (P_ > 1) ? R : Q;           // forward-z output (compact product spectra)
+    from_xlayout(R, Q, spec, nout);
     sa.g = geom();
-    sa.P = Q; sa.Sin = Sin;
+    sa.P = spec; sa.Sin = Sin;
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
     prof_begin(KC_SPEC);
     if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<spec_grid(), 256, 0, st>>>(sa);
@@ -548,7 +704,8 @@ struct Solver : mhdf_handle {
     rhs(reg[iY], sa, true);
     CK(cudaStreamSynchronize(st));
     absorb_red();
-    for (int f = 0; f < F; ++f) unpack_to_host(reg[o] + f * cf, (C*)p + (size_t)f * nkr * ny * nz);
+    const size_t fe = (P_ > 1) ? (size_t)nkr * Kyl * nz : (size_t)nkr * ny * nz;
+    for (int f = 0; f < F; ++f) unpack_to_host(reg[o] + f * cf, (C*)p + (size_t)f * fe);
   }
 
   // ---- API boundary: real / spectral fields ------------------------------------------------
@@ -559,18 +716,18 @@ struct Solver : mhdf_handle {
     check_field(field);
     CK(cudaSetDevice(cfg.device));
     T* re = reinterpret_cast<T*>(R);
-    const size_t n = (size_t)nx * ny * nz;
+    const size_t n = (size_t)nx * ny * nzl;   // this rank's z slab (the whole field on one GPU)
     CK(cudaMemcpyAsync(re, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (phys == MHDF_EMHD)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
+      CK(cudaMemcpyAsync(bst + (size_t)field * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     XArgs<T> xa = xargs();
     xa.real_io = re; xa.out = Q; xa.in = nullptr;
     CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     xa.red = red_d;
     launch_xplain<-1>(xa);
+    allreduce_red();
     CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
-    y_forward(Q, P, 1);
-    z_forward(P, reg[iY] + field * cf, cf, 1);
-    if (phys == MHDF_EMHD)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
-      CK(cudaMemcpyAsync(bst + (size_t)field * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    from_xlayout(Q, R, reg[iY] + field * cf, 1);
     CK(cudaStreamSynchronize(st));
     // vars.* statistics of the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88)
     const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
@@ -586,21 +743,21 @@ struct Solver : mhdf_handle {
   void get_real(int field, int which, void* p) override {
     check_field(field);
     CK(cudaSetDevice(cfg.device));
-    z_inverse(source(which) + field * cf, cf, P, 1);
-    y_inverse(P, Q, 1);
+    to_xlayout(source(which) + field * cf, 1);
     T* re = reinterpret_cast<T*>(R);
     XArgs<T> xa = xargs();
     xa.real_io = re; xa.in = Q; xa.out = nullptr;
     launch_xplain<+1>(xa);
-    CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nz * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nzl * sizeof(T), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
   void set_spectral(int field, const void* p) override {
     check_field(field);
     CK(cudaSetDevice(cfg.device));
-    const size_t n = (size_t)nkr * ny * nz;
+    const int nyh = (P_ > 1) ? Kyl : ny;     // slab runs exchange the local compact ky rows directly
+    const size_t n = (size_t)nkr * nyh * nz;
     CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyHostToDevice, st));
-    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, reg[iY] + field * cf, nkr, ny, nz, Kx, Kxp, by, bz, 0);
+    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, reg[iY] + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
@@ -611,8 +768,9 @@ struct Solver : mhdf_handle {
     return (int)(b < cap ? b : cap);
   }
   void unpack_to_host(const C* comp, C* host) {
-    const size_t n = (size_t)nkr * ny * nz;
-    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, const_cast<C*>(comp), nkr, ny, nz, Kx, Kxp, by, bz, 1);
+    const int nyh = (P_ > 1) ? Kyl : ny;
+    const size_t n = (size_t)nkr * nyh * nz;
+    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, const_cast<C*>(comp), nkr, nyh, nz, Kx, Kxp, by, bz, 1, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDeviceToHost, st));
@@ -652,13 +810,14 @@ struct Solver : mhdf_handle {
     return (double)(T)(cfg.Lx / nx) * (double)(T)(cfg.Ly / ny) * (double)(T)(cfg.Lz / nz);
   }
   void run_diag(int which) {
-    const C* s = source(which);
+    const C* src = source(which);
+    gather_mirror(src);
     CK(cudaMemsetAsync(diag_d, 0, 8 * sizeof(double), st));
-    const C* U = (phys == MHDF_EMHD) ? nullptr : s;
-    const C* B = (phys == MHDF_HD) ? nullptr : (phys == MHDF_EMHD ? s : s + 3 * cf);
-    k_diag<T><<<spec_grid(), 256, 0, st>>>(geom(), U, B, 1.0 / ((double)nx * ny * nz), diag_d);
+    const int has_u = (phys != MHDF_EMHD), has_b = (phys != MHDF_HD), boff = (phys == MHDF_EMHD) ? 0 : 3;
+    k_diag<T><<<spec_grid(), 256, 0, st>>>(geom(), src, has_u, has_b, boff, 1.0 / ((double)nx * ny * nz), diag_d);
     ++launches;
     CK(cudaGetLastError());
+    if (P_ > 1) NK(g_nccl.AllReduce(diag_d, diag_d, 8, ncclFloat64, ncclSum, comm, st));
     CK(cudaMemcpyAsync(diag_h, diag_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
@@ -696,9 +855,11 @@ struct Solver : mhdf_handle {
       spec_cap = nbins;
     }
     CK(cudaMemsetAsync(spec_d, 0, nbins * sizeof(double), st));
-    k_spectrum<T><<<spec_grid(), 256, nbins * sizeof(double), st>>>(geom(), reg[iY] + field * cf, spec_d, nbins);
+    gather_mirror(reg[iY]);
+    k_spectrum<T><<<spec_grid(), 256, nbins * sizeof(double), st>>>(geom(), reg[iY], field, spec_d, nbins);
     ++launches;
     CK(cudaGetLastError());
+    if (P_ > 1) NK(g_nccl.AllReduce(spec_d, spec_d, nbins, ncclFloat64, ncclSum, comm, st));
     CK(cudaMemcpyAsync(Pk, spec_d, nbins * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
@@ -753,7 +914,7 @@ int mhdf_create(const mhdf_config* c, mhdf_handle** out) {
   if (c->physics < MHDF_HD || c->physics > MHDF_EMHD) return bad("physics must be MHDF_HD, MHDF_MHD or MHDF_EMHD");
   if (c->stepper != MHDF_RK4 && c->stepper != MHDF_LSRK54) return bad("stepper must be RK4 or LSRK54 (Problems.jl:123-128)");
   if (c->dtype != MHDF_F32 && c->dtype != MHDF_F64) return bad("dtype must be MHDF_F32 or MHDF_F64");
-  if (c->nranks != 1 || c->rank != 0) return bad("this build supports nranks = 1 only");
+  if (c->nranks < 1 || c->nranks > 64 || c->rank < 0 || c->rank >= c->nranks) return bad("need 0 <= rank < nranks <= 64");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -783,7 +944,13 @@ const char* mhdf_last_error(const mhdf_handle* h) { return h ? h->err.c_str() : 
 int mhdf_nccl_unique_id(void* id128) {
   if (id128 == nullptr) return MHDF_ERR_INVALID;
   std::memset(id128, 0, 128);
-  return MHDF_ERR_NCCL;
+  std::string why;
+  if (!g_nccl.load(why)) { g_create_error = why; return MHDF_ERR_NCCL; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return MHDF_ERR_NCCL; }
+  std::memcpy(id128, &id, 128);
+  return MHDF_OK;
 }
 int mhdf_set_real(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_real(f, p); }); }
 int mhdf_get_real(mhdf_handle* h, int f, int w, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->get_real(f, w, p); }); }

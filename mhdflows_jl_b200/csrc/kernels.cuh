@@ -43,6 +43,11 @@ struct PassArgs {
   int inner;                       // contiguous elements per row to process
   // retained band of the pruned side: rows [0, lo) and [hi0, N) exist, stored contiguously (shift = hi0 - lo)
   int lo, hi0, shift;
+  // TAB variants (slab-decomposed runs): element offset of every row, replacing row * stride.  Indexed by the
+  // compact row on the pruned side and by n on the full side; lets one side live in the blocked
+  // [peer][field][z'][ky'][kx] layout that the all-to-all sends / receives as contiguous pieces.
+  const int* in_tab;
+  const int* out_tab;
 };
 
 // predicated 8/16-byte global accesses (no branches, no speculative address use)
@@ -79,7 +84,7 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
 };
 
 // PIN: the input side is the pruned (band) side (inverse passes); otherwise the output side is (forward passes).
-template <typename T, int N, int E, int TX, int DIR, bool PIN>
+template <typename T, int N, int E, int TX, int DIR, bool PIN, bool TAB>
 __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 2 : 1) k_pass(PassArgs<T> a) {
   using C = Cx<T>;
   constexpr int Tn = N / E;
@@ -100,9 +105,9 @@ __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 
     if (PIN) {
       const bool ok = valid && (n < a.lo || n >= a.hi0);
       const int r = n - (n >= a.hi0 ? a.shift : 0);
-      v[m] = ldg_pred(ip + r * a.in_row, ok);
+      v[m] = ldg_pred(ip + (TAB ? (ok ? __ldg(a.in_tab + r) : 0) : r * a.in_row), ok);
     } else {
-      v[m] = ldg_pred(ip + n * a.in_row, valid);
+      v[m] = ldg_pred(ip + (TAB ? __ldg(a.in_tab + n) : n * a.in_row), valid);
     }
   }
   PassIdx<N, TX, R1, C> idx{c};
@@ -114,9 +119,9 @@ __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 
     if (!PIN) {
       const bool ok = valid && (n < a.lo || n >= a.hi0);
       const int r = n - (n >= a.hi0 ? a.shift : 0);
-      stg_pred(op + r * a.out_row, v[m], ok);
+      stg_pred(op + (TAB ? (ok ? __ldg(a.out_tab + r) : 0) : r * a.out_row), v[m], ok);
     } else {
-      stg_pred(op + n * a.out_row, v[m], valid);
+      stg_pred(op + (TAB ? __ldg(a.out_tab + n) : n * a.out_row), v[m], valid);
     }
   }
 }
@@ -473,29 +478,53 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
 template <typename T>
 struct SpecGeom {
   int Kx, Kxp;
-  Band by, bz;
+  Band by, bz;   // global retained bands
+  int Kyl;       // local compact ky rows (slab of this rank; == by.count() on one GPU; padded rows hold zeros)
+  int ky0;       // global compact row of local row 0
+  int F;         // fields in the state
   const T* kx;   // [Kx]   kr  (reference: grid.kr)
-  const T* ky;   // [Ky]   l on the retained rows
+  const T* ky;   // [Kyl]  l on the local retained rows
   const T* kz;   // [Kz]   m on the retained rows
-  long long field;   // elements per compact field = Kxp*Ky*Kz
+  long long field;   // elements per local compact field = Kxp*Kyl*Kz
+  // slab runs: kr = 0 plane of the stage input gathered from all ranks, [rank][F][Kz][Kyl]; null on one GPU
+  const Cx<T>* mirror;
 };
 
 // element (kx, jc, kc) of a compact field; û^sym on the kr = 0 plane:
 // rfft(irfft(û)) = (û(0,ky,kz) + conj û(0,-ky,-kz)) / 2, a missing (dealiased) mirror counts as 0
 // (reference: the diffusion operand of MHDSolver.jl:91-94,166-168 / HDSolver.jl:82-85).
 template <typename T>
-__device__ __forceinline__ Cx<T> load_sym(const Cx<T>* __restrict__ f, const SpecGeom<T>& g, int ix, int jc, int kc) {
+__device__ __forceinline__ Cx<T> load_sym(const Cx<T>* __restrict__ S, int fi, const SpecGeom<T>& g, int ix, int jc, int kc) {
   using C = Cx<T>;
-  const int Ky = g.by.count();
-  C v = f[((long long)kc * Ky + jc) * g.Kxp + ix];
+  const C* f = S + fi * g.field;
+  C v = f[((long long)kc * g.Kyl + jc) * g.Kxp + ix];
   if (ix == 0) {
-    const int jm = g.by.row_of_wave(-g.by.wave(jc));
+    const int jm = g.by.row_of_wave(-g.by.wave(g.ky0 + jc));   // global compact row of the mirror mode
     const int km = g.bz.row_of_wave(-g.bz.wave(kc));
     C w = mk<C>(0, 0);
-    if (jm >= 0 && km >= 0) w = f[((long long)km * Ky + jm) * g.Kxp];
+    if (jm >= 0 && km >= 0) {
+      if (g.mirror != nullptr) {
+        const int q = jm / g.Kyl, jl = jm - q * g.Kyl;
+        w = g.mirror[(((long long)q * g.F + fi) * g.bz.count() + km) * g.Kyl + jl];
+      } else {
+        w = f[((long long)km * g.Kyl + jm) * g.Kxp];
+      }
+    }
     v = mk<C>((T)0.5 * (v.x + w.x), (T)0.5 * (v.y - w.y));
   }
   return v;
+}
+
+// kr = 0 plane of a compact state, [F][Kz][Kyl] (input of the mirror all-gather)
+template <typename T>
+__global__ void __launch_bounds__(256) k_plane(SpecGeom<T> g, const Cx<T>* __restrict__ S, Cx<T>* __restrict__ out) {
+  const long long total = (long long)g.F * g.bz.count() * g.Kyl;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long fk = e / g.Kyl;           // f * Kz + kc
+    const int jc = (int)(e - fk * g.Kyl);
+    const long long f = fk / g.bz.count(), kc = fk - f * g.bz.count();
+    out[e] = S[f * g.field + (kc * g.Kyl + jc) * g.Kxp];
+  }
 }
 
 enum { STEP_CALCN = 0, STEP_RK4_1 = 1, STEP_RK4_2 = 2, STEP_RK4_3 = 3, STEP_RK4_4 = 4, STEP_LSRK = 5 };
@@ -560,13 +589,14 @@ template <typename T, int PHYS>
 __global__ void __launch_bounds__(256) k_spectral(SpecArgs<T> a) {
   using C = Cx<T>;
   const SpecGeom<T>& g = a.g;
-  const int Ky = g.by.count(), Kz = g.bz.count();
+  const int Ky = g.Kyl, Kz = g.bz.count();
   const long long total = (long long)g.Kxp * Ky * Kz;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(e % g.Kxp);
     if (ix >= g.Kx) continue;
     const long long rowi = e / g.Kxp;
     const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    if (g.ky0 + jc >= g.by.count()) continue;   // padding rows of the last slab
     if constexpr (PHYS == PHYS_EMHD) {
       C N[3], sin[3];
 #pragma unroll
@@ -593,7 +623,7 @@ __global__ void __launch_bounds__(256) k_spectral(SpecArgs<T> a) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const C pr = mk<C>(D[c].x - kk[c] * kD.x, D[c].y - kk[c] * kD.y);   // still missing the factor i
-        const C us = load_sym<T>(a.Sin + c * g.field, g, ix, jc, kc);
+        const C us = load_sym<T>(a.Sin, c, g, ix, jc, kc);
         sin[c] = a.Sin[c * g.field + e];
         const T dc = -(a.nu * k2) - a.nu * hyper;
         N[c] = mk<C>(-pr.y + dc * us.x, pr.x + dc * us.y);
@@ -609,7 +639,7 @@ __global__ void __launch_bounds__(256) k_spectral(SpecArgs<T> a) {
         const T dc = -(a.eta * k2);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const C bsym = load_sym<T>(a.Sin + (3 + c) * g.field, g, ix, jc, kc);
+          const C bsym = load_sym<T>(a.Sin, 3 + c, g, ix, jc, kc);
           sin[3 + c] = a.Sin[(3 + c) * g.field + e];
           N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
         }
@@ -625,7 +655,7 @@ __global__ void __launch_bounds__(256) k_spectral(SpecArgs<T> a) {
 template <typename T>
 __global__ void __launch_bounds__(256) k_emhd_derive(SpecGeom<T> g, const Cx<T>* __restrict__ B, Cx<T>* __restrict__ out) {
   using C = Cx<T>;
-  const int Ky = g.by.count(), Kz = g.bz.count();
+  const int Ky = g.Kyl, Kz = g.bz.count();
   const long long total = (long long)g.Kxp * Ky * Kz;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(e % g.Kxp);
@@ -658,15 +688,16 @@ __global__ void __launch_bounds__(256) k_emhd_derive(SpecGeom<T> g, const Cx<T>*
 // dir = 1: compact -> full (dealiased modes written as zero).
 template <typename T>
 __global__ void __launch_bounds__(256) k_pack(Cx<T>* __restrict__ full, Cx<T>* __restrict__ comp, int nkr, int ny, int nz,
-                                              int Kx, int Kxp, Band by, Band bz, int dir) {
+                                              int Kx, int Kxp, Band by, Band bz, int dir, int ydirect) {
+  // ydirect (slab runs): the host array is (nkr, Kyl, nz) -- its y rows ARE the local compact rows (ny == Kyl)
   using C = Cx<T>;
-  const int Ky = by.count();
+  const int Ky = ydirect ? ny : by.count();
   const long long total = (long long)nkr * ny * nz;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(e % nkr);
     const long long r = e / nkr;
     const int j = (int)(r % ny), k = (int)(r / ny);
-    const int jc = by.row(j), kc = bz.row(k);
+    const int jc = ydirect ? j : by.row(j), kc = bz.row(k);
     const bool kept = ix < Kx && jc >= 0 && kc >= 0;
     if (dir == 0) {
       if (kept) comp[((long long)kc * Ky + jc) * Kxp + ix] = full[e];
@@ -681,10 +712,13 @@ __global__ void __launch_bounds__(256) k_pack(Cx<T>* __restrict__ full, Cx<T>* _
 //   out[4] = sum u.b      -- all as real-space sums over grid points (multiply by dV outside where wanted)
 //   (reference: UserInterface.jl:29,65-86; MHDAnalysis.jl:94-117,165-168)
 template <typename T>
-__global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __restrict__ U, const Cx<T>* __restrict__ B,
+__global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __restrict__ S, int has_u, int has_b, int boff,
                                               double inv_n3, double* __restrict__ out) {
+  // S = state base; velocity fields 0..2 if has_u, magnetic fields boff..boff+2 if has_b
+  const Cx<T>* U = has_u ? S : nullptr;
+  const Cx<T>* B = has_b ? S : nullptr;
   using C = Cx<T>;
-  const int Ky = g.by.count(), Kz = g.bz.count();
+  const int Ky = g.Kyl, Kz = g.bz.count();
   const long long total = (long long)g.Kxp * Ky * Kz;
   double s[5] = {0, 0, 0, 0, 0};
   float dummy[1] = {0.f};
@@ -693,13 +727,14 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
     if (ix >= g.Kx) continue;
     const long long rowi = e / g.Kxp;
     const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    if (g.ky0 + jc >= g.by.count()) continue;
     const double k[3] = {(double)g.kx[ix], (double)g.ky[jc], (double)g.kz[kc]};
     const double k2 = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
     const double w = (ix == 0 ? 1.0 : 2.0) * inv_n3;
     double ur[3] = {0, 0, 0}, ui[3] = {0, 0, 0}, br[3] = {0, 0, 0}, bi[3] = {0, 0, 0};
     if (U != nullptr) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { const C v = load_sym<T>(U + c * g.field, g, ix, jc, kc); ur[c] = v.x; ui[c] = v.y; }
+      for (int c = 0; c < 3; ++c) { const C v = load_sym<T>(U, c, g, ix, jc, kc); ur[c] = v.x; ui[c] = v.y; }
       s[0] += w * (ur[0] * ur[0] + ui[0] * ui[0] + ur[1] * ur[1] + ui[1] * ui[1] + ur[2] * ur[2] + ui[2] * ui[2]);
       // omega = i k x u ; Re(u . conj(omega)) = sum_c Re(u_c conj(i c_c)) with c = k x u:  Re(u conj(i c)) = u_i c_r - u_r c_i
       const double cr[3] = {k[1] * ur[2] - k[2] * ur[1], k[2] * ur[0] - k[0] * ur[2], k[0] * ur[1] - k[1] * ur[0]};
@@ -709,7 +744,7 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
     }
     if (B != nullptr) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { const C v = load_sym<T>(B + c * g.field, g, ix, jc, kc); br[c] = v.x; bi[c] = v.y; }
+      for (int c = 0; c < 3; ++c) { const C v = load_sym<T>(B, boff + c, g, ix, jc, kc); br[c] = v.x; bi[c] = v.y; }
       s[1] += w * (br[0] * br[0] + bi[0] * bi[0] + br[1] * br[1] + bi[1] * bi[1] + br[2] * br[2] + bi[2] * bi[2]);
       if (k2 > 0) {
         // a = i (k x b) / k^2 ; Re(a . conj(b)) = sum_c Re(i c_c conj(b_c)) / k^2 = (c_r b_i - c_i b_r) / k^2
@@ -752,22 +787,23 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
 // (reference: MHDAnalysis.jl:237-255 `spectralline`).  kr = 0 plane symmetrised (what rfft of the
 // real field holds).  Shared-memory histogram per block, then one atomic per bin.
 template <typename T>
-__global__ void __launch_bounds__(256) k_spectrum(SpecGeom<T> g, const Cx<T>* __restrict__ F, double* __restrict__ Pk, int nbins) {
+__global__ void __launch_bounds__(256) k_spectrum(SpecGeom<T> g, const Cx<T>* __restrict__ S, int fi, double* __restrict__ Pk, int nbins) {
   using C = Cx<T>;
   extern __shared__ double hist[];
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0.0;
   __syncthreads();
-  const int Ky = g.by.count(), Kz = g.bz.count();
+  const int Ky = g.Kyl, Kz = g.bz.count();
   const long long total = (long long)g.Kxp * Ky * Kz;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(e % g.Kxp);
     if (ix >= g.Kx) continue;
     const long long rowi = e / g.Kxp;
     const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    if (g.ky0 + jc >= g.by.count()) continue;
     const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
     const T kk = sqrt(kx * kx + ky * ky + kz * kz);
     const int r = (int)rint((double)kk);
-    const C v = load_sym<T>(F, g, ix, jc, kc);
+    const C v = load_sym<T>(S, fi, g, ix, jc, kc);
     if (r < nbins) atomicAdd(&hist[r], (double)v.x * v.x + (double)v.y * v.y);
   }
   __syncthreads();

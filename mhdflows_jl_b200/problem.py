@@ -143,7 +143,8 @@ class Problem:
     def __init__(self, dev=None, *, nx=64, ny=None, nz=None, Lx=2 * math.pi, Ly=None, Lz=None, cs=0.0, dt=0.0,
                  nu=0.0, n_nu=0, eta=0.0, n_eta=0, B_field=False, EMHD=False, Compressibility=False, Shear=False,
                  VP_method=False, Dye_Module=False, stepper="RK4", calcF=nothingfunction, T=np.float32,
-                 aliased_fraction=1 / 3, usr_vars=None, usr_params=None, usr_func=None, **greek):
+                 aliased_fraction=1 / 3, usr_vars=None, usr_params=None, usr_func=None,
+                 rank=0, nranks=1, nccl_id=None, **greek):
         for k, v in greek.items():
             if k == "ν":
                 nu = v
@@ -203,10 +204,26 @@ class Problem:
         self.params = p
         self._names = names
         self.vars = _Vars(self, names)
+        # slab decomposition over `nranks` processes (ours: the reference is single-device, README.md:40-41)
+        self.rank, self.nranks = int(rank), int(nranks)
+        self._idbuf = None
+        if self.nranks > 1:
+            from .dist import SlabLayout
+            self.layout = SlabLayout(nx, ny, nz, self.nranks, self.rank)
+            if nccl_id is None or len(nccl_id) != 128:
+                raise ValueError("nranks > 1 needs the 128-byte nccl_id shared by rank 0 (dist.nccl_id_via_torch())")
+            self._idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+            self._real_shape = (self.layout.nzl, ny, nx)
+            self._spec_shape = (nz, self.layout.Kyl, nx // 2 + 1)
+        else:
+            self.layout = None
+            self._real_shape = (nz, ny, nx)
+            self._spec_shape = (nz, ny, nx // 2 + 1)
         cfg = L.Config(nx=nx, ny=ny, nz=nz, Lx=Lx, Ly=Ly, Lz=Lz, nu=float(nu), eta=float(eta), n_nu=int(n_nu),
                        dt=float(dt), physics=physics, stepper=L.RK4 if stepper == "RK4" else L.LSRK54,
                        dtype=L.F32 if T is np.float32 else L.F64,
-                       device=dev.device if isinstance(dev, GPU) else 0, rank=0, nranks=1, nccl_id=None)
+                       device=dev.device if isinstance(dev, GPU) else 0, rank=self.rank, nranks=self.nranks,
+                       nccl_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None)
         h = C.c_void_p()
         code = L.lib().mhdf_create(C.byref(cfg), C.byref(h))
         if code != L.OK:
@@ -232,28 +249,24 @@ class Problem:
         return self._names[f] if isinstance(f, str) else int(f)
 
     def set_real(self, f, arr):
-        g = self.grid
         a = np.ascontiguousarray(arr, dtype=self.T)
-        if a.shape != (g.nz, g.ny, g.nx):
-            raise ValueError(f"expected shape {(g.nz, g.ny, g.nx)}, got {a.shape}")
+        if a.shape != self._real_shape:
+            raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
         L.check(self._h, L.lib().mhdf_set_real(self._h, self._field_id(f), a.ctypes.data))
 
     def get_real(self, f, which=L.FRESH):
-        g = self.grid
-        out = np.empty((g.nz, g.ny, g.nx), dtype=self.T)
+        out = np.empty(self._real_shape, dtype=self.T)
         L.check(self._h, L.lib().mhdf_get_real(self._h, self._field_id(f), which, out.ctypes.data))
         return out
 
     def set_spectral(self, f, arr):
-        g = self.grid
         a = np.ascontiguousarray(arr, dtype=self.CT)
-        if a.shape != (g.nm, g.nl, g.nkr):
-            raise ValueError(f"expected shape {(g.nm, g.nl, g.nkr)}, got {a.shape}")
+        if a.shape != self._spec_shape:
+            raise ValueError(f"expected shape {self._spec_shape}, got {a.shape}")
         L.check(self._h, L.lib().mhdf_set_spectral(self._h, self._field_id(f), a.ctypes.data))
 
     def get_spectral(self, f, which=L.FRESH):
-        g = self.grid
-        out = np.empty((g.nm, g.nl, g.nkr), dtype=self.CT)
+        out = np.empty(self._spec_shape, dtype=self.CT)
         L.check(self._h, L.lib().mhdf_get_spectral(self._h, self._field_id(f), which, out.ctypes.data))
         return out
 
@@ -269,8 +282,7 @@ class Problem:
 
     def calcN(self):
         """eqn.calcN!(N, sol, t, clock, vars, params, grid) on the current sol -> N (host copy)."""
-        g = self.grid
-        out = np.empty((self.Nl, g.nm, g.nl, g.nkr), dtype=self.CT)
+        out = np.empty((self.Nl,) + self._spec_shape, dtype=self.CT)
         L.check(self._h, L.lib().mhdf_calcN(self._h, out.ctypes.data))
         return out
 
