@@ -41,17 +41,40 @@ ALG_S_PER_STEP = {("mhd", "RK4"): 384, ("mhd", "LSRK54"): 450, ("hd", "RK4"): 21
 XPASS_S_PER_LAUNCH = {"mhd": 15, "hd": 9, "emhd": 19}
 
 
-def tg_fields(n, T=np.float32, pinned=False):
-    """Analytic Taylor-Green u and b on x_i = -pi + 2 pi i / n, shape (nz, ny, nx)."""
-    x = (np.float32(-math.pi) + np.float32(2 * math.pi / n) * np.arange(n)).astype(np.float64)
-    X, Y, Z = x.reshape(1, 1, -1), x.reshape(1, -1, 1), x.reshape(-1, 1, 1)
-    fs = [np.sin(X) * np.cos(Y) * np.cos(Z), -np.cos(X) * np.sin(Y) * np.cos(Z), np.zeros((n, n, n)),
+def grid_for(n, world):
+    """Weak scaling: 256^3-type workload per GPU.  The grid grows along z, then y, then x as ranks double
+    (N=2: n x n x 2n, N=4: n x 2n x 2n, N=8: 2n x 2n x 2n); dx stays 2 pi / n so the physics per point is unchanged."""
+    nx = ny = nz = n
+    w = world
+    for ax in ("z", "y", "x", "z", "y", "x"):
+        if w <= 1:
+            break
+        if ax == "z":
+            nz *= 2
+        elif ax == "y":
+            ny *= 2
+        else:
+            nx *= 2
+        w //= 2
+    return nx, ny, nz
+
+
+def tg_fields(n, T=np.float32, pinned=False, dims=None, zrange=None):
+    """Analytic Taylor-Green u and b on x_i = -L/2 + i dx, dx = 2 pi / n, shape (nz_local, ny, nx)."""
+    nx, ny, nz = dims or (n, n, n)
+    z0, z1 = zrange or (0, nz)
+    dx = 2 * math.pi / n
+    X = (np.float32(-math.pi * nx / n) + np.float32(dx) * np.arange(nx)).astype(np.float64).reshape(1, 1, -1)
+    Y = (np.float32(-math.pi * ny / n) + np.float32(dx) * np.arange(ny)).astype(np.float64).reshape(1, -1, 1)
+    Z = (np.float32(-math.pi * nz / n) + np.float32(dx) * np.arange(z0, z1)).astype(np.float64).reshape(-1, 1, 1)
+    shape = (z1 - z0, ny, nx)
+    fs = [np.sin(X) * np.cos(Y) * np.cos(Z), -np.cos(X) * np.sin(Y) * np.cos(Z), np.zeros(shape),
           np.cos(X) * np.sin(Y) * np.sin(Z), np.sin(X) * np.cos(Y) * np.sin(Z), -2 * np.sin(X) * np.sin(Y) * np.cos(Z)]
     out = []
     for f in fs:
         if pinned:
             import torch
-            t = torch.empty((n, n, n), dtype=torch.float32, pin_memory=True)
+            t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
             a = t.numpy()
             a[...] = f
             out.append((a, t))
@@ -112,14 +135,29 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_problem(kind, n, stepper, nu, eta, dt, device=0):
+def make_problem(kind, n, stepper, nu, eta, dt, device=0, dims=None, rank=0, world=1, nccl_id=None):
     import mhdflows_jl_b200 as M
-    kw = dict(nx=n, nu=nu, eta=eta, dt=dt, stepper=stepper)
+    nx, ny, nz = dims or (n, n, n)
+    L0 = 2 * math.pi
+    kw = dict(nx=nx, ny=ny, nz=nz, Lx=L0 * nx / n, Ly=L0 * ny / n, Lz=L0 * nz / n, nu=nu, eta=eta, dt=dt, stepper=stepper)
     if kind == "mhd":
         kw.update(B_field=True)
     elif kind == "emhd":
         kw.update(B_field=True, EMHD=True)
-    return M, M.Problem(M.GPU(device), **kw)
+    if world > 1:
+        kw.update(rank=rank, nranks=world, nccl_id=nccl_id)
+    p = M.Problem(M.GPU(device), **kw)
+    if world > 1:
+        from mhdflows_jl_b200.dist import enable_peer_exchange
+        enable_peer_exchange(p)
+    return M, p
+
+
+def nid2(world):
+    if world <= 1:
+        return None
+    from mhdflows_jl_b200.dist import nccl_id_via_torch
+    return nccl_id_via_torch()
 
 
 def set_ic(M, p, kind, fields):
@@ -196,6 +234,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = the workload's n^3 points per GPU (default), strong = the workload's grid split over N GPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -221,11 +261,18 @@ def main():
 
     kind, n, stepper, nu, eta, dt = WORKLOADS[wl]
     K, W = args.steps, args.warmup
-    M, p = make_problem(kind, n, stepper, nu, eta, dt, device=local)
-    fields = tg_fields(n, pinned=True)
+    strong = args.scaling == "strong"
+    dims = (n, n, n) if (world == 1 or strong) else grid_for(n, world)
+    nid = None
+    if world > 1:
+        from mhdflows_jl_b200.dist import nccl_id_via_torch
+        nid = nccl_id_via_torch()
+    M, p = make_problem(kind, n, stepper, nu, eta, dt, device=local, dims=dims, rank=rank, world=world, nccl_id=nid)
+    nzl = dims[2] // world
+    fields = tg_fields(n, pinned=True, dims=dims, zrange=(rank * nzl, (rank + 1) * nzl))
     set_ic(M, p, kind, fields)
-    S = 8 * (n // 2 + 1) * n * n
-    npts = n ** 3
+    S = 8 * (dims[0] // 2 + 1) * dims[1] * dims[2]      # one reference-layout spectral field of the whole grid
+    npts = dims[0] * dims[1] * dims[2]
 
     def barrier():
         if dist is not None:
@@ -246,7 +293,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / K
-    value = world * npts * K / (ms * 1e-3)   # replicas only until the slab exchange lands: each rank steps its own grid
+    value = npts * K / (ms * 1e-3)           # whole grid (all ranks) per second
 
     # ---- second pass with per-launch CUDA events: roofline of the dominant kernel ----------
     p.profile(True)
@@ -257,10 +304,10 @@ def main():
     peak, peak_src = measured_peak_hbm()
     x_ms, x_cnt = prof["x_fused"]
     x_avg_s = x_ms * 1e-3 / max(x_cnt, 1)
-    x_bytes = XPASS_S_PER_LAUNCH[kind] * S
+    x_bytes = XPASS_S_PER_LAUNCH[kind] * S // world   # this rank's share of the rows
     achieved = x_bytes / x_avg_s / 1e9
     alg_step = ALG_S_PER_STEP[(kind, stepper)] * S
-    step_ach = alg_step / (ms_per_step * 1e-3) / 1e9
+    step_ach = alg_step / world / (ms_per_step * 1e-3) / 1e9   # per GPU
     shares = {k: v[0] / max(sum(x[0] for x in prof.values()), 1e-12) for k, v in prof.items() if v[1]}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "xfused_traffic.json")
@@ -276,7 +323,8 @@ def main():
     # TimeIntegrator! loop body (getCFL! -> stepforward! -> ProbDiagnostic, scalars D2H each step) +
     # a savefile-style download of every real field (D2H).
     nf = 3 if kind != "mhd" else 6
-    M2, q = make_problem(kind, n, stepper, nu, eta, dt, device=local)
+    p.close()
+    M2, q = make_problem(kind, n, stepper, nu, eta, dt, device=local, dims=dims, rank=rank, world=world, nccl_id=nid2(world))
     set_ic(M2, q, kind, fields)
     M2.stepforward(q, 1)
     barrier()
@@ -299,20 +347,25 @@ def main():
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_val = world * npts * K / e2e_s
-    h2d = nf * npts * 4 / K
-    d2h = nf * npts * 4 / K + 88
+    e2e_val = npts * K / e2e_s
+    h2d = nf * npts * 4 / K          # all ranks together
+    d2h = nf * npts * 4 / K + 88 * world
     del outs
 
     if rank != 0:
+        q.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     line = {
         "metric": "grid-points*steps/s", "value": value, "unit": "pts*steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": wl, "kind": kind, "n": n, "stepper": stepper, "nu": nu, "eta": eta, "dt": dt,
+        "config": {"workload": wl, "kind": kind, "n": n, "grid": list(dims), "stepper": stepper, "nu": nu, "eta": eta, "dt": dt,
                    "ic": "analytic Taylor-Green u and b", "l2": "per-step working set (FFT work buffers) is far larger than the 126 MB L2; no flush needed",
-                   "multi_gpu": "replicas" if world > 1 else "single"},
+                   "multi_gpu": ("slab decomposition (z slabs / ky slabs), transposes = copy-engine pushes into peer HBM over NVLink, "
+                                 + ("fixed grid" if strong else f"{n}^3 points per GPU")) if world > 1 else "single"},
         "roofline": {"bound": "hbm", "kernel": "k_xfused (c2r -> products -> r2c)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": x_bytes, "avg_launch_ms": x_avg_s * 1e3, "launches_timed": int(x_cnt),
@@ -326,7 +379,7 @@ def main():
         "gpu_launches": int(l1 - l0),
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         times = cpu_oracle_sample(kind, n, stepper, nu, eta, dt, nsamples=1, warm=0)
         stages = 4 if stepper == "RK4" else 5
         sec = times[0] * stages
@@ -334,8 +387,10 @@ def main():
                                 "sample": f"one calcN! evaluation of {wl} ({ {'mhd': 36, 'hd': 24, 'emhd': 51}[kind]} 3D FFTs, scipy.fft workers=all), x{stages} stages per step",
                                 "ms_per_step": sec * 1e3}
     print(json.dumps(line), flush=True)
-    p.close()
     q.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -63,6 +63,14 @@ int mhdf_destroy(mhdf_handle* h);
 const char* mhdf_last_error(const mhdf_handle* h);   /* h may be NULL: error of the last failed mhdf_create */
 int mhdf_nccl_unique_id(void* id128);
 
+/* Slab runs only: peer-memory exchange.  Each rank exports a blob (CUDA IPC handles of its two exchange buffers), the
+ * host gathers the nranks blobs (rank order) and hands them to every rank.  Afterwards the global transposes are
+ * copy-engine pushes into the peers' HBM over NVLink instead of NCCL send/recv.  No reference counterpart
+ * (the reference is single-device, README.md:40-41). */
+int mhdf_ipc_blob_size(const mhdf_handle* h);
+int mhdf_ipc_export(mhdf_handle* h, void* blob);
+int mhdf_ipc_import(mhdf_handle* h, const void* all_blobs);
+
 /* SetUpProblemIC! (utils/IC.jl:41-109): copy a real field in and r2c it into sol[:, :, :, field]. */
 int mhdf_set_real(mhdf_handle* h, int field, const void* host_real);
 /* vars.ux ... (c2r on demand).  which = MHDF_FRESH | MHDF_STALE. */

@@ -20,6 +20,7 @@ SYMBOLS = [
     "mhdf_set_spectral", "mhdf_get_spectral", "mhdf_step", "mhdf_calcN", "mhdf_set_dt", "mhdf_set_clock",
     "mhdf_get_clock", "mhdf_cfl_dt", "mhdf_energy", "mhdf_helicity", "mhdf_spectrum", "mhdf_stale_stats",
     "mhdf_step_timed", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
+    "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import",
 ]
 
 
@@ -74,6 +75,9 @@ def lib():
         "mhdf_profile_get": (i, [vp, pd, pll, i]),
         "mhdf_launch_count": (ll, [vp]),
         "mhdf_info": (i, [vp, pi, pi, pi, pi, pi, pll]),
+        "mhdf_ipc_blob_size": (i, [vp]),
+        "mhdf_ipc_export": (i, [vp, vp]),
+        "mhdf_ipc_import": (i, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

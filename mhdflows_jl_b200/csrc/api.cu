@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -98,7 +99,10 @@ struct mhdf_handle {
   virtual void profile_get(double* ms, long long* cnt, int n) = 0;
   virtual long long launch_count() const = 0;
   virtual void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const = 0;
+  virtual void ipc_export(void* blob) = 0;
+  virtual void ipc_import(const void* blobs) = 0;
 };
+struct IpcBlob { cudaIpcMemHandle_t r, q; int device; int pad[15]; };
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
@@ -122,13 +126,20 @@ struct Solver : mhdf_handle {
   // (Kyl rows each, the last slab zero-padded).  One GPU: P_ = 1, nzl = nz, Kyl = Ky.
   int P_ = 1, rank_ = 0, nzl, Kyl, ky0;
   ncclComm_t comm = nullptr;
-  int *tab_zfull_in = nullptr, *tab_zfull_out = nullptr, *tab_kz = nullptr;   // z passes
-  int *tab_ky_in = nullptr, *tab_ky_out = nullptr, *tab_yfull = nullptr;      // y passes
   Cx<T>* plane_loc = nullptr;   // kr = 0 plane of the stage input, local  [F][Kz][Kyl]
   Cx<T>* plane_all = nullptr;   // gathered                                  [P][F][Kz][Kyl]
   int phys, F, nin, nout;
   long long cf;   // elements of one compact field
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;    // compute stream
+  cudaStream_t sc = nullptr;    // communication stream (every NCCL call is issued here, ordered with events)
+  std::vector<cudaEvent_t> dep_ev;
+  size_t dep_next = 0;
+  // peer-memory exchange (after mhdf_ipc_import): peers' R and Q buffers mapped into this process
+  bool ipc_on = false;
+  std::vector<C*> peerR, peerQ;
+  static constexpr int NCS = 4;
+  cudaStream_t cs[NCS] = {nullptr, nullptr, nullptr, nullptr};   // copy streams (copy engines, no SMs)
+  float* bar_d = nullptr;
   // state registers (compact, F fields each)
   C* reg[4] = {nullptr, nullptr, nullptr, nullptr};
   int iY = 0;       // register holding sol
@@ -199,6 +210,9 @@ struct Solver : mhdf_handle {
     nsm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (P_ > 1) {
+      CK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
+      dep_ev.resize(64);
+      for (auto& e : dep_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       std::string why;
       if (!g_nccl.load(why)) throw Err{MHDF_ERR_NCCL, why};
       if (c.nccl_id == nullptr) throw Err{MHDF_ERR_INVALID, "nranks > 1 needs nccl_id (mhdf_nccl_unique_id on rank 0)"};
@@ -244,48 +258,36 @@ struct Solver : mhdf_handle {
     setup_attrs();
   }
 
-  int* upload_tab(const std::vector<int>& h) {
-    int* d = dalloc<int>(h.size());
-    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    return d;
-  }
-  // Row-offset tables of the slab layout.  Exchange buffers are [peer][field][z'][ky'][kx]: the piece for / from one
-  // peer is contiguous, `blk(n)` elements for an n-field batch.
+  // Exchange buffers are [peer][field][z'][ky'][kx]: the piece for / from one peer is contiguous, blk(n) elements for an
+  // n-field batch.
   size_t blk(int nf) const { return (size_t)nf * nzl * Kyl * Kxp; }
   void build_tables() {
-    // the block size depends on the batch (nin / nout / 1): tables hold offsets for a 1-field batch split as
-    // (peer part, in-block part); kernels need a single int per row, so tables are rebuilt per batch size lazily.
     plane_loc = dalloc<C>((size_t)F * Kz * Kyl);
     plane_all = dalloc<C>((size_t)P_ * F * Kz * Kyl);
+    check_blk(CHUNK > 0 ? CHUNK : (nin > nout ? nin : nout));
   }
-  struct Tabs { int *zfull = nullptr, *kz = nullptr, *ky = nullptr, *yfull = nullptr; };
-  std::vector<std::pair<int, Tabs>> tab_cache;
-  const Tabs& tabs_for(int nf) {
-    for (auto& e : tab_cache) if (e.first == nf) return e.second;
-    const long long B = (long long)blk(nf);
-    if ((long long)P_ * B >= (1LL << 31)) throw Err{MHDF_ERR_INVALID, "slab exchange buffer exceeds 2^31 elements per batch"};
-    std::vector<int> zfull(nz), kz(Kz), ky(Ky), yfull(ny);
-    for (int z = 0; z < nz; ++z) zfull[z] = (int)((z / nzl) * B + (long long)(z % nzl) * Kyl * Kxp);
-    for (int k = 0; k < Kz; ++k) kz[k] = k * Kyl * Kxp;
-    for (int j = 0; j < Ky; ++j) ky[j] = (int)((j / Kyl) * B + (long long)(j % Kyl) * Kxp);
-    for (int y = 0; y < ny; ++y) yfull[y] = y * Kxp;
-    Tabs t;
-    t.zfull = upload_tab(zfull); t.kz = upload_tab(kz); t.ky = upload_tab(ky); t.yfull = upload_tab(yfull);
-    tab_cache.push_back({nf, t});
-    return tab_cache.back().second;
+  void check_blk(int nf) const {
+    if ((long long)P_ * (long long)blk(nf) >= (1LL << 31)) throw Err{MHDF_ERR_INVALID, "slab exchange buffer exceeds 2^31 elements per batch"};
   }
-
   ~Solver() override {
     cudaSetDevice(cfg.device);
     if (st) cudaStreamSynchronize(st);
+    if (sc) cudaStreamSynchronize(sc);
+    for (int i = 0; i < NCS; ++i) if (cs[i]) { cudaStreamSynchronize(cs[i]); cudaStreamDestroy(cs[i]); }
+    if (ipc_on) {
+      // peers may still be pushing into our buffers: close the mappings only after a final cross-rank barrier
+      if (comm) { g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc); cudaStreamSynchronize(sc); }
+      for (int q = 0; q < P_; ++q) if (q != rank_) { cudaIpcCloseMemHandle(peerR[q]); cudaIpcCloseMemHandle(peerQ[q]); }
+    }
+    cudaFree(bar_d);
+    for (auto& e : dep_ev) cudaEventDestroy(e);
+    if (sc) cudaStreamDestroy(sc);
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
     cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
-    for (auto& e : tab_cache) { cudaFree(e.second.zfull); cudaFree(e.second.kz); cudaFree(e.second.ky); cudaFree(e.second.yfull); }
     cudaFree(plane_loc); cudaFree(plane_all);
     if (comm) g_nccl.CommDestroy(comm);
     cudaFree(red_d); cudaFree(diag_d); cudaFree(spec_d);
@@ -316,22 +318,33 @@ struct Solver : mhdf_handle {
   }
 
   // ---- profiling brackets ------------------------------------------------------------------
-  void prof_begin(int cls) {
+  // `b` waits for everything enqueued so far on `a`
+  void order(cudaStream_t a, cudaStream_t b) {
+    cudaEvent_t e = dep_ev[dep_next++ % dep_ev.size()];
+    CK(cudaEventRecord(e, a));
+    CK(cudaStreamWaitEvent(b, e, 0));
+  }
+  void sync_all() {
+    CK(cudaStreamSynchronize(st));
+    if (sc) CK(cudaStreamSynchronize(sc));
+  }
+  void prof_begin(int cls, cudaStream_t s = nullptr) {
     if (!prof) return;
+    if (s == nullptr) s = st;
     Ev e;
     if (!ev_free.empty()) { e = ev_free.back(); ev_free.pop_back(); }
     else { CK(cudaEventCreate(&e.a)); CK(cudaEventCreate(&e.b)); }
     e.cls = cls;
-    CK(cudaEventRecord(e.a, st));
+    CK(cudaEventRecord(e.a, s));
     evs.push_back(e);
   }
-  void prof_end() {
+  void prof_end(cudaStream_t s = nullptr) {
     if (!prof) return;
-    CK(cudaEventRecord(evs.back().b, st));
+    CK(cudaEventRecord(evs.back().b, s ? s : st));
     if (evs.size() > 4096) prof_collect();
   }
   void prof_collect() {
-    CK(cudaStreamSynchronize(st));
+    sync_all();
     for (auto& e : evs) {
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, e.a, e.b));
@@ -349,12 +362,16 @@ struct Solver : mhdf_handle {
   static constexpr int XNT = 64;   // threads per block of the x kernels: small blocks, rows decoupled per warp
   static constexpr int xRB(int N) { return XNT / (N / 2 / 8) > 0 ? XNT / (N / 2 / 8) : 1; }
 
+  bool blk_out = false;
   template <int N, int DIR> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
     constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
     constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
     dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
-    if (a.in_tab != nullptr) k_pass<T, N, E, TX, DIR, (DIR > 0), true><<<grid, (N / E) * TX, smem, st>>>(a);
-    else k_pass<T, N, E, TX, DIR, (DIR > 0), false><<<grid, (N / E) * TX, smem, st>>>(a);
+    // the blocked side is the z side of the z passes and the ky side of the y passes: output of inverse-z / forward-y,
+    // input of inverse-y / forward-z
+    if (a.blk_rows == 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 0><<<grid, (N / E) * TX, smem, st>>>(a);
+    else if (blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 2><<<grid, (N / E) * TX, smem, st>>>(a);
+    else k_pass<T, N, E, TX, DIR, (DIR > 0), 1><<<grid, (N / E) * TX, smem, st>>>(a);
     ++launches;
   }
   template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
@@ -440,10 +457,12 @@ struct Solver : mhdf_handle {
     constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
     constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
     if (smem > 48 * 1024) {
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
   }
 
@@ -459,8 +478,9 @@ struct Solver : mhdf_handle {
     a.in_field = in_field; a.out_field = (long long)nzl * Kyl * Kxp * (P_ > 1 ? 1 : P_);
     if (P_ == 1) a.out_field = (long long)nz * Kyl * Kxp;
     a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-    a.in_tab = a.out_tab = nullptr;
-    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.kz; a.out_tab = t.zfull; }
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
+    blk_out = true;
     prof_begin(KC_ZINV);
     launch_pass<+1>(nz, a, 1, nf);
     prof_end();
@@ -472,8 +492,9 @@ struct Solver : mhdf_handle {
     a.in_outer = (long long)Kyl * Kxp; a.out_outer = (long long)ny * Kxp;
     a.in_field = (long long)nzl * Kyl * Kxp; a.out_field = (long long)nzl * ny * Kxp;
     a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-    a.in_tab = a.out_tab = nullptr;
-    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.ky; a.out_tab = t.yfull; }
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    if (P_ > 1) { a.blk_rows = Kyl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + Kyl - 1) / Kyl); }
+    blk_out = false;
     prof_begin(KC_YINV);
     launch_pass<+1>(ny, a, nzl, nf);
     prof_end();
@@ -485,8 +506,9 @@ struct Solver : mhdf_handle {
     a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
     a.in_field = (long long)nzl * ny * Kxp; a.out_field = (long long)nzl * Kyl * Kxp;
     a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-    a.in_tab = a.out_tab = nullptr;
-    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.yfull; a.out_tab = t.ky; }
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    if (P_ > 1) { a.blk_rows = Kyl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + Kyl - 1) / Kyl); }
+    blk_out = true;
     prof_begin(KC_YFWD);
     launch_pass<-1>(ny, a, nzl, nf);
     prof_end();
@@ -499,50 +521,140 @@ struct Solver : mhdf_handle {
     a.in_field = (P_ == 1) ? (long long)nz * Kyl * Kxp : (long long)nzl * Kyl * Kxp;
     a.out_field = out_field;
     a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-    a.in_tab = a.out_tab = nullptr;
-    if (P_ > 1) { const Tabs& t = tabs_for(nf); a.in_tab = t.zfull; a.out_tab = t.kz; }
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
+    blk_out = false;
     prof_begin(KC_ZFWD);
     launch_pass<-1>(nz, a, 1, nf);
     prof_end();
   }
-  // all-to-all of the blocked layout: piece q (blk(nf) elements) goes to / comes from rank q
-  void exchange(const C* send, C* recv, int nf) {
+  // all-to-all of the blocked layout: piece q (blk(nf) elements) goes to / comes from rank q; the own piece is a local
+  // copy.  Two transports: (a) after mhdf_ipc_import, copy-engine pushes straight into the peers' receive buffer over
+  // NVLink (no SMs, overlaps the axis passes), closed by a tiny all-reduce as the cross-rank barrier; (b) NCCL
+  // send/recv.  `recv` must be R or Q (+ offset).
+  void exchange(const C* send, C* recv, int nf, bool first_of_leg = true) {
     const size_t B = blk(nf);
     const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat32 : ncclFloat64;
-    prof_begin(KC_EXCH);
-    NK(g_nccl.GroupStart());
-    for (int q = 0; q < P_; ++q) {
-      NK(g_nccl.Send(send + (size_t)q * B, 2 * B, dt, q, comm, st));
-      NK(g_nccl.Recv(recv + (size_t)q * B, 2 * B, dt, q, comm, st));
+    prof_begin(KC_EXCH, sc);
+    // pushes land in the peers' buffer without the peer posting a receive: before the first push of a leg every rank
+    // must be past its last use of that buffer (stream order on each rank + this barrier)
+    if (ipc_on && first_of_leg) NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));
+    CK(cudaMemcpyAsync(recv + (size_t)rank_ * B, send + (size_t)rank_ * B, B * sizeof(C), cudaMemcpyDeviceToDevice, sc));
+    if (ipc_on) {
+      const bool inR = (recv >= R && recv < R + szR);
+      const size_t off = inR ? (size_t)(recv - R) : (size_t)(recv - Q);
+      for (int i = 0; i < NCS && i < P_ - 1; ++i) order(sc, cs[i]);
+      int k = 0;
+      for (int d = 1; d < P_; ++d, ++k) {
+        const int q = (rank_ + d) % P_;   // stagger the targets so the pushes of all ranks spread over the links
+        C* dst = (inR ? peerR[q] : peerQ[q]) + off + (size_t)rank_ * B;
+        CK(cudaMemcpyAsync(dst, send + (size_t)q * B, B * sizeof(C), cudaMemcpyDeviceToDevice, cs[k % NCS]));
+      }
+      for (int i = 0; i < NCS && i < P_ - 1; ++i) order(cs[i], sc);
+      NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));   // every rank's pushes have landed
+    } else {
+      NK(g_nccl.GroupStart());
+      for (int q = 0; q < P_; ++q) {
+        if (q == rank_) continue;
+        NK(g_nccl.Send(send + (size_t)q * B, 2 * B, dt, q, comm, sc));
+        NK(g_nccl.Recv(recv + (size_t)q * B, 2 * B, dt, q, comm, sc));
+      }
+      NK(g_nccl.GroupEnd());
     }
-    NK(g_nccl.GroupEnd());
-    prof_end();
+    prof_end(sc);
   }
+  void ipc_export(void* blob) override {
+    if (P_ == 1) throw Err{MHDF_ERR_STATE, "peer exchange needs nranks > 1"};
+    IpcBlob b;
+    std::memset(&b, 0, sizeof b);
+    CK(cudaSetDevice(cfg.device));
+    CK(cudaIpcGetMemHandle(&b.r, R));
+    CK(cudaIpcGetMemHandle(&b.q, Q));
+    b.device = cfg.device;
+    std::memcpy(blob, &b, sizeof b);
+  }
+  void ipc_import(const void* blobs) override {
+    if (P_ == 1) throw Err{MHDF_ERR_STATE, "peer exchange needs nranks > 1"};
+    CK(cudaSetDevice(cfg.device));
+    peerR.assign(P_, nullptr); peerQ.assign(P_, nullptr);
+    const IpcBlob* b = reinterpret_cast<const IpcBlob*>(blobs);
+    for (int q = 0; q < P_; ++q) {
+      if (q == rank_) { peerR[q] = R; peerQ[q] = Q; continue; }
+      void *pr = nullptr, *pq = nullptr;
+      CK(cudaIpcOpenMemHandle(&pr, b[q].r, cudaIpcMemLazyEnablePeerAccess));
+      CK(cudaIpcOpenMemHandle(&pq, b[q].q, cudaIpcMemLazyEnablePeerAccess));
+      peerR[q] = reinterpret_cast<C*>(pr); peerQ[q] = reinterpret_cast<C*>(pq);
+    }
+    for (int i = 0; i < NCS; ++i) if (!cs[i]) CK(cudaStreamCreateWithFlags(&cs[i], cudaStreamNonBlocking));
+    if (!bar_d) bar_d = dalloc<float>(1);
+    CK(cudaStreamSynchronize(st));
+    ipc_on = true;
+  }
+  // fields per exchange chunk: the transposes of one chunk overlap the passes of the next (MHDF_EXCH_CHUNK=0: whole batch)
+  int CHUNK = [] { const char* e = getenv("MHDF_EXCH_CHUNK"); return e ? atoi(e) : 3; }();
+  int chunk_fields(int nf) const { return (CHUNK > 0 && nf % CHUNK == 0) ? CHUNK : (CHUNK == 0 ? nf : 1); }
   // spectral compact (src, field stride cf) -> x-pass layout in Q.  Uses P (and R when exchanging).
   void to_xlayout(const C* src, int nf) {
-    z_inverse(src, cf, P, nf);
-    if (P_ > 1) { exchange(P, R, nf); y_inverse(R, Q, nf); }
-    else y_inverse(P, Q, nf);
+    if (P_ == 1) { z_inverse(src, cf, P, nf); y_inverse(P, Q, nf); return; }
+    const int fc = chunk_fields(nf), nc = nf / fc;
+    const size_t cb = (size_t)P_ * blk(fc);
+    std::vector<cudaEvent_t> done(nc);
+    for (int c = 0; c < nc; ++c) {
+      z_inverse(src + (size_t)c * fc * cf, cf, P + c * cb, fc);
+      order(st, sc);
+      exchange(P + c * cb, R + c * cb, fc, c == 0);
+      done[c] = dep_ev[dep_next++ % dep_ev.size()];
+      CK(cudaEventRecord(done[c], sc));
+    }
+    for (int c = 0; c < nc; ++c) {
+      CK(cudaStreamWaitEvent(st, done[c], 0));
+      y_inverse(R + c * cb, Q + (size_t)c * fc * nzl * ny * Kxp, fc);
+    }
   }
   // x-pass layout in `src` (R or Q) -> compact spectral in dst (field stride cf).  Uses P and, when exchanging, `via`.
   void from_xlayout(const C* src, C* via, C* dst, int nf) {
-    y_forward(src, P, nf);
-    if (P_ > 1) { exchange(P, via, nf); z_forward(via, dst, cf, nf); }
-    else z_forward(P, dst, cf, nf);
+    if (P_ == 1) { y_forward(src, P, nf); z_forward(P, dst, cf, nf); return; }
+    const int fc = chunk_fields(nf), nc = nf / fc;
+    const size_t cb = (size_t)P_ * blk(fc);
+    std::vector<cudaEvent_t> done(nc);
+    for (int c = 0; c < nc; ++c) {
+      y_forward(src + (size_t)c * fc * nzl * ny * Kxp, P + c * cb, fc);
+      order(st, sc);
+      exchange(P + c * cb, via + c * cb, fc, c == 0);
+      done[c] = dep_ev[dep_next++ % dep_ev.size()];
+      CK(cudaEventRecord(done[c], sc));
+    }
+    // dst may alias src (R): every forward-y pass has been issued before the first forward-z pass writes
+    for (int c = 0; c < nc; ++c) {
+      CK(cudaStreamWaitEvent(st, done[c], 0));
+      z_forward(via + c * cb, dst + (size_t)c * fc * cf, cf, fc);
+    }
   }
-  // kr = 0 plane of the stage input from every rank (the symmetrised diffusion operand needs the mirror mode)
+  // kr = 0 plane of the stage input from every rank (the symmetrised diffusion operand needs the mirror mode).
+  // Issued on the communication stream; `mirror_ready` is waited for right before the consumer kernel.
+  cudaEvent_t mirror_ready = nullptr;
   void gather_mirror(const C* S) {
     if (P_ == 1) return;
     const long long n = (long long)F * Kz * Kyl;
     k_plane<T><<<(int)((n + 255) / 256), 256, 0, st>>>(geom(), S, plane_loc);
     ++launches;
     CK(cudaGetLastError());
-    NK(g_nccl.AllGather(plane_loc, plane_all, 2 * (size_t)n, sizeof(T) == 4 ? ncclFloat32 : ncclFloat64, comm, st));
+    order(st, sc);
+    NK(g_nccl.AllGather(plane_loc, plane_all, 2 * (size_t)n, sizeof(T) == 4 ? ncclFloat32 : ncclFloat64, comm, sc));
+    mirror_ready = dep_ev[dep_next++ % dep_ev.size()];
+    CK(cudaEventRecord(mirror_ready, sc));
   }
-  void allreduce_red() {
-    if (P_ == 1) return;
-    NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, st));
-    NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint32, ncclMax, comm, st));
+  void wait_mirror() {
+    if (P_ > 1 && mirror_ready) { CK(cudaStreamWaitEvent(st, mirror_ready, 0)); mirror_ready = nullptr; }
+  }
+  // global sums / maxima of the x-kernel reductions, then the host copy
+  void finish_red() {
+    if (P_ == 1) { CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st)); return; }
+    order(st, sc);
+    NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, sc));
+    NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint32, ncclMax, comm, sc));
+    CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, sc));
+    order(sc, st);   // the next memset of red_d must not overtake the copy
   }
 
   XArgs<T> xargs() const {
@@ -579,15 +691,13 @@ struct Solver : mhdf_handle {
     prof_begin(KC_XFUSED);
     launch_xfused(xa);
     prof_end();
-    if (want_red) {
-      allreduce_red();
-      CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
-    }
+    if (want_red) finish_red();
     C* spec = (P_ > 1) ? R : Q;           // forward-z output (compact product spectra)
     from_xlayout(R, Q, spec, nout);
     sa.g = geom();
     sa.P = spec; sa.Sin = Sin;
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
+    wait_mirror();
     prof_begin(KC_SPEC);
     if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<spec_grid(), 256, 0, st>>>(sa);
     else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<spec_grid(), 256, 0, st>>>(sa);
@@ -667,7 +777,7 @@ struct Solver : mhdf_handle {
   void step(int n) override {
     CK(cudaSetDevice(cfg.device));
     for (int i = 0; i < n; ++i) one_step();
-    CK(cudaStreamSynchronize(st));
+    sync_all();
     if (n > 0) {
       absorb_red();
       check_finite();
@@ -681,11 +791,11 @@ struct Solver : mhdf_handle {
     CK(cudaSetDevice(cfg.device));
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    CK(cudaStreamSynchronize(st));
+    sync_all();
     CK(cudaEventRecord(a, st));
     for (int i = 0; i < n; ++i) one_step();
     CK(cudaEventRecord(b, st));
-    CK(cudaStreamSynchronize(st));
+    sync_all();
     float f = 0;
     CK(cudaEventElapsedTime(&f, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
@@ -702,7 +812,7 @@ struct Solver : mhdf_handle {
     SpecArgs<T> sa = blank_args();
     sa.mode = STEP_CALCN; sa.Nout = reg[o];
     rhs(reg[iY], sa, true);
-    CK(cudaStreamSynchronize(st));
+    sync_all();
     absorb_red();
     const size_t fe = (P_ > 1) ? (size_t)nkr * Kyl * nz : (size_t)nkr * ny * nz;
     for (int f = 0; f < F; ++f) unpack_to_host(reg[o] + f * cf, (C*)p + (size_t)f * fe);
@@ -725,10 +835,9 @@ struct Solver : mhdf_handle {
     CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     xa.red = red_d;
     launch_xplain<-1>(xa);
-    allreduce_red();
-    CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st));
+    finish_red();
     from_xlayout(Q, R, reg[iY] + field * cf, 1);
-    CK(cudaStreamSynchronize(st));
+    sync_all();
     // vars.* statistics of the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88)
     const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
     st_sum[slot] = red_h->sumsq[0];
@@ -749,7 +858,7 @@ struct Solver : mhdf_handle {
     xa.real_io = re; xa.in = Q; xa.out = nullptr;
     launch_xplain<+1>(xa);
     CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nzl * sizeof(T), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    sync_all();
   }
   void set_spectral(int field, const void* p) override {
     check_field(field);
@@ -760,7 +869,7 @@ struct Solver : mhdf_handle {
     k_pack<T><<<pack_grid(), 256, 0, st>>>(R, reg[iY] + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
+    sync_all();
   }
   int pack_grid() const {
     long long b = ((long long)nkr * ny * nz + 255) / 256;
@@ -774,7 +883,7 @@ struct Solver : mhdf_handle {
     ++launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    sync_all();
   }
   void get_spectral(int field, int which, void* p) override {
     check_field(field);
@@ -814,12 +923,13 @@ struct Solver : mhdf_handle {
     gather_mirror(src);
     CK(cudaMemsetAsync(diag_d, 0, 8 * sizeof(double), st));
     const int has_u = (phys != MHDF_EMHD), has_b = (phys != MHDF_HD), boff = (phys == MHDF_EMHD) ? 0 : 3;
+    wait_mirror();
     k_diag<T><<<spec_grid(), 256, 0, st>>>(geom(), src, has_u, has_b, boff, 1.0 / ((double)nx * ny * nz), diag_d);
     ++launches;
     CK(cudaGetLastError());
-    if (P_ > 1) NK(g_nccl.AllReduce(diag_d, diag_d, 8, ncclFloat64, ncclSum, comm, st));
+    if (P_ > 1) { order(st, sc); NK(g_nccl.AllReduce(diag_d, diag_d, 8, ncclFloat64, ncclSum, comm, sc)); order(sc, st); }
     CK(cudaMemcpyAsync(diag_h, diag_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    sync_all();
   }
   void energy(int which, double* KE, double* ME) override {
     CK(cudaSetDevice(cfg.device));
@@ -856,12 +966,13 @@ struct Solver : mhdf_handle {
     }
     CK(cudaMemsetAsync(spec_d, 0, nbins * sizeof(double), st));
     gather_mirror(reg[iY]);
+    wait_mirror();
     k_spectrum<T><<<spec_grid(), 256, nbins * sizeof(double), st>>>(geom(), reg[iY], field, spec_d, nbins);
     ++launches;
     CK(cudaGetLastError());
-    if (P_ > 1) NK(g_nccl.AllReduce(spec_d, spec_d, nbins, ncclFloat64, ncclSum, comm, st));
+    if (P_ > 1) { order(st, sc); NK(g_nccl.AllReduce(spec_d, spec_d, nbins, ncclFloat64, ncclSum, comm, sc)); order(sc, st); }
     CK(cudaMemcpyAsync(Pk, spec_d, nbins * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    sync_all();
   }
   void stale_stats(double* mx, double* sm) const override {
     for (int i = 0; i < 6; ++i) { if (mx) mx[i] = st_max[i]; if (sm) sm[i] = st_sum[i]; }
@@ -977,6 +1088,9 @@ int mhdf_stale_stats(const mhdf_handle* h, double* mx, double* sm) {
 int mhdf_step_timed(mhdf_handle* h, int n, double* ms) { return guard(h, [&] { if (n < 0 || !ms) throw Err{MHDF_ERR_INVALID, "bad argument"}; h->step_timed(n, ms); }); }
 int mhdf_profile(mhdf_handle* h, int en) { return guard(h, [&] { h->profile(en); }); }
 int mhdf_profile_get(mhdf_handle* h, double* ms, long long* cnt, int n) { return guard(h, [&] { h->profile_get(ms, cnt, n); }); }
+int mhdf_ipc_blob_size(const mhdf_handle*) { return (int)sizeof(IpcBlob); }
+int mhdf_ipc_export(mhdf_handle* h, void* blob) { return guard(h, [&] { if (!blob) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_export(blob); }); }
+int mhdf_ipc_import(mhdf_handle* h, const void* blobs) { return guard(h, [&] { if (!blobs) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_import(blobs); }); }
 long long mhdf_launch_count(const mhdf_handle* h) { return h ? h->launch_count() : -1; }
 int mhdf_info(const mhdf_handle* h, int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) {
   if (!h) return MHDF_ERR_INVALID;

@@ -43,12 +43,16 @@ struct PassArgs {
   int inner;                       // contiguous elements per row to process
   // retained band of the pruned side: rows [0, lo) and [hi0, N) exist, stored contiguously (shift = hi0 - lo)
   int lo, hi0, shift;
-  // TAB variants (slab-decomposed runs): element offset of every row, replacing row * stride.  Indexed by the
-  // compact row on the pruned side and by n on the full side; lets one side live in the blocked
-  // [peer][field][z'][ky'][kx] layout that the all-to-all sends / receives as contiguous pieces.
-  const int* in_tab;
-  const int* out_tab;
+  // BLK variants (slab-decomposed runs): one side lives in the blocked exchange layout [peer][field][z'][ky'][kx] that
+  // the all-to-all moves as contiguous pieces.  Row r of that side sits at  q * blk_stride + (r - q * blk_rows) * row,
+  // q = r / blk_rows computed as mulhi(r, blk_magic)  (blk_magic = ceil(2^32 / blk_rows), exact for r < 2^16).
+  int blk_rows, blk_stride;
+  unsigned blk_magic;
 };
+__device__ __forceinline__ int blk_off(int r, int rows, int stride, unsigned magic, int rowstride) {
+  const int q = (int)__umulhi((unsigned)r, magic);
+  return q * stride + (r - q * rows) * rowstride;
+}
 
 // predicated 8/16-byte global accesses (no branches, no speculative address use)
 __device__ __forceinline__ float2 ldg_pred(const float2* p, bool ok) {
@@ -84,7 +88,8 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
 };
 
 // PIN: the input side is the pruned (band) side (inverse passes); otherwise the output side is (forward passes).
-template <typename T, int N, int E, int TX, int DIR, bool PIN, bool TAB>
+// BLK: 0 = plain strides, 1 = input side blocked, 2 = output side blocked
+template <typename T, int N, int E, int TX, int DIR, bool PIN, int BLK>
 __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 2 : 1) k_pass(PassArgs<T> a) {
   using C = Cx<T>;
   constexpr int Tn = N / E;
@@ -105,9 +110,9 @@ __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 
     if (PIN) {
       const bool ok = valid && (n < a.lo || n >= a.hi0);
       const int r = n - (n >= a.hi0 ? a.shift : 0);
-      v[m] = ldg_pred(ip + (TAB ? (ok ? __ldg(a.in_tab + r) : 0) : r * a.in_row), ok);
+      v[m] = ldg_pred(ip + (BLK == 1 ? blk_off(r, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : r * a.in_row), ok);
     } else {
-      v[m] = ldg_pred(ip + (TAB ? __ldg(a.in_tab + n) : n * a.in_row), valid);
+      v[m] = ldg_pred(ip + (BLK == 1 ? blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : n * a.in_row), valid);
     }
   }
   PassIdx<N, TX, R1, C> idx{c};
@@ -119,9 +124,9 @@ __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 
     if (!PIN) {
       const bool ok = valid && (n < a.lo || n >= a.hi0);
       const int r = n - (n >= a.hi0 ? a.shift : 0);
-      stg_pred(op + (TAB ? (ok ? __ldg(a.out_tab + r) : 0) : r * a.out_row), v[m], ok);
+      stg_pred(op + (BLK == 2 ? blk_off(r, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : r * a.out_row), v[m], ok);
     } else {
-      stg_pred(op + (TAB ? __ldg(a.out_tab + n) : n * a.out_row), v[m], valid);
+      stg_pred(op + (BLK == 2 ? blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : n * a.out_row), v[m], valid);
     }
   }
 }

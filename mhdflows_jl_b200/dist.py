@@ -109,6 +109,20 @@ def nccl_id_via_torch(group=None):
     return obj[0]
 
 
+def enable_peer_exchange(prob, group=None):
+    """Exchange CUDA IPC handles of the transpose buffers between the ranks (through torch.distributed) so the global
+    transposes become copy-engine pushes into peer HBM over NVLink (overlapping the axis passes) instead of NCCL
+    send/recv kernels."""
+    import torch.distributed as dist
+    n = L.lib().mhdf_ipc_blob_size(prob._h)
+    blob = C.create_string_buffer(n)
+    L.check(prob._h, L.lib().mhdf_ipc_export(prob._h, blob))
+    blobs = [None] * dist.get_world_size(group)
+    dist.all_gather_object(blobs, blob.raw, group=group)
+    allb = C.create_string_buffer(b"".join(blobs), n * len(blobs))
+    L.check(prob._h, L.lib().mhdf_ipc_import(prob._h, allb))
+
+
 def emulated_forward(real_slab, lay: SlabLayout, group=None):
     """NumPy emulation of the distributed forward transform (x r2c -> y pass -> all-to-all -> z pass) over
     torch.distributed, using the SAME blocked exchange layout and row tables as the CUDA path.

@@ -28,6 +28,9 @@ def run(kind, n, stepper, T, nsteps, timing=False):
     nid = nccl_id_via_torch()
     dp = M.Problem(M.GPU(local), rank=r, nranks=P, nccl_id=nid, **kw)
     lay = dp.layout
+    if os.environ.get("MHDF_PEER", "1") == "1":
+        from mhdflows_jl_b200.dist import enable_peer_exchange
+        enable_peer_exchange(dp)
     M.SetUpProblemIC(dp, **{k: lay.scatter_real(v) for k, v in ic.items()})
     M.stepforward(dp, nsteps)
     slabs = [dp.get_spectral(i) for i in range(dp.Nl)]
