@@ -137,8 +137,9 @@ struct Solver : mhdf_handle {
   // peer-memory exchange (after mhdf_ipc_import): peers' R and Q buffers mapped into this process
   bool ipc_on = false;
   std::vector<C*> peerR, peerQ;
-  static constexpr int NCS = 4;
-  cudaStream_t cs[NCS] = {nullptr, nullptr, nullptr, nullptr};   // copy streams (copy engines, no SMs)
+  static constexpr int NCS_MAX = 8;
+  int NCS = [] { const char* e = getenv("MHDF_COPY_STREAMS"); int n = e ? atoi(e) : 7; return n < 1 ? 1 : (n > NCS_MAX ? NCS_MAX : n); }();
+  cudaStream_t cs[NCS_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copy streams (copy engines, no SMs)
   float* bar_d = nullptr;
   // state registers (compact, F fields each)
   C* reg[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -397,13 +398,47 @@ struct Solver : mhdf_handle {
     long long g = (long long)nsm * 16;
     return (int)(sets < g ? sets : g);
   }
+  // tuning experiment (MHDF_X_VARIANT = "E,MINB"): alternative register budgets / elements per thread of the fused x
+  // kernel, Float32 MHD without reductions at 256 and 1024 only
+  template <int N, int E, int MINB> bool launch_xvariant(XArgs<T>& a) {
+    if constexpr (sizeof(T) == 4 && (N == 256 || N == 1024)) {
+      constexpr int Tm = N / 2 / E, RB = (XNT / Tm > 0) ? XNT / Tm : 1, M = N / 2, R1 = imin(E, M);
+      const size_t smem = (size_t)2 * RB * RowIdx<M, R1>::SIZE * sizeof(C);
+      const int grid = x_grid(a.rows, RB);
+      k_xfused<T, N, E, RB, PHYS_MHD, false, MINB><<<grid, Tm * RB, smem, st>>>(a);
+      ++launches;
+      return true;
+    }
+    return false;
+  }
+  template <int N> bool try_xvariant(XArgs<T>& a) {
+    static const char* env = getenv("MHDF_X_VARIANT");
+    if (!env || phys != MHDF_MHD || a.red != nullptr) return false;
+    int e = 8, mb = 1;
+    sscanf(env, "%d,%d", &e, &mb);
+    if (e == 8 && mb == 5) return launch_xvariant<N, 8, 5>(a);
+    if (e == 8 && mb == 6) return launch_xvariant<N, 8, 6>(a);
+    if (e == 8 && mb == 8) return launch_xvariant<N, 8, 8>(a);
+    if (e == 4 && mb == 1) return launch_xvariant<N, 4, 1>(a);
+    if (e == 4 && mb == 6) return launch_xvariant<N, 4, 6>(a);
+    if (e == 4 && mb == 8) return launch_xvariant<N, 4, 8>(a);
+    return false;
+  }
   template <int N> void launch_xfused_n(XArgs<T>& a) {
+    if (try_xvariant<N>(a)) return;
     constexpr int E = xE(N), RB = xRB(N);
     const int grid = x_grid(a.rows, RB);
     const int threads = (N / 2 / E) * RB;
-    if (phys == MHDF_MHD) k_xfused<T, N, E, RB, PHYS_MHD><<<grid, threads, x_smem<N>(), st>>>(a);
-    else if (phys == MHDF_HD) k_xfused<T, N, E, RB, PHYS_HD><<<grid, threads, x_smem<N>(), st>>>(a);
-    else k_xfused<T, N, E, RB, PHYS_EMHD><<<grid, threads, x_smem<N>(), st>>>(a);
+    const bool red = a.red != nullptr;
+#define XLAUNCH(PH)                                                                          \
+    do {                                                                                     \
+      if (red) k_xfused<T, N, E, RB, PH, true><<<grid, threads, x_smem<N>(), st>>>(a);       \
+      else k_xfused<T, N, E, RB, PH, false><<<grid, threads, x_smem<N>(), st>>>(a);          \
+    } while (0)
+    if (phys == MHDF_MHD) XLAUNCH(PHYS_MHD);
+    else if (phys == MHDF_HD) XLAUNCH(PHYS_HD);
+    else XLAUNCH(PHYS_EMHD);
+#undef XLAUNCH
     ++launches;
   }
   template <int N, int DIR> void launch_xplain_n(XArgs<T>& a) {
@@ -446,9 +481,12 @@ struct Solver : mhdf_handle {
     constexpr int E = xE(N), RB = xRB(N);
     const int smem = (int)x_smem<N>();
     if (smem > 48 * 1024) {
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }

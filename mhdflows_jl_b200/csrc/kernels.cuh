@@ -277,8 +277,10 @@ enum { PHYS_HD = 0, PHYS_MHD = 1, PHYS_EMHD = 2 };
 //         (reference: MHDSolver.jl:73 and :150; HDSolver.jl:62)
 //   EMHD: in A(3), dB(9), dA(9), B(3) spectral + stale b (3, real)   out G_i (3), fresh b -> real_io
 //         G_i = sum_j A_j d_j B_i - b^stale_j d_j A_i   (reference: MHDSolver.jl:241-266, 323-325)
-template <typename T, int N, int E, int RB, int PHYS>
-__global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
+// RED: accumulate the per-field sum f^2 / max f^2 / sum u.b reductions (only the launch whose real-space fields
+// the reference's stale `vars` correspond to needs them; the other stages skip the work and the registers)
+template <typename T, int N, int E, int RB, int PHYS, bool RED, int MINB = 1>
+__global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   // a row owned by at most one warp synchronises with __syncwarp only: rows are fully decoupled
@@ -321,17 +323,19 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
       for (int i = 0; i < NF; ++i) {
         row_c2r<T, N, E, SYNC>(f[i], in + i * a.in_field, a.Kx, a.scale, t, sm, a.tw);
-        float s = 0.f, mx = 0.f;
+        if constexpr (RED) {
+          float s = 0.f, mx = 0.f;
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-          const float x2 = (float)(f[i][m].x * f[i][m].x), y2 = (float)(f[i][m].y * f[i][m].y);
-          s += x2 + y2;
-          mx = fmaxf(mx, fmaxf(x2, y2));
+          for (int m = 0; m < E; ++m) {
+            const float x2 = (float)(f[i][m].x * f[i][m].x), y2 = (float)(f[i][m].y * f[i][m].y);
+            s += x2 + y2;
+            mx = fmaxf(mx, fmaxf(x2, y2));
+          }
+          rs[i] += (double)s;
+          rm[i] = fmaxf(rm[i], mx);
         }
-        rs[i] += (double)s;
-        rm[i] = fmaxf(rm[i], mx);
       }
-      if constexpr (PHYS == PHYS_MHD) {
+      if constexpr (PHYS == PHYS_MHD && RED) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
@@ -382,9 +386,11 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         float s = 0.f, mx = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-          const float x2 = (float)(A[i][m].x * A[i][m].x), y2 = (float)(A[i][m].y * A[i][m].y);
-          s += x2 + y2;
-          mx = fmaxf(mx, fmaxf(x2, y2));
+          if constexpr (RED) {
+            const float x2 = (float)(A[i][m].x * A[i][m].x), y2 = (float)(A[i][m].y * A[i][m].y);
+            s += x2 + y2;
+            mx = fmaxf(mx, fmaxf(x2, y2));
+          }
           bs[i][m] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
         }
         rs[i] += (double)s;
@@ -415,9 +421,11 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         float s = 0.f, mx = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-          const float x2 = (float)(g[m].x * g[m].x), y2 = (float)(g[m].y * g[m].y);
-          s += x2 + y2;
-          mx = fmaxf(mx, fmaxf(x2, y2));
+          if constexpr (RED) {
+            const float x2 = (float)(g[m].x * g[m].x), y2 = (float)(g[m].y * g[m].y);
+            s += x2 + y2;
+            mx = fmaxf(mx, fmaxf(x2, y2));
+          }
           reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
         }
         rs[3 + i] += (double)s;
@@ -425,7 +433,9 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
       }
     }
   }
-  if (a.red != nullptr) block_reduce_commit<7, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
+  if constexpr (RED) {
+    if (a.red != nullptr) block_reduce_commit<7, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
+  }
 }
 
 // Plain x passes for the API boundary (set_real / get_real): real rows <-> spectral rows.

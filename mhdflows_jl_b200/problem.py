@@ -254,8 +254,12 @@ class Problem:
             raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
         L.check(self._h, L.lib().mhdf_set_real(self._h, self._field_id(f), a.ctypes.data))
 
-    def get_real(self, f, which=L.FRESH):
-        out = np.empty(self._real_shape, dtype=self.T)
+    def get_real(self, f, which=L.FRESH, out=None):
+        """Real-space field (c2r on demand).  `out`: optional preallocated (e.g. pinned) array to receive it."""
+        if out is None:
+            out = np.empty(self._real_shape, dtype=self.T)
+        elif out.shape != self._real_shape or out.dtype != self.T or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
         L.check(self._h, L.lib().mhdf_get_real(self._h, self._field_id(f), which, out.ctypes.data))
         return out
 

@@ -69,7 +69,11 @@ def run(kind, n, stepper, T, nsteps, timing=False):
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "check"
-if which == "check":
+if which == "check64":
+    run("mhd", 64, "RK4", np.float32, 3)
+    run("hd", 64, "LSRK54", np.float32, 2)
+    run("emhd", 64, "RK4", np.float64, 2)
+elif which == "check":
     run("mhd", 64, "RK4", np.float32, 3)
     run("hd", 64, "LSRK54", np.float32, 2)
     run("emhd", 64, "RK4", np.float64, 2)

@@ -37,7 +37,7 @@ t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 p.profile(True); p.step_timed(steps); pr = p.profile_get(); p.profile(False)
 e = p.energy(M.FRESH)
 if r == 0:
-    print(f"timing P={P} mhd {nx}x{ny}x{nz} chunk={os.environ.get('MHDF_EXCH_CHUNK','3')} peer={os.environ.get('MHDF_PEER','1')}: {t.item():.3f} ms/step  {nx*ny*nz / t.item() * 1e3:.3e} pts*steps/s  E={e[0]:.4f},{e[1]:.4f} ; ms/step: " +
+    print(f"timing P={P} mhd {nx}x{ny}x{nz} chunk={os.environ.get('MHDF_EXCH_CHUNK','3')} peer={os.environ.get('MHDF_PEER','1')} ncs={os.environ.get('MHDF_COPY_STREAMS','7')}: {t.item():.3f} ms/step  {nx*ny*nz / t.item() * 1e3:.3e} pts*steps/s  E={e[0]:.4f},{e[1]:.4f} ; ms/step: " +
           " ".join(f"{k}={v[0] / steps:.3f}" for k, v in pr.items() if v[1]), flush=True)
 p.close()
 dist.destroy_process_group()
