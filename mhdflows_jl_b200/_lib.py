@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmhdflows_b200.so")
+LIB_PATH = os.environ.get("MHDF_LIB") or os.path.join(HERE, "libmhdflows_b200.so")   # MHDF_LIB: A/B builds when tuning
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NONFINITE, ERR_STATE = 0, -1, -2, -3, -4, -5
 F32, F64 = 0, 1

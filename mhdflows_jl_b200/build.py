@@ -35,7 +35,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = True) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
+    extra = os.environ.get("MHDF_NVCC_EXTRA", "").split()     # tuning builds, e.g. -DMHDF_XTW_SHARED
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES
     if verbose:
         print("[mhdflows_jl_b200] " + " ".join(cmd), file=sys.stderr)
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)

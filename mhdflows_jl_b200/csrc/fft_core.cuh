@@ -101,10 +101,17 @@ template <int R, int DIR, typename C> struct Bfly {
 constexpr __host__ __device__ int imin(int a, int b) { return a < b ? a : b; }
 constexpr __host__ __device__ int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 
-// One radix-R step on the register file of thread t (no shared memory).
-// tw[i] = (cos(2*pi*i/NTW), -sin(2*pi*i/NTW)), NTW = N * TWS (TWS = table stride, 1 or 2).
-template <typename C, int N, int E, int R, int NS, int DIR, int TWS>
-__device__ __forceinline__ void fft_step(C (&v)[E], int t, const C* __restrict__ tw) {
+// Twiddle source.  tw[i] = (cos(2*pi*i/NTW), -sin(2*pi*i/NTW)), NTW = N * TWS (TWS = table stride, 1 or 2): read-only
+// global table indexed by the twiddle exponent (a policy type so other sources can be plugged in; SLOT0 numbers the
+// twiddles of a plan for such sources).
+template <typename C> struct TwGlobal {
+  const C* tw;
+  __device__ __forceinline__ C get(int, unsigned gi) const { return __ldg(tw + gi); }
+};
+
+// One radix-R step on the register file of thread t (no shared memory).  SLOT0 = first twiddle slot of this step.
+template <typename C, int N, int E, int R, int NS, int DIR, int TWS, int SLOT0, typename TW>
+__device__ __forceinline__ void fft_step(C (&v)[E], int t, TW tw) {
   constexpr int Tn = N / E;
   constexpr int Q = E / R;
 #pragma unroll
@@ -114,11 +121,11 @@ __device__ __forceinline__ void fft_step(C (&v)[E], int t, const C* __restrict__
     for (int r = 0; r < R; ++r) x[r] = v[q + r * Q];
     if (NS > 1) {
       const int j = t + q * Tn;
-      const int k = j & (NS - 1);
-      constexpr int STR = (N / (NS * R)) * TWS;
+      constexpr unsigned STR = (N / (NS * R)) * TWS;
+      const unsigned ks = (unsigned)(j & (NS - 1)) * STR;
 #pragma unroll
       for (int r = 1; r < R; ++r) {
-        C w = __ldg(&tw[(r * k) * STR]);
+        C w = tw.get(SLOT0 + q * (R - 1) + (r - 1), (unsigned)r * ks);
         x[r] = (DIR < 0) ? cmul(x[r], w) : cmulc(x[r], w);
       }
     }
@@ -158,32 +165,33 @@ struct SyncWarp  { static __device__ __forceinline__ void sync() { __syncwarp();
 // of the same buffer after passing the barrier of the exchange in between, by which time every
 // thread has finished reading it.  The caller must ensure sm0 is free on entry (one barrier since
 // its last read).  Returns with data in registers in natural order n = t + Tn*m.
-template <typename C, int N, int E, int DIR, int TWS, int NS, int PAR, typename SYNC, typename IDX>
-__device__ __forceinline__ void fft_run(C (&v)[E], int t, C* __restrict__ sm0, C* __restrict__ sm1,
-                                        const C* __restrict__ tw, IDX idx) {
+template <typename C, int N, int E, int DIR, int TWS, int NS, int PAR, typename SYNC, typename IDX, typename TW, int SLOT0 = 0>
+__device__ __forceinline__ void fft_run(C (&v)[E], int t, C* __restrict__ sm0, C* __restrict__ sm1, TW tw, IDX idx) {
   constexpr int R = imin(E, N / NS);
-  fft_step<C, N, E, R, NS, DIR, TWS>(v, t, tw);
+  fft_step<C, N, E, R, NS, DIR, TWS, SLOT0>(v, t, tw);
   if constexpr (NS * R < N) {
     C* sm = PAR ? sm1 : sm0;
     fft_scatter<C, N, E, R, NS>(v, t, sm, idx);
     SYNC::sync();
     fft_gather<C, N, E>(v, t, sm, idx);
-    fft_run<C, N, E, DIR, TWS, NS * R, PAR ^ 1, SYNC, IDX>(v, t, sm0, sm1, tw, idx);
+    constexpr int NEXT = SLOT0 + (NS > 1 ? (E / R) * (R - 1) : 0);
+    fft_run<C, N, E, DIR, TWS, NS * R, PAR ^ 1, SYNC, IDX, TW, NEXT>(v, t, sm0, sm1, tw, idx);
   }
 }
 
 // Single-buffer variant (strided passes, where shared memory limits occupancy): two barriers per
 // exchange.  The buffer must be free on entry; it is free again on return.
-template <typename C, int N, int E, int DIR, int TWS, int NS, typename IDX>
-__device__ __forceinline__ void fft_run_sb(C (&v)[E], int t, C* __restrict__ sm, const C* __restrict__ tw, IDX idx) {
+template <typename C, int N, int E, int DIR, int TWS, int NS, typename IDX, typename TW, int SLOT0 = 0>
+__device__ __forceinline__ void fft_run_sb(C (&v)[E], int t, C* __restrict__ sm, TW tw, IDX idx) {
   constexpr int R = imin(E, N / NS);
-  fft_step<C, N, E, R, NS, DIR, TWS>(v, t, tw);
+  fft_step<C, N, E, R, NS, DIR, TWS, SLOT0>(v, t, tw);
   if constexpr (NS * R < N) {
     if constexpr (NS > 1) __syncthreads();   // previous gather finished
     fft_scatter<C, N, E, R, NS>(v, t, sm, idx);
     __syncthreads();
     fft_gather<C, N, E>(v, t, sm, idx);
-    fft_run_sb<C, N, E, DIR, TWS, NS * R, IDX>(v, t, sm, tw, idx);
+    constexpr int NEXT = SLOT0 + (NS > 1 ? (E / R) * (R - 1) : 0);
+    fft_run_sb<C, N, E, DIR, TWS, NS * R, IDX, TW, NEXT>(v, t, sm, tw, idx);
   }
 }
 

@@ -82,7 +82,7 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
   // float2 with TX = 8: two rows share one 128-byte bank line; shift by 8 slots every R1 rows so
   // rows n and n+R1 (written together in the first exchange) land in different halves.
   static constexpr bool PAD = (sizeof(C) == 8 && TX == 8);
-  static constexpr int SIZE = N * TX + (PAD ? (N / R1) * 8 : 0);
+  static constexpr int SIZE = N * TX + (PAD ? (N / R1) * 8 : 0);   // exchange buffer; the twiddle table follows it
   int c;
   __device__ __forceinline__ int operator()(int n) const { return n * TX + c + (PAD ? (n / R1) * 8 : 0); }
 };
@@ -102,31 +102,45 @@ __global__ void __launch_bounds__((N / E) * TX, (N >= 1024 && sizeof(T) == 4) ? 
   const bool valid = col < a.inner;
   const C* ip = a.in + ((long long)blockIdx.z * a.in_field + (long long)blockIdx.y * a.in_outer + col);
   C* op = a.out + ((long long)blockIdx.z * a.out_field + (long long)blockIdx.y * a.out_outer + col);
+  const C* twp = a.tw;
+  asm volatile("" : "+l"(twp));
 
+  // 32-bit unsigned element offsets from one materialised 64-bit base per side, so every access costs one IMAD.WIDE
+  // (the empty asm keeps the compiler from re-deriving base + index * 8 from the kernel parameters per access)
+  const unsigned irow = (unsigned)a.in_row, orow = (unsigned)a.out_row;
+  asm volatile("" : "+l"(ip));
+  asm volatile("" : "+l"(op));
   C v[E];
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int n = t + Tn * m;
     if (PIN) {
-      const bool ok = valid && (n < a.lo || n >= a.hi0);
-      const int r = n - (n >= a.hi0 ? a.shift : 0);
-      v[m] = ldg_pred(ip + (BLK == 1 ? blk_off(r, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : r * a.in_row), ok);
+      const bool hi = n >= a.hi0;
+      const bool ok = valid && (n < a.lo || hi);
+      const unsigned r = (unsigned)(n - (hi ? a.shift : 0));
+      const unsigned off = (BLK == 1) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : r * irow;
+      v[m] = ldg_pred(ip + off, ok);
     } else {
-      v[m] = ldg_pred(ip + (BLK == 1 ? blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : n * a.in_row), valid);
+      const unsigned off = (BLK == 1) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : (unsigned)n * irow;
+      v[m] = ldg_pred(ip + off, valid);
     }
   }
   PassIdx<N, TX, R1, C> idx{c};
-  // single exchange buffer: two barriers per exchange (scatter | gather | next scatter)
-  fft_run_sb<C, N, E, DIR, 1, 1>(v, t, sm, a.tw, idx);
+  // single exchange buffer: two barriers per exchange (scatter | gather | next scatter); twiddles straight from the
+  // (L1-resident) global table -- a per-block shared copy does not pay off for one tile per block
+  fft_run_sb<C, N, E, DIR, 1, 1>(v, t, sm, TwGlobal<C>{twp}, idx);
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int n = t + Tn * m;
     if (!PIN) {
-      const bool ok = valid && (n < a.lo || n >= a.hi0);
-      const int r = n - (n >= a.hi0 ? a.shift : 0);
-      stg_pred(op + (BLK == 2 ? blk_off(r, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : r * a.out_row), v[m], ok);
+      const bool hi = n >= a.hi0;
+      const bool ok = valid && (n < a.lo || hi);
+      const unsigned r = (unsigned)(n - (hi ? a.shift : 0));
+      const unsigned off = (BLK == 2) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : r * orow;
+      stg_pred(op + off, v[m], ok);
     } else {
-      stg_pred(op + (BLK == 2 ? blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : n * a.out_row), v[m], valid);
+      const unsigned off = (BLK == 2) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : (unsigned)n * orow;
+      stg_pred(op + off, v[m], valid);
     }
   }
 }
@@ -150,25 +164,41 @@ template <typename C> struct RowSmem {
 
 // c2r of one row: X[k], k < Kx (others zero) -> v = z[n] = x[2n] + i x[2n+1], n = t + Tm*m,
 // unnormalised inverse times `scale`.  Im X[0] is ignored like every c2r does.
+// Twiddles of the x kernels come from the global table; they do not depend on the row or the field, so the compiler
+// keeps them in registers across the 15 transforms of a row set (a shared-memory copy measured 20 % slower).
+template <typename T, int N, int E> struct XTwSrc {
+  using C = Cx<T>;
+  static __device__ __forceinline__ TwGlobal<C> fft(const C* tw) { return TwGlobal<C>{tw}; }
+  static __device__ __forceinline__ C wn(const C* tw, int, int k) { return __ldg(tw + (unsigned)k); }
+};
+
 template <typename T, int N, int E, typename SYNC>
 __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__ X, int Kx, T scale, int t,
                                         RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
+#ifndef MHDF_XOPT_OFF
+  asm volatile("" : "+l"(X));
+#endif
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int k = t + Tm * m;
     const int k2 = M - k;
+#ifndef MHDF_XOPT_OFF
+    C x1 = ldg_pred(X + (unsigned)k, k < Kx);
+    C x2 = cconj(ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx));
+#else
     C x1 = mk<C>(0, 0), x2 = mk<C>(0, 0);
     if (k < Kx) x1 = X[k];
     if (k2 < Kx) x2 = cconj(X[k2]);
+#endif
     if (k == 0) x1.y = 0;
-    const C w = cconj(__ldg(&tw[k]));                       // exp(+2 pi i k / N)
+    const C w = cconj(XTwSrc<T, N, E>::wn(tw, m, k));       // exp(+2 pi i k / N)
     const C s = cadd(x1, x2), d = cmul(csub(x1, x2), w);    // Z = s + i d
     v[m] = mk<C>((s.x - d.y) * scale, (s.y + d.x) * scale);
   }
   constexpr int NEX = fft_num_steps(M, E) - 1;
-  fft_run<C, M, E, +1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, tw, RowIdx<M, R1>());
+  fft_run<C, M, E, +1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>());
   if (NEX & 1) sm.swap();
 }
 
@@ -179,12 +209,26 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   constexpr int NEX = fft_num_steps(M, E) - 1;
-  fft_run<C, M, E, -1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, tw, RowIdx<M, R1>());
+  fft_run<C, M, E, -1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>());
   if (NEX & 1) sm.swap();
   RowIdx<M, R1> idx;
 #pragma unroll
   for (int m = 0; m < E; ++m) sm.a[idx(t + Tm * m)] = v[m];
   SYNC::sync();
+#ifndef MHDF_XOPT_OFF
+  asm volatile("" : "+l"(Xout));
+#pragma unroll
+  for (int m = 0; m < E; ++m) {
+    const int k = t + Tm * m;
+    // columns k >= Kx are never stored; their arithmetic is harmless and keeps the code branch-free
+    const C z1 = v[m];
+    const C z2 = cconj(sm.a[idx((M - k) & (M - 1))]);
+    const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
+    const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
+    const C w = XTwSrc<T, N, E>::wn(tw, m, k);                               // exp(-2 pi i k / N)
+    stg_pred(Xout + (unsigned)k, cadd(ev, cmul(od, w)), k < Kx);
+  }
+#else
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int k = t + Tm * m;
@@ -193,10 +237,11 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
       const C z2 = cconj(sm.a[idx((M - k) & (M - 1))]);
       const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
       const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
-      const C w = __ldg(&tw[k]);                                              // exp(-2 pi i k / N)
+      const C w = XTwSrc<T, N, E>::wn(tw, m, k);                              // exp(-2 pi i k / N)
       Xout[k] = cadd(ev, cmul(od, w));
     }
   }
+#endif
   sm.swap();
 }
 
@@ -292,6 +337,8 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
   RowSmem<C> sm;
   sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
   sm.b = sm.a + RS;
+  const C* twt = a.tw;
+  asm volatile("" : "+l"(twt));
 
   double rs[7];
   float rm[6];
@@ -322,7 +369,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
       C f[NF][E];
 #pragma unroll
       for (int i = 0; i < NF; ++i) {
-        row_c2r<T, N, E, SYNC>(f[i], in + i * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+        row_c2r<T, N, E, SYNC>(f[i], in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
         if constexpr (RED) {
           float s = 0.f, mx = 0.f;
 #pragma unroll
@@ -358,7 +405,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
             else
               v[m] = mk<C>(-(f[i][m].x * f[j][m].x), -(f[i][m].y * f[j][m].y));
           }
-          row_r2c<T, N, E, SYNC>(v, out + p * a.out_field, a.Kx, t, sm, a.tw);
+          row_r2c<T, N, E, SYNC>(v, out + p * a.out_field, a.Kx, t, sm, twt);
           ++p;
         }
       }
@@ -373,7 +420,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
           for (int m = 0; m < E; ++m)
             v[m] = mk<C>(f[j][m].x * f[3 + k][m].x - f[k][m].x * f[3 + j][m].x,
                          f[j][m].y * f[3 + k][m].y - f[k][m].y * f[3 + j][m].y);
-          row_r2c<T, N, E, SYNC>(v, out + (6 + i) * a.out_field, a.Kx, t, sm, a.tw);
+          row_r2c<T, N, E, SYNC>(v, out + (6 + i) * a.out_field, a.Kx, t, sm, twt);
         }
       }
     } else {
@@ -382,7 +429,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
       C* breal = reinterpret_cast<C*>(a.real_io + row * (long long)N);
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        row_c2r<T, N, E, SYNC>(A[i], in + i * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+        row_c2r<T, N, E, SYNC>(A[i], in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
         float s = 0.f, mx = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
@@ -404,20 +451,20 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           C g[E];
-          row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+          row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
           for (int m = 0; m < E; ++m) { acc[m].x += A[j][m].x * g[m].x; acc[m].y += A[j][m].y * g[m].y; }
-          row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+          row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
           for (int m = 0; m < E; ++m) { acc[m].x -= bs[j][m].x * g[m].x; acc[m].y -= bs[j][m].y * g[m].y; }
         }
-        row_r2c<T, N, E, SYNC>(acc, out + i * a.out_field, a.Kx, t, sm, a.tw);
+        row_r2c<T, N, E, SYNC>(acc, out + i * a.out_field, a.Kx, t, sm, twt);
       }
       // refresh the real-space b (vars.b*) from the current stage input
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         C g[E];
-        row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, a.tw);
+        row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
         float s = 0.f, mx = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
@@ -451,6 +498,8 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
   RowSmem<C> sm;
   sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
   sm.b = sm.a + RS;
+  const C* twt = a.tw;
+  asm volatile("" : "+l"(twt));
   double rs[1] = {0.0};
   float rm[1] = {0.f};
   const long long nsets = a.rows / RB;
@@ -469,9 +518,9 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
       }
       rs[0] += (double)s;
       rm[0] = fmaxf(rm[0], mx);
-      row_r2c<T, N, E, SYNC>(v, a.out + row * a.Kxp, a.Kx, t, sm, a.tw);
+      row_r2c<T, N, E, SYNC>(v, a.out + row * a.Kxp, a.Kx, t, sm, twt);
     } else {                   // spectral -> real
-      row_c2r<T, N, E, SYNC>(v, a.in + row * a.Kxp, a.Kx, a.scale, t, sm, a.tw);
+      row_c2r<T, N, E, SYNC>(v, a.in + row * a.Kxp, a.Kx, a.scale, t, sm, twt);
       float s = 0.f, mx = 0.f;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
