@@ -719,27 +719,30 @@ struct Solver : mhdf_handle {
       prof_end();
       zin = D;
     }
+    sa.g = geom();
+    sa.Sin = Sin;
+    sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
+    if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     to_xlayout(zin, nin);
     XArgs<T> xa = xargs();
     xa.real_io = bst;
-    if (want_red) {
-      CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
-      xa.red = red_d;
-    }
+    if (want_red) xa.red = red_d;
     prof_begin(KC_XFUSED);
     launch_xfused(xa);
     prof_end();
     if (want_red) finish_red();
     C* spec = (P_ > 1) ? R : Q;           // forward-z output (compact product spectra)
     from_xlayout(R, Q, spec, nout);
-    sa.g = geom();
-    sa.P = spec; sa.Sin = Sin;
-    sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
+    sa.P = spec;
     wait_mirror();
+    launch_spectral(sa);
+  }
+  void launch_spectral(SpecArgs<T>& sa) {
     prof_begin(KC_SPEC);
-    if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<spec_grid(), 256, 0, st>>>(sa);
-    else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<spec_grid(), 256, 0, st>>>(sa);
-    else k_spectral<T, PHYS_EMHD><<<spec_grid(), 256, 0, st>>>(sa);
+    const int grid = spec_grid();
+    if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
+    else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<grid, 256, 0, st>>>(sa);
+    else k_spectral<T, PHYS_EMHD><<<grid, 256, 0, st>>>(sa);
     ++launches;
     CK(cudaGetLastError());
     prof_end();

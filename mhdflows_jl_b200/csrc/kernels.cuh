@@ -371,23 +371,24 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
       for (int i = 0; i < NF; ++i) {
         row_c2r<T, N, E, SYNC>(f[i], in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
         if constexpr (RED) {
-          float s = 0.f, mx = 0.f;
+          T s = 0;
+          float mx = 0.f;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
-            const float x2 = (float)(f[i][m].x * f[i][m].x), y2 = (float)(f[i][m].y * f[i][m].y);
+            const T x2 = f[i][m].x * f[i][m].x, y2 = f[i][m].y * f[i][m].y;
             s += x2 + y2;
-            mx = fmaxf(mx, fmaxf(x2, y2));
+            mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
           }
           rs[i] += (double)s;
           rm[i] = fmaxf(rm[i], mx);
         }
       }
       if constexpr (PHYS == PHYS_MHD && RED) {
-        float s = 0.f;
+        T s = 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int m = 0; m < E; ++m) s += (float)(f[i][m].x * f[i + 3][m].x + f[i][m].y * f[i + 3][m].y);
+          for (int m = 0; m < E; ++m) s += f[i][m].x * f[i + 3][m].x + f[i][m].y * f[i + 3][m].y;
         rs[6] += (double)s;
       }
       // symmetric tensor (xx, xy, xz, yy, yz, zz)
@@ -430,13 +431,14 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         row_c2r<T, N, E, SYNC>(A[i], in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
-        float s = 0.f, mx = 0.f;
+        T s = 0;
+        float mx = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           if constexpr (RED) {
-            const float x2 = (float)(A[i][m].x * A[i][m].x), y2 = (float)(A[i][m].y * A[i][m].y);
+            const T x2 = A[i][m].x * A[i][m].x, y2 = A[i][m].y * A[i][m].y;
             s += x2 + y2;
-            mx = fmaxf(mx, fmaxf(x2, y2));
+            mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
           }
           bs[i][m] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
         }
@@ -465,13 +467,14 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
       for (int i = 0; i < 3; ++i) {
         C g[E];
         row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
-        float s = 0.f, mx = 0.f;
+        T s = 0;
+        float mx = 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           if constexpr (RED) {
-            const float x2 = (float)(g[m].x * g[m].x), y2 = (float)(g[m].y * g[m].y);
+            const T x2 = g[m].x * g[m].x, y2 = g[m].y * g[m].y;
             s += x2 + y2;
-            mx = fmaxf(mx, fmaxf(x2, y2));
+            mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
           }
           reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
         }
@@ -508,26 +511,28 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
     C* re = reinterpret_cast<C*>(a.real_io + row * (long long)N);
     C v[E];
     if constexpr (DIR < 0) {   // real -> spectral
-      float s = 0.f, mx = 0.f;
+      T s = 0;
+      float mx = 0.f;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
         v[m] = re[t + Tm * m];
-        const float x2 = (float)(v[m].x * v[m].x), y2 = (float)(v[m].y * v[m].y);
+        const T x2 = v[m].x * v[m].x, y2 = v[m].y * v[m].y;
         s += x2 + y2;
-        mx = fmaxf(mx, fmaxf(x2, y2));
+        mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
       }
       rs[0] += (double)s;
       rm[0] = fmaxf(rm[0], mx);
       row_r2c<T, N, E, SYNC>(v, a.out + row * a.Kxp, a.Kx, t, sm, twt);
     } else {                   // spectral -> real
       row_c2r<T, N, E, SYNC>(v, a.in + row * a.Kxp, a.Kx, a.scale, t, sm, twt);
-      float s = 0.f, mx = 0.f;
+      T s = 0;
+      float mx = 0.f;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
         re[t + Tm * m] = v[m];
-        const float x2 = (float)(v[m].x * v[m].x), y2 = (float)(v[m].y * v[m].y);
+        const T x2 = v[m].x * v[m].x, y2 = v[m].y * v[m].y;
         s += x2 + y2;
-        mx = fmaxf(mx, fmaxf(x2, y2));
+        mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
       }
       rs[0] += (double)s;
       rm[0] = fmaxf(rm[0], mx);
