@@ -80,6 +80,12 @@ int mhdf_get_real(mhdf_handle* h, int field, int which, void* host_real);
 int mhdf_set_spectral(mhdf_handle* h, int field, const void* host_spec);
 int mhdf_get_spectral(mhdf_handle* h, int field, int which, void* host_spec);
 
+/* Constant forcing: the reference's `calcF!` hook (pgen.jl:231-234) for a time-independent forcing given in real space,
+ * e.g. N97ForceDriving! (pgen/TaylorGreenDynamo.jl:12-34): N[:, :, :, field] += rfft(F) on every RHS evaluation.
+ * host_real = NULL removes the forcing of that field.  Like the reference, it acts on the MHD path only: HDcalcN! adds
+ * the forcing BEFORE the advection zeroes N (pgen.jl:176-178, HDSolver.jl:55) and EMHDcalcN! never calls it. */
+int mhdf_set_forcing(mhdf_handle* h, int field, const void* host_real);
+
 /* stepforward! (timestepper/timestepper.jl:4-6): nsteps steps of clock.dt. */
 int mhdf_step(mhdf_handle* h, int nsteps);
 /* eqn.calcN!(N, sol, t, clock, vars, params, grid) (pgen.jl:153-181) on the current sol:

@@ -5,9 +5,10 @@ The compute lives in libmhdflows_b200.so (hand-written CUDA, C ABI in include/mh
 is the thin host mirror of the Julia API.  No CPU fallback exists.
 """
 from ._lib import EMHD, F32, F64, FRESH, HD, LSRK54, MHD, RK4, STALE, MHDFlowsError  # noqa: F401
-from .problem import (CPU, GPU, Diagnostic, DivFreeSpectraMap, ProbDiagnostic, Problem, SetUpProblemIC,  # noqa: F401
-                      TimeIntegrator, getCFL, increment, nothingfunction, spectralline, stepforward)
+from .problem import (CPU, GPU, Diagnostic, DivFreeSpectraMap, GetN97vars_And_function, N97ForceDriving,  # noqa: F401
+                      ProbDiagnostic, Problem, SetUpN97, SetUpProblemIC, TimeIntegrator, getCFL, increment,
+                      nothingfunction, spectralline, stepforward)
 
 __all__ = ["Problem", "SetUpProblemIC", "stepforward", "TimeIntegrator", "getCFL", "ProbDiagnostic", "Diagnostic",
-           "increment", "DivFreeSpectraMap", "spectralline", "CPU", "GPU", "nothingfunction", "MHDFlowsError",
+           "increment", "DivFreeSpectraMap", "spectralline", "N97ForceDriving", "GetN97vars_And_function", "SetUpN97", "CPU", "GPU", "nothingfunction", "MHDFlowsError",
            "FRESH", "STALE"]

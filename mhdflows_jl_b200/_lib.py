@@ -20,7 +20,7 @@ SYMBOLS = [
     "mhdf_set_spectral", "mhdf_get_spectral", "mhdf_step", "mhdf_calcN", "mhdf_set_dt", "mhdf_set_clock",
     "mhdf_get_clock", "mhdf_cfl_dt", "mhdf_energy", "mhdf_helicity", "mhdf_spectrum", "mhdf_stale_stats",
     "mhdf_step_timed", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
-    "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import",
+    "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
 ]
 
 
@@ -78,8 +78,11 @@ def lib():
         "mhdf_ipc_blob_size": (i, [vp]),
         "mhdf_ipc_export": (i, [vp, vp]),
         "mhdf_ipc_import": (i, [vp, vp]),
+        "mhdf_set_forcing": (i, [vp, i, vp]),
     }
     for name, (res, args) in sig.items():
+        if not hasattr(L, name) and os.environ.get("MHDF_LIB"):
+            continue                     # A/B against an older tuning build
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args

@@ -99,6 +99,7 @@ struct mhdf_handle {
   virtual void profile_get(double* ms, long long* cnt, int n) = 0;
   virtual long long launch_count() const = 0;
   virtual void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const = 0;
+  virtual void set_forcing(int field, const void* p) = 0;
   virtual void ipc_export(void* blob) = 0;
   virtual void ipc_import(const void* blobs) = 0;
 };
@@ -148,6 +149,8 @@ struct Solver : mhdf_handle {
   C *P = nullptr, *Q = nullptr, *R = nullptr, *D = nullptr;
   size_t szP = 0, szQ = 0, szR = 0, szD = 0;
   T* bst = nullptr;   // EMHD stale real b [3][nz][ny][nx]
+  C* force = nullptr; // constant spectral forcing [F][compact] (calcF! hook)
+  unsigned fmask = 0;
   C *twx = nullptr, *twy = nullptr, *twz = nullptr;
   T *kxv = nullptr, *kyv = nullptr, *kzv = nullptr;
   XRed* red_d = nullptr;
@@ -286,7 +289,7 @@ struct Solver : mhdf_handle {
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
-    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst);
+    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
     cudaFree(plane_loc); cudaFree(plane_all);
@@ -722,6 +725,7 @@ struct Solver : mhdf_handle {
     sa.g = geom();
     sa.Sin = Sin;
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
+    sa.force = fmask ? force : nullptr; sa.fmask = fmask;
     if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     to_xlayout(zin, nin);
     XArgs<T> xa = xargs();
@@ -863,28 +867,40 @@ struct Solver : mhdf_handle {
   void check_field(int f) const {
     if (f < 0 || f >= F) throw Err{MHDF_ERR_INVALID, "field index out of range"};
   }
-  void set_real(int field, const void* p) override {
-    check_field(field);
-    CK(cudaSetDevice(cfg.device));
+  // host real field (this rank's z slab) -> compact spectral field at dst; leaves the sum / max of f^2 in red_h
+  void real_to_compact(const void* p, C* dst, int emhd_slot) {
     T* re = reinterpret_cast<T*>(R);
-    const size_t n = (size_t)nx * ny * nzl;   // this rank's z slab (the whole field on one GPU)
+    const size_t n = (size_t)nx * ny * nzl;
     CK(cudaMemcpyAsync(re, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (phys == MHDF_EMHD)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
-      CK(cudaMemcpyAsync(bst + (size_t)field * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (emhd_slot >= 0)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
+      CK(cudaMemcpyAsync(bst + (size_t)emhd_slot * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     XArgs<T> xa = xargs();
     xa.real_io = re; xa.out = Q; xa.in = nullptr;
     CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     xa.red = red_d;
     launch_xplain<-1>(xa);
     finish_red();
-    from_xlayout(Q, R, reg[iY] + field * cf, 1);
+    from_xlayout(Q, R, dst, 1);
     sync_all();
+  }
+  void set_real(int field, const void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    real_to_compact(p, reg[iY] + field * cf, phys == MHDF_EMHD ? field : -1);
     // vars.* statistics of the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88)
     const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
     st_sum[slot] = red_h->sumsq[0];
     float f;
     std::memcpy(&f, &red_h->maxsq[0], 4);
     st_max[slot] = (double)f;
+  }
+  void set_forcing(int field, const void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    if (p == nullptr) { fmask &= ~(1u << field); return; }
+    if (!force) force = dalloc<C>((size_t)F * cf);
+    real_to_compact(p, force + field * cf, -1);
+    fmask |= 1u << field;
   }
   const C* source(int which) const {
     if (which == MHDF_STALE && iStale >= 0) return reg[iStale];
@@ -1129,6 +1145,7 @@ int mhdf_stale_stats(const mhdf_handle* h, double* mx, double* sm) {
 int mhdf_step_timed(mhdf_handle* h, int n, double* ms) { return guard(h, [&] { if (n < 0 || !ms) throw Err{MHDF_ERR_INVALID, "bad argument"}; h->step_timed(n, ms); }); }
 int mhdf_profile(mhdf_handle* h, int en) { return guard(h, [&] { h->profile(en); }); }
 int mhdf_profile_get(mhdf_handle* h, double* ms, long long* cnt, int n) { return guard(h, [&] { h->profile_get(ms, cnt, n); }); }
+int mhdf_set_forcing(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { h->set_forcing(f, p); }); }
 int mhdf_ipc_blob_size(const mhdf_handle*) { return (int)sizeof(IpcBlob); }
 int mhdf_ipc_export(mhdf_handle* h, void* blob) { return guard(h, [&] { if (!blob) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_export(blob); }); }
 int mhdf_ipc_import(mhdf_handle* h, const void* blobs) { return guard(h, [&] { if (!blobs) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_import(blobs); }); }

@@ -33,6 +33,31 @@ def nothingfunction(*args, **kw):  # pgen.jl:7
     return None
 
 
+def N97ForceDriving(*args, **kw):
+    """N97ForceDriving! (pgen/TaylorGreenDynamo.jl:12-16): pass as `calcF` to Problem, then call SetUpN97(prob).
+    The forcing itself is applied inside the CUDA library (mhdf_set_forcing); this object is only the selector."""
+    raise RuntimeError("N97ForceDriving is applied by the library; it is not called from the host")
+
+
+def GetN97vars_And_function(dev=None, nx=None, ny=None, nz=None, T=np.float32):
+    """GetN97vars_And_function(dev, nx, ny, nz; T) (pgen/TaylorGreenDynamo.jl:36-40) -> (usr_vars, calcF)."""
+    return {}, N97ForceDriving
+
+
+def SetUpN97(prob, F0=1, kf=2):
+    """SetUpN97!(prob; F0, kf) (pgen/TaylorGreenDynamo.jl:18-34): Taylor-Green forcing of Nore et al. (1997),
+    f = F0 (sin kf x cos kf y cos kf z, -cos kf x sin kf y cos kf z, 0), added to N[ux], N[uy] on every RHS."""
+    if prob.params.calcF is not N97ForceDriving:
+        raise ValueError("construct the problem with calcF=N97ForceDriving (GetN97vars_And_function)")
+    g = prob.grid
+    z0 = prob.rank * prob._real_shape[0] if prob.nranks > 1 else 0
+    X = g.x.astype(np.float64).reshape(1, 1, -1)
+    Y = g.y.astype(np.float64).reshape(1, -1, 1)
+    Z = g.z.astype(np.float64)[z0:z0 + prob._real_shape[0]].reshape(-1, 1, 1)
+    prob.set_forcing("ux", F0 * np.sin(kf * X) * np.cos(kf * Y) * np.cos(kf * Z))
+    prob.set_forcing("uy", -F0 * np.cos(kf * X) * np.sin(kf * Y) * np.cos(kf * Z))
+
+
 class _Clock:
     """FourierFlows.Clock{T}(dt, t, step) (Problems.jl:120) backed by the library's clock."""
 
@@ -164,8 +189,11 @@ class Problem:
             raise ValueError("Shear haven't fully implemented yet!")        # pgen.jl:103-105
         if Compressibility or VP_method or Dye_Module:
             raise NotImplementedError("Compressibility / VP_method / Dye_Module are outside the B200 hot path (SURVEY 8)")
-        if calcF is not nothingfunction and calcF is not None:
-            raise NotImplementedError("forcing callbacks are not supported on this path yet (SURVEY 8b)")
+        if calcF is None:
+            calcF = nothingfunction
+        if calcF is not nothingfunction and calcF is not N97ForceDriving:
+            raise NotImplementedError("arbitrary forcing callbacks cannot run on the device; constant forcings go through "
+                                      "set_forcing / N97ForceDriving (SURVEY 8b, 8f)")
         if EMHD and not B_field:
             raise ValueError("EMHD requires B_field=true (datastructure.jl:78-88)")
         if stepper == "HM89":
@@ -253,6 +281,16 @@ class Problem:
         if a.shape != self._real_shape:
             raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
         L.check(self._h, L.lib().mhdf_set_real(self._h, self._field_id(f), a.ctypes.data))
+
+    def set_forcing(self, f, arr):
+        """Constant real-space forcing of field `f` (the calcF! hook for time-independent forcings); None removes it."""
+        if arr is None:
+            L.check(self._h, L.lib().mhdf_set_forcing(self._h, self._field_id(f), None))
+            return
+        a = np.ascontiguousarray(arr, dtype=self.T)
+        if a.shape != self._real_shape:
+            raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
+        L.check(self._h, L.lib().mhdf_set_forcing(self._h, self._field_id(f), a.ctypes.data))
 
     def get_real(self, f, which=L.FRESH, out=None):
         """Real-space field (c2r on demand).  `out`: optional preallocated (e.g. pinned) array to receive it."""

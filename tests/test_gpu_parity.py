@@ -245,3 +245,49 @@ def test_large_grid_properties_256(M, O):
         div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
         assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < 1e-5
     gp.close()
+
+
+def test_n97_taylor_green_forcing(M, O):
+    """The calcF! hook with the reference's N97 Taylor-Green forcing (pgen/TaylorGreenDynamo.jl): MHD is forced,
+    HD forcing is silently lost like in the reference (pgen.jl:176-178 + HDSolver.jl:55)."""
+    F0, kf = 0.5, 2
+    for B_field in (True, False):
+        kw = dict(nx=32, T=np.float32, nu=2e-2, dt=4e-3)
+        if B_field:
+            kw.update(eta=3e-2, B_field=True)
+        g0 = O.Grid(32, T=np.float32)
+        X, Y, Z = (g0.x.astype(np.float64).reshape(1, 1, -1), g0.y.astype(np.float64).reshape(1, -1, 1),
+                   g0.z.astype(np.float64).reshape(-1, 1, 1))
+        fxh = g0.rfft((F0 * np.sin(kf * X) * np.cos(kf * Y) * np.cos(kf * Z)).astype(np.float32))
+        fyh = g0.rfft((-F0 * np.cos(kf * X) * np.sin(kf * Y) * np.cos(kf * Z)).astype(np.float32))
+
+        def calcF(N, sol, t, clock, vars, params, grid):
+            N[params.ux_ind] += fxh
+            N[params.uy_ind] += fyh
+
+        op = O.Problem(calcF=calcF, **kw)
+        uvars, fn = M.GetN97vars_And_function(M.GPU(), 32, 32, 32)
+        gp = M.Problem(M.GPU(), calcF=fn, usr_vars=uvars, **kw)
+        u, b = O.random_phase_ic(op.grid, 11), O.random_phase_ic(op.grid, 12)
+        if B_field:
+            O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+            M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+        else:
+            O.SetUpProblemIC(op, *u)
+            M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2])
+        M.SetUpN97(gp, F0=F0, kf=kf)
+        unforced = None
+        if B_field:
+            q = O.Problem(**kw)
+            O.SetUpProblemIC(q, *u, bx=b[0], by=b[1], bz=b[2])
+            for _ in range(10):
+                O.stepforward(q)
+            unforced = q.grid.dealias(q.sol.copy())
+        for _ in range(10):
+            O.stepforward(op)
+        M.stepforward(gp, 10)
+        ref = op.grid.dealias(op.sol.copy())
+        assert O.rel_l2(gp.sol, ref) < F32_TOL
+        if B_field:
+            assert O.rel_l2(ref, unforced) > 1e-4      # the forcing really acted
+        gp.close()
