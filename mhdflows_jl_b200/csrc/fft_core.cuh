@@ -165,17 +165,26 @@ struct SyncWarp  { static __device__ __forceinline__ void sync() { __syncwarp();
 // of the same buffer after passing the barrier of the exchange in between, by which time every
 // thread has finished reading it.  The caller must ensure sm0 is free on entry (one barrier since
 // its last read).  Returns with data in registers in natural order n = t + Tn*m.
-template <typename C, int N, int E, int DIR, int TWS, int NS, int PAR, typename SYNC, typename IDX, typename TW, int SLOT0 = 0>
-__device__ __forceinline__ void fft_run(C (&v)[E], int t, C* __restrict__ sm0, C* __restrict__ sm1, TW tw, IDX idx) {
+// idx maps element -> slot for the first exchange, idx2 for the later ones (each exchange writes and reads one buffer
+// with one map, so the maps may differ: the scatter patterns of the first and the later steps need different padding
+// to be bank-conflict free).
+template <typename C, int N, int E, int DIR, int TWS, int NS, int PAR, typename SYNC, typename IDX, typename IDX2, typename TW, int SLOT0 = 0>
+__device__ __forceinline__ void fft_run(C (&v)[E], int t, C* __restrict__ sm0, C* __restrict__ sm1, TW tw, IDX idx, IDX2 idx2) {
   constexpr int R = imin(E, N / NS);
   fft_step<C, N, E, R, NS, DIR, TWS, SLOT0>(v, t, tw);
   if constexpr (NS * R < N) {
     C* sm = PAR ? sm1 : sm0;
-    fft_scatter<C, N, E, R, NS>(v, t, sm, idx);
-    SYNC::sync();
-    fft_gather<C, N, E>(v, t, sm, idx);
+    if constexpr (NS == 1) {
+      fft_scatter<C, N, E, R, NS>(v, t, sm, idx);
+      SYNC::sync();
+      fft_gather<C, N, E>(v, t, sm, idx);
+    } else {
+      fft_scatter<C, N, E, R, NS>(v, t, sm, idx2);
+      SYNC::sync();
+      fft_gather<C, N, E>(v, t, sm, idx2);
+    }
     constexpr int NEXT = SLOT0 + (NS > 1 ? (E / R) * (R - 1) : 0);
-    fft_run<C, N, E, DIR, TWS, NS * R, PAR ^ 1, SYNC, IDX, TW, NEXT>(v, t, sm0, sm1, tw, idx);
+    fft_run<C, N, E, DIR, TWS, NS * R, PAR ^ 1, SYNC, IDX, IDX2, TW, NEXT>(v, t, sm0, sm1, tw, idx, idx2);
   }
 }
 

@@ -156,8 +156,14 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
 // One pad slot per 16 elements: 16 consecutive elements (gathers, natural-order accesses, mirrored reads) and the
 // first radix-8/16 scatter are bank-conflict free; offsets r*NS still fold into immediate operands.
 template <int M, int R1> struct RowIdx {
-  static constexpr int SIZE = M + M / 16 + 1;
+  static constexpr int SIZE = M + M / 8 + 1;   // large enough for both maps
   __device__ __forceinline__ int operator()(int n) const { return n + (n >> 4); }
+};
+// Map of the second and later exchanges: 8 pad slots per 64 elements.  Their scatter writes 64*(t>>3) + (t&7) + 8r'
+// (radix 8 after a radix-8 step): threads t and t+8 land in different bank halves, 16 consecutive elements stay
+// conflict free, and offsets r*NS still fold into immediates.
+template <int M> struct RowIdx2 {
+  __device__ __forceinline__ int operator()(int n) const { return n + ((n >> 6) << 3); }
 };
 
 // Shared-memory context of one row: two alternating exchange buffers.
@@ -203,7 +209,7 @@ __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__
     v[m] = mk<C>((s.x - d.y) * scale, (s.y + d.x) * scale);
   }
   constexpr int NEX = fft_num_steps(M, E) - 1;
-  fft_run<C, M, E, +1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>());
+  fft_run<C, M, E, +1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>(), RowIdx2<M>());
   if (NEX & 1) sm.swap();
 }
 
@@ -214,7 +220,7 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   constexpr int NEX = fft_num_steps(M, E) - 1;
-  fft_run<C, M, E, -1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>());
+  fft_run<C, M, E, -1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>(), RowIdx2<M>());
   if (NEX & 1) sm.swap();
   RowIdx<M, R1> idx;
 #pragma unroll
