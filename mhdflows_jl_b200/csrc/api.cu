@@ -401,34 +401,7 @@ struct Solver : mhdf_handle {
     long long g = (long long)nsm * 16;
     return (int)(sets < g ? sets : g);
   }
-  // tuning experiment (MHDF_X_VARIANT = "E,MINB"): alternative register budgets / elements per thread of the fused x
-  // kernel, Float32 MHD without reductions at 256 and 1024 only
-  template <int N, int E, int MINB> bool launch_xvariant(XArgs<T>& a) {
-    if constexpr (sizeof(T) == 4 && (N == 256 || N == 1024)) {
-      constexpr int Tm = N / 2 / E, RB = (XNT / Tm > 0) ? XNT / Tm : 1, M = N / 2, R1 = imin(E, M);
-      const size_t smem = (size_t)2 * RB * RowIdx<M, R1>::SIZE * sizeof(C);
-      const int grid = x_grid(a.rows, RB);
-      k_xfused<T, N, E, RB, PHYS_MHD, false, MINB><<<grid, Tm * RB, smem, st>>>(a);
-      ++launches;
-      return true;
-    }
-    return false;
-  }
-  template <int N> bool try_xvariant(XArgs<T>& a) {
-    static const char* env = getenv("MHDF_X_VARIANT");
-    if (!env || phys != MHDF_MHD || a.red != nullptr) return false;
-    int e = 8, mb = 1;
-    sscanf(env, "%d,%d", &e, &mb);
-    if (e == 8 && mb == 5) return launch_xvariant<N, 8, 5>(a);
-    if (e == 8 && mb == 6) return launch_xvariant<N, 8, 6>(a);
-    if (e == 8 && mb == 8) return launch_xvariant<N, 8, 8>(a);
-    if (e == 4 && mb == 1) return launch_xvariant<N, 4, 1>(a);
-    if (e == 4 && mb == 6) return launch_xvariant<N, 4, 6>(a);
-    if (e == 4 && mb == 8) return launch_xvariant<N, 4, 8>(a);
-    return false;
-  }
   template <int N> void launch_xfused_n(XArgs<T>& a) {
-    if (try_xvariant<N>(a)) return;
     constexpr int E = xE(N), RB = xRB(N);
     const int grid = x_grid(a.rows, RB);
     const int threads = (N / 2 / E) * RB;

@@ -188,21 +188,13 @@ __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__
                                         RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
-#ifndef MHDF_XOPT_OFF
   asm volatile("" : "+l"(X));
-#endif
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int k = t + Tm * m;
     const int k2 = M - k;
-#ifndef MHDF_XOPT_OFF
     C x1 = ldg_pred(X + (unsigned)k, k < Kx);
     C x2 = cconj(ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx));
-#else
-    C x1 = mk<C>(0, 0), x2 = mk<C>(0, 0);
-    if (k < Kx) x1 = X[k];
-    if (k2 < Kx) x2 = cconj(X[k2]);
-#endif
     if (k == 0) x1.y = 0;
     const C w = cconj(XTwSrc<T, N, E>::wn(tw, m, k));       // exp(+2 pi i k / N)
     const C s = cadd(x1, x2), d = cmul(csub(x1, x2), w);    // Z = s + i d
@@ -222,38 +214,43 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
   constexpr int NEX = fft_num_steps(M, E) - 1;
   fft_run<C, M, E, -1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>(), RowIdx2<M>());
   if (NEX & 1) sm.swap();
-  RowIdx<M, R1> idx;
+  if constexpr (Tm <= 32) {
+    // Z[M-k] sits in the registers of lane (Tm - t) of the same row (slot E-1-m), or in this thread's own slot E-m when
+    // t == 0: two warp shuffles per element replace the shared-memory round trip (and its barrier)
+    asm volatile("" : "+l"(Xout));
+    const int lane = threadIdx.x & 31;
+    const int src = (lane & ~(Tm - 1)) | ((Tm - t) & (Tm - 1));
 #pragma unroll
-  for (int m = 0; m < E; ++m) sm.a[idx(t + Tm * m)] = v[m];
-  SYNC::sync();
-#ifndef MHDF_XOPT_OFF
-  asm volatile("" : "+l"(Xout));
+    for (int m = 0; m < E; ++m) {
+      const int k = t + Tm * m;
+      const C z1 = v[m];
+      C z2 = mk<C>(__shfl_sync(0xffffffffu, v[E - 1 - m].x, src), __shfl_sync(0xffffffffu, v[E - 1 - m].y, src));
+      if (t == 0) z2 = v[(E - m) % E];
+      z2 = cconj(z2);
+      const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
+      const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
+      const C w = XTwSrc<T, N, E>::wn(tw, m, k);                               // exp(-2 pi i k / N)
+      stg_pred(Xout + (unsigned)k, cadd(ev, cmul(od, w)), k < Kx);
+    }
+  } else {
+    RowIdx<M, R1> idx;
 #pragma unroll
-  for (int m = 0; m < E; ++m) {
-    const int k = t + Tm * m;
-    // columns k >= Kx are never stored; their arithmetic is harmless and keeps the code branch-free
-    const C z1 = v[m];
-    const C z2 = cconj(sm.a[idx((M - k) & (M - 1))]);
-    const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
-    const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
-    const C w = XTwSrc<T, N, E>::wn(tw, m, k);                               // exp(-2 pi i k / N)
-    stg_pred(Xout + (unsigned)k, cadd(ev, cmul(od, w)), k < Kx);
-  }
-#else
+    for (int m = 0; m < E; ++m) sm.a[idx(t + Tm * m)] = v[m];
+    SYNC::sync();
+    asm volatile("" : "+l"(Xout));
 #pragma unroll
-  for (int m = 0; m < E; ++m) {
-    const int k = t + Tm * m;
-    if (k < Kx) {
-      const C z1 = sm.a[idx(k)];
+    for (int m = 0; m < E; ++m) {
+      const int k = t + Tm * m;
+      // columns k >= Kx are never stored; their arithmetic is harmless and keeps the code branch-free
+      const C z1 = v[m];
       const C z2 = cconj(sm.a[idx((M - k) & (M - 1))]);
       const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
       const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
-      const C w = XTwSrc<T, N, E>::wn(tw, m, k);                              // exp(-2 pi i k / N)
-      Xout[k] = cadd(ev, cmul(od, w));
+      const C w = XTwSrc<T, N, E>::wn(tw, m, k);                               // exp(-2 pi i k / N)
+      stg_pred(Xout + (unsigned)k, cadd(ev, cmul(od, w)), k < Kx);
     }
+    sm.swap();
   }
-#endif
-  sm.swap();
 }
 
 // rows owned by <= 32 threads: warp barrier; otherwise the block must hold exactly one row
@@ -335,8 +332,10 @@ enum { PHYS_HD = 0, PHYS_MHD = 1, PHYS_EMHD = 2 };
 //         G_i = sum_j A_j d_j B_i - b^stale_j d_j A_i   (reference: MHDSolver.jl:241-266, 323-325)
 // RED: accumulate the per-field sum f^2 / max f^2 / sum u.b reductions (only the launch whose real-space fields
 // the reference's stale `vars` correspond to needs them; the other stages skip the work and the registers)
-template <typename T, int N, int E, int RB, int PHYS, bool RED, int MINB = 1>
-__global__ void __launch_bounds__((N / 2 / E) * RB, MINB) k_xfused(XArgs<T> a) {
+// Register budget: measured on B200 (256^3 / 1024-wide rows), forcing more resident blocks (5, 6, 8 per SM) or 4
+// elements per thread was 2-23 % slower than letting the kernel keep the whole row set in 255 registers.
+template <typename T, int N, int E, int RB, int PHYS, bool RED>
+__global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   // a row owned by at most one warp synchronises with __syncwarp only: rows are fully decoupled
