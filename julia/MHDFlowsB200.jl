@@ -8,7 +8,8 @@
 module MHDFlowsB200
 
 export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDiagnostic, Diagnostic,
-       increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum
+       increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum,
+       N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!
 
 const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
 
@@ -83,7 +84,8 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   câ‚› == 0.0 && Compressibility && error("You should define câ‚›")
   Shear && error("Shear haven't fully implemented yet!")
   (Compressibility || VP_method || Dye_Module) && error("outside the B200 hot path")
-  calcF === nothingfunction || error("forcing callbacks are not supported on this path yet")
+  (calcF === nothingfunction || calcF === N97ForceDriving!) ||
+    error("arbitrary forcing callbacks cannot run on the device; constant forcings go through setforcing! / N97ForceDriving!")
   stepper in ("RK4", "LSRK54") || error("stepper must be \"RK4\" or \"LSRK54\" on the B200 path")
   physics = EMHD ? MHDF_EMHD : (B_field ? MHDF_MHD : MHDF_HD)
   cfg = MhdfConfig(nx, ny, nz, Lx, Ly, Lz, Î½, Î·, nÎ½, dt, physics, stepper == "RK4" ? 0 : 1,
@@ -124,6 +126,24 @@ function sol(prob, i::Int)
   A = Array{Complex{T},3}(undef, g.nx Ã· 2 + 1, g.ny, g.nz)
   check(prob.h, ccall((:mhdf_get_spectral, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), prob.h, i - 1, 0, A))
   A
+end
+
+"constant real-space forcing of one field: the calcF! hook for time-independent forcings (pgen.jl:231-234)"
+function setforcing!(prob, s::Symbol, F)
+  T = typeof(prob).parameters[1]
+  check(prob.h, ccall((:mhdf_set_forcing, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, fieldid(prob, s), Array{T,3}(F)))
+end
+"N97 Taylor-Green forcing (pgen/TaylorGreenDynamo.jl:12-40): pass N97ForceDriving! as calcF, then SetUpN97!(prob; F0, kf)"
+N97ForceDriving!(args...) = error("N97ForceDriving! is applied inside the library")
+GetN97vars_And_function(dev, nx, ny, nz; T = Float32) = ([], N97ForceDriving!)
+function SetUpN97!(prob; F0 = 1, kf = 2)
+  g = prob.grid
+  x = reshape([-g.Lx/2 + (i-1)*g.dx for i in 1:g.nx], (g.nx, 1, 1))
+  y = reshape([-g.Ly/2 + (i-1)*g.dy for i in 1:g.ny], (1, g.ny, 1))
+  z = reshape([-g.Lz/2 + (i-1)*g.dz for i in 1:g.nz], (1, 1, g.nz))
+  setforcing!(prob, :ux, @. F0 *  sin(kf*x) * cos(kf*y) * cos(kf*z))
+  setforcing!(prob, :uy, @. F0 * -cos(kf*x) * sin(kf*y) * cos(kf*z))
+  nothing
 end
 
 "stepforward!(prob) == stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)"
