@@ -265,7 +265,7 @@ struct Solver : mhdf_handle {
   // Exchange buffers are [peer][field][z'][ky'][kx]: the piece for / from one peer is contiguous, blk(n) elements for an
   // n-field batch.
   size_t blk(int nf) const { return (size_t)nf * nzl * Kyl * Kxp; }
-  void build_tables() {
+  void build_tables() {   // slab runs: mirror-plane buffers, exchange-size check
     plane_loc = dalloc<C>((size_t)F * Kz * Kyl);
     plane_all = dalloc<C>((size_t)P_ * F * Kz * Kyl);
     check_blk(CHUNK > 0 ? CHUNK : (nin > nout ? nin : nout));
@@ -489,8 +489,7 @@ struct Solver : mhdf_handle {
     a.in = in; a.out = out; a.tw = twz;
     a.in_row = a.out_row = Kyl * Kxp;
     a.in_outer = a.out_outer = 0;
-    a.in_field = in_field; a.out_field = (long long)nzl * Kyl * Kxp * (P_ > 1 ? 1 : P_);
-    if (P_ == 1) a.out_field = (long long)nz * Kyl * Kxp;
+    a.in_field = in_field; a.out_field = (long long)nzl * Kyl * Kxp;   // nzl == nz on one GPU; in-block field stride otherwise
     a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
     a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
     if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
@@ -532,7 +531,7 @@ struct Solver : mhdf_handle {
     a.in = in; a.out = out; a.tw = twz;
     a.in_row = a.out_row = Kyl * Kxp;
     a.in_outer = a.out_outer = 0;
-    a.in_field = (P_ == 1) ? (long long)nz * Kyl * Kxp : (long long)nzl * Kyl * Kxp;
+    a.in_field = (long long)nzl * Kyl * Kxp;
     a.out_field = out_field;
     a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
     a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
