@@ -183,6 +183,14 @@ struct Solver : mhdf_handle {
   }
 
   explicit Solver(const mhdf_config& c) : cfg(c) {
+    try {
+      init(c);
+    } catch (...) {   // e.g. cudaMalloc failed half-way: release what exists before reporting
+      release();
+      throw;
+    }
+  }
+  void init(const mhdf_config& c) {
     nx = c.nx; ny = c.ny; nz = c.nz;
     nkr = nx / 2 + 1;
     int iL, iR;
@@ -273,7 +281,8 @@ struct Solver : mhdf_handle {
   void check_blk(int nf) const {
     if ((long long)P_ * (long long)blk(nf) >= (1LL << 31)) throw Err{MHDF_ERR_INVALID, "slab exchange buffer exceeds 2^31 elements per batch"};
   }
-  ~Solver() override {
+  ~Solver() override { release(); }
+  void release() {
     cudaSetDevice(cfg.device);
     if (st) cudaStreamSynchronize(st);
     if (sc) cudaStreamSynchronize(sc);
@@ -298,6 +307,12 @@ struct Solver : mhdf_handle {
     if (red_h) cudaFreeHost(red_h);
     if (diag_h) cudaFreeHost(diag_h);
     if (st) cudaStreamDestroy(st);
+    st = sc = nullptr; comm = nullptr; ipc_on = false; red_h = nullptr; diag_h = nullptr;
+    for (int i = 0; i < 4; ++i) reg[i] = nullptr;
+    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
+    red_d = nullptr; diag_d = nullptr; spec_d = nullptr; plane_loc = plane_all = nullptr; bar_d = nullptr;
+    dep_ev.clear(); evs.clear(); ev_free.clear();
+    for (int i = 0; i < NCS_MAX; ++i) cs[i] = nullptr;
   }
 
   C* make_tw(int n) {
