@@ -37,6 +37,10 @@ WORKLOADS = {
 # algorithmic bytes per step in units of S = 8 (N/2+1) N^2 bytes
 ALG_S_PER_STEP = {("mhd", "RK4"): 384, ("mhd", "LSRK54"): 450, ("hd", "RK4"): 216, ("hd", "LSRK54"): 5 * 48,
                   ("emhd", "RK4"): 424, ("emhd", "LSRK54"): 5 * 100}
+# the reference's only published number for this metric and config -- MHD Taylor-Green 256^3
+# Float32 RK4, 0.271 s per iteration on an RTX 3080 (README.md:78) = 6.19e7 grid-points*steps/s.  Other hardware; quoted
+# because it is the only published figure.  No published number exists for any other workload or for N > 1.
+PUBLISHED_PTS_STEPS_PER_S = {"mhd256": 256 ** 3 / 0.271}
 # x-pass share of the model: (n_in + n_out) S per launch (one launch per stage)
 XPASS_S_PER_LAUNCH = {"mhd": 15, "hd": 9, "emhd": 19}
 
@@ -364,9 +368,11 @@ def main():
         return
     line = {
         "metric": "grid-points*steps/s", "value": value, "unit": "pts*steps/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": (value / PUBLISHED_PTS_STEPS_PER_S[wl]) if (world == 1 and wl in PUBLISHED_PTS_STEPS_PER_S) else None,
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl, "kind": kind, "n": n, "grid": list(dims), "stepper": stepper, "nu": nu, "eta": eta, "dt": dt,
+                   "baseline": "MHDFlows.jl README.md:78: 0.271 s/iteration, MHD TG 256^3 Float32 RK4 on an RTX 3080 (CUDA.jl)" if wl in PUBLISHED_PTS_STEPS_PER_S else None,
                    "ic": "analytic Taylor-Green u and b", "l2": "per-step working set (FFT work buffers) is far larger than the 126 MB L2; no flush needed",
                    "multi_gpu": ("slab decomposition (z slabs / ky slabs), transposes = copy-engine pushes into peer HBM over NVLink, "
                                  + ("fixed grid" if strong else f"{n}^3 points per GPU")) if world > 1 else "single"},

@@ -1,0 +1,37 @@
+"""bench.py host-side helpers (no GPU): weak-scaling grids, analytic Taylor-Green slabs, workload table."""
+import math
+
+import numpy as np
+
+import bench
+
+
+def test_weak_scaling_grids_keep_points_per_gpu():
+    for w in (1, 2, 4, 8):
+        nx, ny, nz = bench.grid_for(256, w)
+        assert nx * ny * nz == w * 256 ** 3 and nz % w == 0
+    assert bench.grid_for(256, 8) == (512, 512, 512)
+
+
+def test_taylor_green_slabs_tile_the_full_field_and_are_solenoidal():
+    n, dims = 16, (16, 32, 32)
+    full = bench.tg_fields(n, dims=dims)
+    lo = bench.tg_fields(n, dims=dims, zrange=(0, 16))
+    hi = bench.tg_fields(n, dims=dims, zrange=(16, 32))
+    for f, a, b in zip(full, lo, hi):
+        assert np.array_equal(np.concatenate([a[0], b[0]], axis=0), f[0])
+    # divergence of u and b by centred spectral derivative on the periodic box
+    nx, ny, nz = dims
+    k = [np.fft.fftfreq(m, 1.0 / m) * (2 * math.pi / (2 * math.pi * m / n)) for m in (nx, ny, nz)]
+    for base in (0, 3):
+        fh = [np.fft.fftn(full[base + i][0].astype(np.float64)) for i in range(3)]
+        div = (1j * k[0].reshape(1, 1, -1) * fh[0] + 1j * k[1].reshape(1, -1, 1) * fh[1] + 1j * k[2].reshape(-1, 1, 1) * fh[2])
+        assert np.abs(div).max() < 1e-4 * np.abs(fh[0]).max()
+
+
+def test_workload_table_matches_baseline_configs():
+    assert bench.WORKLOADS["mhd256"][:3] == ("mhd", 256, "RK4")
+    assert bench.WORKLOADS["mhd512_lsrk"][:3] == ("mhd", 512, "LSRK54")
+    assert bench.WORKLOADS["emhd512"][:3] == ("emhd", 512, "RK4")
+    assert bench.ALG_S_PER_STEP[("mhd", "RK4")] == 384 and bench.XPASS_S_PER_LAUNCH["mhd"] == 15
+    assert abs(bench.PUBLISHED_PTS_STEPS_PER_S["mhd256"] - 6.19e7) / 6.19e7 < 1e-2
