@@ -87,6 +87,31 @@ def rhs_emhd(sol, grid: O.Grid, b_stale):
     return grid.dealias(N), b_new, A
 
 
+def rhs_emhd_div(sol, grid: O.Grid, b_stale, bh_stale):
+    """EMHD divergence form (SURVEY A.6 iii): 7 c2r + 12 r2c instead of 24 + 3.
+        N_i = sum_j i k_j F[A_j B_i - b^st_j A_i] + F[A_i div(b^st)]
+    `b_stale` is the stale real-space b (vars.b*), `bh_stale` its spectrum (the previous stage input), needed for
+    div(b^st).  Groundwork for the round-2 CUDA path.  Exact away from the truncation edge; ~1e-10 per step off on
+    broadband fields (unpaired edge modes alias differently) -- see tests/test_fused_model.py."""
+    CT = grid.CT
+    s = grid.dealias(sol.copy())
+    ks = (grid.kr, grid.l, grid.m)
+    Bh = [s[0], s[1], s[2]]
+    Ah = [CT(1j) * (ks[1] * Bh[2] - ks[2] * Bh[1]),
+          CT(1j) * (ks[2] * Bh[0] - ks[0] * Bh[2]),
+          CT(1j) * (ks[0] * Bh[1] - ks[1] * Bh[0])]
+    A = [grid.irfft(a.copy()) for a in Ah]                     # 3 c2r
+    B = [grid.irfft(x.copy()) for x in Bh]                     # 3 c2r (also the next stale b)
+    divb = grid.irfft(CT(1j) * (ks[0] * bh_stale[0] + ks[1] * bh_stale[1] + ks[2] * bh_stale[2]))   # 1 c2r
+    N = np.zeros_like(s)
+    for i in range(3):
+        acc = grid.rfft(A[i] * divb)                           # 3 r2c
+        for j in range(3):
+            acc = acc + CT(1j) * ks[j] * grid.rfft(A[j] * B[i] - b_stale[j] * A[i])   # 9 r2c
+        N[i] = acc
+    return grid.dealias(N), B, A, [x.copy() for x in Bh]
+
+
 class FusedProblem:
     """3-register RK4 / 2N LSRK54 on the masked state, mirroring the CUDA library's stepping."""
 
@@ -98,12 +123,18 @@ class FusedProblem:
         self.sol = p.grid.dealias(p.sol.copy())
         # stale real-space b for EMHD = the (undealiased) IC real field (IC.jl:86-90)
         self.b_stale = [p.vars.bx.copy(), p.vars.by.copy(), p.vars.bz.copy()] if p.flag.e else None
+        self.bh_stale = [self.sol[i].copy() for i in range(3)] if p.flag.e else None   # spectrum of the stale b
+        self.emhd_div_form = False
         self.last_real = None
 
     def rhs(self, s):
         g, pr = self.grid, self.params
         if self.flag.e:
-            N, bnew, A = rhs_emhd(s, g, self.b_stale)
+            if self.emhd_div_form:
+                N, bnew, A, bh = rhs_emhd_div(s, g, self.b_stale, self.bh_stale)
+                self.bh_stale = bh
+            else:
+                N, bnew, A = rhs_emhd(s, g, self.b_stale)
             self.b_stale = bnew
             self.last_real = (A, bnew)
             return N
