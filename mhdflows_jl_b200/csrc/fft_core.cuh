@@ -99,7 +99,6 @@ template <int R, int DIR, typename C> struct Bfly {
 };
 
 constexpr __host__ __device__ int imin(int a, int b) { return a < b ? a : b; }
-constexpr __host__ __device__ int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 
 // Twiddle source.  tw[i] = (cos(2*pi*i/NTW), -sin(2*pi*i/NTW)), NTW = N * TWS (TWS = table stride, 1 or 2): read-only
 // global table indexed by the twiddle exponent (a policy type so other sources can be plugged in; SLOT0 numbers the

@@ -27,7 +27,6 @@ struct Band {
     return (-w <= n - hi0) ? count() + w : -1;
   }
 };
-__host__ __device__ inline Band band_full(int n) { Band b; b.n = n; b.lo = n; b.hi0 = n; return b; }
 
 // ------------------------------------------------------------------------------------------------
 // Strided axis pass (y or z): a block transforms TX adjacent columns of length N.
@@ -812,7 +811,6 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
   const int Ky = g.Kyl, Kz = g.bz.count();
   const long long total = (long long)g.Kxp * Ky * Kz;
   double s[5] = {0, 0, 0, 0, 0};
-  float dummy[1] = {0.f};
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ix = (int)(e % g.Kxp);
     if (ix >= g.Kx) continue;
@@ -850,8 +848,6 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
       }
     }
   }
-  unsigned* nomax = nullptr;
-  // reuse the block reducer (no maxima)
   {
     __shared__ double sh[32][5];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -871,7 +867,6 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
       }
     }
   }
-  (void)nomax; (void)dummy;
 }
 
 // Shell spectrum of one compact field: Pk[round(|k|)] += |f^|^2 over the HALF spectrum, no weights
