@@ -223,7 +223,7 @@ struct Solver : mhdf_handle {
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (P_ > 1) {
       CK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-      dep_ev.resize(64);
+      dep_ev.resize(1024);   // cyclic pool; far more than one RHS evaluation can take between a record and its wait
       for (auto& e : dep_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       std::string why;
       if (!g_nccl.load(why)) throw Err{MHDF_ERR_NCCL, why};
@@ -298,7 +298,7 @@ struct Solver : mhdf_handle {
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
-    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force);
+    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
     cudaFree(plane_loc); cudaFree(plane_all);
@@ -309,7 +309,7 @@ struct Solver : mhdf_handle {
     if (st) cudaStreamDestroy(st);
     st = sc = nullptr; comm = nullptr; ipc_on = false; red_h = nullptr; diag_h = nullptr;
     for (int i = 0; i < 4; ++i) reg[i] = nullptr;
-    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
+    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
     red_d = nullptr; diag_d = nullptr; spec_d = nullptr; plane_loc = plane_all = nullptr; bar_d = nullptr;
     dep_ev.clear(); evs.clear(); ev_free.clear();
     for (int i = 0; i < NCS_MAX; ++i) cs[i] = nullptr;
@@ -391,6 +391,8 @@ struct Solver : mhdf_handle {
     // the blocked side is the z side of the z passes and the ky side of the y passes: output of inverse-z / forward-y,
     // input of inverse-y / forward-z
     if (a.blk_rows == 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 0><<<grid, (N / E) * TX, smem, st>>>(a);
+    else if (a.blk2_rows > 0 && blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 4><<<grid, (N / E) * TX, smem, st>>>(a);
+    else if (a.blk2_rows > 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 3><<<grid, (N / E) * TX, smem, st>>>(a);
     else if (blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 2><<<grid, (N / E) * TX, smem, st>>>(a);
     else k_pass<T, N, E, TX, DIR, (DIR > 0), 1><<<grid, (N / E) * TX, smem, st>>>(a);
     ++launches;
@@ -494,6 +496,8 @@ struct Solver : mhdf_handle {
       CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
   }
 
@@ -508,7 +512,7 @@ struct Solver : mhdf_handle {
     a.in_outer = a.out_outer = 0;
     a.in_field = in_field; a.out_field = (long long)nzl * Kyl * Kxp;   // nzl == nz on one GPU; in-block field stride otherwise
     a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
     if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
     blk_out = true;
     prof_begin(KC_ZINV);
@@ -522,7 +526,7 @@ struct Solver : mhdf_handle {
     a.in_outer = (long long)Kyl * Kxp; a.out_outer = (long long)ny * Kxp;
     a.in_field = (long long)nzl * Kyl * Kxp; a.out_field = (long long)nzl * ny * Kxp;
     a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
     if (P_ > 1) { a.blk_rows = Kyl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + Kyl - 1) / Kyl); }
     blk_out = false;
     prof_begin(KC_YINV);
@@ -536,7 +540,7 @@ struct Solver : mhdf_handle {
     a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
     a.in_field = (long long)nzl * ny * Kxp; a.out_field = (long long)nzl * Kyl * Kxp;
     a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
     if (P_ > 1) { a.blk_rows = Kyl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + Kyl - 1) / Kyl); }
     blk_out = true;
     prof_begin(KC_YFWD);
@@ -551,7 +555,7 @@ struct Solver : mhdf_handle {
     a.in_field = (long long)nzl * Kyl * Kxp;
     a.out_field = out_field;
     a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0;
+    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
     if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
     blk_out = false;
     prof_begin(KC_ZFWD);
@@ -562,8 +566,8 @@ struct Solver : mhdf_handle {
   // copy.  Two transports: (a) after mhdf_ipc_import, copy-engine pushes straight into the peers' receive buffer over
   // NVLink (no SMs, overlaps the axis passes), closed by a tiny all-reduce as the cross-rank barrier; (b) NCCL
   // send/recv.  `recv` must be R or Q (+ offset).
-  void exchange(const C* send, C* recv, int nf, bool first_of_leg = true) {
-    const size_t B = blk(nf);
+  void exchange(const C* send, C* recv, int nf, bool first_of_leg = true, size_t block_elems = 0) {
+    const size_t B = block_elems ? block_elems : blk(nf);
     const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat32 : ncclFloat64;
     prof_begin(KC_EXCH, sc);
     // pushes land in the peers' buffer without the peer posting a receive: before the first push of a leg every rank
@@ -699,8 +703,142 @@ struct Solver : mhdf_handle {
     return a;
   }
 
+  // ---- z-chunk pipelined slab path (opt-in: MHDF_ZCHUNKS = 2, 4, ...) ---------------------------------------------
+  // The local z slab is cut into NZC chunks; exchange pieces are [chunk][peer][field][z''][ky'][kx].  After the inverse z
+  // pass the inverse pushes of all chunks are queued on the communication stream; as soon as chunk c has arrived, its
+  // inverse y pass, fused x pass and forward y pass run and its forward pushes are queued -- so the x pass of one chunk
+  // overlaps the pushes of the others.  Only the first inverse and the last forward exchange stay exposed.
+  // Separate buffers keep pushes from peers (which land in R / Q unannounced) away from live data:
+  //   P inverse send, R inverse receive, Xin x-pass input (later the product spectra), Xout x-pass output,
+  //   P2 forward send, Q forward receive.
+  // NOT YET VERIFIED ON HARDWARE (written after the round's GPU budget was spent); off unless MHDF_ZCHUNKS is set.
+  int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
+  C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
+  bool pipe_ok() const {
+    if (P_ == 1 || zchunks <= 1 || nzl % zchunks != 0) return false;
+    const int zc = nzl / zchunks, rb = 1024 / nx > 1 ? 1024 / nx : 1;
+    if ((long long)(nin > nout ? nin : nout) * nz * Kyl * Kxp >= (1LL << 31)) return false;   // 32-bit row offsets
+    return ((long long)ny * zc) % rb == 0;
+  }
+  void pipe_alloc() {
+    if (Xin) return;
+    const size_t e_zy = (size_t)nzl * ny * Kxp, e_zK = (size_t)nz * Kyl * Kxp;
+    Xin = dalloc<C>((size_t)(nin > nout ? nin : nout) * e_zy);
+    Xout = dalloc<C>((size_t)nout * e_zy);
+    P2 = dalloc<C>((size_t)nout * e_zK);
+  }
+  void set_blk(PassArgs<T>& a, int rows, size_t stride) {
+    a.blk_rows = rows; a.blk_stride = (int)stride; a.blk_magic = (unsigned)((0x100000000ULL + rows - 1) / rows);
+  }
+  void rhs_pipe(const C* Sin, SpecArgs<T> sa, bool want_red) {
+    pipe_alloc();
+    const int NZC = zchunks, zc = nzl / NZC;
+    const size_t Bi = (size_t)nin * zc * Kyl * Kxp, Bo = (size_t)nout * zc * Kyl * Kxp;   // one (chunk, peer) piece
+    const long long fld = (long long)zc * Kyl * Kxp;                                      // field stride inside a piece
+    const C* zin = Sin;
+    if (phys != MHDF_EMHD) gather_mirror(Sin);
+    if (phys == MHDF_EMHD) {
+      prof_begin(KC_DERIVE);
+      k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
+      ++launches;
+      CK(cudaGetLastError());
+      prof_end();
+      zin = D;
+    }
+    sa.g = geom();
+    sa.Sin = Sin;
+    sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
+    sa.force = fmask ? force : nullptr; sa.fmask = fmask;
+    if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+    {   // inverse z pass of every field into the two-level send layout
+      PassArgs<T> a;
+      a.in = zin; a.out = P; a.tw = twz;
+      a.in_row = a.out_row = Kyl * Kxp;
+      a.in_outer = a.out_outer = 0;
+      a.in_field = cf; a.out_field = fld;
+      a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+      set_blk(a, nzl, Bi);
+      a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bi); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
+      blk_out = true;
+      prof_begin(KC_ZINV);
+      launch_pass<+1>(nz, a, 1, nin);
+      prof_end();
+    }
+    order(st, sc);
+    std::vector<cudaEvent_t> inv(NZC), fwd(NZC);
+    for (int c = 0; c < NZC; ++c) {
+      exchange(P + (size_t)c * P_ * Bi, R + (size_t)c * P_ * Bi, nin, c == 0, Bi);
+      inv[c] = dep_ev[dep_next++ % dep_ev.size()];
+      CK(cudaEventRecord(inv[c], sc));
+    }
+    for (int c = 0; c < NZC; ++c) {
+      const size_t zoff = (size_t)c * zc * ny * Kxp;
+      CK(cudaStreamWaitEvent(st, inv[c], 0));
+      {   // inverse y pass of chunk c: received pieces -> x-pass layout
+        PassArgs<T> a;
+        a.in = R + (size_t)c * P_ * Bi; a.out = Xin + zoff; a.tw = twy;
+        a.in_row = a.out_row = Kxp;
+        a.in_outer = (long long)Kyl * Kxp; a.out_outer = (long long)ny * Kxp;
+        a.in_field = fld; a.out_field = (long long)nzl * ny * Kxp;
+        a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
+        set_blk(a, Kyl, Bi);
+        a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
+        blk_out = false;
+        prof_begin(KC_YINV);
+        launch_pass<+1>(ny, a, zc, nin);
+        prof_end();
+      }
+      XArgs<T> xa = xargs();
+      xa.in = Xin + zoff; xa.out = Xout + zoff;
+      xa.real_io = bst ? bst + (size_t)c * zc * ny * nx : nullptr;
+      xa.rows = (long long)ny * zc;
+      xa.red = want_red ? red_d : nullptr;
+      prof_begin(KC_XFUSED);
+      launch_xfused(xa);
+      prof_end();
+      {   // forward y pass of chunk c into the forward send layout
+        PassArgs<T> a;
+        a.in = Xout + zoff; a.out = P2 + (size_t)c * P_ * Bo; a.tw = twy;
+        a.in_row = a.out_row = Kxp;
+        a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
+        a.in_field = (long long)nzl * ny * Kxp; a.out_field = fld;
+        a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
+        set_blk(a, Kyl, Bo);
+        a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
+        blk_out = true;
+        prof_begin(KC_YFWD);
+        launch_pass<-1>(ny, a, zc, nout);
+        prof_end();
+      }
+      if (want_red && c == NZC - 1) finish_red();
+      order(st, sc);
+      exchange(P2 + (size_t)c * P_ * Bo, Q + (size_t)c * P_ * Bo, nout, c == 0, Bo);
+      fwd[c] = dep_ev[dep_next++ % dep_ev.size()];
+      CK(cudaEventRecord(fwd[c], sc));
+    }
+    for (int c = 0; c < NZC; ++c) CK(cudaStreamWaitEvent(st, fwd[c], 0));
+    {   // forward z pass from the two-level receive layout to the compact product spectra (in Xin, free by now)
+      PassArgs<T> a;
+      a.in = Q; a.out = Xin; a.tw = twz;
+      a.in_row = a.out_row = Kyl * Kxp;
+      a.in_outer = a.out_outer = 0;
+      a.in_field = fld; a.out_field = cf;
+      a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+      set_blk(a, nzl, Bo);
+      a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bo); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
+      blk_out = false;
+      prof_begin(KC_ZFWD);
+      launch_pass<-1>(nz, a, 1, nout);
+      prof_end();
+    }
+    sa.P = Xin;
+    wait_mirror();
+    launch_spectral(sa);
+  }
+
   // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
   void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
+    if (pipe_ok()) { rhs_pipe(Sin, sa, want_red); return; }
     const C* zin = Sin;
     if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {

@@ -47,10 +47,21 @@ struct PassArgs {
   // q = r / blk_rows computed as mulhi(r, blk_magic)  (blk_magic = ceil(2^32 / blk_rows), exact for r < 2^16).
   int blk_rows, blk_stride;
   unsigned blk_magic;
+  // two-level variant (z-chunk pipelined slab runs, BLK 3 / 4): inside a peer's blk_rows rows, chunks of blk2_rows rows
+  // are blk2_stride apart and the peer pieces blk_stride apart:  [chunk][peer][field][row in chunk][ky'][kx]
+  int blk2_rows, blk2_stride;
+  unsigned blk2_magic;
 };
 __device__ __forceinline__ int blk_off(int r, int rows, int stride, unsigned magic, int rowstride) {
   const int q = (int)__umulhi((unsigned)r, magic);
   return q * stride + (r - q * rows) * rowstride;
+}
+template <typename T>
+__device__ __forceinline__ int blk_off2(int r, const PassArgs<T>& a, int rowstride) {
+  const int q = (int)__umulhi((unsigned)r, a.blk_magic);
+  const int rem = r - q * a.blk_rows;
+  const int c = (int)__umulhi((unsigned)rem, a.blk2_magic);
+  return c * a.blk2_stride + q * a.blk_stride + (rem - c * a.blk2_rows) * rowstride;
 }
 
 // predicated 8/16-byte global accesses (no branches, no speculative address use)
@@ -87,7 +98,7 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
 };
 
 // PIN: the input side is the pruned (band) side (inverse passes); otherwise the output side is (forward passes).
-// BLK: 0 = plain strides, 1 = input side blocked, 2 = output side blocked
+// BLK: 0 = plain strides, 1 = input side blocked, 2 = output side blocked, 3 / 4 = input / output side two-level blocked
 // Float32: at most 64 registers per thread (launch bound) -- measured 13 % faster per 512^3 step than the 76-80
 // registers the compiler takes otherwise, because one more block fits per SM.
 constexpr int pass_minb(int threads, int tsize) {
@@ -122,10 +133,12 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
       const bool hi = n >= a.hi0;
       const bool ok = valid && (n < a.lo || hi);
       const unsigned r = (unsigned)(n - (hi ? a.shift : 0));
-      const unsigned off = (BLK == 1) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : r * irow;
+      const unsigned off = (BLK == 1) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row)
+                         : (BLK == 3) ? (unsigned)blk_off2<T>((int)r, a, a.in_row) : r * irow;
       v[m] = ldg_pred(ip + off, ok);
     } else {
-      const unsigned off = (BLK == 1) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row) : (unsigned)n * irow;
+      const unsigned off = (BLK == 1) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row)
+                         : (BLK == 3) ? (unsigned)blk_off2<T>(n, a, a.in_row) : (unsigned)n * irow;
       v[m] = ldg_pred(ip + off, valid);
     }
   }
@@ -140,10 +153,12 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
       const bool hi = n >= a.hi0;
       const bool ok = valid && (n < a.lo || hi);
       const unsigned r = (unsigned)(n - (hi ? a.shift : 0));
-      const unsigned off = (BLK == 2) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : r * orow;
+      const unsigned off = (BLK == 2) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row)
+                         : (BLK == 4) ? (unsigned)blk_off2<T>((int)r, a, a.out_row) : r * orow;
       stg_pred(op + off, v[m], ok);
     } else {
-      const unsigned off = (BLK == 2) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row) : (unsigned)n * orow;
+      const unsigned off = (BLK == 2) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row)
+                         : (BLK == 4) ? (unsigned)blk_off2<T>(n, a, a.out_row) : (unsigned)n * orow;
       stg_pred(op + off, v[m], valid);
     }
   }
