@@ -12,7 +12,11 @@
 // Replaces, for this path, the cuFFT/FFTW plans behind `mul!(yh, grid.rfftplan, y)` /
 // `ldiv!(y, grid.rfftplan, yh)` (reference: src/Solver/MHDSolver.jl:74,93,152,167,333-338).
 #pragma once
+#ifdef MHDF_CPU_EMU
+#include "cuda_emu.h"   // tests/cpu_emu: the same kernels compiled as plain C++ for the CPU test-suite
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace mhdf {
 

@@ -10,6 +10,16 @@
 #pragma once
 #include "fft_core.cuh"
 
+// MHDF_KEEP_PTR: make the compiler treat a pointer as an opaque 64-bit value from here on (so accesses become
+// base + 32-bit offset, one IMAD.WIDE each).  MHDF_DYN_SMEM: the block's dynamic shared memory.
+#ifdef MHDF_CPU_EMU
+#define MHDF_KEEP_PTR(p) ((void)0)
+#define MHDF_DYN_SMEM(type, name)
+#else
+#define MHDF_KEEP_PTR(p) asm volatile("" : "+l"(p))
+#define MHDF_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#endif
+
 namespace mhdf {
 
 // Retained-band descriptor of one axis: full index n -> compact row, or -1 if dealiased.
@@ -65,6 +75,10 @@ __device__ __forceinline__ int blk_off2(int r, const PassArgs<T>& a, int rowstri
 }
 
 // predicated 8/16-byte global accesses (no branches, no speculative address use)
+#ifdef MHDF_CPU_EMU
+template <typename C> inline C ldg_pred(const C* p, bool ok) { C z; z.x = 0; z.y = 0; return ok ? *p : z; }
+template <typename C> inline void stg_pred(C* p, C v, bool ok) { if (ok) *p = v; }
+#else
 __device__ __forceinline__ float2 ldg_pred(const float2* p, bool ok) {
   float2 v;
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
@@ -87,6 +101,7 @@ __device__ __forceinline__ void stg_pred(double2* p, double2 v, bool ok) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.f64 [%0], {%1, %2};\n\t}"
                :: "l"(p), "d"(v.x), "d"(v.y), "r"((int)ok) : "memory");
 }
+#endif
 
 template <int N, int TX, int R1, typename C> struct PassIdx {
   // float2 with TX = 8: two rows share one 128-byte bank line; shift by 8 slots every R1 rows so
@@ -109,7 +124,7 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
   using C = Cx<T>;
   constexpr int Tn = N / E;
   constexpr int R1 = imin(E, N);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MHDF_DYN_SMEM(unsigned char, smem_raw);
   C* sm = reinterpret_cast<C*>(smem_raw);
   const int c = threadIdx.x % TX;
   const int t = threadIdx.x / TX;
@@ -118,13 +133,13 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
   const C* ip = a.in + ((long long)blockIdx.z * a.in_field + (long long)blockIdx.y * a.in_outer + col);
   C* op = a.out + ((long long)blockIdx.z * a.out_field + (long long)blockIdx.y * a.out_outer + col);
   const C* twp = a.tw;
-  asm volatile("" : "+l"(twp));
+  MHDF_KEEP_PTR(twp);
 
   // 32-bit unsigned element offsets from one materialised 64-bit base per side, so every access costs one IMAD.WIDE
   // (the empty asm keeps the compiler from re-deriving base + index * 8 from the kernel parameters per access)
   const unsigned irow = (unsigned)a.in_row, orow = (unsigned)a.out_row;
-  asm volatile("" : "+l"(ip));
-  asm volatile("" : "+l"(op));
+  MHDF_KEEP_PTR(ip);
+  MHDF_KEEP_PTR(op);
   C v[E];
 #pragma unroll
   for (int m = 0; m < E; ++m) {
@@ -202,7 +217,7 @@ __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__
                                         RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
-  asm volatile("" : "+l"(X));
+  MHDF_KEEP_PTR(X);
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int k = t + Tm * m;
@@ -231,7 +246,7 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
   if constexpr (Tm <= 32) {
     // Z[M-k] sits in the registers of lane (Tm - t) of the same row (slot E-1-m), or in this thread's own slot E-m when
     // t == 0: two warp shuffles per element replace the shared-memory round trip (and its barrier)
-    asm volatile("" : "+l"(Xout));
+    MHDF_KEEP_PTR(Xout);
     const int lane = threadIdx.x & 31;
     const int src = (lane & ~(Tm - 1)) | ((Tm - t) & (Tm - 1));
 #pragma unroll
@@ -251,7 +266,7 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
 #pragma unroll
     for (int m = 0; m < E; ++m) sm.a[idx(t + Tm * m)] = v[m];
     SYNC::sync();
-    asm volatile("" : "+l"(Xout));
+    MHDF_KEEP_PTR(Xout);
 #pragma unroll
     for (int m = 0; m < E; ++m) {
       const int k = t + Tm * m;
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   // a row owned by at most one warp synchronises with __syncwarp only: rows are fully decoupled
   using SYNC = typename XSync<(Tm <= 32), RB>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MHDF_DYN_SMEM(unsigned char, smem_raw);
   const int r = threadIdx.x / Tm;
   const int t = threadIdx.x % Tm;
   constexpr int RS = RowIdx<M, R1>::SIZE;
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
   sm.b = sm.a + RS;
   const C* twt = a.tw;
-  asm volatile("" : "+l"(twt));
+  MHDF_KEEP_PTR(twt);
 
   double rs[7];
   float rm[6];
@@ -385,7 +400,11 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         const int bytes = a.Kx * (int)sizeof(C);
         for (int f = 0; f < NINF; ++f)
           for (int o = t * 128; o < bytes; o += Tm * 128)
+#ifndef MHDF_CPU_EMU
             asm volatile("prefetch.global.L2 [%0];" :: "l"(nb + (long long)f * a.in_field * (long long)sizeof(C) + o));
+#else
+            (void)nb;
+#endif
       }
     }
     if constexpr (PHYS == PHYS_HD || PHYS == PHYS_MHD) {
@@ -518,7 +537,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   using SYNC = typename XSync<(Tm <= 32), RB>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MHDF_DYN_SMEM(unsigned char, smem_raw);
   const int r = threadIdx.x / Tm;
   const int t = threadIdx.x % Tm;
   constexpr int RS = RowIdx<M, R1>::SIZE;
@@ -526,7 +545,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
   sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
   sm.b = sm.a + RS;
   const C* twt = a.tw;
-  asm volatile("" : "+l"(twt));
+  MHDF_KEEP_PTR(twt);
   double rs[1] = {0.0};
   float rm[1] = {0.f};
   const long long nsets = a.rows / RB;
@@ -890,7 +909,7 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
 template <typename T>
 __global__ void __launch_bounds__(256) k_spectrum(SpecGeom<T> g, const Cx<T>* __restrict__ S, int fi, double* __restrict__ Pk, int nbins) {
   using C = Cx<T>;
-  extern __shared__ double hist[];
+  MHDF_DYN_SMEM(double, hist);
   for (int i = threadIdx.x; i < nbins; i += blockDim.x) hist[i] = 0.0;
   __syncthreads();
   const int Ky = g.Kyl, Kz = g.bz.count();

@@ -1,0 +1,549 @@
+// CPU emulation tests of the CUDA kernels (same source, compiled with -DMHDF_CPU_EMU; see cuda_emu.h).
+// Built and run by tests/test_kernel_emulation.py.  Prints one "PASS name" / "FAIL name ..." line per check.
+#include <complex>
+#include <cstdio>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace mhdf;
+using cd = std::complex<double>;
+static int g_fail = 0;
+static void report(const std::string& name, bool ok, double err = 0) {
+  std::printf("%s %s (err %.3e)\n", ok ? "PASS" : "FAIL", name.c_str(), err);
+  if (!ok) ++g_fail;
+}
+static void alias_range(int nk, int* iL, int* iR) {   // == api.cu
+  const double af = 1.0 / 3.0, L = (1.0 - af) / 2.0, R = (1.0 + af) / 2.0;
+  *iL = (int)std::floor(L * nk) + 1;
+  *iR = (int)std::ceil(R * nk);
+}
+static Band band_of(int n) {
+  int iL, iR;
+  alias_range(n, &iL, &iR);
+  Band b; b.n = n; b.lo = iL - 1; b.hi0 = iR;
+  return b;
+}
+template <typename T> std::vector<Cx<T>> make_tw(int n) {
+  std::vector<Cx<T>> h(n);
+  for (int i = 0; i < n; ++i) { h[i].x = (T)std::cos(2 * M_PI * i / n); h[i].y = (T)(-std::sin(2 * M_PI * i / n)); }
+  return h;
+}
+template <typename T> std::vector<Cx<T>> randc(size_t n, unsigned seed) {
+  std::mt19937 g(seed);
+  std::uniform_real_distribution<double> u(-1, 1);
+  std::vector<Cx<T>> v(n);
+  for (auto& c : v) { c.x = (T)u(g); c.y = (T)u(g); }
+  return v;
+}
+template <typename T> double rel_err(const std::vector<Cx<T>>& a, const std::vector<cd>& b) {
+  double num = 0, den = 0;
+  for (size_t i = 0; i < a.size(); ++i) { num += std::norm(cd(a[i].x, a[i].y) - b[i]); den += std::norm(b[i]); }
+  return std::sqrt(num / (den > 0 ? den : 1));
+}
+static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
+
+template <typename T, int N, int DIR, int BLK>
+void run_pass(PassArgs<T> a, int n_outer, int n_fields) {
+  constexpr int E = passE(N), TX = sizeof(T) == 4 ? 16 : 8;
+  dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
+  emu::launch(k_pass<T, N, E, TX, DIR, (DIR > 0), BLK>, grid, (N / E) * TX, a);
+}
+static void zero_blk(PassArgs<float>& a) { a.blk_rows = a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = a.blk2_stride = 0; a.blk2_magic = 0; }
+static void zero_blk(PassArgs<double>& a) { a.blk_rows = a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = a.blk2_stride = 0; a.blk2_magic = 0; }
+static unsigned magic(int r) { return (unsigned)((0x100000000ULL + r - 1) / r); }
+
+// ---- A. one strided pass against a naive DFT ------------------------------------------------------------------
+template <typename T, int N> void test_pass() {
+  using C = Cx<T>;
+  const Band b = band_of(N);
+  const int K = b.count(), inner = 24, outer = 2, nf = 2;
+  auto tw = make_tw<T>(N);
+  // forward: full rows in, retained rows out
+  auto in = randc<T>((size_t)nf * outer * N * inner, 1);
+  std::vector<C> out((size_t)nf * outer * K * inner);
+  PassArgs<T> a;
+  a.in = in.data(); a.out = out.data(); a.tw = tw.data();
+  a.in_row = a.out_row = inner;
+  a.in_outer = (long long)N * inner; a.out_outer = (long long)K * inner;
+  a.in_field = (long long)outer * N * inner; a.out_field = (long long)outer * K * inner;
+  a.inner = inner; a.lo = b.lo; a.hi0 = b.hi0; a.shift = b.hi0 - b.lo;
+  zero_blk(a);
+  run_pass<T, N, -1, 0>(a, outer, nf);
+  std::vector<cd> ref(out.size());
+  for (int f = 0; f < nf; ++f) for (int o = 0; o < outer; ++o) for (int c = 0; c < inner; ++c)
+    for (int kc = 0; kc < K; ++kc) {
+      const int k = kc < b.lo ? kc : kc + (b.hi0 - b.lo);
+      cd s = 0;
+      for (int n = 0; n < N; ++n) { const C v = in[((size_t)(f * outer + o) * N + n) * inner + c]; s += cd(v.x, v.y) * std::polar(1.0, -2 * M_PI * k * n / N); }
+      ref[((size_t)(f * outer + o) * K + kc) * inner + c] = s;
+    }
+  double e = rel_err<T>(out, ref);
+  report("pass forward N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64"), e < (sizeof(T) == 4 ? 2e-6 : 1e-14), e);
+  // inverse: retained rows in (others zero), full rows out
+  auto in2 = randc<T>((size_t)nf * outer * K * inner, 2);
+  std::vector<C> out2((size_t)nf * outer * N * inner);
+  a.in = in2.data(); a.out = out2.data();
+  a.in_outer = (long long)K * inner; a.out_outer = (long long)N * inner;
+  a.in_field = (long long)outer * K * inner; a.out_field = (long long)outer * N * inner;
+  run_pass<T, N, +1, 0>(a, outer, nf);
+  std::vector<cd> ref2(out2.size());
+  for (int f = 0; f < nf; ++f) for (int o = 0; o < outer; ++o) for (int c = 0; c < inner; ++c)
+    for (int n = 0; n < N; ++n) {
+      cd s = 0;
+      for (int kc = 0; kc < K; ++kc) {
+        const int k = kc < b.lo ? kc : kc + (b.hi0 - b.lo);
+        const C v = in2[((size_t)(f * outer + o) * K + kc) * inner + c];
+        s += cd(v.x, v.y) * std::polar(1.0, +2 * M_PI * k * n / N);
+      }
+      ref2[((size_t)(f * outer + o) * N + n) * inner + c] = s;
+    }
+  e = rel_err<T>(out2, ref2);
+  report("pass inverse N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64"), e < (sizeof(T) == 4 ? 2e-6 : 1e-14), e);
+}
+
+// ---- B. slab transposes: blocked (one- and two-level) addressing must reproduce the single-rank passes exactly ----
+template <int NZC> void test_slab() {
+  using T = float; using C = Cx<T>;
+  constexpr int NY = 16, NZ = 32, P = 2, NF = 3;
+  const int Kxp = 8;
+  const Band by = band_of(NY), bz = band_of(NZ);
+  const int Ky = by.count(), Kz = bz.count(), Kyl = (Ky + P - 1) / P, nzl = NZ / P, zc = nzl / NZC;
+  auto twy = make_tw<T>(NY); auto twz = make_tw<T>(NZ);
+  // global compact state [f][Kz][P*Kyl][Kxp] (rows >= Ky are zero padding), and per-rank slabs [f][Kz][Kyl][Kxp]
+  const int KyP = P * Kyl;
+  auto g = randc<T>((size_t)NF * Kz * KyP * Kxp, 7);
+  for (int f = 0; f < NF; ++f) for (int k = 0; k < Kz; ++k) for (int j = Ky; j < KyP; ++j) for (int x = 0; x < Kxp; ++x)
+    g[(((size_t)f * Kz + k) * KyP + j) * Kxp + x] = mk<C>(0, 0);
+  // ---- single rank reference: z inverse -> y inverse -> (identity x) -> y forward -> z forward
+  std::vector<C> r1((size_t)NF * NZ * KyP * Kxp), r2((size_t)NF * NZ * NY * Kxp), r3((size_t)NF * NZ * KyP * Kxp), r4(g.size());
+  PassArgs<T> a;
+  zero_blk(a);
+  a.tw = twz.data(); a.in = g.data(); a.out = r1.data();
+  a.in_row = a.out_row = KyP * Kxp; a.in_outer = a.out_outer = 0;
+  a.in_field = (long long)Kz * KyP * Kxp; a.out_field = (long long)NZ * KyP * Kxp;
+  a.inner = KyP * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+  run_pass<T, NZ, +1, 0>(a, 1, NF);
+  a.tw = twy.data(); a.in = r1.data(); a.out = r2.data();
+  a.in_row = a.out_row = Kxp; a.in_outer = (long long)KyP * Kxp; a.out_outer = (long long)NY * Kxp;
+  a.in_field = (long long)NZ * KyP * Kxp; a.out_field = (long long)NZ * NY * Kxp;
+  a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
+  run_pass<T, NY, +1, 0>(a, NZ, NF);
+  a.in = r2.data(); a.out = r3.data();
+  a.in_outer = (long long)NY * Kxp; a.out_outer = (long long)KyP * Kxp;
+  a.in_field = (long long)NZ * NY * Kxp; a.out_field = (long long)NZ * KyP * Kxp;
+  run_pass<T, NY, -1, 0>(a, NZ, NF);
+  a.tw = twz.data(); a.in = r3.data(); a.out = r4.data();
+  a.in_row = a.out_row = KyP * Kxp; a.in_outer = a.out_outer = 0;
+  a.in_field = (long long)NZ * KyP * Kxp; a.out_field = (long long)Kz * KyP * Kxp;
+  a.inner = KyP * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
+  run_pass<T, NZ, -1, 0>(a, 1, NF);
+
+  // ---- P ranks with the exchange layout of api.cu ([chunk][peer][field][z''][ky'][kx]; NZC = 1: single level)
+  const size_t B = (size_t)NF * zc * Kyl * Kxp;           // one (chunk, peer) piece
+  const long long fld = (long long)zc * Kyl * Kxp;
+  std::vector<std::vector<C>> loc(P), send(P), recv(P), xin(P), fsend(P), frecv(P), spec(P);
+  for (int r = 0; r < P; ++r) {
+    loc[r].resize((size_t)NF * Kz * Kyl * Kxp);
+    for (int f = 0; f < NF; ++f) for (int k = 0; k < Kz; ++k) for (int j = 0; j < Kyl; ++j) for (int x = 0; x < Kxp; ++x)
+      loc[r][(((size_t)f * Kz + k) * Kyl + j) * Kxp + x] = g[(((size_t)f * Kz + k) * KyP + r * Kyl + j) * Kxp + x];
+    send[r].assign((size_t)NZC * P * B, mk<C>(0, 0)); recv[r] = send[r]; fsend[r] = send[r]; frecv[r] = send[r];
+    xin[r].resize((size_t)NF * nzl * NY * Kxp); spec[r].resize(loc[r].size());
+  }
+  auto set2 = [&](PassArgs<T>& p) {
+    p.blk_rows = nzl; p.blk_stride = (int)B; p.blk_magic = magic(nzl);
+    if (NZC > 1) { p.blk2_rows = zc; p.blk2_stride = (int)((size_t)P * B); p.blk2_magic = magic(zc); }
+    else { p.blk2_rows = 0; p.blk2_stride = 0; p.blk2_magic = 0; }
+  };
+  for (int r = 0; r < P; ++r) {   // inverse z into the send layout
+    PassArgs<T> p; zero_blk(p);
+    p.tw = twz.data(); p.in = loc[r].data(); p.out = send[r].data();
+    p.in_row = p.out_row = Kyl * Kxp; p.in_outer = p.out_outer = 0;
+    p.in_field = (long long)Kz * Kyl * Kxp; p.out_field = fld;
+    p.inner = Kyl * Kxp; p.lo = bz.lo; p.hi0 = bz.hi0; p.shift = bz.hi0 - bz.lo;
+    set2(p);
+    if (NZC > 1) run_pass<T, NZ, +1, 4>(p, 1, NF); else run_pass<T, NZ, +1, 2>(p, 1, NF);
+  }
+  auto exchange = [&](std::vector<std::vector<C>>& s, std::vector<std::vector<C>>& d) {
+    for (int c = 0; c < NZC; ++c) for (int r = 0; r < P; ++r) for (int q = 0; q < P; ++q)   // rank r's piece for q lands at slot r of q
+      std::copy(s[r].begin() + ((size_t)c * P + q) * B, s[r].begin() + ((size_t)c * P + q + 1) * B, d[q].begin() + ((size_t)c * P + r) * B);
+  };
+  exchange(send, recv);
+  double worst = 0;
+  for (int r = 0; r < P; ++r) {
+    for (int c = 0; c < NZC; ++c) {   // inverse y per chunk, then forward y per chunk (x pass = identity here)
+      PassArgs<T> p; zero_blk(p);
+      p.tw = twy.data(); p.in = recv[r].data() + (size_t)c * P * B; p.out = xin[r].data() + (size_t)c * zc * NY * Kxp;
+      p.in_row = p.out_row = Kxp; p.in_outer = (long long)Kyl * Kxp; p.out_outer = (long long)NY * Kxp;
+      p.in_field = fld; p.out_field = (long long)nzl * NY * Kxp;
+      p.inner = Kxp; p.lo = by.lo; p.hi0 = by.hi0; p.shift = by.hi0 - by.lo;
+      p.blk_rows = Kyl; p.blk_stride = (int)B; p.blk_magic = magic(Kyl);
+      run_pass<T, NY, +1, 1>(p, zc, NF);
+      PassArgs<T> q2 = p;
+      q2.in = xin[r].data() + (size_t)c * zc * NY * Kxp; q2.out = fsend[r].data() + (size_t)c * P * B;
+      q2.in_outer = (long long)NY * Kxp; q2.out_outer = (long long)Kyl * Kxp;
+      q2.in_field = (long long)nzl * NY * Kxp; q2.out_field = fld;
+      run_pass<T, NY, -1, 2>(q2, zc, NF);
+    }
+    // x-pass layout of rank r must equal the reference restricted to its z planes (bit for bit)
+    for (int f = 0; f < NF; ++f) for (int z = 0; z < nzl; ++z) for (int y = 0; y < NY; ++y) for (int x = 0; x < Kxp; ++x) {
+      const C u = xin[r][(((size_t)f * nzl + z) * NY + y) * Kxp + x], v = r2[(((size_t)f * NZ + r * nzl + z) * NY + y) * Kxp + x];
+      worst = std::max(worst, (double)std::max(std::fabs(u.x - v.x), std::fabs(u.y - v.y)));
+    }
+  }
+  report(std::string("slab inverse leg bit-identical, NZC=") + std::to_string(NZC), worst == 0.0, worst);
+  exchange(fsend, frecv);
+  worst = 0;
+  for (int r = 0; r < P; ++r) {
+    PassArgs<T> p; zero_blk(p);
+    p.tw = twz.data(); p.in = frecv[r].data(); p.out = spec[r].data();
+    p.in_row = p.out_row = Kyl * Kxp; p.in_outer = p.out_outer = 0;
+    p.in_field = fld; p.out_field = (long long)Kz * Kyl * Kxp;
+    p.inner = Kyl * Kxp; p.lo = bz.lo; p.hi0 = bz.hi0; p.shift = bz.hi0 - bz.lo;
+    set2(p);
+    if (NZC > 1) run_pass<T, NZ, -1, 3>(p, 1, NF); else run_pass<T, NZ, -1, 1>(p, 1, NF);
+    for (int f = 0; f < NF; ++f) for (int k = 0; k < Kz; ++k) for (int j = 0; j < Kyl; ++j) for (int x = 0; x < Kxp; ++x) {
+      const C u = spec[r][(((size_t)f * Kz + k) * Kyl + j) * Kxp + x], v = r4[(((size_t)f * Kz + k) * KyP + r * Kyl + j) * Kxp + x];
+      worst = std::max(worst, (double)std::max(std::fabs(u.x - v.x), std::fabs(u.y - v.y)));
+    }
+  }
+  report(std::string("slab forward leg bit-identical, NZC=") + std::to_string(NZC), worst == 0.0, worst);
+}
+
+// ---- C. fused x kernel (MHD) against a direct evaluation -------------------------------------------------------
+template <int N, typename T = float> void test_xfused() {
+  using C = Cx<T>;
+  constexpr int E = 8, Tm = N / 2 / E, RB = (64 / Tm > 0) ? 64 / Tm : 1;
+  const Band bx = band_of(N);
+  const int Kx = bx.lo, Kxp = (Kx + 7) / 8 * 8;
+  const long long rows = 2 * RB;
+  auto tw = make_tw<T>(N);
+  auto in = randc<T>((size_t)6 * rows * Kxp, 11);
+  for (int f = 0; f < 6; ++f) for (long long r = 0; r < rows; ++r) for (int k = Kx; k < Kxp; ++k) in[((size_t)f * rows + r) * Kxp + k] = mk<C>(0, 0);
+  std::vector<C> out((size_t)9 * rows * Kxp, mk<C>(0, 0));
+  XRed red; std::memset(&red, 0, sizeof red);
+  XArgs<T> a;
+  a.in = in.data(); a.out = out.data(); a.tw = tw.data(); a.real_io = nullptr;
+  a.in_field = a.out_field = rows * Kxp; a.real_field = 0; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp;
+  a.scale = (T)(1.0 / N); a.red = &red;
+  emu::launch(k_xfused<T, N, E, RB, PHYS_MHD, true>, dim3(2, 1, 1), Tm * RB, a);
+  // reference
+  std::vector<cd> ref(out.size(), 0);
+  double sum[6] = {0, 0, 0, 0, 0, 0}, cross = 0;
+  for (long long r = 0; r < rows; ++r) {
+    std::vector<std::vector<double>> f(6, std::vector<double>(N));
+    for (int q = 0; q < 6; ++q)
+      for (int n = 0; n < N; ++n) {
+        double s = 0;
+        for (int k = 0; k < Kx; ++k) {
+          const C v = in[((size_t)q * rows + r) * Kxp + k];
+          const cd X = (k == 0) ? cd(v.x, 0) : cd(v.x, v.y);
+          const cd term = X * std::polar(1.0, 2 * M_PI * k * n / N);
+          s += (k == 0) ? term.real() : 2 * term.real();
+        }
+        f[q][n] = s / N;
+        sum[q] += f[q][n] * f[q][n];
+      }
+    for (int n = 0; n < N; ++n) for (int i = 0; i < 3; ++i) cross += f[i][n] * f[3 + i][n];
+    std::vector<std::vector<double>> prod(9, std::vector<double>(N));
+    int p = 0;
+    for (int i = 0; i < 3; ++i) for (int j = i; j < 3; ++j, ++p)
+      for (int n = 0; n < N; ++n) prod[p][n] = f[3 + i][n] * f[3 + j][n] - f[i][n] * f[j][n];
+    const int n1[3] = {1, 2, 0}, n2[3] = {2, 0, 1};
+    for (int i = 0; i < 3; ++i) for (int n = 0; n < N; ++n) prod[6 + i][n] = f[n1[i]][n] * f[3 + n2[i]][n] - f[n2[i]][n] * f[3 + n1[i]][n];
+    for (int q = 0; q < 9; ++q) for (int k = 0; k < Kx; ++k) {
+      cd s = 0;
+      for (int n = 0; n < N; ++n) s += prod[q][n] * std::polar(1.0, -2 * M_PI * k * n / N);
+      ref[((size_t)q * rows + r) * Kxp + k] = s;
+    }
+  }
+  double e = rel_err<T>(out, ref);
+  const bool f32 = sizeof(T) == 4;
+  report("xfused MHD N=" + std::to_string(N) + (f32 ? " f32" : " f64"), e < (f32 ? 3e-6 : 1e-13), e);
+  double er = 0;
+  for (int q = 0; q < 6; ++q) er = std::max(er, std::fabs(red.sumsq[q] - sum[q]) / sum[q]);
+  er = std::max(er, std::fabs(red.cross - cross) / (std::fabs(cross) + 1e-30));
+  report("xfused reductions N=" + std::to_string(N) + (f32 ? " f32" : " f64"), er < (f32 ? 1e-5 : 1e-12), er);
+}
+
+// real row reference helpers
+static std::vector<double> c2r_ref(const float2* X, int Kx, int N) {
+  std::vector<double> f(N);
+  for (int n = 0; n < N; ++n) {
+    double s = 0;
+    for (int k = 0; k < Kx; ++k) {
+      const cd v = (k == 0) ? cd(X[k].x, 0) : cd(X[k].x, X[k].y);
+      const cd t = v * std::polar(1.0, 2 * M_PI * k * n / N);
+      s += (k == 0) ? t.real() : 2 * t.real();
+    }
+    f[n] = s / N;
+  }
+  return f;
+}
+static std::vector<cd> r2c_ref(const std::vector<double>& f, int Kx) {
+  const int N = (int)f.size();
+  std::vector<cd> X(Kx);
+  for (int k = 0; k < Kx; ++k) { cd s = 0; for (int n = 0; n < N; ++n) s += f[n] * std::polar(1.0, -2 * M_PI * k * n / N); X[k] = s; }
+  return X;
+}
+
+// HD products and the EMHD gradient form (with the stale real b read from / the fresh b written to real_io)
+template <int N> void test_xfused_hd_emhd() {
+  using T = float; using C = Cx<T>;
+  constexpr int E = 8, Tm = N / 2 / E, RB = (64 / Tm > 0) ? 64 / Tm : 1;
+  const Band bx = band_of(N);
+  const int Kx = bx.lo, Kxp = (Kx + 7) / 8 * 8;
+  const long long rows = RB;
+  auto tw = make_tw<T>(N);
+  {   // HD: T_ij = -u_i u_j
+    auto in = randc<T>((size_t)3 * rows * Kxp, 21);
+    for (size_t i = 0; i < in.size(); ++i) if ((int)(i % Kxp) >= Kx) in[i] = mk<C>(0, 0);
+    std::vector<C> out((size_t)6 * rows * Kxp, mk<C>(0, 0));
+    XArgs<T> a;
+    a.in = in.data(); a.out = out.data(); a.tw = tw.data(); a.real_io = nullptr;
+    a.in_field = a.out_field = rows * Kxp; a.real_field = 0; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp; a.scale = (T)(1.0 / N); a.red = nullptr;
+    emu::launch(k_xfused<T, N, E, RB, PHYS_HD, false>, dim3(1, 1, 1), Tm * RB, a);
+    std::vector<cd> ref(out.size(), 0);
+    for (long long r = 0; r < rows; ++r) {
+      std::vector<std::vector<double>> u(3);
+      for (int q = 0; q < 3; ++q) u[q] = c2r_ref(&in[((size_t)q * rows + r) * Kxp], Kx, N);
+      int p = 0;
+      for (int i = 0; i < 3; ++i) for (int j = i; j < 3; ++j, ++p) {
+        std::vector<double> pr(N);
+        for (int n = 0; n < N; ++n) pr[n] = -u[i][n] * u[j][n];
+        auto X = r2c_ref(pr, Kx);
+        for (int k = 0; k < Kx; ++k) ref[((size_t)p * rows + r) * Kxp + k] = X[k];
+      }
+    }
+    const double e = rel_err<T>(out, ref);
+    report("xfused HD N=" + std::to_string(N), e < 3e-6, e);
+  }
+  {   // EMHD: G_i = sum_j A_j dB_ij - bst_j dA_ij ; fresh b written back
+    auto in = randc<T>((size_t)24 * rows * Kxp, 22);
+    for (size_t i = 0; i < in.size(); ++i) if ((int)(i % Kxp) >= Kx) in[i] = mk<C>(0, 0);
+    std::vector<C> out((size_t)3 * rows * Kxp, mk<C>(0, 0));
+    std::vector<T> bst((size_t)3 * rows * N);
+    std::mt19937 g(5); std::uniform_real_distribution<double> u01(-1, 1);
+    for (auto& x : bst) x = (T)u01(g);
+    const std::vector<T> bst0 = bst;
+    XRed red; std::memset(&red, 0, sizeof red);
+    XArgs<T> a;
+    a.in = in.data(); a.out = out.data(); a.tw = tw.data(); a.real_io = bst.data();
+    a.in_field = a.out_field = rows * Kxp; a.real_field = rows * N; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp; a.scale = (T)(1.0 / N); a.red = &red;
+    emu::launch(k_xfused<T, N, E, RB, PHYS_EMHD, true>, dim3(1, 1, 1), Tm * RB, a);
+    std::vector<cd> ref(out.size(), 0);
+    double eb = 0, nb = 0;
+    for (long long r = 0; r < rows; ++r) {
+      std::vector<std::vector<double>> F(24);
+      for (int q = 0; q < 24; ++q) F[q] = c2r_ref(&in[((size_t)q * rows + r) * Kxp], Kx, N);
+      for (int i = 0; i < 3; ++i) {
+        std::vector<double> acc(N, 0.0);
+        for (int j = 0; j < 3; ++j) for (int n = 0; n < N; ++n)
+          acc[n] += F[j][n] * F[3 + 3 * i + j][n] - (double)bst0[((size_t)j * rows + r) * N + n] * F[12 + 3 * i + j][n];
+        auto X = r2c_ref(acc, Kx);
+        for (int k = 0; k < Kx; ++k) ref[((size_t)i * rows + r) * Kxp + k] = X[k];
+        for (int n = 0; n < N; ++n) { const double d = bst[((size_t)i * rows + r) * N + n] - F[21 + i][n]; eb += d * d; nb += F[21 + i][n] * F[21 + i][n]; }
+      }
+    }
+    const double e = rel_err<T>(out, ref);
+    report("xfused EMHD N=" + std::to_string(N), e < 5e-6, e);
+    report("xfused EMHD fresh-b writeback N=" + std::to_string(N), std::sqrt(eb / nb) < 2e-6, std::sqrt(eb / nb));
+  }
+}
+
+// plain x passes of the API boundary: r2c then c2r gives back the band-limited row
+template <int N> void test_xplain() {
+  using T = float; using C = Cx<T>;
+  constexpr int E = 8, Tm = N / 2 / E, RB = (64 / Tm > 0) ? 64 / Tm : 1;
+  const Band bx = band_of(N);
+  const int Kx = bx.lo, Kxp = (Kx + 7) / 8 * 8;
+  const long long rows = RB;
+  auto tw = make_tw<T>(N);
+  std::vector<T> re((size_t)rows * N);
+  std::mt19937 g(9); std::uniform_real_distribution<double> u01(-1, 1);
+  for (auto& x : re) x = (T)u01(g);
+  std::vector<C> sp((size_t)rows * Kxp, mk<C>(0, 0));
+  XArgs<T> a;
+  a.in = nullptr; a.out = sp.data(); a.tw = tw.data(); a.real_io = re.data();
+  a.in_field = a.out_field = rows * Kxp; a.real_field = rows * N; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp; a.scale = (T)(1.0 / N); a.red = nullptr;
+  emu::launch(k_xplain<T, N, E, RB, -1>, dim3(1, 1, 1), Tm * RB, a);
+  std::vector<cd> ref(sp.size(), 0);
+  for (long long r = 0; r < rows; ++r) {
+    std::vector<double> f(re.begin() + r * N, re.begin() + (r + 1) * N);
+    auto X = r2c_ref(f, Kx);
+    for (int k = 0; k < Kx; ++k) ref[(size_t)r * Kxp + k] = X[k];
+  }
+  double e = rel_err<T>(sp, ref);
+  report("xplain r2c N=" + std::to_string(N), e < 2e-6, e);
+  std::vector<T> back((size_t)rows * N, 0);
+  a.in = sp.data(); a.out = nullptr; a.real_io = back.data();
+  emu::launch(k_xplain<T, N, E, RB, +1>, dim3(1, 1, 1), Tm * RB, a);
+  double num = 0, den = 0;
+  for (long long r = 0; r < rows; ++r) {
+    auto f = c2r_ref(&sp[(size_t)r * Kxp], Kx, N);
+    for (int n = 0; n < N; ++n) { const double d = back[(size_t)r * N + n] - f[n]; num += d * d; den += f[n] * f[n]; }
+  }
+  report("xplain c2r N=" + std::to_string(N), std::sqrt(num / den) < 2e-6, std::sqrt(num / den));
+}
+
+// ---- D. spectral kernel: RHS assembly + stage updates against the formulas in double ----------------------------
+template <int PHYS> void test_spectral(int mode, bool forced, int P = 1, int rank = 0) {
+  using T = double; using C = Cx<T>;
+  const int nx = 16, ny = 16, nz = 16;
+  const Band bx = band_of(nx), by = band_of(ny), bz = band_of(nz);
+  const int Kx = bx.lo, Kxp = 8, Ky = by.count(), Kz = bz.count(), Kyl = (Ky + P - 1) / P, ky0 = rank * Kyl;
+  constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3, NOUT = (PHYS == PHYS_MHD) ? 9 : (PHYS == PHYS_HD ? 6 : 3);
+  const long long cf = (long long)Kxp * Kyl * Kz;
+  std::vector<T> kx(Kx), ky(Kyl), kz(Kz);
+  for (int i = 0; i < Kx; ++i) kx[i] = i * 1.0;
+  for (int j = 0; j < Kyl; ++j) ky[j] = (ky0 + j < Ky) ? by.wave(ky0 + j) * 0.5 : 0.0;     // Ly = 4 pi
+  for (int k = 0; k < Kz; ++k) kz[k] = bz.wave(k) * 2.0;                                    // Lz = pi
+  // global state on all ranks (needed for the mirror), local views for this rank
+  auto Sg = randc<T>((size_t)F * Kz * (P * Kyl) * Kxp, 31);
+  auto loc = [&](const std::vector<C>& g, int nfld) {
+    std::vector<C> v((size_t)nfld * cf);
+    for (int f = 0; f < nfld; ++f) for (int k = 0; k < Kz; ++k) for (int j = 0; j < Kyl; ++j) for (int x = 0; x < Kxp; ++x)
+      v[(((size_t)f * Kz + k) * Kyl + j) * Kxp + x] = g[(((size_t)f * Kz + k) * (P * Kyl) + ky0 + j) * Kxp + x];
+    return v;
+  };
+  std::vector<C> Sin = loc(Sg, F), Pp = randc<T>((size_t)NOUT * cf, 32), Y = randc<T>((size_t)F * cf, 33), A = randc<T>((size_t)F * cf, 34);
+  std::vector<C> force = randc<T>((size_t)F * cf, 35), Sout((size_t)F * cf, mk<C>(0, 0)), Nout((size_t)F * cf, mk<C>(0, 0));
+  const std::vector<C> A0 = A;
+  // gathered kr = 0 planes [rank][F][Kz][Kyl]
+  std::vector<C> mirror((size_t)P * F * Kz * Kyl);
+  for (int q = 0; q < P; ++q) for (int f = 0; f < F; ++f) for (int k = 0; k < Kz; ++k) for (int j = 0; j < Kyl; ++j)
+    mirror[(((size_t)q * F + f) * Kz + k) * Kyl + j] = Sg[(((size_t)f * Kz + k) * (P * Kyl) + q * Kyl + j) * Kxp];
+  SpecArgs<T> a; std::memset(&a, 0, sizeof a);
+  a.g.Kx = Kx; a.g.Kxp = Kxp; a.g.by = by; a.g.bz = bz; a.g.Kyl = Kyl; a.g.ky0 = ky0; a.g.F = F;
+  a.g.kx = kx.data(); a.g.ky = ky.data(); a.g.kz = kz.data(); a.g.field = cf; a.g.mirror = (P > 1) ? mirror.data() : nullptr;
+  a.P = Pp.data(); a.Sin = Sin.data(); a.Y = Y.data(); a.Sout = Sout.data(); a.A = A.data(); a.Nout = Nout.data();
+  a.nu = 0.013; a.eta = 0.021; a.n_nu = forced ? 2 : 0; a.ca = 0.37; a.cs = 0.59; a.dt = 0.11; a.mode = mode; a.first = 0;
+  a.force = forced ? force.data() : nullptr; a.fmask = forced ? 0x2Bu : 0;
+  emu::launch(k_spectral<T, PHYS>, dim3(3, 1, 1), 256, a);
+  // reference
+  double worst = 0;
+  long checked = 0;
+  auto at = [&](const std::vector<C>& v, int f, int k, int j, int x) { const C c = v[(((size_t)f * Kz + k) * Kyl + j) * Kxp + x]; return cd(c.x, c.y); };
+  auto sym = [&](int f, int k, int j, int x) {
+    cd v = at(Sin, f, k, j, x);
+    if (x == 0) {
+      const int jm = by.row_of_wave(-by.wave(ky0 + j)), km = bz.row_of_wave(-bz.wave(k));
+      cd w = 0;
+      if (jm >= 0 && km >= 0) { const C c = Sg[(((size_t)f * Kz + km) * (P * Kyl) + jm) * Kxp]; w = cd(c.x, c.y); }
+      v = 0.5 * (v + std::conj(w));
+    }
+    return v;
+  };
+  const cd I(0, 1);
+  for (int k = 0; k < Kz; ++k) for (int j = 0; j < Kyl; ++j) for (int x = 0; x < Kx; ++x) {
+    if (ky0 + j >= Ky) continue;
+    const double K[3] = {kx[x], ky[j], kz[k]};
+    const double k2 = K[0] * K[0] + K[1] * K[1] + K[2] * K[2], ik2 = k2 > 0 ? 1 / k2 : 0;
+    cd N[6];
+    if (PHYS == PHYS_EMHD) {
+      for (int f = 0; f < 3; ++f) N[f] = at(Pp, f, k, j, x);
+    } else {
+      const cd Tt[6] = {at(Pp, 0, k, j, x), at(Pp, 1, k, j, x), at(Pp, 2, k, j, x), at(Pp, 3, k, j, x), at(Pp, 4, k, j, x), at(Pp, 5, k, j, x)};
+      const cd D[3] = {I * (K[0] * Tt[0] + K[1] * Tt[1] + K[2] * Tt[2]), I * (K[0] * Tt[1] + K[1] * Tt[3] + K[2] * Tt[4]), I * (K[0] * Tt[2] + K[1] * Tt[4] + K[2] * Tt[5])};
+      const cd kD = (K[0] * D[0] + K[1] * D[1] + K[2] * D[2]) * ik2;
+      for (int c = 0; c < 3; ++c) {
+        N[c] = D[c] - K[c] * kD - a.nu * k2 * sym(c, k, j, x);
+        if (a.n_nu > 1) N[c] -= a.nu * std::pow(k2, a.n_nu) * sym(c, k, j, x);
+      }
+      if (PHYS == PHYS_MHD) {
+        const cd Ev[3] = {at(Pp, 6, k, j, x), at(Pp, 7, k, j, x), at(Pp, 8, k, j, x)};
+        const cd Cv[3] = {K[1] * Ev[2] - K[2] * Ev[1], K[2] * Ev[0] - K[0] * Ev[2], K[0] * Ev[1] - K[1] * Ev[0]};
+        for (int c = 0; c < 3; ++c) N[3 + c] = I * Cv[c] - a.eta * k2 * sym(3 + c, k, j, x);
+        if (forced) for (int f = 0; f < 6; ++f) if ((a.fmask >> f) & 1u) N[f] += at(force, f, k, j, x);
+      }
+    }
+    for (int f = 0; f < F; ++f) {
+      cd expS = 0, expA = at(A0, f, k, j, x), gotS = at(Sout, f, k, j, x), gotA = at(A, f, k, j, x);
+      switch (mode) {
+        case STEP_CALCN: worst = std::max(worst, std::abs(at(Nout, f, k, j, x) - N[f])); checked += std::abs(N[f]) > 0; continue;
+        case STEP_RK4_1: expA = at(Y, f, k, j, x) + a.ca * N[f]; expS = at(Y, f, k, j, x) + a.cs * N[f]; break;
+        case STEP_RK4_2: case STEP_RK4_3: expA = at(A0, f, k, j, x) + a.ca * N[f]; expS = at(Y, f, k, j, x) + a.cs * N[f]; break;
+        case STEP_RK4_4: expS = at(A0, f, k, j, x) + a.ca * N[f]; break;
+        default: { const cd s2 = a.ca * at(A0, f, k, j, x) + a.dt * N[f]; expA = s2; expS = at(Sin, f, k, j, x) + a.cs * s2; }
+      }
+      worst = std::max(worst, std::max(std::abs(gotS - expS), std::abs(gotA - expA)));
+      checked += std::abs(expS) > 0;
+    }
+  }
+  if (checked < (long)F * Kx * 4) worst = 1e30;   // the comparison must really have covered the retained modes
+  report("spectral phys=" + std::to_string(PHYS) + " mode=" + std::to_string(mode) + (forced ? " forced+hyper" : "") + " P=" + std::to_string(P) + " rank=" + std::to_string(rank),
+         worst < 1e-11, worst);
+}
+
+// EMHD derived spectra and the full <-> compact packing
+static void test_derive_and_pack() {
+  using T = double; using C = Cx<T>;
+  const int nx = 16, ny = 16, nz = 16, nkr = nx / 2 + 1;
+  const Band bx = band_of(nx), by = band_of(ny), bz = band_of(nz);
+  const int Kx = bx.lo, Kxp = 8, Ky = by.count(), Kz = bz.count();
+  const long long cf = (long long)Kxp * Ky * Kz;
+  std::vector<T> kx(Kx), ky(Ky), kz(Kz);
+  for (int i = 0; i < Kx; ++i) kx[i] = i;
+  for (int j = 0; j < Ky; ++j) ky[j] = by.wave(j);
+  for (int k = 0; k < Kz; ++k) kz[k] = bz.wave(k);
+  SpecGeom<T> g; std::memset(&g, 0, sizeof g);
+  g.Kx = Kx; g.Kxp = Kxp; g.by = by; g.bz = bz; g.Kyl = Ky; g.ky0 = 0; g.F = 3; g.kx = kx.data(); g.ky = ky.data(); g.kz = kz.data(); g.field = cf;
+  auto B = randc<T>((size_t)3 * cf, 41);
+  std::vector<C> out((size_t)24 * cf, mk<C>(0, 0));
+  struct DArgs { SpecGeom<T> g; const C* B; C* out; } da{g, B.data(), out.data()};
+  emu::launch([](const DArgs& d) { k_emhd_derive<T>(d.g, d.B, d.out); }, dim3(2, 1, 1), 256, da);
+  double worst = 0;
+  const cd I(0, 1);
+  for (int k = 0; k < Kz; ++k) for (int j = 0; j < Ky; ++j) for (int x = 0; x < Kx; ++x) {
+    const size_t e = ((size_t)k * Ky + j) * Kxp + x;
+    const double K[3] = {kx[x], ky[j], kz[k]};
+    cd b[3], A[3];
+    for (int i = 0; i < 3; ++i) b[i] = cd(B[i * cf + e].x, B[i * cf + e].y);
+    A[0] = I * (K[1] * b[2] - K[2] * b[1]); A[1] = I * (K[2] * b[0] - K[0] * b[2]); A[2] = I * (K[0] * b[1] - K[1] * b[0]);
+    auto got = [&](int f) { return cd(out[f * cf + e].x, out[f * cf + e].y); };
+    for (int i = 0; i < 3; ++i) {
+      worst = std::max(worst, std::abs(got(i) - A[i]));
+      worst = std::max(worst, std::abs(got(21 + i) - b[i]));
+      for (int jj = 0; jj < 3; ++jj) {
+        worst = std::max(worst, std::abs(got(3 + 3 * i + jj) - I * K[jj] * b[i]));
+        worst = std::max(worst, std::abs(got(12 + 3 * i + jj) - I * K[jj] * A[i]));
+      }
+    }
+  }
+  report("emhd_derive", worst < 1e-12, worst);
+  // pack: full (nkr, ny, nz) -> compact -> full gives the dealiased array
+  auto full = randc<T>((size_t)nkr * ny * nz, 42);
+  std::vector<C> comp((size_t)cf, mk<C>(0, 0)), back((size_t)nkr * ny * nz, mk<C>(9, 9));
+  struct PArgs { C* full; C* comp; int nkr, ny, nz, Kx, Kxp; Band by, bz; int dir; } pa{full.data(), comp.data(), nkr, ny, nz, Kx, Kxp, by, bz, 0};
+  auto pk = [](const PArgs& q) { k_pack<T>(q.full, q.comp, q.nkr, q.ny, q.nz, q.Kx, q.Kxp, q.by, q.bz, q.dir, 0); };
+  emu::launch(pk, dim3(2, 1, 1), 256, pa);
+  pa.full = back.data(); pa.dir = 1;
+  emu::launch(pk, dim3(2, 1, 1), 256, pa);
+  worst = 0;
+  for (int k = 0; k < nz; ++k) for (int j = 0; j < ny; ++j) for (int x = 0; x < nkr; ++x) {
+    const size_t e = ((size_t)k * ny + j) * nkr + x;
+    const bool kept = x < Kx && by.row(j) >= 0 && bz.row(k) >= 0;
+    const cd want = kept ? cd(full[e].x, full[e].y) : cd(0, 0);
+    worst = std::max(worst, std::abs(cd(back[e].x, back[e].y) - want));
+  }
+  report("pack / unpack", worst == 0.0, worst);
+}
+
+int main() {
+  test_pass<float, 16>(); test_pass<float, 32>(); test_pass<float, 64>(); test_pass<double, 16>(); test_pass<double, 32>();
+  test_pass<float, 128>();
+  test_slab<1>(); test_slab<2>(); test_slab<4>();
+  test_xfused<16>(); test_xfused<32>(); test_xfused<64>(); test_xfused<128>(); test_xfused<256>();
+  test_xfused<512>(); test_xfused<1024>();        // Tm = 32 (one warp per row) and Tm = 64 (block barrier, shared-memory post-step)
+  test_xfused<32, double>(); test_xfused<256, double>();
+  test_xfused_hd_emhd<32>(); test_xfused_hd_emhd<128>();
+  test_xplain<16>(); test_xplain<64>(); test_xplain<1024>();
+  for (int mode : {STEP_CALCN, STEP_RK4_1, STEP_RK4_2, STEP_RK4_4, STEP_LSRK}) test_spectral<PHYS_MHD>(mode, mode == STEP_RK4_2);
+  test_spectral<PHYS_HD>(STEP_RK4_3, true); test_spectral<PHYS_EMHD>(STEP_LSRK, false);
+  test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 0); test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 1);   // slab ranks: gathered mirror plane
+  test_derive_and_pack();
+  std::printf("%s: %d failure(s)\n", g_fail ? "FAILED" : "ALL PASS", g_fail);
+  return g_fail ? 1 : 0;
+}
