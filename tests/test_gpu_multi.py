@@ -35,3 +35,21 @@ def test_slab_run_equals_single_gpu(peer):
         assert m, l
         assert float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l      # bit-identical state
         assert float(m.group(3)) < 1e-10, l                                 # reductions: summation order differs
+
+
+@pytest.mark.xfail(strict=False, reason="z-chunk pipelined slab path (MHDF_ZCHUNKS) was written after round 1's GPU budget "
+                                        "was spent: its kernel addressing is verified on the CPU emulator, its stream / event "
+                                        "orchestration has not run on hardware yet")
+def test_pipelined_slab_run_equals_single_gpu():
+    if _ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    env = dict(os.environ, MHDF_PEER="1", MHDF_ZCHUNKS="2")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "tools", "dist_check.py"), "check64"],
+                         capture_output=True, text=True, timeout=150, env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("dist-vs-single")]
+    assert len(lines) == 3
+    for l in lines:
+        m = re.search(r"spectral max rel diff ([0-9.e+-]+)\s+real ([0-9.e+-]+)", l)
+        assert m and float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l
