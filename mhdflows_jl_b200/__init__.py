@@ -9,6 +9,8 @@ from .problem import (CPU, GPU, Diagnostic, DivFreeSpectraMap, GetN97vars_And_fu
                       ProbDiagnostic, Problem, SetUpN97, SetUpProblemIC, TimeIntegrator, getCFL, increment,
                       nothingfunction, spectralline, stepforward)
 
-__all__ = ["Problem", "SetUpProblemIC", "stepforward", "TimeIntegrator", "getCFL", "ProbDiagnostic", "Diagnostic",
+from .io import Restart, readMHDFlows, savefile  # noqa: F401,E402
+
+__all__ = ["savefile", "Restart", "readMHDFlows", "Problem", "SetUpProblemIC", "stepforward", "TimeIntegrator", "getCFL", "ProbDiagnostic", "Diagnostic",
            "increment", "DivFreeSpectraMap", "spectralline", "N97ForceDriving", "GetN97vars_And_function", "SetUpN97", "CPU", "GPU", "nothingfunction", "MHDFlowsError",
            "FRESH", "STALE"]

@@ -476,11 +476,16 @@ def TimeIntegrator(prob, t0, N0, *, usr_dt=0.0, CFL_Coef=0.25, CFL_function=noth
                    dump_dt=0, quiet=True):
     """TimeIntegrator!(prob, t0, N0; ...) (integrator.jl:31-156): CFL -> stepforward! -> diagnostics per step.
     Keeps the reference's quirks: clock.step is reset to 0 (:76) and the loop runs while
-    N0 >= step && t0 >= t, i.e. N0+1 steps (:104).  HDF5 saving is outside this path."""
+    N0 >= step && t0 >= t, i.e. N0+1 steps (:104).  `save=True` dumps through mhdflows_jl_b200.io.savefile (.npz with the
+    reference's dataset names; no HDF5 library exists here)."""
+    file_path_and_name = ""
     if save:
+        from .io import savefile
         if len(save_loc) == 0 or len(filename) == 0 or dump_dt == 0:
             raise ValueError("Save Function Turned ON but save_loc/filename/dump_dt is not declared!\n")   # :47
-        raise NotImplementedError("HDF5 output is outside the B200 hot path (SURVEY 8f)")
+        file_path_and_name = save_loc + filename
+        savefile(prob, file_number, file_path_and_name=file_path_and_name)                                # :50-51
+        file_number += 1
     if CFL_function is not nothingfunction and usr_dt > 0.0:
         raise ValueError("User define both CFL_function and usr_dt")                                       # :202
     updateCFL = getCFL if CFL_function is nothingfunction else CFL_function
@@ -496,6 +501,7 @@ def TimeIntegrator(prob, t0, N0, *, usr_dt=0.0, CFL_Coef=0.25, CFL_function=noth
         t_diff = math.inf
     else:
         t_diff = CFL_Coef * dl ** nv / vi if nv > 1 else CFL_Coef * dl ** 2 / vi                         # :72
+    t_next_save = prob.clock.t + dump_dt                                                               # :75
     prob.clock.step = 0
     usr_declared_dt = usr_dt != 0.0
     if usr_declared_dt:
@@ -508,6 +514,11 @@ def TimeIntegrator(prob, t0, N0, *, usr_dt=0.0, CFL_Coef=0.25, CFL_function=noth
         increment(list(diags))
         for foo in prob.usr_func:
             foo(prob)
+        if save and prob.clock.t >= t_next_save:                                                       # :136-141
+            ProbDiagnostic(prob)
+            savefile(prob, file_number, file_path_and_name=file_path_and_name)
+            t_next_save += dump_dt
+            file_number += 1
         if not quiet and (dynamic_dashboard or prob.clock.step % loop_number == 0):
             d = ProbDiagnostic(prob)
             print(f"           n = {prob.clock.step:8d}, t = {_round_sig(prob.clock.t):8}, diag = {d}")

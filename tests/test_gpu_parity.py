@@ -292,3 +292,23 @@ def test_n97_taylor_green_forcing(M, O):
         if B_field:
             assert O.rel_l2(ref, unforced) > 1e-4      # the forcing really acted
         gp.close()
+
+
+def test_time_integrator_save_and_restart(M, O, tmp_path):
+    """save=true path of TimeIntegrator! (integrator.jl:44-51,136-141) and Restart! (:208-257): dumps hold the stale vars
+    and the time; a restarted problem starts from exactly those fields."""
+    op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float32, turb=False)
+    M.TimeIntegrator(gp, 1e9, 3, usr_dt=1e-3, save=True, save_loc=str(tmp_path) + "/", filename="run", dump_dt=2e-3)
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert files[0] == "run_t_0000.npz" and len(files) >= 2
+    last = str(tmp_path / files[-1])
+    d = M.readMHDFlows(last)
+    assert set(d) == {"i_velocity", "j_velocity", "k_velocity", "i_mag_field", "j_mag_field", "k_mag_field", "time"}
+    kw = dict(nx=32, T=np.float32, nu=2e-2, eta=3e-2, B_field=True, dt=1e-3)
+    rp = M.Problem(M.GPU(), **kw)
+    M.Restart(rp, last)
+    assert abs(rp.clock.t - float(d["time"])) < 1e-9 and rp.clock.step == 0
+    assert O.rel_l2(rp.get_real("ux", M.FRESH), d["i_velocity"]) < 1e-6
+    assert O.rel_l2(rp.get_real("bz", M.FRESH), d["k_mag_field"]) < 1e-6
+    rp.close()
+    gp.close()

@@ -77,3 +77,42 @@ def test_diagnostic_recorder_semantics():
 def test_round_sig_matches_julia_round_sigdigits():
     assert P._round_sig(42.8134) == 42.8 and P._round_sig(0.0123456) == 0.0123 and P._round_sig(123456.0) == 123000.0
     assert P._round_sig(0.0) == 0.0 and math.isnan(P._round_sig(float("nan")))
+
+
+class _FakeFieldProb:
+    """Duck-typed problem for the host-only checkpoint logic (mhdflows_jl_b200/io.py)."""
+
+    def __init__(self, b=True, e=False):
+        from mhdflows_jl_b200.problem import _Flag
+        self.flag = _Flag(b, e)
+        self.clock = _FakeClock()
+        rng = np.random.default_rng(0)
+        names = ["bx", "by", "bz"] if e else ["ux", "uy", "uz"] + (["bx", "by", "bz"] if b else [])
+        self.fields = {n: rng.standard_normal((4, 4, 4)).astype(np.float32) for n in names}
+        self.which = []
+
+    def get_real(self, f, which=0):
+        self.which.append(which)
+        return self.fields[f].copy()
+
+    def set_real(self, f, arr):
+        self.fields[f] = np.array(arr, dtype=np.float32)
+
+
+@pytest.mark.parametrize("b,e", [(False, False), (True, False), (True, True)])
+def test_savefile_restart_roundtrip(tmp_path, b, e):
+    """savefile / Restart! (integrator.jl:208-288): dataset names of the reference, stale vars, clock.t restored only."""
+    p = _FakeFieldProb(b, e)
+    p.clock.t, p.clock.step = 1.25, 7
+    path = M.savefile(p, 3, file_path_and_name=str(tmp_path / "run"))
+    assert path.endswith("run_t_0003.npz") and set(p.which) == {M.STALE}
+    d = M.readMHDFlows(path)
+    want = {"time"} | ({"i_mag_field", "j_mag_field", "k_mag_field"} if b else set()) | (set() if e else {"i_velocity", "j_velocity", "k_velocity"})
+    assert set(d) == want and float(d["time"]) == 1.25
+    q = _FakeFieldProb(b, e)
+    for k in q.fields:
+        q.fields[k][...] = 0
+    M.Restart(q, path)
+    assert q.clock.t == 1.25 and q.clock.step == 0
+    for k in p.fields:
+        assert np.array_equal(q.fields[k], p.fields[k])
