@@ -30,16 +30,59 @@ template <> struct RealOf<float2>  { using type = float; };
 template <> struct RealOf<double2> { using type = double; };
 
 template <typename C> __device__ __forceinline__ C mk(typename RealOf<C>::type x, typename RealOf<C>::type y) { C c; c.x = x; c.y = y; return c; }
-template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return mk<C>(a.x + b.x, a.y + b.y); }
-template <typename C> __device__ __forceinline__ C csub(C a, C b) { return mk<C>(a.x - b.x, a.y - b.y); }
+
+// ---- lane-wise pair arithmetic ---------------------------------------------------------------------------------
+// A complex number (or two neighbouring real samples) is a pair; l* act on both lanes alike.  With -DMHDF_F32X2 the
+// Float32 pairs map onto the sm_100 packed instructions add/sub/mul/fma.rn.f32x2 (SASS FADD2 / FMUL2 / FFMA2: one issue
+// slot for both lanes, IEEE results identical to the scalar forms); ptxas folds the lane swaps, broadcasts and sign flips
+// written below as plain `mk(...)` into operand modifiers (.LO_HI, .F32, -R, .NP).  Opt-in until measured on hardware
+// (DESIGN.md section 7); the default build keeps the scalar forms.
+template <typename C> __device__ __forceinline__ C ladd(C a, C b) { return mk<C>(a.x + b.x, a.y + b.y); }
+template <typename C> __device__ __forceinline__ C lsub(C a, C b) { return mk<C>(a.x - b.x, a.y - b.y); }
+template <typename C> __device__ __forceinline__ C lmul(C a, C b) { return mk<C>(a.x * b.x, a.y * b.y); }
+// a * b + c and a * b - c * d per lane
+template <typename C> __device__ __forceinline__ C lfma(C a, C b, C c) { return mk<C>(a.x * b.x + c.x, a.y * b.y + c.y); }
+template <typename C> __device__ __forceinline__ C lmulsub(C a, C b, C c, C d) { return mk<C>(a.x * b.x - c.x * d.x, a.y * b.y - c.y * d.y); }
+template <typename C> __device__ __forceinline__ C lneg(C a) { return mk<C>(-a.x, -a.y); }
+template <typename C> __device__ __forceinline__ C lbc(typename RealOf<C>::type s) { return mk<C>(s, s); }
+
+#ifdef MHDF_F32X2
+#ifndef MHDF_CPU_EMU
+__device__ __forceinline__ unsigned long long pk2_(float2 a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2 up2_(unsigned long long v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ float2 ladd(float2 a, float2 b) { unsigned long long r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2_(a)), "l"(pk2_(b))); return up2_(r); }
+__device__ __forceinline__ float2 lsub(float2 a, float2 b) { unsigned long long r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2_(a)), "l"(pk2_(b))); return up2_(r); }
+__device__ __forceinline__ float2 lmul(float2 a, float2 b) { unsigned long long r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2_(a)), "l"(pk2_(b))); return up2_(r); }
+__device__ __forceinline__ float2 lfma(float2 a, float2 b, float2 c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2_(a)), "l"(pk2_(b)), "l"(pk2_(c))); return up2_(r); }
+#else
+// CPU emulation of the packed forms (same rounding: one fused multiply-add per lane)
+inline float2 lfma(float2 a, float2 b, float2 c) { return mk<float2>(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
+#endif
+__device__ __forceinline__ float2 lmulsub(float2 a, float2 b, float2 c, float2 d) { return lfma(lneg(c), d, lmul(a, b)); }
+#endif
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return ladd(a, b); }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { return lsub(a, b); }
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) { return mk<C>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 template <typename C> __device__ __forceinline__ C cmulc(C a, C b) { return mk<C>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 template <typename C> __device__ __forceinline__ C cconj(C a) { return mk<C>(a.x, -a.y); }
-template <typename C> __device__ __forceinline__ C cscale(C a, typename RealOf<C>::type s) { return mk<C>(a.x * s, a.y * s); }
+template <typename C> __device__ __forceinline__ C cscale(C a, typename RealOf<C>::type s) { return lmul(a, lbc<C>(s)); }
 // multiply by +i / -i
 template <typename C> __device__ __forceinline__ C cmuli(C a)  { return mk<C>(-a.y, a.x); }
 template <typename C> __device__ __forceinline__ C cmulmi(C a) { return mk<C>(a.y, -a.x); }
+#ifdef MHDF_F32X2
+// a * b = a.x * (b.x, b.y) + (-t.x, t.y),  t = a.y * (b.y, b.x);   a * conj(b) = a.y * (b.y, b.x) + (u.x, -u.y),  u = a.x * b:
+// the one-lane sign flip sits on the addend, where FFMA2 has a per-lane negate modifier
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  const float2 t = lmul(lbc<float2>(a.y), mk<float2>(b.y, b.x));
+  return lfma(lbc<float2>(a.x), b, mk<float2>(-t.x, t.y));
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  const float2 u = lmul(lbc<float2>(a.x), b);
+  return lfma(lbc<float2>(a.y), mk<float2>(b.y, b.x), mk<float2>(u.x, -u.y));
+}
+#endif
 
 // DIR = -1: forward (exp(-i..)), DIR = +1: inverse (exp(+i..)), both unnormalised.
 
@@ -94,7 +137,7 @@ template <int R, int DIR, typename C> struct Bfly {
       else {
         const T wc = (T)c16(k * (16 / R));
         const T ws = (T)(DIR * s16(k * (16 / R)));
-        t = mk<C>(o[k].x * wc - o[k].y * ws, o[k].x * ws + o[k].y * wc);
+        t = cmul(o[k], mk<C>(wc, ws));
       }
       v[k] = cadd(e[k], t);
       v[k + R / 2] = csub(e[k], t);

@@ -212,6 +212,40 @@ template <typename T, int N, int E> struct XTwSrc {
   static __device__ __forceinline__ C wn(const C* tw, int, int k) { return __ldg(tw + (unsigned)k); }
 };
 
+// Pre-step of the half-length c2r and post-step of the half-length r2c for one mode k (uniform in k, including k = 0 and
+// k = M/2).  x1 = X[k], x2 = X[M-k] (not conjugated), w = exp(-2 pi i k / N); z1 = Z[k], z2 = Z[M-k].
+//   c2r:  Z[k] = (x1 + conj x2) + i (x1 - conj x2) exp(+2 pi i k / N)
+//   r2c:  X[k] = ((z1 + conj z2) - i (z1 - conj z2) w) / 2
+// The default build keeps the operation order that was measured on hardware; the packed-FP32 build (MHDF_F32X2) uses the
+// forms whose sign flips and lane swaps fold into FADD2 / FFMA2 operand modifiers (6 instructions each).
+template <typename C, typename T>
+__device__ __forceinline__ C c2r_pre(C x1, C x2, C w, T scale) {
+#ifdef MHDF_F32X2
+  const C x2c = cconj(x2);
+  const C s = cadd(x1, x2c), d = cmulc(csub(x1, x2c), w);
+  return cscale(cadd(s, cmuli(d)), scale);
+#else
+  x2 = cconj(x2);
+  w = cconj(w);                                               // exp(+2 pi i k / N)
+  const C s = cadd(x1, x2), d = cmul(csub(x1, x2), w);        // Z = s + i d
+  return cscale(cadd(s, cmuli(d)), scale);
+#endif
+}
+template <typename C>
+__device__ __forceinline__ C r2c_post(C z1, C z2, C w) {
+  using T = typename RealOf<C>::type;
+#ifdef MHDF_F32X2
+  const C z2c = cconj(z2);
+  const C t = cmul(csub(z1, z2c), w);
+  return cscale(cadd(cadd(z1, z2c), cmulmi(t)), (T)0.5);
+#else
+  z2 = cconj(z2);
+  const C ev = cscale(cadd(z1, z2), (T)0.5);
+  const C od = cscale(cmulmi(csub(z1, z2)), (T)0.5);          // -i (z1 - z2) / 2
+  return cadd(ev, cmul(od, w));
+#endif
+}
+
 template <typename T, int N, int E, typename SYNC>
 __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__ X, int Kx, T scale, int t,
                                         RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
@@ -223,11 +257,9 @@ __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__
     const int k = t + Tm * m;
     const int k2 = M - k;
     C x1 = ldg_pred(X + (unsigned)k, k < Kx);
-    C x2 = cconj(ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx));
+    const C x2 = ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx);
     if (k == 0) x1.y = 0;
-    const C w = cconj(XTwSrc<T, N, E>::wn(tw, m, k));       // exp(+2 pi i k / N)
-    const C s = cadd(x1, x2), d = cmul(csub(x1, x2), w);    // Z = s + i d
-    v[m] = mk<C>((s.x - d.y) * scale, (s.y + d.x) * scale);
+    v[m] = c2r_pre(x1, x2, XTwSrc<T, N, E>::wn(tw, m, k), scale);
   }
   constexpr int NEX = fft_num_steps(M, E) - 1;
   fft_run<C, M, E, +1, 2, 1, 0, SYNC>(v, t, sm.a, sm.b, XTwSrc<T, N, E>::fft(tw), RowIdx<M, R1>(), RowIdx2<M>());
@@ -255,11 +287,7 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
       const C z1 = v[m];
       C z2 = mk<C>(__shfl_sync(0xffffffffu, v[E - 1 - m].x, src), __shfl_sync(0xffffffffu, v[E - 1 - m].y, src));
       if (t == 0) z2 = v[(E - m) % E];
-      z2 = cconj(z2);
-      const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
-      const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
-      const C w = XTwSrc<T, N, E>::wn(tw, m, k);                               // exp(-2 pi i k / N)
-      stg_pred(Xout + (unsigned)k, cadd(ev, cmul(od, w)), k < Kx);
+      stg_pred(Xout + (unsigned)k, r2c_post(z1, z2, XTwSrc<T, N, E>::wn(tw, m, k)), k < Kx);
     }
   } else {
     RowIdx<M, R1> idx;
@@ -272,11 +300,8 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
       const int k = t + Tm * m;
       // columns k >= Kx are never stored; their arithmetic is harmless and keeps the code branch-free
       const C z1 = v[m];
-      const C z2 = cconj(sm.a[idx((M - k) & (M - 1))]);
-      const C ev = mk<C>((T)0.5 * (z1.x + z2.x), (T)0.5 * (z1.y + z2.y));
-      const C od = mk<C>((T)0.5 * (z1.y - z2.y), (T)-0.5 * (z1.x - z2.x));   // -i (z1 - z2) / 2
-      const C w = XTwSrc<T, N, E>::wn(tw, m, k);                               // exp(-2 pi i k / N)
-      stg_pred(Xout + (unsigned)k, cadd(ev, cmul(od, w)), k < Kx);
+      const C z2 = sm.a[idx((M - k) & (M - 1))];
+      stg_pred(Xout + (unsigned)k, r2c_post(z1, z2, XTwSrc<T, N, E>::wn(tw, m, k)), k < Kx);
     }
     sm.swap();
   }
@@ -418,9 +443,9 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
           float mx = 0.f;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
-            const T x2 = f[i][m].x * f[i][m].x, y2 = f[i][m].y * f[i][m].y;
-            s += x2 + y2;
-            mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
+            const C sq = lmul(f[i][m], f[i][m]);
+            s += sq.x + sq.y;
+            mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
           }
           rs[i] += (double)s;
           rm[i] = fmaxf(rm[i], mx);
@@ -431,7 +456,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int m = 0; m < E; ++m) s += f[i][m].x * f[i + 3][m].x + f[i][m].y * f[i + 3][m].y;
+          for (int m = 0; m < E; ++m) { const C ub = lmul(f[i][m], f[i + 3][m]); s += ub.x + ub.y; }
         rs[6] += (double)s;
       }
       // symmetric tensor (xx, xy, xz, yy, yz, zz)
@@ -444,10 +469,9 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
           for (int m = 0; m < E; ++m) {
             if constexpr (PHYS == PHYS_MHD)
-              v[m] = mk<C>(f[3 + i][m].x * f[3 + j][m].x - f[i][m].x * f[j][m].x,
-                           f[3 + i][m].y * f[3 + j][m].y - f[i][m].y * f[j][m].y);
+              v[m] = lmulsub(f[3 + i][m], f[3 + j][m], f[i][m], f[j][m]);
             else
-              v[m] = mk<C>(-(f[i][m].x * f[j][m].x), -(f[i][m].y * f[j][m].y));
+              v[m] = lneg(lmul(f[i][m], f[j][m]));
           }
           row_r2c<T, N, E, SYNC>(v, out + p * a.out_field, a.Kx, t, sm, twt);
           ++p;
@@ -462,8 +486,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
           C v[E];
 #pragma unroll
           for (int m = 0; m < E; ++m)
-            v[m] = mk<C>(f[j][m].x * f[3 + k][m].x - f[k][m].x * f[3 + j][m].x,
-                         f[j][m].y * f[3 + k][m].y - f[k][m].y * f[3 + j][m].y);
+            v[m] = lmulsub(f[j][m], f[3 + k][m], f[k][m], f[3 + j][m]);
           row_r2c<T, N, E, SYNC>(v, out + (6 + i) * a.out_field, a.Kx, t, sm, twt);
         }
       }
@@ -479,9 +502,9 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           if constexpr (RED) {
-            const T x2 = A[i][m].x * A[i][m].x, y2 = A[i][m].y * A[i][m].y;
-            s += x2 + y2;
-            mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
+            const C sq = lmul(A[i][m], A[i][m]);
+            s += sq.x + sq.y;
+            mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
           }
           bs[i][m] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
         }
@@ -498,10 +521,10 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
           C g[E];
           row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
-          for (int m = 0; m < E; ++m) { acc[m].x += A[j][m].x * g[m].x; acc[m].y += A[j][m].y * g[m].y; }
+          for (int m = 0; m < E; ++m) acc[m] = lfma(A[j][m], g[m], acc[m]);
           row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
-          for (int m = 0; m < E; ++m) { acc[m].x -= bs[j][m].x * g[m].x; acc[m].y -= bs[j][m].y * g[m].y; }
+          for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(bs[j][m]), g[m], acc[m]);
         }
         row_r2c<T, N, E, SYNC>(acc, out + i * a.out_field, a.Kx, t, sm, twt);
       }
@@ -515,9 +538,9 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           if constexpr (RED) {
-            const T x2 = g[m].x * g[m].x, y2 = g[m].y * g[m].y;
-            s += x2 + y2;
-            mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
+            const C sq = lmul(g[m], g[m]);
+            s += sq.x + sq.y;
+            mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
           }
           reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
         }

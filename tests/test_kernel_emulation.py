@@ -3,7 +3,9 @@
 addressing of the very source the GPU runs are checked against naive DFTs / direct formulas on tiny problems.
 Covers: strided passes (16..128 points, f32/f64), one- and two-level slab addressing (bit-identical to the single-rank
 passes), the fused x kernel for HD / MHD / EMHD up to 1024-point rows, the plain x passes, the spectral kernel in every
-stage mode (with forcing, hyperviscosity and the gathered mirror plane), emhd_derive and pack/unpack."""
+stage mode (with forcing, hyperviscosity and the gathered mirror plane), emhd_derive and pack/unpack.
+Runs twice: the default (scalar) code shape and the packed-FP32 shape (-DMHDF_F32X2: the formulas that map onto the
+sm_100 add/mul/fma.f32x2 instructions, with the packed primitives emulated lane by lane)."""
 import os
 import shutil
 import subprocess
@@ -13,13 +15,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emu_binary(tmp_path_factory):
+@pytest.fixture(scope="module", params=["scalar", "f32x2"])
+def emu_binary(request, tmp_path_factory):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
     out = str(tmp_path_factory.mktemp("emu") / "emu_test")
-    cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", "-I", os.path.join(ROOT, "tests", "cpu_emu"),
+    extra = ["-DMHDF_F32X2"] if request.param == "f32x2" else []
+    cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *extra, "-I", os.path.join(ROOT, "tests", "cpu_emu"),
            "-I", os.path.join(ROOT, "mhdflows_jl_b200", "csrc"), "-I", "/usr/local/cuda/include",
            "-o", out, os.path.join(ROOT, "tests", "cpu_emu", "test_kernels.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)

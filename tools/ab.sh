@@ -1,8 +1,11 @@
 #!/bin/bash
 # A/B of two library builds on the same box: prints ms/step + per-class times for 256^3 and 512^3 MHD, alternating.
+#   tools/ab.sh [other-library]     default other library: mhdflows_jl_b200/libmhdflows_b200_prev.so
+#   e.g.  python -m mhdflows_jl_b200.build --variant=f32x2 && gpurun -- 'bash tools/ab.sh mhdflows_jl_b200/libmhdflows_b200_f32x2.so'
+OTHER=${1:-mhdflows_jl_b200/libmhdflows_b200_prev.so}
 for rep in 1 2; do
 for lib in prev new; do
-  if [ $lib = prev ]; then export MHDF_LIB=$PWD/mhdflows_jl_b200/libmhdflows_b200_prev.so; else unset MHDF_LIB; fi
+  if [ $lib = prev ]; then export MHDF_LIB=$PWD/$OTHER; else unset MHDF_LIB; fi
   python - <<PY
 import os, sys
 sys.path.insert(0, os.getcwd())
