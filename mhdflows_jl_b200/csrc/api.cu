@@ -712,6 +712,7 @@ struct Solver : mhdf_handle {
   //   P inverse send, R inverse receive, Xin x-pass input (later the product spectra), Xout x-pass output,
   //   P2 forward send, Q forward receive.
   // NOT YET VERIFIED ON HARDWARE (written after the round's GPU budget was spent); off unless MHDF_ZCHUNKS is set.
+  bool spec2 = [] { const char* e = getenv("MHDF_SPEC2"); return e && atoi(e) != 0; }();
   int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
   C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
   bool pipe_ok() const {
@@ -868,12 +869,30 @@ struct Solver : mhdf_handle {
     wait_mirror();
     launch_spectral(sa);
   }
+  template <int PHYS> void launch_spectral2(const SpecArgs<T>& sa) {
+    const unsigned plane = (unsigned)Kxp * (unsigned)Kyl;
+    const dim3 grid((plane + 255u) / 256u, (unsigned)Kz);
+    switch (sa.mode) {
+      case STEP_CALCN: k_spectral2<T, PHYS, STEP_CALCN><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_1: k_spectral2<T, PHYS, STEP_RK4_1><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_2: k_spectral2<T, PHYS, STEP_RK4_2><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_3: k_spectral2<T, PHYS, STEP_RK4_3><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_4: k_spectral2<T, PHYS, STEP_RK4_4><<<grid, 256, 0, st>>>(sa); break;
+      default:         k_spectral2<T, PHYS, STEP_LSRK><<<grid, 256, 0, st>>>(sa); break;
+    }
+  }
   void launch_spectral(SpecArgs<T>& sa) {
     prof_begin(KC_SPEC);
-    const int grid = spec_grid();
-    if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
-    else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<grid, 256, 0, st>>>(sa);
-    else k_spectral<T, PHYS_EMHD><<<grid, 256, 0, st>>>(sa);
+    if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
+      if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD>(sa);
+      else if (phys == MHDF_HD) launch_spectral2<PHYS_HD>(sa);
+      else launch_spectral2<PHYS_EMHD>(sa);
+    } else {
+      const int grid = spec_grid();
+      if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
+      else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<grid, 256, 0, st>>>(sa);
+      else k_spectral<T, PHYS_EMHD><<<grid, 256, 0, st>>>(sa);
+    }
     ++launches;
     CK(cudaGetLastError());
     prof_end();

@@ -725,6 +725,112 @@ __device__ __forceinline__ void spec_commit(const SpecArgs<T>& a, long long e, c
 #ifndef MHDF_SPEC_MINB
 #define MHDF_SPEC_MINB 4   // <= 64 registers: a streaming kernel wants the occupancy, not the registers
 #endif
+// Mirror operand of the kr = 0 symmetrisation, resolved once per mode for all fields (k_spectral2): base pointer of
+// field 0 and the field stride, or null when the mode is off the plane / its mirror is dealiased.
+template <typename T> struct SymSrc {
+  const Cx<T>* base;
+  long long stride;
+  bool plane;
+};
+template <typename T>
+__device__ __forceinline__ SymSrc<T> sym_src(const Cx<T>* __restrict__ S, const SpecGeom<T>& g, int ix, int jc, int kc) {
+  SymSrc<T> r;
+  r.base = nullptr; r.stride = 0; r.plane = (ix == 0);
+  if (r.plane) {
+    const int jm = g.by.row_of_wave(-g.by.wave(g.ky0 + jc));
+    const int km = g.bz.row_of_wave(-g.bz.wave(kc));
+    if (jm >= 0 && km >= 0) {
+      if (g.mirror != nullptr) {
+        const int q = jm / g.Kyl, jl = jm - q * g.Kyl;
+        r.base = g.mirror + (((long long)q * g.F) * g.bz.count() + km) * g.Kyl + jl;
+        r.stride = (long long)g.bz.count() * g.Kyl;
+      } else {
+        r.base = S + ((long long)km * g.Kyl + jm) * g.Kxp;
+        r.stride = g.field;
+      }
+    }
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ Cx<T> sym_apply(const SymSrc<T>& r, int fi, Cx<T> v) {
+  using C = Cx<T>;
+  if (r.plane) {
+    const C w = (r.base != nullptr) ? r.base[fi * r.stride] : mk<C>(0, 0);
+    v = mk<C>((T)0.5 * (v.x + w.x), (T)0.5 * (v.y - w.y));
+  }
+  return v;
+}
+
+// RHS of one retained mode e = (ix, jc, kc): N[] and the stage input sin[] at that mode.  V2: the mirror operand is
+// resolved once for all fields and the stage input is loaded once (same values, same arithmetic as the V1 form).
+template <typename T, int PHYS, bool V2, typename IDX>
+__device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, int jc, int kc,
+                                         Cx<T> (&N)[PHYS == PHYS_MHD ? 6 : 3], Cx<T> (&sin)[PHYS == PHYS_MHD ? 6 : 3]) {
+  using C = Cx<T>;
+  const SpecGeom<T>& g = a.g;
+  if constexpr (PHYS == PHYS_EMHD) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) { N[f] = a.P[f * g.field + e]; sin[f] = a.Sin[f * g.field + e]; }
+  } else {
+    constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
+    const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
+    const T k2 = kx * kx + ky * ky + kz * kz;
+    const T ik2 = (k2 > (T)0) ? (T)1 / k2 : (T)0;
+    C Tt[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) Tt[p] = a.P[p * g.field + e];
+    // D_j = i sum_i k_i T_ij   (xx,xy,xz,yy,yz,zz)
+    C D[3];
+    D[0] = mk<C>(kx * Tt[0].x + ky * Tt[1].x + kz * Tt[2].x, kx * Tt[0].y + ky * Tt[1].y + kz * Tt[2].y);
+    D[1] = mk<C>(kx * Tt[1].x + ky * Tt[3].x + kz * Tt[4].x, kx * Tt[1].y + ky * Tt[3].y + kz * Tt[4].y);
+    D[2] = mk<C>(kx * Tt[2].x + ky * Tt[4].x + kz * Tt[5].x, kx * Tt[2].y + ky * Tt[4].y + kz * Tt[5].y);
+    const C kD = mk<C>((kx * D[0].x + ky * D[1].x + kz * D[2].x) * ik2, (kx * D[0].y + ky * D[1].y + kz * D[2].y) * ik2);
+    const T kk[3] = {kx, ky, kz};
+    SymSrc<T> sy;
+    if constexpr (V2) {
+      sy = sym_src<T>(a.Sin, g, ix, jc, kc);
+#pragma unroll
+      for (int f = 0; f < F; ++f) sin[f] = a.Sin[f * g.field + e];
+    }
+    T hyper = (T)0;
+    if (a.n_nu > 1) { hyper = (T)1; for (int q = 0; q < a.n_nu; ++q) hyper *= k2; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const C pr = mk<C>(D[c].x - kk[c] * kD.x, D[c].y - kk[c] * kD.y);   // still missing the factor i
+      C us;
+      if constexpr (V2) us = sym_apply<T>(sy, c, sin[c]);
+      else { us = load_sym<T>(a.Sin, c, g, ix, jc, kc); sin[c] = a.Sin[c * g.field + e]; }
+      const T dc = -(a.nu * k2) - a.nu * hyper;
+      N[c] = mk<C>(-pr.y + dc * us.x, pr.x + dc * us.y);
+    }
+    if constexpr (PHYS == PHYS_MHD) {
+      C Ev[3];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) Ev[p] = a.P[(6 + p) * g.field + e];
+      C Cv[3];
+      Cv[0] = mk<C>(ky * Ev[2].x - kz * Ev[1].x, ky * Ev[2].y - kz * Ev[1].y);
+      Cv[1] = mk<C>(kz * Ev[0].x - kx * Ev[2].x, kz * Ev[0].y - kx * Ev[2].y);
+      Cv[2] = mk<C>(kx * Ev[1].x - ky * Ev[0].x, kx * Ev[1].y - ky * Ev[0].y);
+      const T dc = -(a.eta * k2);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        C bsym;
+        if constexpr (V2) bsym = sym_apply<T>(sy, 3 + c, sin[3 + c]);
+        else { bsym = load_sym<T>(a.Sin, 3 + c, g, ix, jc, kc); sin[3 + c] = a.Sin[(3 + c) * g.field + e]; }
+        N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
+      }
+    }
+    if constexpr (PHYS == PHYS_MHD) {   // addforcing! after the advection (pgen.jl:159); HD / EMHD: no effect, like the reference
+      if (a.force != nullptr) {
+#pragma unroll
+        for (int f = 0; f < F; ++f)
+          if ((a.fmask >> f) & 1u) { const C w = a.force[f * g.field + e]; N[f].x += w.x; N[f].y += w.y; }
+      }
+    }
+  }
+}
+
 template <typename T, int PHYS>
 __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a) {
   using C = Cx<T>;
@@ -737,61 +843,59 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a)
     const long long rowi = e / g.Kxp;
     const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
     if (g.ky0 + jc >= g.by.count()) continue;   // padding rows of the last slab
-    if constexpr (PHYS == PHYS_EMHD) {
-      C N[3], sin[3];
+    constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
+    C N[F], sin[F];
+    spec_rhs<T, PHYS, false>(a, e, ix, jc, kc, N, sin);
+    spec_commit<T, F>(a, e, N, sin);
+  }
+}
+
+// Variant with the stage mode as a template parameter, a (plane, kz) grid and 32-bit element indices: no 64-bit
+// division per mode (three in k_spectral, about a third of its 650 instructions per mode), no run-time switch, and the
+// Y / A operands of the stage update are requested before the RHS arithmetic instead of after it.  Same arithmetic in the
+// same order: results are bit-identical to k_spectral.  Opt-in (MHDF_SPEC2=1) until measured on hardware.
+// Needs F_total * field < 2^32 elements (true up to 1024^3 with 9 product fields).
+template <typename T, int PHYS, int MODE>
+__global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral2(SpecArgs<T> a) {
+  using C = Cx<T>;
+  const SpecGeom<T>& g = a.g;
+  constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
+  const unsigned plane = (unsigned)g.Kxp * (unsigned)g.Kyl;
+  const unsigned e2 = blockIdx.x * 256u + threadIdx.x;
+  if (e2 >= plane) return;
+  const unsigned jc = e2 / (unsigned)g.Kxp, ix = e2 - jc * (unsigned)g.Kxp;
+  if (ix >= (unsigned)g.Kx || g.ky0 + (int)jc >= g.by.count()) return;
+  const int kc = blockIdx.y;
+  const unsigned e = (unsigned)kc * plane + e2;
+  const unsigned fld = (unsigned)g.field;
+  // operands of the stage update first: their latency overlaps the RHS arithmetic
+  C y[F], ac[F];
 #pragma unroll
-      for (int f = 0; f < 3; ++f) { N[f] = a.P[f * g.field + e]; sin[f] = a.Sin[f * g.field + e]; }
-      spec_commit<T, 3>(a, e, N, sin);
-    } else {
-      constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
-      const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
-      const T k2 = kx * kx + ky * ky + kz * kz;
-      const T ik2 = (k2 > (T)0) ? (T)1 / k2 : (T)0;
-      C Tt[6];
+  for (int f = 0; f < F; ++f) {
+    if constexpr (MODE == STEP_RK4_1 || MODE == STEP_RK4_2 || MODE == STEP_RK4_3) y[f] = a.Y[f * fld + e];
+    if constexpr (MODE == STEP_RK4_2 || MODE == STEP_RK4_3 || MODE == STEP_RK4_4) ac[f] = a.A[f * fld + e];
+    if constexpr (MODE == STEP_LSRK) ac[f] = a.first ? mk<C>(0, 0) : a.A[f * fld + e];
+  }
+  C N[F], sin[F];
+  spec_rhs<T, PHYS, true>(a, e, (int)ix, (int)jc, kc, N, sin);
 #pragma unroll
-      for (int p = 0; p < 6; ++p) Tt[p] = a.P[p * g.field + e];
-      // D_j = i sum_i k_i T_ij   (xx,xy,xz,yy,yz,zz)
-      C D[3];
-      D[0] = mk<C>(kx * Tt[0].x + ky * Tt[1].x + kz * Tt[2].x, kx * Tt[0].y + ky * Tt[1].y + kz * Tt[2].y);
-      D[1] = mk<C>(kx * Tt[1].x + ky * Tt[3].x + kz * Tt[4].x, kx * Tt[1].y + ky * Tt[3].y + kz * Tt[4].y);
-      D[2] = mk<C>(kx * Tt[2].x + ky * Tt[4].x + kz * Tt[5].x, kx * Tt[2].y + ky * Tt[4].y + kz * Tt[5].y);
-      const C kD = mk<C>((kx * D[0].x + ky * D[1].x + kz * D[2].x) * ik2, (kx * D[0].y + ky * D[1].y + kz * D[2].y) * ik2);
-      const T kk[3] = {kx, ky, kz};
-      C N[F], sin[F];
-      T hyper = (T)0;
-      if (a.n_nu > 1) { hyper = (T)1; for (int q = 0; q < a.n_nu; ++q) hyper *= k2; }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const C pr = mk<C>(D[c].x - kk[c] * kD.x, D[c].y - kk[c] * kD.y);   // still missing the factor i
-        const C us = load_sym<T>(a.Sin, c, g, ix, jc, kc);
-        sin[c] = a.Sin[c * g.field + e];
-        const T dc = -(a.nu * k2) - a.nu * hyper;
-        N[c] = mk<C>(-pr.y + dc * us.x, pr.x + dc * us.y);
-      }
-      if constexpr (PHYS == PHYS_MHD) {
-        C Ev[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) Ev[p] = a.P[(6 + p) * g.field + e];
-        C Cv[3];
-        Cv[0] = mk<C>(ky * Ev[2].x - kz * Ev[1].x, ky * Ev[2].y - kz * Ev[1].y);
-        Cv[1] = mk<C>(kz * Ev[0].x - kx * Ev[2].x, kz * Ev[0].y - kx * Ev[2].y);
-        Cv[2] = mk<C>(kx * Ev[1].x - ky * Ev[0].x, kx * Ev[1].y - ky * Ev[0].y);
-        const T dc = -(a.eta * k2);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const C bsym = load_sym<T>(a.Sin, 3 + c, g, ix, jc, kc);
-          sin[3 + c] = a.Sin[(3 + c) * g.field + e];
-          N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
-        }
-      }
-      if constexpr (PHYS == PHYS_MHD) {   // addforcing! after the advection (pgen.jl:159); HD / EMHD: no effect, like the reference
-        if (a.force != nullptr) {
-#pragma unroll
-          for (int f = 0; f < F; ++f)
-            if ((a.fmask >> f) & 1u) { const C w = a.force[f * g.field + e]; N[f].x += w.x; N[f].y += w.y; }
-        }
-      }
-      spec_commit<T, F>(a, e, N, sin);
+  for (int f = 0; f < F; ++f) {
+    const unsigned o = f * fld + e;
+    if constexpr (MODE == STEP_CALCN) {
+      a.Nout[o] = N[f];
+    } else if constexpr (MODE == STEP_RK4_1) {   // Sin == Y
+      a.A[o] = mk<C>(y[f].x + a.ca * N[f].x, y[f].y + a.ca * N[f].y);
+      a.Sout[o] = mk<C>(y[f].x + a.cs * N[f].x, y[f].y + a.cs * N[f].y);
+    } else if constexpr (MODE == STEP_RK4_2 || MODE == STEP_RK4_3) {
+      a.A[o] = mk<C>(ac[f].x + a.ca * N[f].x, ac[f].y + a.ca * N[f].y);
+      a.Sout[o] = mk<C>(y[f].x + a.cs * N[f].x, y[f].y + a.cs * N[f].y);
+    } else if constexpr (MODE == STEP_RK4_4) {
+      a.Sout[o] = mk<C>(ac[f].x + a.ca * N[f].x, ac[f].y + a.ca * N[f].y);
+    } else {                                     // LSRK54: S2 = A_i S2 + dt N ; sol += B_i S2
+      C s2 = mk<C>(a.dt * N[f].x, a.dt * N[f].y);
+      if (!a.first) { s2.x += a.ca * ac[f].x; s2.y += a.ca * ac[f].y; }
+      a.A[o] = s2;
+      a.Sout[o] = mk<C>(sin[f].x + a.cs * s2.x, sin[f].y + a.cs * s2.y);
     }
   }
 }

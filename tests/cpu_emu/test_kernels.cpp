@@ -389,6 +389,16 @@ template <int N> void test_xplain() {
 }
 
 // ---- D. spectral kernel: RHS assembly + stage updates against the formulas in double ----------------------------
+template <typename T, int PHYS> void launch_spec2(const SpecArgs<T>& a, dim3 grid) {
+  switch (a.mode) {
+    case STEP_CALCN: emu::launch(k_spectral2<T, PHYS, STEP_CALCN>, grid, 256, a); break;
+    case STEP_RK4_1: emu::launch(k_spectral2<T, PHYS, STEP_RK4_1>, grid, 256, a); break;
+    case STEP_RK4_2: emu::launch(k_spectral2<T, PHYS, STEP_RK4_2>, grid, 256, a); break;
+    case STEP_RK4_3: emu::launch(k_spectral2<T, PHYS, STEP_RK4_3>, grid, 256, a); break;
+    case STEP_RK4_4: emu::launch(k_spectral2<T, PHYS, STEP_RK4_4>, grid, 256, a); break;
+    default:         emu::launch(k_spectral2<T, PHYS, STEP_LSRK>, grid, 256, a); break;
+  }
+}
 template <int PHYS> void test_spectral(int mode, bool forced, int P = 1, int rank = 0) {
   using T = double; using C = Cx<T>;
   const int nx = 16, ny = 16, nz = 16;
@@ -421,7 +431,17 @@ template <int PHYS> void test_spectral(int mode, bool forced, int P = 1, int ran
   a.P = Pp.data(); a.Sin = Sin.data(); a.Y = Y.data(); a.Sout = Sout.data(); a.A = A.data(); a.Nout = Nout.data();
   a.nu = 0.013; a.eta = 0.021; a.n_nu = forced ? 2 : 0; a.ca = 0.37; a.cs = 0.59; a.dt = 0.11; a.mode = mode; a.first = 0;
   a.force = forced ? force.data() : nullptr; a.fmask = forced ? 0x2Bu : 0;
-  emu::launch(k_spectral<T, PHYS>, dim3(3, 1, 1), 256, a);
+  {
+    // the (plane, kz)-grid variant must reproduce k_spectral bit for bit
+    std::vector<C> A2 = A, Sout2 = Sout, Nout2 = Nout;
+    SpecArgs<T> a2 = a;
+    a2.A = A2.data(); a2.Sout = Sout2.data(); a2.Nout = Nout2.data();
+    launch_spec2<T, PHYS>(a2, dim3((Kxp * Kyl + 255) / 256, Kz, 1));
+    emu::launch(k_spectral<T, PHYS>, dim3(3, 1, 1), 256, a);
+    const bool same = std::memcmp(A2.data(), A.data(), A.size() * sizeof(C)) == 0 && std::memcmp(Sout2.data(), Sout.data(), Sout.size() * sizeof(C)) == 0 &&
+                      std::memcmp(Nout2.data(), Nout.data(), Nout.size() * sizeof(C)) == 0;
+    report("spectral2 == spectral phys=" + std::to_string(PHYS) + " mode=" + std::to_string(mode) + " P=" + std::to_string(P), same, same ? 0.0 : 1.0);
+  }
   // reference
   double worst = 0;
   long checked = 0;

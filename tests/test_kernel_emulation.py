@@ -38,5 +38,5 @@ def test_kernels_on_the_cpu_emulator(emu_binary):
     assert lines[-1].startswith("ALL PASS")
     names = " ".join(lines)
     for needle in ("pass forward N=128", "slab inverse leg bit-identical, NZC=4", "xfused MHD N=1024", "xfused EMHD N=128",
-                   "xplain c2r N=1024", "spectral phys=1 mode=5", "P=2 rank=1", "emhd_derive", "pack / unpack"):
+                   "xplain c2r N=1024", "spectral phys=1 mode=5", "spectral2 == spectral phys=1 mode=2", "P=2 rank=1", "emhd_derive", "pack / unpack"):
         assert needle in names, needle
