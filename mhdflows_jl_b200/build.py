@@ -10,12 +10,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmhdflows_b200.so")
-SOURCES = [os.path.join(CSRC, "api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "fft_core.cuh"),
+# one translation unit per precision (the Solver<T> template with all its kernels) + the extern "C" boundary: they compile
+# in parallel and are linked into one shared object
+SOURCES = [os.path.join(CSRC, f) for f in ("api.cu", "solver_f32.cu", "solver_f64.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, "solver.cuh"), os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "fft_core.cuh"),
                   os.path.join(ROOT, "include", "mhdflows_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-I/usr/include", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-ldl"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+LINK_FLAGS = ["-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-ldl"]
 
 
 def nvcc_path() -> str:
@@ -38,34 +41,46 @@ def needs_build() -> bool:
 VARIANTS = {"f32x2": ["-DMHDF_F32X2"]}
 
 
-def build_variant(name: str, verbose: bool = True) -> str:
-    out = os.path.join(HERE, f"libmhdflows_b200_{name}.so")
-    cmd = [nvcc_path()] + NVCC_FLAGS + VARIANTS[name] + ["-o", out] + SOURCES
+def _compile_and_link(out: str, extra: list, tag: str, verbose: bool) -> str:
+    """nvcc -c every source concurrently (objects under build/<tag>/), then link `out`; ptxas -v output is kept in
+    build/ptxas<_tag>.log."""
+    nvcc = nvcc_path()
+    objdir = os.path.join(ROOT, "build", tag or "default")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, src]
+        if verbose:
+            print("[mhdflows_jl_b200] " + " ".join(cmd), file=sys.stderr)
+        jobs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = [], False
+    for obj, p in jobs:
+        o, _ = p.communicate()
+        log.append(o)
+        failed |= p.returncode != 0
+    with open(os.path.join(ROOT, "build", f"ptxas{'_' + tag if tag else ''}.log"), "w") as f:
+        f.write("".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "".join(log)[-4000:])
+    cmd = [nvcc] + LINK_FLAGS + ["-o", out] + [obj for obj, _ in jobs]
     if verbose:
         print("[mhdflows_jl_b200] " + " ".join(cmd), file=sys.stderr)
-    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
-    with open(os.path.join(ROOT, "build", f"ptxas_{name}.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + (res.stdout + res.stderr)[-4000:])
+        raise RuntimeError("link failed:\n" + (res.stdout + res.stderr)[-4000:])
     return out
+
+
+def build_variant(name: str, verbose: bool = True) -> str:
+    return _compile_and_link(os.path.join(HERE, f"libmhdflows_b200_{name}.so"), VARIANTS[name], name, verbose)
 
 
 def build(force: bool = False, verbose: bool = True) -> str:
     if not force and not needs_build():
         return LIB
     extra = os.environ.get("MHDF_NVCC_EXTRA", "").split()     # tuning builds, e.g. -DMHDF_SPEC_MINB=3
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-o", LIB] + SOURCES
-    if verbose:
-        print("[mhdflows_jl_b200] " + " ".join(cmd), file=sys.stderr)
-    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    with open(os.path.join(ROOT, "build", "ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + (res.stdout + res.stderr)[-4000:])
-    return LIB
+    return _compile_and_link(LIB, extra, "", verbose)
 
 
 if __name__ == "__main__":

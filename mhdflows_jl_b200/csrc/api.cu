@@ -1,1204 +1,6 @@
-// api.cu -- handle, orchestration and the extern "C" boundary declared in include/mhdflows_b200.h.
-//
-// One RHS evaluation (reference: MHDcalcN!/HDcalcN!/EMHDcalcN!, src/pgen.jl:153-181) is
-//   [EMHD: derive] -> inverse z pass -> inverse y pass -> fused x pass (c2r, products, r2c)
-//   -> forward y pass -> forward z pass -> spectral assembly + Runge-Kutta stage update
-// on a compact state that stores only the modes FourierFlows' dealias!() keeps.
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-#include <nccl.h>
-
-#include <cmath>
-#include <cstdlib>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/mhdflows_b200.h"
-#include "kernels.cuh"
-
-using namespace mhdf;
-
-static thread_local std::string g_create_error;
-
-#define CK(call)                                                                                   \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      char buf_[512];                                                                              \
-      snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
-      throw Err{MHDF_ERR_CUDA, buf_};                                                              \
-    }                                                                                              \
-  } while (0)
-
-struct Err {
-  int code;
-  std::string msg;
-};
-
-// NCCL is bound at run time (dlopen) so the library has no link-time dependency on a particular libnccl; when
-// the host process already loaded one (e.g. PyTorch's) that copy is used.
-struct NcclApi {
-  void* so = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-  bool load(std::string& why) {
-    if (so) return true;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) { so = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (so) break; }
-    if (!so) { why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
-#define LD(f) f = reinterpret_cast<decltype(f)>(dlsym(so, "nccl" #f)); if (!f) { why = "libnccl lacks nccl" #f; return false; }
-    LD(GetUniqueId) LD(CommInitRank) LD(CommDestroy) LD(Send) LD(Recv) LD(GroupStart) LD(GroupEnd) LD(AllReduce) LD(AllGather)
-    LD(GetErrorString)
-#undef LD
-    return true;
-  }
-};
-static NcclApi g_nccl;
-
-#define NK(call)                                                                                   \
-  do {                                                                                             \
-    ncclResult_t r_ = (call);                                                                      \
-    if (r_ != ncclSuccess) {                                                                       \
-      char buf_[512];                                                                              \
-      snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
-      throw Err{MHDF_ERR_NCCL, buf_};                                                              \
-    }                                                                                              \
-  } while (0)
-
-enum { KC_ZINV = 0, KC_YINV, KC_XFUSED, KC_YFWD, KC_ZFWD, KC_SPEC, KC_DERIVE, KC_EXCH, KC_COUNT };
-
-struct mhdf_handle {
-  std::string err;
-  virtual ~mhdf_handle() {}
-  virtual void set_real(int field, const void* p) = 0;
-  virtual void get_real(int field, int which, void* p) = 0;
-  virtual void set_spectral(int field, const void* p) = 0;
-  virtual void get_spectral(int field, int which, void* p) = 0;
-  virtual void step(int n) = 0;
-  virtual void calcN(void* p) = 0;
-  virtual void set_dt(double dt) = 0;
-  virtual void set_clock(double t, long long step) = 0;
-  virtual void get_clock(double* t, double* dt, long long* step) const = 0;
-  virtual void cfl_dt(double coef, double t_diff, double* dt) = 0;
-  virtual void energy(int which, double* KE, double* ME) = 0;
-  virtual void helicity(double* Hk, double* Hm, double* Hc) = 0;
-  virtual void spectrum(int field, double* Pk, int nbins) = 0;
-  virtual void stale_stats(double* mx, double* sm) const = 0;
-  virtual void step_timed(int n, double* ms) = 0;
-  virtual void profile(int enable) = 0;
-  virtual void profile_get(double* ms, long long* cnt, int n) = 0;
-  virtual long long launch_count() const = 0;
-  virtual void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const = 0;
-  virtual void set_forcing(int field, const void* p) = 0;
-  virtual void ipc_export(void* blob) = 0;
-  virtual void ipc_import(const void* blobs) = 0;
-};
-struct IpcBlob { cudaIpcMemHandle_t r, q; int device; int pad[15]; };
-
-static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
-
-// FourierFlows.getaliasedwavenumbers with aliased_fraction = 1/3, evaluated in Float64 exactly like
-// the Julia expression: 1-based inclusive [iL, iR].
-static void alias_range(int nk, int* iL, int* iR) {
-  const double af = 1.0 / 3.0;
-  const double L = (1.0 - af) / 2.0, R = (1.0 + af) / 2.0;
-  *iL = (int)std::floor(L * nk) + 1;
-  *iR = (int)std::ceil(R * nk);
-}
-
-template <typename T>
-struct Solver : mhdf_handle {
-  using C = Cx<T>;
-  mhdf_config cfg;
-  int nx, ny, nz, nkr;
-  int Kx, Kxp, Ky, Kz;
-  Band by, bz;
-  // slab decomposition: P_ ranks; real space split along z (nzl planes each), spectral space along compact ky rows
-  // (Kyl rows each, the last slab zero-padded).  One GPU: P_ = 1, nzl = nz, Kyl = Ky.
-  int P_ = 1, rank_ = 0, nzl, Kyl, ky0;
-  ncclComm_t comm = nullptr;
-  Cx<T>* plane_loc = nullptr;   // kr = 0 plane of the stage input, local  [F][Kz][Kyl]
-  Cx<T>* plane_all = nullptr;   // gathered                                  [P][F][Kz][Kyl]
-  int phys, F, nin, nout;
-  long long cf;   // elements of one compact field
-  cudaStream_t st = nullptr;    // compute stream
-  cudaStream_t sc = nullptr;    // communication stream (every NCCL call is issued here, ordered with events)
-  std::vector<cudaEvent_t> dep_ev;
-  size_t dep_next = 0;
-  // peer-memory exchange (after mhdf_ipc_import): peers' R and Q buffers mapped into this process
-  bool ipc_on = false;
-  std::vector<C*> peerR, peerQ;
-  static constexpr int NCS_MAX = 8;
-  int NCS = [] { const char* e = getenv("MHDF_COPY_STREAMS"); int n = e ? atoi(e) : 7; return n < 1 ? 1 : (n > NCS_MAX ? NCS_MAX : n); }();
-  cudaStream_t cs[NCS_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copy streams (copy engines, no SMs)
-  float* bar_d = nullptr;
-  // state registers (compact, F fields each)
-  C* reg[4] = {nullptr, nullptr, nullptr, nullptr};
-  int iY = 0;       // register holding sol
-  int iStale = -1;  // register holding the last stage input (RK4), -1 if none
-  C *P = nullptr, *Q = nullptr, *R = nullptr, *D = nullptr;
-  size_t szP = 0, szQ = 0, szR = 0, szD = 0;
-  T* bst = nullptr;   // EMHD stale real b [3][nz][ny][nx]
-  C* force = nullptr; // constant spectral forcing [F][compact] (calcF! hook)
-  unsigned fmask = 0;
-  C *twx = nullptr, *twy = nullptr, *twz = nullptr;
-  T *kxv = nullptr, *kyv = nullptr, *kzv = nullptr;
-  XRed* red_d = nullptr;
-  XRed* red_h = nullptr;   // pinned
-  double* diag_d = nullptr;
-  double* diag_h = nullptr;  // pinned
-  double* spec_d = nullptr;
-  int spec_cap = 0;
-  // stale vars statistics (getCFL!/ProbDiagnostic read vars.* of the last RHS evaluation)
-  double st_max[6] = {0, 0, 0, 0, 0, 0}, st_sum[6] = {0, 0, 0, 0, 0, 0}, st_cross = 0;
-  T t_, dt_;
-  long long step_ = 0;
-  long long launches = 0;
-  long long bytes_dev = 0;
-  int nsm = 148;
-  // profiling
-  bool prof = false;
-  struct Ev { cudaEvent_t a, b; int cls; };
-  std::vector<Ev> evs;
-  std::vector<Ev> ev_free;
-  double prof_ms[KC_COUNT];
-  long long prof_cnt[KC_COUNT];
-
-  template <typename U> U* dalloc(size_t n) {
-    U* p = nullptr;
-    CK(cudaMalloc(&p, n * sizeof(U)));
-    CK(cudaMemsetAsync(p, 0, n * sizeof(U), st));
-    bytes_dev += (long long)(n * sizeof(U));
-    return p;
-  }
-
-  explicit Solver(const mhdf_config& c) : cfg(c) {
-    try {
-      init(c);
-    } catch (...) {   // e.g. cudaMalloc failed half-way: release what exists before reporting
-      release();
-      throw;
-    }
-  }
-  void init(const mhdf_config& c) {
-    nx = c.nx; ny = c.ny; nz = c.nz;
-    nkr = nx / 2 + 1;
-    int iL, iR;
-    alias_range(nx, &iL, &iR);
-    Kx = iL - 1;
-    Kxp = (Kx + 7) / 8 * 8;
-    alias_range(ny, &iL, &iR);
-    by.n = ny; by.lo = iL - 1; by.hi0 = iR;
-    alias_range(nz, &iL, &iR);
-    bz.n = nz; bz.lo = iL - 1; bz.hi0 = iR;
-    Ky = by.count(); Kz = bz.count();
-    P_ = c.nranks; rank_ = c.rank;
-    nzl = nz / P_;
-    Kyl = (Ky + P_ - 1) / P_;
-    ky0 = rank_ * Kyl;
-    if (P_ > 1 && (nz % P_ != 0 || (P_ - 1) * Kyl >= Ky))
-      throw Err{MHDF_ERR_INVALID, "grid too small for this many ranks (need nz % nranks == 0 and a non-empty ky slab per rank)"};
-    phys = c.physics;
-    F = (phys == MHDF_MHD) ? 6 : 3;
-    nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 24);
-    nout = (phys == MHDF_MHD) ? 9 : (phys == MHDF_HD ? 6 : 3);
-    cf = (long long)Kxp * Kyl * Kz;
-    t_ = (T)0; dt_ = (T)c.dt;
-    for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
-
-    CK(cudaSetDevice(c.device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, c.device));
-    nsm = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    if (P_ > 1) {
-      CK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-      dep_ev.resize(1024);   // cyclic pool; far more than one RHS evaluation can take between a record and its wait
-      for (auto& e : dep_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      std::string why;
-      if (!g_nccl.load(why)) throw Err{MHDF_ERR_NCCL, why};
-      if (c.nccl_id == nullptr) throw Err{MHDF_ERR_INVALID, "nranks > 1 needs nccl_id (mhdf_nccl_unique_id on rank 0)"};
-      ncclUniqueId id;
-      std::memcpy(&id, c.nccl_id, sizeof id);
-      NK(g_nccl.CommInitRank(&comm, P_, id, rank_));
-    }
-    const int nreg = (c.stepper == MHDF_RK4) ? 4 : 3;
-    for (int i = 0; i < nreg; ++i) reg[i] = dalloc<C>((size_t)F * cf);
-    // work buffers (elements).  P: inverse-z output / forward-y output (send layouts);  Q: inverse-y output (x input)
-    // / second exchange target;  R: first exchange target / x output / forward-z output / API staging.
-    const size_t e_zK = (size_t)nz * Kyl * Kxp;          // one field after a z pass      [nz][Kyl][Kxp]  (== P_ blocks)
-    const size_t e_zy = (size_t)nzl * ny * Kxp;          // one field in x-pass layout    [nzl][ny][Kxp]
-    const size_t need_stage = ((size_t)nkr * Kyl * nz > (size_t)nx * ny * nzl / 2 ? (size_t)nkr * Kyl * nz : (size_t)nx * ny * nzl / 2) + 16;
-    auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
-    szP = mx((size_t)nin * e_zK, (size_t)nout * e_zK);
-    szQ = mx((size_t)nin * e_zy, (size_t)nout * e_zK);
-    szR = mx(mx((size_t)nin * e_zK, (size_t)nout * e_zy), mx((size_t)nout * (size_t)cf, need_stage));
-    if (P_ == 1) szQ = mx(szQ, (size_t)nout * (size_t)cf);
-    P = dalloc<C>(szP); Q = dalloc<C>(szQ); R = dalloc<C>(szR);
-    if (phys == MHDF_EMHD) {
-      szD = (size_t)24 * cf;
-      D = dalloc<C>(szD);
-      bst = dalloc<T>((size_t)3 * nx * ny * nzl);
-    }
-    twx = make_tw(nx); twy = make_tw(ny); twz = make_tw(nz);
-    // wavenumbers: built in Float64 then converted to T (FourierFlows ThreeDGrid; mirror utils/utils.jl:60-64)
-    std::vector<T> hx(Kx), hy(Kyl), hz(Kz);
-    for (int i = 0; i < Kx; ++i) hx[i] = (T)(i * (2.0 * M_PI / c.Lx));
-    for (int j = 0; j < Kyl; ++j) hy[j] = (ky0 + j < Ky) ? (T)(by.wave(ky0 + j) * (2.0 * M_PI / c.Ly)) : (T)0;
-    for (int k = 0; k < Kz; ++k) hz[k] = (T)(bz.wave(k) * (2.0 * M_PI / c.Lz));
-    kxv = dalloc<T>(Kx); kyv = dalloc<T>(Kyl); kzv = dalloc<T>(Kz);
-    CK(cudaMemcpyAsync(kxv, hx.data(), Kx * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(kyv, hy.data(), Kyl * sizeof(T), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(kzv, hz.data(), Kz * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (P_ > 1) build_tables();
-    red_d = dalloc<XRed>(1);
-    diag_d = dalloc<double>(8);
-    CK(cudaMallocHost(&red_h, sizeof(XRed)));
-    CK(cudaMallocHost(&diag_h, 8 * sizeof(double)));
-    std::memset(red_h, 0, sizeof(XRed));
-    CK(cudaStreamSynchronize(st));
-    setup_attrs();
-  }
-
-  // Exchange buffers are [peer][field][z'][ky'][kx]: the piece for / from one peer is contiguous, blk(n) elements for an
-  // n-field batch.
-  size_t blk(int nf) const { return (size_t)nf * nzl * Kyl * Kxp; }
-  void build_tables() {   // slab runs: mirror-plane buffers, exchange-size check
-    plane_loc = dalloc<C>((size_t)F * Kz * Kyl);
-    plane_all = dalloc<C>((size_t)P_ * F * Kz * Kyl);
-    check_blk(CHUNK > 0 ? CHUNK : (nin > nout ? nin : nout));
-  }
-  void check_blk(int nf) const {
-    if ((long long)P_ * (long long)blk(nf) >= (1LL << 31)) throw Err{MHDF_ERR_INVALID, "slab exchange buffer exceeds 2^31 elements per batch"};
-  }
-  ~Solver() override { release(); }
-  void release() {
-    cudaSetDevice(cfg.device);
-    if (st) cudaStreamSynchronize(st);
-    if (sc) cudaStreamSynchronize(sc);
-    for (int i = 0; i < NCS; ++i) if (cs[i]) { cudaStreamSynchronize(cs[i]); cudaStreamDestroy(cs[i]); }
-    if (ipc_on) {
-      // peers may still be pushing into our buffers: close the mappings only after a final cross-rank barrier
-      if (comm) { g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc); cudaStreamSynchronize(sc); }
-      for (int q = 0; q < P_; ++q) if (q != rank_) { cudaIpcCloseMemHandle(peerR[q]); cudaIpcCloseMemHandle(peerQ[q]); }
-    }
-    cudaFree(bar_d);
-    for (auto& e : dep_ev) cudaEventDestroy(e);
-    if (sc) cudaStreamDestroy(sc);
-    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
-    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
-    cudaFree(twx); cudaFree(twy); cudaFree(twz);
-    cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
-    cudaFree(plane_loc); cudaFree(plane_all);
-    if (comm) g_nccl.CommDestroy(comm);
-    cudaFree(red_d); cudaFree(diag_d); cudaFree(spec_d);
-    if (red_h) cudaFreeHost(red_h);
-    if (diag_h) cudaFreeHost(diag_h);
-    if (st) cudaStreamDestroy(st);
-    st = sc = nullptr; comm = nullptr; ipc_on = false; red_h = nullptr; diag_h = nullptr;
-    for (int i = 0; i < 4; ++i) reg[i] = nullptr;
-    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
-    red_d = nullptr; diag_d = nullptr; spec_d = nullptr; plane_loc = plane_all = nullptr; bar_d = nullptr;
-    dep_ev.clear(); evs.clear(); ev_free.clear();
-    for (int i = 0; i < NCS_MAX; ++i) cs[i] = nullptr;
-  }
-
-  C* make_tw(int n) {
-    std::vector<C> h(n);
-    for (int i = 0; i < n; ++i) {
-      const double a = 2.0 * M_PI * (double)i / (double)n;
-      h[i].x = (T)std::cos(a);
-      h[i].y = (T)(-std::sin(a));
-    }
-    C* d = dalloc<C>(n);
-    CK(cudaMemcpyAsync(d, h.data(), n * sizeof(C), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    return d;
-  }
-
-  SpecGeom<T> geom() const {
-    SpecGeom<T> g;
-    g.Kx = Kx; g.Kxp = Kxp; g.by = by; g.bz = bz; g.Kyl = Kyl; g.ky0 = ky0; g.F = F;
-    g.kx = kxv; g.ky = kyv; g.kz = kzv; g.field = cf;
-    g.mirror = (P_ > 1) ? plane_all : nullptr;
-    return g;
-  }
-
-  // ---- profiling brackets ------------------------------------------------------------------
-  // `b` waits for everything enqueued so far on `a`
-  void order(cudaStream_t a, cudaStream_t b) {
-    cudaEvent_t e = dep_ev[dep_next++ % dep_ev.size()];
-    CK(cudaEventRecord(e, a));
-    CK(cudaStreamWaitEvent(b, e, 0));
-  }
-  void sync_all() {
-    CK(cudaStreamSynchronize(st));
-    if (sc) CK(cudaStreamSynchronize(sc));
-  }
-  void prof_begin(int cls, cudaStream_t s = nullptr) {
-    if (!prof) return;
-    if (s == nullptr) s = st;
-    Ev e;
-    if (!ev_free.empty()) { e = ev_free.back(); ev_free.pop_back(); }
-    else { CK(cudaEventCreate(&e.a)); CK(cudaEventCreate(&e.b)); }
-    e.cls = cls;
-    CK(cudaEventRecord(e.a, s));
-    evs.push_back(e);
-  }
-  void prof_end(cudaStream_t s = nullptr) {
-    if (!prof) return;
-    CK(cudaEventRecord(evs.back().b, s ? s : st));
-    if (evs.size() > 4096) prof_collect();
-  }
-  void prof_collect() {
-    sync_all();
-    for (auto& e : evs) {
-      float ms = 0;
-      CK(cudaEventElapsedTime(&ms, e.a, e.b));
-      prof_ms[e.cls] += ms;
-      prof_cnt[e.cls] += 1;
-      ev_free.push_back(e);
-    }
-    evs.clear();
-  }
-
-  // ---- kernel dispatch ------------------------------------------------------------------------
-  static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
-  // columns per block: 16 (128-byte row segments); 8 at N = 1024 so two 512-thread blocks fit per SM (16 columns in one
-  // 1024-thread block measured 4 % slower per step on a 256 x 1024 x 1024 grid)
-  static constexpr int passTX(int N) { return sizeof(T) == 4 ? (N >= 1024 ? 8 : 16) : (N >= 1024 ? 4 : 8); }
-  static constexpr int xE(int) { return 8; }
-  static constexpr int XNT = 64;   // threads per block of the x kernels: small blocks, rows decoupled per warp
-  static constexpr int xRB(int N) { return XNT / (N / 2 / 8) > 0 ? XNT / (N / 2 / 8) : 1; }
-
-  bool blk_out = false;
-  template <int N, int DIR> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
-    constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
-    constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
-    dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
-    // the blocked side is the z side of the z passes and the ky side of the y passes: output of inverse-z / forward-y,
-    // input of inverse-y / forward-z
-    if (a.blk_rows == 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 0><<<grid, (N / E) * TX, smem, st>>>(a);
-    else if (a.blk2_rows > 0 && blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 4><<<grid, (N / E) * TX, smem, st>>>(a);
-    else if (a.blk2_rows > 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 3><<<grid, (N / E) * TX, smem, st>>>(a);
-    else if (blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 2><<<grid, (N / E) * TX, smem, st>>>(a);
-    else k_pass<T, N, E, TX, DIR, (DIR > 0), 1><<<grid, (N / E) * TX, smem, st>>>(a);
-    ++launches;
-  }
-  template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
-    switch (N) {
-      case 16: launch_pass_n<16, DIR>(a, n_outer, n_fields); break;
-      case 32: launch_pass_n<32, DIR>(a, n_outer, n_fields); break;
-      case 64: launch_pass_n<64, DIR>(a, n_outer, n_fields); break;
-      case 128: launch_pass_n<128, DIR>(a, n_outer, n_fields); break;
-      case 256: launch_pass_n<256, DIR>(a, n_outer, n_fields); break;
-      case 512: launch_pass_n<512, DIR>(a, n_outer, n_fields); break;
-      case 1024: launch_pass_n<1024, DIR>(a, n_outer, n_fields); break;
-      default: throw Err{MHDF_ERR_INVALID, "unsupported axis length"};
-    }
-    CK(cudaGetLastError());
-  }
-
-  template <int N> static size_t x_smem() {
-    constexpr int E = xE(N), M = N / 2, R1 = imin(E, M);
-    return (size_t)2 * xRB(N) * RowIdx<M, R1>::SIZE * sizeof(C);
-  }
-  int x_grid(long long rows, int RB) const {
-    long long sets = rows / RB;
-    long long g = (long long)nsm * 16;
-    return (int)(sets < g ? sets : g);
-  }
-  template <int N> void launch_xfused_n(XArgs<T>& a) {
-    constexpr int E = xE(N), RB = xRB(N);
-    const int grid = x_grid(a.rows, RB);
-    const int threads = (N / 2 / E) * RB;
-    const bool red = a.red != nullptr;
-#define XLAUNCH(PH)                                                                          \
-    do {                                                                                     \
-      if (red) k_xfused<T, N, E, RB, PH, true><<<grid, threads, x_smem<N>(), st>>>(a);       \
-      else k_xfused<T, N, E, RB, PH, false><<<grid, threads, x_smem<N>(), st>>>(a);          \
-    } while (0)
-    if (phys == MHDF_MHD) XLAUNCH(PHYS_MHD);
-    else if (phys == MHDF_HD) XLAUNCH(PHYS_HD);
-    else XLAUNCH(PHYS_EMHD);
-#undef XLAUNCH
-    ++launches;
-  }
-  template <int N, int DIR> void launch_xplain_n(XArgs<T>& a) {
-    constexpr int E = xE(N), RB = xRB(N);
-    k_xplain<T, N, E, RB, DIR><<<x_grid(a.rows, RB), (N / 2 / E) * RB, x_smem<N>(), st>>>(a);
-    ++launches;
-  }
-  void launch_xfused(XArgs<T>& a) {
-    switch (nx) {
-      case 16: launch_xfused_n<16>(a); break;
-      case 32: launch_xfused_n<32>(a); break;
-      case 64: launch_xfused_n<64>(a); break;
-      case 128: launch_xfused_n<128>(a); break;
-      case 256: launch_xfused_n<256>(a); break;
-      case 512: launch_xfused_n<512>(a); break;
-      case 1024: launch_xfused_n<1024>(a); break;
-      default: throw Err{MHDF_ERR_INVALID, "unsupported nx"};
-    }
-    CK(cudaGetLastError());
-  }
-  template <int DIR> void launch_xplain(XArgs<T>& a) {
-    switch (nx) {
-      case 16: launch_xplain_n<16, DIR>(a); break;
-      case 32: launch_xplain_n<32, DIR>(a); break;
-      case 64: launch_xplain_n<64, DIR>(a); break;
-      case 128: launch_xplain_n<128, DIR>(a); break;
-      case 256: launch_xplain_n<256, DIR>(a); break;
-      case 512: launch_xplain_n<512, DIR>(a); break;
-      case 1024: launch_xplain_n<1024, DIR>(a); break;
-      default: throw Err{MHDF_ERR_INVALID, "unsupported nx"};
-    }
-    CK(cudaGetLastError());
-  }
-  void setup_attrs() {
-    // opt in to > 48 KB dynamic shared memory where a plan needs it
-    set_pass_attr<256>(); set_pass_attr<512>(); set_pass_attr<1024>();
-    set_x_attr<16>(); set_x_attr<32>(); set_x_attr<64>(); set_x_attr<128>(); set_x_attr<256>(); set_x_attr<512>(); set_x_attr<1024>();
-  }
-  template <int N> void set_x_attr() {
-    constexpr int E = xE(N), RB = xRB(N);
-    const int smem = (int)x_smem<N>();
-    if (smem > 48 * 1024) {
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
-  }
-  template <int N> void set_pass_attr() {
-    constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
-    constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
-    if (smem > 48 * 1024) {
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, +1, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
-  }
-
-  // ---- 3D transform legs -------------------------------------------------------------------
-  // One GPU:  compact [nf][Kz][Ky][Kxp] <-> [nf][nz][Ky][Kxp] <-> [nf][nz][ny][Kxp].
-  // Slabs:    the [nz][Kyl][Kxp] side of the z passes and the ky side of the y passes live in the blocked exchange
-  //           layout [peer][nf][nzl][Kyl][Kxp]; the all-to-all in between swaps "all z, my ky" for "my z, all ky".
-  void z_inverse(const C* in, long long in_field, C* out, int nf) {
-    PassArgs<T> a;
-    a.in = in; a.out = out; a.tw = twz;
-    a.in_row = a.out_row = Kyl * Kxp;
-    a.in_outer = a.out_outer = 0;
-    a.in_field = in_field; a.out_field = (long long)nzl * Kyl * Kxp;   // nzl == nz on one GPU; in-block field stride otherwise
-    a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
-    if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
-    blk_out = true;
-    prof_begin(KC_ZINV);
-    launch_pass<+1>(nz, a, 1, nf);
-    prof_end();
-  }
-  void y_inverse(const C* in, C* out, int nf) {
-    PassArgs<T> a;
-    a.in = in; a.out = out; a.tw = twy;
-    a.in_row = a.out_row = Kxp;
-    a.in_outer = (long long)Kyl * Kxp; a.out_outer = (long long)ny * Kxp;
-    a.in_field = (long long)nzl * Kyl * Kxp; a.out_field = (long long)nzl * ny * Kxp;
-    a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
-    if (P_ > 1) { a.blk_rows = Kyl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + Kyl - 1) / Kyl); }
-    blk_out = false;
-    prof_begin(KC_YINV);
-    launch_pass<+1>(ny, a, nzl, nf);
-    prof_end();
-  }
-  void y_forward(const C* in, C* out, int nf) {
-    PassArgs<T> a;
-    a.in = in; a.out = out; a.tw = twy;
-    a.in_row = a.out_row = Kxp;
-    a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
-    a.in_field = (long long)nzl * ny * Kxp; a.out_field = (long long)nzl * Kyl * Kxp;
-    a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
-    if (P_ > 1) { a.blk_rows = Kyl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + Kyl - 1) / Kyl); }
-    blk_out = true;
-    prof_begin(KC_YFWD);
-    launch_pass<-1>(ny, a, nzl, nf);
-    prof_end();
-  }
-  void z_forward(const C* in, C* out, long long out_field, int nf) {
-    PassArgs<T> a;
-    a.in = in; a.out = out; a.tw = twz;
-    a.in_row = a.out_row = Kyl * Kxp;
-    a.in_outer = a.out_outer = 0;
-    a.in_field = (long long)nzl * Kyl * Kxp;
-    a.out_field = out_field;
-    a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-    a.blk_rows = 0; a.blk_stride = 0; a.blk_magic = 0; a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
-    if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
-    blk_out = false;
-    prof_begin(KC_ZFWD);
-    launch_pass<-1>(nz, a, 1, nf);
-    prof_end();
-  }
-  // all-to-all of the blocked layout: piece q (blk(nf) elements) goes to / comes from rank q; the own piece is a local
-  // copy.  Two transports: (a) after mhdf_ipc_import, copy-engine pushes straight into the peers' receive buffer over
-  // NVLink (no SMs, overlaps the axis passes), closed by a tiny all-reduce as the cross-rank barrier; (b) NCCL
-  // send/recv.  `recv` must be R or Q (+ offset).
-  void exchange(const C* send, C* recv, int nf, bool first_of_leg = true, size_t block_elems = 0) {
-    const size_t B = block_elems ? block_elems : blk(nf);
-    const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat32 : ncclFloat64;
-    prof_begin(KC_EXCH, sc);
-    // pushes land in the peers' buffer without the peer posting a receive: before the first push of a leg every rank
-    // must be past its last use of that buffer (stream order on each rank + this barrier)
-    if (ipc_on && first_of_leg) NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));
-    CK(cudaMemcpyAsync(recv + (size_t)rank_ * B, send + (size_t)rank_ * B, B * sizeof(C), cudaMemcpyDeviceToDevice, sc));
-    if (ipc_on) {
-      const bool inR = (recv >= R && recv < R + szR);
-      const size_t off = inR ? (size_t)(recv - R) : (size_t)(recv - Q);
-      for (int i = 0; i < NCS && i < P_ - 1; ++i) order(sc, cs[i]);
-      int k = 0;
-      for (int d = 1; d < P_; ++d, ++k) {
-        const int q = (rank_ + d) % P_;   // stagger the targets so the pushes of all ranks spread over the links
-        C* dst = (inR ? peerR[q] : peerQ[q]) + off + (size_t)rank_ * B;
-        CK(cudaMemcpyAsync(dst, send + (size_t)q * B, B * sizeof(C), cudaMemcpyDeviceToDevice, cs[k % NCS]));
-      }
-      for (int i = 0; i < NCS && i < P_ - 1; ++i) order(cs[i], sc);
-      NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));   // every rank's pushes have landed
-    } else {
-      NK(g_nccl.GroupStart());
-      for (int q = 0; q < P_; ++q) {
-        if (q == rank_) continue;
-        NK(g_nccl.Send(send + (size_t)q * B, 2 * B, dt, q, comm, sc));
-        NK(g_nccl.Recv(recv + (size_t)q * B, 2 * B, dt, q, comm, sc));
-      }
-      NK(g_nccl.GroupEnd());
-    }
-    prof_end(sc);
-  }
-  void ipc_export(void* blob) override {
-    if (P_ == 1) throw Err{MHDF_ERR_STATE, "peer exchange needs nranks > 1"};
-    IpcBlob b;
-    std::memset(&b, 0, sizeof b);
-    CK(cudaSetDevice(cfg.device));
-    CK(cudaIpcGetMemHandle(&b.r, R));
-    CK(cudaIpcGetMemHandle(&b.q, Q));
-    b.device = cfg.device;
-    std::memcpy(blob, &b, sizeof b);
-  }
-  void ipc_import(const void* blobs) override {
-    if (P_ == 1) throw Err{MHDF_ERR_STATE, "peer exchange needs nranks > 1"};
-    CK(cudaSetDevice(cfg.device));
-    peerR.assign(P_, nullptr); peerQ.assign(P_, nullptr);
-    const IpcBlob* b = reinterpret_cast<const IpcBlob*>(blobs);
-    for (int q = 0; q < P_; ++q) {
-      if (q == rank_) { peerR[q] = R; peerQ[q] = Q; continue; }
-      void *pr = nullptr, *pq = nullptr;
-      CK(cudaIpcOpenMemHandle(&pr, b[q].r, cudaIpcMemLazyEnablePeerAccess));
-      CK(cudaIpcOpenMemHandle(&pq, b[q].q, cudaIpcMemLazyEnablePeerAccess));
-      peerR[q] = reinterpret_cast<C*>(pr); peerQ[q] = reinterpret_cast<C*>(pq);
-    }
-    for (int i = 0; i < NCS; ++i) if (!cs[i]) CK(cudaStreamCreateWithFlags(&cs[i], cudaStreamNonBlocking));
-    if (!bar_d) bar_d = dalloc<float>(1);
-    CK(cudaStreamSynchronize(st));
-    ipc_on = true;
-  }
-  // fields per exchange chunk: the transposes of one chunk overlap the passes of the next (MHDF_EXCH_CHUNK=0: whole batch)
-  int CHUNK = [] { const char* e = getenv("MHDF_EXCH_CHUNK"); return e ? atoi(e) : 3; }();
-  int chunk_fields(int nf) const { return (CHUNK > 0 && nf % CHUNK == 0) ? CHUNK : (CHUNK == 0 ? nf : 1); }
-  // spectral compact (src, field stride cf) -> x-pass layout in Q.  Uses P (and R when exchanging).
-  void to_xlayout(const C* src, int nf) {
-    if (P_ == 1) { z_inverse(src, cf, P, nf); y_inverse(P, Q, nf); return; }
-    const int fc = chunk_fields(nf), nc = nf / fc;
-    const size_t cb = (size_t)P_ * blk(fc);
-    std::vector<cudaEvent_t> done(nc);
-    for (int c = 0; c < nc; ++c) {
-      z_inverse(src + (size_t)c * fc * cf, cf, P + c * cb, fc);
-      order(st, sc);
-      exchange(P + c * cb, R + c * cb, fc, c == 0);
-      done[c] = dep_ev[dep_next++ % dep_ev.size()];
-      CK(cudaEventRecord(done[c], sc));
-    }
-    for (int c = 0; c < nc; ++c) {
-      CK(cudaStreamWaitEvent(st, done[c], 0));
-      y_inverse(R + c * cb, Q + (size_t)c * fc * nzl * ny * Kxp, fc);
-    }
-  }
-  // x-pass layout in `src` (R or Q) -> compact spectral in dst (field stride cf).  Uses P and, when exchanging, `via`.
-  void from_xlayout(const C* src, C* via, C* dst, int nf) {
-    if (P_ == 1) { y_forward(src, P, nf); z_forward(P, dst, cf, nf); return; }
-    const int fc = chunk_fields(nf), nc = nf / fc;
-    const size_t cb = (size_t)P_ * blk(fc);
-    std::vector<cudaEvent_t> done(nc);
-    for (int c = 0; c < nc; ++c) {
-      y_forward(src + (size_t)c * fc * nzl * ny * Kxp, P + c * cb, fc);
-      order(st, sc);
-      exchange(P + c * cb, via + c * cb, fc, c == 0);
-      done[c] = dep_ev[dep_next++ % dep_ev.size()];
-      CK(cudaEventRecord(done[c], sc));
-    }
-    // dst may alias src (R): every forward-y pass has been issued before the first forward-z pass writes
-    for (int c = 0; c < nc; ++c) {
-      CK(cudaStreamWaitEvent(st, done[c], 0));
-      z_forward(via + c * cb, dst + (size_t)c * fc * cf, cf, fc);
-    }
-  }
-  // kr = 0 plane of the stage input from every rank (the symmetrised diffusion operand needs the mirror mode).
-  // Issued on the communication stream; `mirror_ready` is waited for right before the consumer kernel.
-  cudaEvent_t mirror_ready = nullptr;
-  void gather_mirror(const C* S) {
-    if (P_ == 1) return;
-    const long long n = (long long)F * Kz * Kyl;
-    k_plane<T><<<(int)((n + 255) / 256), 256, 0, st>>>(geom(), S, plane_loc);
-    ++launches;
-    CK(cudaGetLastError());
-    order(st, sc);
-    NK(g_nccl.AllGather(plane_loc, plane_all, 2 * (size_t)n, sizeof(T) == 4 ? ncclFloat32 : ncclFloat64, comm, sc));
-    mirror_ready = dep_ev[dep_next++ % dep_ev.size()];
-    CK(cudaEventRecord(mirror_ready, sc));
-  }
-  void wait_mirror() {
-    if (P_ > 1 && mirror_ready) { CK(cudaStreamWaitEvent(st, mirror_ready, 0)); mirror_ready = nullptr; }
-  }
-  // global sums / maxima of the x-kernel reductions, then the host copy
-  void finish_red() {
-    if (P_ == 1) { CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st)); return; }
-    order(st, sc);
-    NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, sc));
-    NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint32, ncclMax, comm, sc));
-    CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, sc));
-    order(sc, st);   // the next memset of red_d must not overtake the copy
-  }
-
-  XArgs<T> xargs() const {
-    XArgs<T> a;
-    a.in = Q; a.out = R; a.tw = twx; a.real_io = nullptr;
-    a.in_field = a.out_field = (long long)nzl * ny * Kxp;
-    a.real_field = (long long)nx * ny * nzl;
-    a.rows = (long long)ny * nzl;
-    a.Kx = Kx; a.Kxp = Kxp;
-    a.scale = (T)(1.0 / ((double)nx * ny * nz));
-    a.red = nullptr;
-    return a;
-  }
-
-  // ---- z-chunk pipelined slab path (opt-in: MHDF_ZCHUNKS = 2, 4, ...) ---------------------------------------------
-  // The local z slab is cut into NZC chunks; exchange pieces are [chunk][peer][field][z''][ky'][kx].  After the inverse z
-  // pass the inverse pushes of all chunks are queued on the communication stream; as soon as chunk c has arrived, its
-  // inverse y pass, fused x pass and forward y pass run and its forward pushes are queued -- so the x pass of one chunk
-  // overlaps the pushes of the others.  Only the first inverse and the last forward exchange stay exposed.
-  // Separate buffers keep pushes from peers (which land in R / Q unannounced) away from live data:
-  //   P inverse send, R inverse receive, Xin x-pass input (later the product spectra), Xout x-pass output,
-  //   P2 forward send, Q forward receive.
-  // NOT YET VERIFIED ON HARDWARE (written after the round's GPU budget was spent); off unless MHDF_ZCHUNKS is set.
-  bool spec2 = [] { const char* e = getenv("MHDF_SPEC2"); return e && atoi(e) != 0; }();
-  int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
-  C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
-  bool pipe_ok() const {
-    if (P_ == 1 || zchunks <= 1 || nzl % zchunks != 0) return false;
-    const int zc = nzl / zchunks, rb = 1024 / nx > 1 ? 1024 / nx : 1;
-    if ((long long)(nin > nout ? nin : nout) * nz * Kyl * Kxp >= (1LL << 31)) return false;   // 32-bit row offsets
-    return ((long long)ny * zc) % rb == 0;
-  }
-  void pipe_alloc() {
-    if (Xin) return;
-    const size_t e_zy = (size_t)nzl * ny * Kxp, e_zK = (size_t)nz * Kyl * Kxp;
-    Xin = dalloc<C>((size_t)(nin > nout ? nin : nout) * e_zy);
-    Xout = dalloc<C>((size_t)nout * e_zy);
-    P2 = dalloc<C>((size_t)nout * e_zK);
-  }
-  void set_blk(PassArgs<T>& a, int rows, size_t stride) {
-    a.blk_rows = rows; a.blk_stride = (int)stride; a.blk_magic = (unsigned)((0x100000000ULL + rows - 1) / rows);
-  }
-  void rhs_pipe(const C* Sin, SpecArgs<T> sa, bool want_red) {
-    pipe_alloc();
-    const int NZC = zchunks, zc = nzl / NZC;
-    const size_t Bi = (size_t)nin * zc * Kyl * Kxp, Bo = (size_t)nout * zc * Kyl * Kxp;   // one (chunk, peer) piece
-    const long long fld = (long long)zc * Kyl * Kxp;                                      // field stride inside a piece
-    const C* zin = Sin;
-    if (phys != MHDF_EMHD) gather_mirror(Sin);
-    if (phys == MHDF_EMHD) {
-      prof_begin(KC_DERIVE);
-      k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
-      ++launches;
-      CK(cudaGetLastError());
-      prof_end();
-      zin = D;
-    }
-    sa.g = geom();
-    sa.Sin = Sin;
-    sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
-    sa.force = fmask ? force : nullptr; sa.fmask = fmask;
-    if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
-    {   // inverse z pass of every field into the two-level send layout
-      PassArgs<T> a;
-      a.in = zin; a.out = P; a.tw = twz;
-      a.in_row = a.out_row = Kyl * Kxp;
-      a.in_outer = a.out_outer = 0;
-      a.in_field = cf; a.out_field = fld;
-      a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-      set_blk(a, nzl, Bi);
-      a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bi); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
-      blk_out = true;
-      prof_begin(KC_ZINV);
-      launch_pass<+1>(nz, a, 1, nin);
-      prof_end();
-    }
-    order(st, sc);
-    std::vector<cudaEvent_t> inv(NZC), fwd(NZC);
-    for (int c = 0; c < NZC; ++c) {
-      exchange(P + (size_t)c * P_ * Bi, R + (size_t)c * P_ * Bi, nin, c == 0, Bi);
-      inv[c] = dep_ev[dep_next++ % dep_ev.size()];
-      CK(cudaEventRecord(inv[c], sc));
-    }
-    for (int c = 0; c < NZC; ++c) {
-      const size_t zoff = (size_t)c * zc * ny * Kxp;
-      CK(cudaStreamWaitEvent(st, inv[c], 0));
-      {   // inverse y pass of chunk c: received pieces -> x-pass layout
-        PassArgs<T> a;
-        a.in = R + (size_t)c * P_ * Bi; a.out = Xin + zoff; a.tw = twy;
-        a.in_row = a.out_row = Kxp;
-        a.in_outer = (long long)Kyl * Kxp; a.out_outer = (long long)ny * Kxp;
-        a.in_field = fld; a.out_field = (long long)nzl * ny * Kxp;
-        a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-        set_blk(a, Kyl, Bi);
-        a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
-        blk_out = false;
-        prof_begin(KC_YINV);
-        launch_pass<+1>(ny, a, zc, nin);
-        prof_end();
-      }
-      XArgs<T> xa = xargs();
-      xa.in = Xin + zoff; xa.out = Xout + zoff;
-      xa.real_io = bst ? bst + (size_t)c * zc * ny * nx : nullptr;
-      xa.rows = (long long)ny * zc;
-      xa.red = want_red ? red_d : nullptr;
-      prof_begin(KC_XFUSED);
-      launch_xfused(xa);
-      prof_end();
-      {   // forward y pass of chunk c into the forward send layout
-        PassArgs<T> a;
-        a.in = Xout + zoff; a.out = P2 + (size_t)c * P_ * Bo; a.tw = twy;
-        a.in_row = a.out_row = Kxp;
-        a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
-        a.in_field = (long long)nzl * ny * Kxp; a.out_field = fld;
-        a.inner = Kxp; a.lo = by.lo; a.hi0 = by.hi0; a.shift = by.hi0 - by.lo;
-        set_blk(a, Kyl, Bo);
-        a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
-        blk_out = true;
-        prof_begin(KC_YFWD);
-        launch_pass<-1>(ny, a, zc, nout);
-        prof_end();
-      }
-      if (want_red && c == NZC - 1) finish_red();
-      order(st, sc);
-      exchange(P2 + (size_t)c * P_ * Bo, Q + (size_t)c * P_ * Bo, nout, c == 0, Bo);
-      fwd[c] = dep_ev[dep_next++ % dep_ev.size()];
-      CK(cudaEventRecord(fwd[c], sc));
-    }
-    for (int c = 0; c < NZC; ++c) CK(cudaStreamWaitEvent(st, fwd[c], 0));
-    {   // forward z pass from the two-level receive layout to the compact product spectra (in Xin, free by now)
-      PassArgs<T> a;
-      a.in = Q; a.out = Xin; a.tw = twz;
-      a.in_row = a.out_row = Kyl * Kxp;
-      a.in_outer = a.out_outer = 0;
-      a.in_field = fld; a.out_field = cf;
-      a.inner = Kyl * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
-      set_blk(a, nzl, Bo);
-      a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bo); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
-      blk_out = false;
-      prof_begin(KC_ZFWD);
-      launch_pass<-1>(nz, a, 1, nout);
-      prof_end();
-    }
-    sa.P = Xin;
-    wait_mirror();
-    launch_spectral(sa);
-  }
-
-  // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
-  void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
-    if (pipe_ok()) { rhs_pipe(Sin, sa, want_red); return; }
-    const C* zin = Sin;
-    if (phys != MHDF_EMHD) gather_mirror(Sin);
-    if (phys == MHDF_EMHD) {
-      prof_begin(KC_DERIVE);
-      k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
-      ++launches;
-      CK(cudaGetLastError());
-      prof_end();
-      zin = D;
-    }
-    sa.g = geom();
-    sa.Sin = Sin;
-    sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
-    sa.force = fmask ? force : nullptr; sa.fmask = fmask;
-    if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
-    to_xlayout(zin, nin);
-    XArgs<T> xa = xargs();
-    xa.real_io = bst;
-    if (want_red) xa.red = red_d;
-    prof_begin(KC_XFUSED);
-    launch_xfused(xa);
-    prof_end();
-    if (want_red) finish_red();
-    C* spec = (P_ > 1) ? R : Q;           // forward-z output (compact product spectra)
-    from_xlayout(R, Q, spec, nout);
-    sa.P = spec;
-    wait_mirror();
-    launch_spectral(sa);
-  }
-  template <int PHYS> void launch_spectral2(const SpecArgs<T>& sa) {
-    const unsigned plane = (unsigned)Kxp * (unsigned)Kyl;
-    const dim3 grid((plane + 255u) / 256u, (unsigned)Kz);
-    switch (sa.mode) {
-      case STEP_CALCN: k_spectral2<T, PHYS, STEP_CALCN><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_1: k_spectral2<T, PHYS, STEP_RK4_1><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_2: k_spectral2<T, PHYS, STEP_RK4_2><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_3: k_spectral2<T, PHYS, STEP_RK4_3><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_4: k_spectral2<T, PHYS, STEP_RK4_4><<<grid, 256, 0, st>>>(sa); break;
-      default:         k_spectral2<T, PHYS, STEP_LSRK><<<grid, 256, 0, st>>>(sa); break;
-    }
-  }
-  void launch_spectral(SpecArgs<T>& sa) {
-    prof_begin(KC_SPEC);
-    if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
-      if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD>(sa);
-      else if (phys == MHDF_HD) launch_spectral2<PHYS_HD>(sa);
-      else launch_spectral2<PHYS_EMHD>(sa);
-    } else {
-      const int grid = spec_grid();
-      if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
-      else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<grid, 256, 0, st>>>(sa);
-      else k_spectral<T, PHYS_EMHD><<<grid, 256, 0, st>>>(sa);
-    }
-    ++launches;
-    CK(cudaGetLastError());
-    prof_end();
-  }
-  int spec_grid() const {
-    long long b = (cf + 255) / 256;
-    long long cap = (long long)nsm * 16;
-    return (int)(b < cap ? b : cap);
-  }
-
-  void absorb_red() {   // after a stream sync: stale vars statistics of the last RHS evaluation
-    for (int i = 0; i < 6; ++i) {
-      st_sum[i] = red_h->sumsq[i];
-      float f;
-      std::memcpy(&f, &red_h->maxsq[i], 4);
-      st_max[i] = (double)f;
-    }
-    st_cross = red_h->cross;
-  }
-
-  SpecArgs<T> blank_args() const {
-    SpecArgs<T> sa;
-    std::memset(&sa, 0, sizeof sa);
-    sa.dt = dt_;
-    return sa;
-  }
-
-  void one_step() {
-    const T dt = dt_;
-    if (cfg.stepper == MHDF_RK4) {
-      // registers: Y = reg[iY]; two stage buffers and the accumulator are the other three
-      int o[3], n = 0;
-      for (int i = 0; i < 4; ++i) if (i != iY) o[n++] = i;
-      C *Y = reg[iY], *S0 = reg[o[0]], *S1 = reg[o[1]], *A = reg[o[2]];
-      SpecArgs<T> sa = blank_args();
-      sa.Y = Y; sa.A = A;
-      sa.mode = STEP_RK4_1; sa.ca = dt / (T)6; sa.cs = dt / (T)2; sa.Sout = S0;
-      rhs(Y, sa, false);
-      sa.mode = STEP_RK4_2; sa.ca = dt / (T)3; sa.cs = dt / (T)2; sa.Sout = S1;
-      rhs(S0, sa, false);
-      sa.mode = STEP_RK4_3; sa.ca = dt / (T)3; sa.cs = dt; sa.Sout = S0;
-      rhs(S1, sa, false);
-      sa.mode = STEP_RK4_4; sa.ca = dt / (T)6; sa.cs = 0; sa.Sout = Y;
-      rhs(S0, sa, true);
-      iStale = o[0];
-    } else {
-      static const double LA[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
-                                   -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
-      static const double LB[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
-                                   1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
-                                   2277821191437.0 / 14882151754819.0};
-      // registers: sol ping-pongs between two buffers, S2 is the third
-      int o[2], n = 0;
-      for (int i = 0; i < 3; ++i) if (i != iY) o[n++] = i;
-      int cur = iY, oth = o[0];
-      C* S2 = reg[o[1]];
-      for (int i = 0; i < 5; ++i) {
-        SpecArgs<T> sa = blank_args();
-        sa.mode = STEP_LSRK; sa.A = S2; sa.ca = (T)LA[i]; sa.cs = (T)LB[i]; sa.first = (i == 0);
-        sa.Sout = reg[oth];
-        rhs(reg[cur], sa, i == 4);
-        int tmp = cur; cur = oth; oth = tmp;
-      }
-      // after 5 swaps `cur` holds the new sol, `oth` the 5th stage input (= stale vars source)
-      iY = cur;
-      iStale = oth;
-      // keep S2 where it is: the third register
-    }
-    t_ = t_ + dt;
-    step_ += 1;
-  }
-
-  void step(int n) override {
-    CK(cudaSetDevice(cfg.device));
-    for (int i = 0; i < n; ++i) one_step();
-    sync_all();
-    if (n > 0) {
-      absorb_red();
-      check_finite();
-    }
-  }
-  void check_finite() {
-    for (int i = 0; i < 6; ++i)
-      if (!std::isfinite(st_sum[i])) throw Err{MHDF_ERR_NONFINITE, "detected NaN! Quit the simulation right now."};
-  }
-  void step_timed(int n, double* ms) override {
-    CK(cudaSetDevice(cfg.device));
-    cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    sync_all();
-    CK(cudaEventRecord(a, st));
-    for (int i = 0; i < n; ++i) one_step();
-    CK(cudaEventRecord(b, st));
-    sync_all();
-    float f = 0;
-    CK(cudaEventElapsedTime(&f, a, b));
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    *ms = f;
-    if (n > 0) { absorb_red(); check_finite(); }
-  }
-
-  void calcN(void* p) override {
-    CK(cudaSetDevice(cfg.device));
-    // N goes to a register that is dead between steps
-    int o = -1;
-    const int nreg = (cfg.stepper == MHDF_RK4) ? 4 : 3;
-    for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
-    SpecArgs<T> sa = blank_args();
-    sa.mode = STEP_CALCN; sa.Nout = reg[o];
-    rhs(reg[iY], sa, true);
-    sync_all();
-    absorb_red();
-    const size_t fe = (P_ > 1) ? (size_t)nkr * Kyl * nz : (size_t)nkr * ny * nz;
-    for (int f = 0; f < F; ++f) unpack_to_host(reg[o] + f * cf, (C*)p + (size_t)f * fe);
-  }
-
-  // ---- API boundary: real / spectral fields ------------------------------------------------
-  void check_field(int f) const {
-    if (f < 0 || f >= F) throw Err{MHDF_ERR_INVALID, "field index out of range"};
-  }
-  // host real field (this rank's z slab) -> compact spectral field at dst; leaves the sum / max of f^2 in red_h
-  void real_to_compact(const void* p, C* dst, int emhd_slot) {
-    T* re = reinterpret_cast<T*>(R);
-    const size_t n = (size_t)nx * ny * nzl;
-    CK(cudaMemcpyAsync(re, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
-    if (emhd_slot >= 0)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
-      CK(cudaMemcpyAsync(bst + (size_t)emhd_slot * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    XArgs<T> xa = xargs();
-    xa.real_io = re; xa.out = Q; xa.in = nullptr;
-    CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
-    xa.red = red_d;
-    launch_xplain<-1>(xa);
-    finish_red();
-    from_xlayout(Q, R, dst, 1);
-    sync_all();
-  }
-  void set_real(int field, const void* p) override {
-    check_field(field);
-    CK(cudaSetDevice(cfg.device));
-    real_to_compact(p, reg[iY] + field * cf, phys == MHDF_EMHD ? field : -1);
-    // vars.* statistics of the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88)
-    const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
-    st_sum[slot] = red_h->sumsq[0];
-    float f;
-    std::memcpy(&f, &red_h->maxsq[0], 4);
-    st_max[slot] = (double)f;
-  }
-  void set_forcing(int field, const void* p) override {
-    check_field(field);
-    CK(cudaSetDevice(cfg.device));
-    if (p == nullptr) { fmask &= ~(1u << field); return; }
-    if (!force) force = dalloc<C>((size_t)F * cf);
-    real_to_compact(p, force + field * cf, -1);
-    fmask |= 1u << field;
-  }
-  const C* source(int which) const {
-    if (which == MHDF_STALE && iStale >= 0) return reg[iStale];
-    return reg[iY];
-  }
-  void get_real(int field, int which, void* p) override {
-    check_field(field);
-    CK(cudaSetDevice(cfg.device));
-    to_xlayout(source(which) + field * cf, 1);
-    T* re = reinterpret_cast<T*>(R);
-    XArgs<T> xa = xargs();
-    xa.real_io = re; xa.in = Q; xa.out = nullptr;
-    launch_xplain<+1>(xa);
-    CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nzl * sizeof(T), cudaMemcpyDeviceToHost, st));
-    sync_all();
-  }
-  void set_spectral(int field, const void* p) override {
-    check_field(field);
-    CK(cudaSetDevice(cfg.device));
-    const int nyh = (P_ > 1) ? Kyl : ny;     // slab runs exchange the local compact ky rows directly
-    const size_t n = (size_t)nkr * nyh * nz;
-    CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyHostToDevice, st));
-    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, reg[iY] + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
-    ++launches;
-    CK(cudaGetLastError());
-    sync_all();
-  }
-  int pack_grid() const {
-    long long b = ((long long)nkr * ny * nz + 255) / 256;
-    long long cap = (long long)nsm * 16;
-    return (int)(b < cap ? b : cap);
-  }
-  void unpack_to_host(const C* comp, C* host) {
-    const int nyh = (P_ > 1) ? Kyl : ny;
-    const size_t n = (size_t)nkr * nyh * nz;
-    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, const_cast<C*>(comp), nkr, nyh, nz, Kx, Kxp, by, bz, 1, P_ > 1);
-    ++launches;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDeviceToHost, st));
-    sync_all();
-  }
-  void get_spectral(int field, int which, void* p) override {
-    check_field(field);
-    CK(cudaSetDevice(cfg.device));
-    unpack_to_host(source(which) + field * cf, (C*)p);
-  }
-
-  // ---- clock, CFL, diagnostics ----------------------------------------------------------------
-  void set_dt(double dt) override { dt_ = (T)dt; }
-  void set_clock(double t, long long s) override { t_ = (T)t; step_ = s; }
-  void get_clock(double* t, double* dt, long long* s) const override {
-    if (t) *t = (double)t_;
-    if (dt) *dt = (double)dt_;
-    if (s) *s = step_;
-  }
-  void cfl_dt(double coef, double t_diff, double* dt) override {
-    // integrator.jl:158-198 on the stale maxima (vars.* of the last RHS evaluation)
-    double vmax = std::sqrt(std::fmax(st_max[0], std::fmax(st_max[1], st_max[2])));   // u, or curl B for EMHD
-    if (phys != MHDF_HD) {
-      const double va = std::sqrt(std::fmax(st_max[3], std::fmax(st_max[4], st_max[5])));
-      vmax = std::fmax(vmax, va);
-    }
-    const double dx = cfg.Lx / nx, dy = cfg.Ly / ny, dz = cfg.Lz / nz;
-    double dl = std::fmin(dx, std::fmin(dy, dz));
-    if (phys == MHDF_EMHD) dl = dl * dl;
-    double d = coef * dl / vmax;
-    if (!(d < t_diff)) d = t_diff;
-    dt_ = (T)d;
-    if (dt) *dt = (double)dt_;
-  }
-  double dV() const {
-    // ProbDiagnostic: dV = diff(x)[1]*diff(y)[1]*diff(z)[1] with x = range(T(x0), step=T(dx)) (UserInterface.jl:66-67)
-    return (double)(T)(cfg.Lx / nx) * (double)(T)(cfg.Ly / ny) * (double)(T)(cfg.Lz / nz);
-  }
-  void run_diag(int which) {
-    const C* src = source(which);
-    gather_mirror(src);
-    CK(cudaMemsetAsync(diag_d, 0, 8 * sizeof(double), st));
-    const int has_u = (phys != MHDF_EMHD), has_b = (phys != MHDF_HD), boff = (phys == MHDF_EMHD) ? 0 : 3;
-    wait_mirror();
-    k_diag<T><<<spec_grid(), 256, 0, st>>>(geom(), src, has_u, has_b, boff, 1.0 / ((double)nx * ny * nz), diag_d);
-    ++launches;
-    CK(cudaGetLastError());
-    if (P_ > 1) { order(st, sc); NK(g_nccl.AllReduce(diag_d, diag_d, 8, ncclFloat64, ncclSum, comm, sc)); order(sc, st); }
-    CK(cudaMemcpyAsync(diag_h, diag_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    sync_all();
-  }
-  void energy(int which, double* KE, double* ME) override {
-    CK(cudaSetDevice(cfg.device));
-    double ke, me;
-    if (which == MHDF_STALE) {
-      if (phys == MHDF_EMHD) { ke = 0; me = (st_sum[3] + st_sum[4] + st_sum[5]) * dV(); }
-      else { ke = (st_sum[0] + st_sum[1] + st_sum[2]) * dV(); me = (st_sum[3] + st_sum[4] + st_sum[5]) * dV(); }
-      if (phys == MHDF_HD) me = 0;
-    } else {
-      run_diag(MHDF_FRESH);
-      ke = diag_h[0] * dV(); me = diag_h[1] * dV();
-    }
-    if (std::isnan(ke) || std::isnan(me)) throw Err{MHDF_ERR_NONFINITE, "detected NaN! Quit the simulation right now."};
-    if (KE) *KE = ke;
-    if (ME) *ME = me;
-  }
-  void helicity(double* Hk, double* Hm, double* Hc) override {
-    CK(cudaSetDevice(cfg.device));
-    run_diag(MHDF_FRESH);
-    const double dv = (cfg.Lx / nx) * (cfg.Ly / ny) * (cfg.Lz / nz);
-    if (Hk) *Hk = diag_h[2] * dv;
-    if (Hm) *Hm = diag_h[3];
-    if (Hc) *Hc = diag_h[4] * dv;
-  }
-  void spectrum(int field, double* Pk, int nbins) override {
-    check_field(field);
-    if (nbins <= 0 || nbins > 4096) throw Err{MHDF_ERR_INVALID, "nbins must be in 1..4096"};
-    CK(cudaSetDevice(cfg.device));
-    if (spec_cap < nbins) {
-      if (spec_d) cudaFree(spec_d);
-      spec_d = nullptr;
-      CK(cudaMalloc(&spec_d, nbins * sizeof(double)));
-      spec_cap = nbins;
-    }
-    CK(cudaMemsetAsync(spec_d, 0, nbins * sizeof(double), st));
-    gather_mirror(reg[iY]);
-    wait_mirror();
-    k_spectrum<T><<<spec_grid(), 256, nbins * sizeof(double), st>>>(geom(), reg[iY], field, spec_d, nbins);
-    ++launches;
-    CK(cudaGetLastError());
-    if (P_ > 1) { order(st, sc); NK(g_nccl.AllReduce(spec_d, spec_d, nbins, ncclFloat64, ncclSum, comm, sc)); order(sc, st); }
-    CK(cudaMemcpyAsync(Pk, spec_d, nbins * sizeof(double), cudaMemcpyDeviceToHost, st));
-    sync_all();
-  }
-  void stale_stats(double* mx, double* sm) const override {
-    for (int i = 0; i < 6; ++i) { if (mx) mx[i] = st_max[i]; if (sm) sm[i] = st_sum[i]; }
-  }
-  void profile(int enable) override {
-    if (prof && !enable) prof_collect();
-    prof = enable != 0;
-    if (enable) for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
-  }
-  void profile_get(double* ms, long long* cnt, int n) override {
-    prof_collect();
-    for (int i = 0; i < n && i < KC_COUNT; ++i) { if (ms) ms[i] = prof_ms[i]; if (cnt) cnt[i] = prof_cnt[i]; }
-  }
-  long long launch_count() const override { return launches; }
-  void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const override {
-    if (nf) *nf = F;
-    if (kx) *kx = Kx;
-    if (kxp) *kxp = Kxp;
-    if (ky) *ky = Ky;
-    if (kz) *kz = Kz;
-    if (bytes) *bytes = bytes_dev;
-  }
-};
+// api.cu -- the extern "C" boundary declared in include/mhdflows_b200.h: argument checks, error translation, dispatch
+// to the Solver<T> behind the handle (solver.cuh).
+#include "solver.cuh"
 
 // ---- extern "C" --------------------------------------------------------------------------------
 template <typename Fn> static int guard(mhdf_handle* h, Fn fn) {
@@ -1237,8 +39,8 @@ int mhdf_create(const mhdf_config* c, mhdf_handle** out) {
   }
   if (c->device < 0 || c->device >= ndev) return bad("device ordinal out of range");
   try {
-    if (c->dtype == MHDF_F32) *out = new Solver<float>(*c);
-    else *out = new Solver<double>(*c);
+    if (c->dtype == MHDF_F32) *out = mhdf_make_solver_f32(*c);
+    else *out = mhdf_make_solver_f64(*c);
     return MHDF_OK;
   } catch (const Err& er) {
     g_create_error = er.msg;

@@ -3,7 +3,7 @@
 Real space is split along z (`nzl = nz / P` planes per rank); the compact spectral state along the retained ky rows
 (`Kyl = ceil(Ky / P)` rows per rank, the last slab zero-padded).  A 3D transform needs one all-to-all between the
 z and the y passes; the exchange buffers are `[peer][field][z'][ky'][kx]` so every piece is contiguous.  The same
-index formulas are used by csrc/api.cu (`tabs_for`); tests/test_dist_gloo.py runs them over gloo on CPU.
+index formulas are used by csrc/solver.cuh (`tabs_for`); tests/test_dist_gloo.py runs them over gloo on CPU.
 
 The reference has no multi-device mode (README.md:40-41), so the distributed array conventions are ours:
   local real field      (nzl, ny, nx)        z planes  [rank*nzl, (rank+1)*nzl)

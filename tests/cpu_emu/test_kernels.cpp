@@ -15,7 +15,7 @@ static void report(const std::string& name, bool ok, double err = 0) {
   std::printf("%s %s (err %.3e)\n", ok ? "PASS" : "FAIL", name.c_str(), err);
   if (!ok) ++g_fail;
 }
-static void alias_range(int nk, int* iL, int* iR) {   // == api.cu
+static void alias_range(int nk, int* iL, int* iR) {   // == solver.cuh
   const double af = 1.0 / 3.0, L = (1.0 - af) / 2.0, R = (1.0 + af) / 2.0;
   *iL = (int)std::floor(L * nk) + 1;
   *iR = (int)std::ceil(R * nk);
@@ -141,7 +141,7 @@ template <int NZC> void test_slab() {
   a.inner = KyP * Kxp; a.lo = bz.lo; a.hi0 = bz.hi0; a.shift = bz.hi0 - bz.lo;
   run_pass<T, NZ, -1, 0>(a, 1, NF);
 
-  // ---- P ranks with the exchange layout of api.cu ([chunk][peer][field][z''][ky'][kx]; NZC = 1: single level)
+  // ---- P ranks with the exchange layout of solver.cuh ([chunk][peer][field][z''][ky'][kx]; NZC = 1: single level)
   const size_t B = (size_t)NF * zc * Kyl * Kxp;           // one (chunk, peer) piece
   const long long fld = (long long)zc * Kyl * Kxp;
   std::vector<std::vector<C>> loc(P), send(P), recv(P), xin(P), fsend(P), frecv(P), spec(P);
