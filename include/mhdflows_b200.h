@@ -86,6 +86,30 @@ int mhdf_get_spectral(mhdf_handle* h, int field, int which, void* host_spec);
  * the forcing BEFORE the advection zeroes N (pgen.jl:176-178, HDSolver.jl:55) and EMHDcalcN! never calls it. */
 int mhdf_set_forcing(mhdf_handle* h, int field, const void* host_real);
 
+/* Random solenoidal driving (Alvelius 1999): the reference's `calcF!` = A99ForceDriving!.  Every RHS evaluation adds
+ *   N_u += amp * Fk(k) * (e^{i th1} g_i e1(k) + e^{i th2} g_j e2(k)),   Fk = sqrt(exp(-(k-kf)^2/sigma2) / 2pi) / k
+ * with fresh uniform random th1, th2, Phi per mode.  variant selects which of the reference's two implementations is
+ * restated (basis vectors, real or complex Phi, treatment of the kr = 0 plane):
+ *   MHDF_A99_HOST  top-level A99ForceDriving! with the tables of SetUpFk (pgen/A99ForceDriving.jl:33-60, 93-127)
+ *   MHDF_A99_GPU   module A99GPU (pgen/A99ForceDriving_GPU.jl:49-130)
+ * amp = usr_vars.A times the normalisation A of SetUpFk (the host computes it, as the reference does).
+ * Random numbers: Philox4x32-10, key = seed, counter = (index of the mode in the (nx/2+1, ny, nz) array, number of the RHS
+ * evaluation): reproducible, independent of the number of GPUs; `call` is the evaluation number to start from (restart).
+ * Acts on the MHD path only, like mhdf_set_forcing.  p = NULL removes the driving. */
+enum { MHDF_A99_HOST = 1, MHDF_A99_GPU = 2 };
+typedef struct {
+  int variant;
+  double amp, kf, sigma2, b;
+  unsigned long long seed, call;
+} mhdf_a99;
+int mhdf_set_forcing_a99(mhdf_handle* h, const mhdf_a99* p);
+int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls);
+
+/* DivVCorrection! (group 0) / DivBCorrection! (group 1) (Solver/VPSolver.jl:61-137): sol_i -= k_i (k . sol) / k^2 on the
+ * three fields of the group, then the real-space `vars` of that group are refreshed from the corrected sol (stale view,
+ * CFL maxima, energies). */
+int mhdf_div_correction(mhdf_handle* h, int group);
+
 /* stepforward! (timestepper/timestepper.jl:4-6): nsteps steps of clock.dt. */
 int mhdf_step(mhdf_handle* h, int nsteps);
 /* eqn.calcN!(N, sol, t, clock, vars, params, grid) (pgen.jl:153-181) on the current sol:

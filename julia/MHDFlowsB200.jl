@@ -9,7 +9,8 @@ module MHDFlowsB200
 
 export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDiagnostic, Diagnostic,
        increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum,
-       N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!
+       N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!,
+       A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!
 
 const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
 
@@ -57,6 +58,8 @@ struct Flag; b::Bool; e::Bool; vp::Bool; c::Bool; s::Bool; end
 struct Grid{T}; nx::Int; ny::Int; nz::Int; Lx::Float64; Ly::Float64; Lz::Float64; dx::Float64; dy::Float64; dz::Float64; end
 struct Params; Î½::Float64; Î·::Float64; nÎ½::Int; nÎ·::Int; end
 
+mutable struct Vars; usr_vars::Any; end
+
 mutable struct MHDFlowsProblem{T}
   h::Ptr{Cvoid}
   clock::Clock{T}
@@ -65,6 +68,7 @@ mutable struct MHDFlowsProblem{T}
   flag::Flag
   Nl::Int
   usr_func::Vector{Any}
+  vars::Vars            # vars.usr_vars as in the reference (datastructure.jl:5-35); the fields are read with realfield()
 end
 
 function check(h, code)
@@ -84,7 +88,7 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   câ‚› == 0.0 && Compressibility && error("You should define câ‚›")
   Shear && error("Shear haven't fully implemented yet!")
   (Compressibility || VP_method || Dye_Module) && error("outside the B200 hot path")
-  (calcF === nothingfunction || calcF === N97ForceDriving!) ||
+  (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! || calcF === A99GPU.A99ForceDriving!) ||
     error("arbitrary forcing callbacks cannot run on the device; constant forcings go through setforcing! / N97ForceDriving!")
   stepper in ("RK4", "LSRK54") || error("stepper must be \"RK4\" or \"LSRK54\" on the B200 path")
   physics = EMHD ? MHDF_EMHD : (B_field ? MHDF_MHD : MHDF_HD)
@@ -95,7 +99,8 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   code == 0 || check(C_NULL, code)
   prob = MHDFlowsProblem{T}(h[], Clock{T}(h[]), Grid{T}(nx, ny, nz, Lx, Ly, Lz, Lx/nx, Ly/ny, Lz/nz),
                             Params(Î½, Î·, nÎ½, 0), Flag(B_field, EMHD, false, false, false),
-                            physics == MHDF_MHD ? 6 : 3, isempty(usr_func) ? Any[nothingfunction] : collect(Any, usr_func))
+                            physics == MHDF_MHD ? 6 : 3, isempty(usr_func) ? Any[nothingfunction] : collect(Any, usr_func),
+                            Vars(usr_vars))
   finalizer(p -> ccall((:mhdf_destroy, lib), Cint, (Ptr{Cvoid},), p.h), prob)
   return prob
 end
@@ -145,6 +150,69 @@ function SetUpN97!(prob; F0 = 1, kf = 2)
   setforcing!(prob, :uy, @. F0 * -cos(kf*x) * sin(kf*y) * cos(kf*z))
   nothing
 end
+
+# mirrors `mhdf_a99` in include/mhdflows_b200.h
+struct MhdfA99
+  variant::Cint
+  amp::Cdouble; kf::Cdouble; sigma2::Cdouble; b::Cdouble
+  seed::Culonglong; call::Culonglong
+end
+"A99_vars (pgen/A99ForceDriving.jl:5-16): A, b are the user knobs; the spectral tables are evaluated per mode on the device"
+mutable struct A99_vars{T}
+  A::T; b::T; ÏƒÂ²::T; kf::T
+  Fk_A::Float64       # normalisation inside the Fk table (SetUpFk)
+  seed::UInt64
+  variant::Int
+end
+A99ForceDriving!(args...) = error("A99ForceDriving! is applied inside the library")
+"GetA99vars_And_function(dev, nx, ny, nz; T)   (pgen/A99ForceDriving.jl:18-31)"
+GetA99vars_And_function(dev, nx, ny, nz; T = Float32, C = false, seed = 0) =
+  C ? error("A99ForceDriving_Compressible! is outside the B200 hot path") :
+      (A99_vars{T}(1, 1, 1, 1, NaN, seed, 1), A99ForceDriving!)
+function _a99_integral(g, kf, ÏƒÂ²)
+  tot = 0.0
+  for iz in 0:g.nz-1, iy in 0:g.ny-1, ix in 0:g.nxÃ·2
+    ky = (iy < g.ny Ã· 2 ? iy : iy - g.ny) * 2Ï€ / g.Ly
+    kz = (iz < g.nz Ã· 2 ? iz : iz - g.nz) * 2Ï€ / g.Lz
+    k = sqrt((ix * 2Ï€ / g.Lx)^2 + ky^2 + kz^2)
+    tot += exp(-(k - kf)^2 / ÏƒÂ²) / (k + 1)^2
+  end
+  tot
+end
+function _push_a99(prob, uv::A99_vars)
+  calls = Ref{Culonglong}(0)
+  check(prob.h, ccall((:mhdf_forcing_a99_calls, lib), Cint, (Ptr{Cvoid}, Ref{Culonglong}), prob.h, calls))
+  a = MhdfA99(uv.variant, Float64(uv.A) * uv.Fk_A, uv.kf, uv.ÏƒÂ², uv.b, uv.seed, calls[])
+  check(prob.h, ccall((:mhdf_set_forcing_a99, lib), Cint, (Ptr{Cvoid}, Ref{MhdfA99}), prob.h, a))
+end
+"SetUpFk(prob; kf, P, ÏƒÂ²)   (pgen/A99ForceDriving.jl:93-127)"
+function SetUpFk(prob; kf = 2, P = 1, ÏƒÂ² = 1)
+  g = prob.grid
+  uv = prob.vars.usr_vars::A99_vars
+  uv.Fk_A = sqrt(P * 3 * (g.Lx/g.dx) * (g.Ly/g.dy) * (g.Lz/g.dz) / _a99_integral(g, kf, ÏƒÂ²) * (1/g.dx/g.dy/g.dz))
+  uv.kf = kf; uv.ÏƒÂ² = ÏƒÂ²
+  _push_a99(prob, uv)
+end
+"module A99GPU (pgen/A99ForceDriving_GPU.jl): own basis vectors, real Î¦, clipped gáµ¢, Im N = 0 on the kr = 0 plane"
+module A99GPU
+  import ..A99_vars, .._a99_integral, .._push_a99
+  A99ForceDriving!(args...) = error("A99GPU.A99ForceDriving! is applied inside the library")
+  GetA99vars_And_function(dev, nx, ny, nz; T = Float32, seed = 0) =
+    (A99_vars{T}(1, 1, 1, 1, NaN, seed, 2), A99ForceDriving!, SetUpFk!)
+  function SetUpFk!(prob; kf = 2.0, P = 1.0, Ïƒ = 1.0, b = 1.0)
+    g = prob.grid
+    uv = prob.vars.usr_vars::A99_vars
+    A = sqrt(P * 3 * (g.Lx/g.dx) * (g.Ly/g.dy) * (g.Lz/g.dz) / _a99_integral(g, kf, Ïƒ^2) * (1/g.dx/g.dy/g.dz))
+    uv.A = A; uv.ÏƒÂ² = Ïƒ^2; uv.b = b
+    uv.kf = b                  # sic (pgen/A99ForceDriving_GPU.jl:45)
+    uv.Fk_A = Float64(uv.A)    # the kernel multiplies A twice (:89, :106)
+    _push_a99(prob, uv)
+  end
+end
+
+"DivVCorrection!(prob) / DivBCorrection!(prob)   (Solver/VPSolver.jl:61-137)"
+DivVCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, 0))
+DivBCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, 1))
 
 "stepforward!(prob) == stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)"
 stepforward!(prob, n::Int = 1) = check(prob.h, ccall((:mhdf_step, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, n))

@@ -21,7 +21,9 @@ SYMBOLS = [
     "mhdf_get_clock", "mhdf_cfl_dt", "mhdf_energy", "mhdf_helicity", "mhdf_spectrum", "mhdf_stale_stats",
     "mhdf_step_timed", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
     "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
+    "mhdf_set_forcing_a99", "mhdf_forcing_a99_calls", "mhdf_div_correction",
 ]
+A99_HOST, A99_GPU = 1, 2
 
 
 class Config(C.Structure):
@@ -30,6 +32,11 @@ class Config(C.Structure):
                 ("nu", C.c_double), ("eta", C.c_double), ("n_nu", C.c_int), ("dt", C.c_double),
                 ("physics", C.c_int), ("stepper", C.c_int), ("dtype", C.c_int), ("device", C.c_int),
                 ("rank", C.c_int), ("nranks", C.c_int), ("nccl_id", C.c_void_p)]
+
+
+class A99(C.Structure):   # mhdf_a99
+    _fields_ = [("variant", C.c_int), ("amp", C.c_double), ("kf", C.c_double), ("sigma2", C.c_double), ("b", C.c_double),
+                ("seed", C.c_ulonglong), ("call", C.c_ulonglong)]
 
 
 class MHDFlowsError(RuntimeError):
@@ -79,6 +86,9 @@ def lib():
         "mhdf_ipc_export": (i, [vp, vp]),
         "mhdf_ipc_import": (i, [vp, vp]),
         "mhdf_set_forcing": (i, [vp, i, vp]),
+        "mhdf_set_forcing_a99": (i, [vp, C.POINTER(A99)]),
+        "mhdf_forcing_a99_calls": (i, [vp, C.POINTER(C.c_ulonglong)]),
+        "mhdf_div_correction": (i, [vp, i]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(L, name) and os.environ.get("MHDF_LIB"):

@@ -94,6 +94,13 @@ int mhdf_step_timed(mhdf_handle* h, int n, double* ms) { return guard(h, [&] { i
 int mhdf_profile(mhdf_handle* h, int en) { return guard(h, [&] { h->profile(en); }); }
 int mhdf_profile_get(mhdf_handle* h, double* ms, long long* cnt, int n) { return guard(h, [&] { h->profile_get(ms, cnt, n); }); }
 int mhdf_set_forcing(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { h->set_forcing(f, p); }); }
+int mhdf_set_forcing_a99(mhdf_handle* h, const mhdf_a99* p) { return guard(h, [&] { h->set_forcing_a99(p); }); }
+int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls) {
+  if (!h || !calls) return MHDF_ERR_INVALID;
+  *calls = h->a99_calls();
+  return MHDF_OK;
+}
+int mhdf_div_correction(mhdf_handle* h, int group) { return guard(h, [&] { h->div_correction(group); }); }
 int mhdf_ipc_blob_size(const mhdf_handle*) { return (int)sizeof(IpcBlob); }
 int mhdf_ipc_export(mhdf_handle* h, void* blob) { return guard(h, [&] { if (!blob) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_export(blob); }); }
 int mhdf_ipc_import(mhdf_handle* h, const void* blobs) { return guard(h, [&] { if (!blobs) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_import(blobs); }); }

@@ -662,6 +662,112 @@ __global__ void __launch_bounds__(256) k_plane(SpecGeom<T> g, const Cx<T>* __res
   }
 }
 
+// ---- A99 random solenoidal driving (Alvelius 1999): the reference's `calcF!` = A99ForceDriving! ------------------------
+// Counter-based random numbers: Philox4x32-10 (Salmon et al. 2011), key = seed, counter = (global mode index in the
+// reference's (nkr, ny, nz) array, RHS-evaluation number): the stream depends neither on the compact layout nor on the
+// slab decomposition, and the CPU test-suite regenerates it bit for bit in NumPy.
+struct Philox4 { unsigned v[4]; };
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 c, unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = 0xD2511F53ULL * c.v[0], p1 = 0xCD9E8D57ULL * c.v[2];
+    Philox4 n;
+    n.v[0] = (unsigned)(p1 >> 32) ^ c.v[1] ^ k0;
+    n.v[1] = (unsigned)p1;
+    n.v[2] = (unsigned)(p0 >> 32) ^ c.v[3] ^ k1;
+    n.v[3] = (unsigned)p0;
+    c = n;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__host__ __device__ __forceinline__ float u01(unsigned a, unsigned, float) { return (float)(a >> 8) * 5.9604644775390625e-8f; }   // 24 bits
+__host__ __device__ __forceinline__ double u01(unsigned a, unsigned b, double) {                                                    // 53 bits
+  return (double)((((unsigned long long)a << 32) | b) >> 11) * 1.1102230246251565404e-16;
+}
+enum { A99_OFF = 0, A99_HOST = 1, A99_GPU = 2 };
+template <typename T>
+struct A99Args {
+  int variant;       // A99_HOST: top-level A99ForceDriving! (pgen/A99ForceDriving.jl:33-60, tables of SetUpFk :93-127)
+                     // A99_GPU:  module A99GPU (pgen/A99ForceDriving_GPU.jl:49-130)
+  int nkr;           // nx/2 + 1 (mode numbering)
+  T amp;             // usr_vars.A times the A inside Fk
+  T kf, sig2, b, itanh;   // itanh = 1 / tanh(b pi/2)
+  unsigned seed_lo, seed_hi;
+  unsigned call_lo, call_hi;   // RHS-evaluation number
+};
+// four uniforms in [0,1) of mode `mode` for this RHS evaluation
+template <typename T>
+__host__ __device__ __forceinline__ void a99_uniforms(const A99Args<T>& q, unsigned long long mode, T (&r)[4]) {
+  Philox4 c;
+  c.v[0] = (unsigned)mode; c.v[1] = (unsigned)(mode >> 32); c.v[2] = q.call_lo; c.v[3] = q.call_hi << 1;
+  const Philox4 a = philox4x32_10(c, q.seed_lo, q.seed_hi);
+  if constexpr (sizeof(T) == 4) {
+    r[0] = u01(a.v[0], 0u, T()); r[1] = u01(a.v[1], 0u, T()); r[2] = u01(a.v[2], 0u, T()); r[3] = u01(a.v[3], 0u, T());
+  } else {
+    c.v[3] |= 1u;
+    const Philox4 b = philox4x32_10(c, q.seed_lo, q.seed_hi);
+    r[0] = u01(a.v[0], a.v[1], T()); r[1] = u01(a.v[2], a.v[3], T()); r[2] = u01(b.v[0], b.v[1], T()); r[3] = u01(b.v[2], b.v[3], T());
+  }
+}
+__device__ __forceinline__ void sincos2pi(float r, float& s, float& c) { sincospif(2.f * r, &s, &c); }
+__device__ __forceinline__ void sincos2pi(double r, double& s, double& c) { sincospi(2.0 * r, &s, &c); }
+// The forcing of one mode: f[0..2] += amp Fk (e^{i th1} g_i e1 + e^{i th2} g_j e2), Fk = sqrt(exp(-(k-kf)^2/sig2)/2pi)/k.
+//   A99_HOST: e1 = (ky,-kx,0)/kp, e2 = (kx kz, ky kz, -kp^2)/(kp k), kp^2 = kx^2+ky^2, 0/0 -> 0, Fk = 0 on the kr = 0 plane
+//             (:112-125).  SetUpFk builds e1x, e1y as (nkr, nl, 1) arrays and copyto!()s them into (nkr, nl, nm) tables
+//             (:121-122): only the first z plane (kz index 0) of the e1 tables is ever filled -- `e1_plane` says whether
+//             this mode lies on it.  Phi = pi rand() is drawn into the COMPLEX scratch array nonlinh1 (:46), so g_i = -tanh(b(Phi-pi/2))/
+//             tanh(b pi/2) and g_j = sqrt(1-g_i^2) are complex numbers there -- restated literally.
+//   A99_GPU:  e1 = (kz,0,-kx)/kp, e2 = (kx ky, -kp^2, kz ky)/(kp k), kp^2 = kx^2+kz^2, real Phi, |g_i| clipped to 1
+//             (:92-113); afterwards Im N_u = 0 on the kr = 0 plane (:115-121) -- applied by the caller.
+template <typename T>
+__device__ __forceinline__ void a99_force(const A99Args<T>& q, unsigned long long mode, int ix, bool e1_plane, T kx, T ky, T kz, Cx<T> (&f)[3]) {
+  using C = Cx<T>;
+  const T PI = (T)3.14159265358979323846;
+  f[0] = f[1] = f[2] = mk<C>(0, 0);
+  if (q.variant == A99_HOST && ix == 0) return;
+  const T k2 = kx * kx + ky * ky + kz * kz;
+  if (!(k2 > (T)0)) return;
+  const T k = sqrt(k2), ik = (T)1 / k, d = k - q.kf;
+  const T Fk = q.amp * sqrt(exp(-(d * d) / q.sig2) / (T)2 / PI) * ik;
+  T r[4];
+  a99_uniforms<T>(q, mode, r);
+  T s1, c1, s2, c2;
+  sincos2pi(r[0], s1, c1);
+  sincos2pi(r[3], s2, c2);
+  T e1[3], e2[3];
+  C gi, gj;
+  if (q.variant == A99_HOST) {
+    const T kp = sqrt(kx * kx + ky * ky);
+    const bool ok = kp > (T)0;
+    e1[0] = (ok && e1_plane) ? ky / kp : (T)0; e1[1] = (ok && e1_plane) ? -kx / kp : (T)0; e1[2] = (T)0;
+    e2[0] = ok ? kx * kz / kp * ik : (T)0; e2[1] = ok ? ky * kz / kp * ik : (T)0; e2[2] = -kp * ik;
+    // tanh(x + i y) = (sinh 2x + i sin 2y) / (cosh 2x + cos 2y),  x + i y = b (Phi - pi/2),  Phi = pi (r1 + i r2)
+    const T x2 = (T)2 * q.b * (PI * r[1] - PI / (T)2), y2 = (T)2 * q.b * (PI * r[2]);
+    const T den = cosh(x2) + cos(y2);
+    gi = mk<C>(-sinh(x2) / den * q.itanh, -sin(y2) / den * q.itanh);
+    // principal sqrt(1 - gi^2)
+    const T u = (T)1 - (gi.x * gi.x - gi.y * gi.y), v = -(T)2 * gi.x * gi.y;
+    const T m = sqrt(u * u + v * v);
+    if (m == (T)0) gj = mk<C>(0, 0);
+    else if (u >= (T)0) { const T s = sqrt((T)0.5 * (m + u)); gj = mk<C>(s, v / ((T)2 * s)); }
+    else { const T s = sqrt((T)0.5 * (m - u)); gj = mk<C>(fabs(v) / ((T)2 * s), v < (T)0 ? -s : s); }
+  } else {
+    const T kp = sqrt(kx * kx + kz * kz);
+    const bool ok = kp > (T)0;
+    e1[0] = ok ? kz / kp : (T)0; e1[1] = (T)0; e1[2] = ok ? -kx / kp : (T)0;
+    e2[0] = ok ? kx * ky / kp * ik : (T)0; e2[1] = -kp * ik; e2[2] = ok ? kz * ky / kp * ik : (T)0;
+    T g = -tanh(q.b * (r[1] * PI - PI / (T)2)) * q.itanh;
+    if (fabs(g) >= (T)1) g = g < (T)0 ? (T)-1 : (T)1;
+    gi = mk<C>(g, 0);
+    gj = mk<C>(sqrt((T)1 - g * g), 0);
+  }
+  const C p1 = mk<C>(c1 * gi.x - s1 * gi.y, c1 * gi.y + s1 * gi.x);   // e^{i th1} g_i
+  const C p2 = mk<C>(c2 * gj.x - s2 * gj.y, c2 * gj.y + s2 * gj.x);   // e^{i th2} g_j
+#pragma unroll
+  for (int c = 0; c < 3; ++c) f[c] = mk<C>(Fk * (p1.x * e1[c] + p2.x * e2[c]), Fk * (p1.y * e1[c] + p2.y * e2[c]));
+}
+
 enum { STEP_CALCN = 0, STEP_RK4_1 = 1, STEP_RK4_2 = 2, STEP_RK4_3 = 3, STEP_RK4_4 = 4, STEP_LSRK = 5 };
 
 template <typename T>
@@ -681,6 +787,7 @@ struct SpecArgs {
   int first;             // LSRK: stage 1 (S2 treated as zero)
   const Cx<T>* force;    // constant spectral forcing [F][compact] (calcF! hook), or null
   unsigned fmask;        // bit f set: field f is forced
+  A99Args<T> a99;        // random driving (variant = A99_OFF: none)
 };
 
 template <typename T, int F>
@@ -827,6 +934,17 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
         for (int f = 0; f < F; ++f)
           if ((a.fmask >> f) & 1u) { const C w = a.force[f * g.field + e]; N[f].x += w.x; N[f].y += w.y; }
       }
+      if (a.a99.variant != A99_OFF) {
+        const int jg = g.ky0 + jc;
+        const unsigned iy = (unsigned)(jg < g.by.lo ? jg : jg + (g.by.hi0 - g.by.lo));
+        const unsigned iz = (unsigned)(kc < g.bz.lo ? kc : kc + (g.bz.hi0 - g.bz.lo));
+        const unsigned long long mode = (unsigned)ix + (unsigned long long)a.a99.nkr * (iy + (unsigned long long)g.by.n * iz);
+        C fr[3];
+        a99_force<T>(a.a99, mode, ix, iz == 0u, kx, ky, kz, fr);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { N[c].x += fr[c].x; N[c].y += fr[c].y; }
+        if (a.a99.variant == A99_GPU && ix == 0) N[0].y = N[1].y = N[2].y = (T)0;
+      }
     }
   }
 }
@@ -932,6 +1050,30 @@ __global__ void __launch_bounds__(256) k_emhd_derive(SpecGeom<T> g, const Cx<T>*
         out[(12 + 3 * i + j) * g.field + e] = cmuli(cscale(A[i], k[j]));
       }
     }
+  }
+}
+
+// DivVCorrection! / DivBCorrection! (Solver/VPSolver.jl:61-137): Phi = -i (k.f^) / k^2, f^_i -= i k_i Phi on three
+// consecutive fields of a compact state, same operation order as the reference's broadcasts.
+template <typename T>
+__global__ void __launch_bounds__(256) k_divclean(SpecGeom<T> g, Cx<T>* __restrict__ S) {
+  using C = Cx<T>;
+  const int Ky = g.Kyl, Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    const T k[3] = {g.kx[ix], g.ky[jc], g.kz[kc]};
+    const T k2 = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
+    const T ik2 = (k2 > (T)0) ? (T)1 / k2 : (T)0;   // invKrsq[1,1,1] = 0
+    C f[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) f[i] = S[i * g.field + e];
+    const C s = mk<C>((k[0] * f[0].x + k[1] * f[1].x + k[2] * f[2].x) * ik2, (k[0] * f[0].y + k[1] * f[1].y + k[2] * f[2].y) * ik2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) S[i * g.field + e] = mk<C>(f[i].x - k[i] * s.x, f[i].y - k[i] * s.y);
   }
 }
 

@@ -103,6 +103,9 @@ struct mhdf_handle {
   virtual long long launch_count() const = 0;
   virtual void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const = 0;
   virtual void set_forcing(int field, const void* p) = 0;
+  virtual void set_forcing_a99(const mhdf_a99* p) = 0;
+  virtual unsigned long long a99_calls() const = 0;
+  virtual void div_correction(int group) = 0;
   virtual void ipc_export(void* blob) = 0;
   virtual void ipc_import(const void* blobs) = 0;
 };
@@ -154,6 +157,8 @@ struct Solver : mhdf_handle {
   T* bst = nullptr;   // EMHD stale real b [3][nz][ny][nx]
   C* force = nullptr; // constant spectral forcing [F][compact] (calcF! hook)
   unsigned fmask = 0;
+  A99Args<T> a99{};   // random driving (A99ForceDriving!), variant = A99_OFF: none
+  unsigned long long a99_call = 0;   // forcing evaluations so far = the Philox counter word
   C *twx = nullptr, *twy = nullptr, *twz = nullptr;
   T *kxv = nullptr, *kyv = nullptr, *kzv = nullptr;
   XRed* red_d = nullptr;
@@ -753,6 +758,7 @@ struct Solver : mhdf_handle {
     sa.Sin = Sin;
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
     sa.force = fmask ? force : nullptr; sa.fmask = fmask;
+    next_a99(sa);
     if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     {   // inverse z pass of every field into the two-level send layout
       PassArgs<T> a;
@@ -840,6 +846,13 @@ struct Solver : mhdf_handle {
     launch_spectral(sa);
   }
 
+  // calcF! = A99ForceDriving!: every RHS evaluation draws fresh random numbers (counter word = evaluation number)
+  void next_a99(SpecArgs<T>& sa) {
+    sa.a99 = a99;
+    if (a99.variant == A99_OFF) return;
+    sa.a99.call_lo = (unsigned)a99_call; sa.a99.call_hi = (unsigned)(a99_call >> 32);
+    ++a99_call;
+  }
   // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
   void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
     if (pipe_ok()) { rhs_pipe(Sin, sa, want_red); return; }
@@ -857,6 +870,7 @@ struct Solver : mhdf_handle {
     sa.Sin = Sin;
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
     sa.force = fmask ? force : nullptr; sa.fmask = fmask;
+    next_a99(sa);
     if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
     to_xlayout(zin, nin);
     XArgs<T> xa = xargs();
@@ -1050,6 +1064,50 @@ struct Solver : mhdf_handle {
     if (!force) force = dalloc<C>((size_t)F * cf);
     real_to_compact(p, force + field * cf, -1);
     fmask |= 1u << field;
+  }
+  void set_forcing_a99(const mhdf_a99* p) override {
+    if (p == nullptr) { a99.variant = A99_OFF; return; }
+    if (p->variant != A99_HOST && p->variant != A99_GPU) throw Err{MHDF_ERR_INVALID, "a99.variant must be MHDF_A99_HOST or MHDF_A99_GPU"};
+    if (!(p->sigma2 > 0) || !std::isfinite(p->amp) || !std::isfinite(p->kf) || !(p->b != 0)) throw Err{MHDF_ERR_INVALID, "a99: need sigma2 > 0, b != 0, finite amp and kf"};
+    a99.variant = p->variant; a99.nkr = nkr;
+    a99.amp = (T)p->amp; a99.kf = (T)p->kf; a99.sig2 = (T)p->sigma2; a99.b = (T)p->b;
+    a99.itanh = (T)(1.0 / std::tanh((double)(T)p->b * 3.14159265358979323846 / 2));
+    a99.seed_lo = (unsigned)p->seed; a99.seed_hi = (unsigned)(p->seed >> 32);
+    a99_call = p->call;
+  }
+  unsigned long long a99_calls() const override { return a99_call; }
+  // DivVCorrection! (group 0) / DivBCorrection! (group 1), Solver/VPSolver.jl:61-137: project sol, then refresh the
+  // real-space vars of that group (ldiv!(vars.bx, rfftplan, deepcopy(bxh)) ...) = the stale view and its statistics.
+  void div_correction(int group) override {
+    CK(cudaSetDevice(cfg.device));
+    int f0;
+    if (group == 0) { if (phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "DivVCorrection!: the EMHD state has no velocity"}; f0 = 0; }
+    else if (group == 1) { if (phys == MHDF_HD) throw Err{MHDF_ERR_INVALID, "DivBCorrection!: the HD state has no magnetic field"}; f0 = (phys == MHDF_EMHD) ? 0 : 3; }
+    else throw Err{MHDF_ERR_INVALID, "group must be 0 (velocity) or 1 (magnetic field)"};
+    C* Y = reg[iY] + (size_t)f0 * cf;
+    k_divclean<T><<<spec_grid(), 256, 0, st>>>(geom(), Y);
+    ++launches;
+    CK(cudaGetLastError());
+    if (iStale >= 0 && iStale != iY)
+      CK(cudaMemcpyAsync(reg[iStale] + (size_t)f0 * cf, Y, 3 * (size_t)cf * sizeof(C), cudaMemcpyDeviceToDevice, st));
+    T* re = reinterpret_cast<T*>(R);
+    const size_t n = (size_t)nx * ny * nzl;
+    for (int i = 0; i < 3; ++i) {
+      to_xlayout(Y + (size_t)i * cf, 1);
+      XArgs<T> xa = xargs();
+      xa.real_io = re; xa.in = Q; xa.out = nullptr;
+      CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+      xa.red = red_d;
+      launch_xplain<+1>(xa);
+      if (phys == MHDF_EMHD) CK(cudaMemcpyAsync(bst + (size_t)i * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      finish_red();
+      sync_all();
+      const int slot = (phys == MHDF_EMHD) ? 3 + i : f0 + i;
+      st_sum[slot] = red_h->sumsq[0];
+      float f;
+      std::memcpy(&f, &red_h->maxsq[0], 4);
+      st_max[slot] = (double)f;
+    }
   }
   const C* source(int which) const {
     if (which == MHDF_STALE && iStale >= 0) return reg[iStale];

@@ -58,6 +58,89 @@ def SetUpN97(prob, F0=1, kf=2):
     prob.set_forcing("uy", -F0 * np.cos(kf * X) * np.sin(kf * Y) * np.cos(kf * Z))
 
 
+class A99_vars:
+    """A99_vars (pgen/A99ForceDriving.jl:5-16; module A99GPU: pgen/A99ForceDriving_GPU.jl:7-12): `A` and `b` are the
+    user-visible knobs; the spectral tables of the reference (Fk, e1x ... e2z) are not stored -- the spectral kernel
+    evaluates them per mode.  `seed` keys the device random-number stream (ours: Julia's stream cannot be reproduced)."""
+
+    def __init__(self, variant, T, seed=0):
+        self.variant, self.T = variant, np.dtype(T).type
+        self.A, self.b = self.T(1.0), self.T(1.0)
+        self.σ2, self.kf = self.T(1.0), self.T(1.0)      # A99GPU fields σ², kf
+        self.Fk_A = None                                  # normalisation inside the Fk table, set by SetUpFk
+        self.seed = int(seed)
+        self._pushed = None
+
+
+def A99ForceDriving(*args, **kw):
+    """A99ForceDriving! (pgen/A99ForceDriving.jl:33-60): pass as `calcF` to Problem together with the `usr_vars` of
+    GetA99vars_And_function, then call SetUpFk(prob).  Applied inside the CUDA library (mhdf_set_forcing_a99)."""
+    raise RuntimeError("A99ForceDriving is applied by the library; it is not called from the host")
+
+
+def GetA99vars_And_function(dev=None, nx=None, ny=None, nz=None, T=np.float32, C=False, seed=0):
+    """GetA99vars_And_function(dev, nx, ny, nz; T, C) (pgen/A99ForceDriving.jl:18-31) -> (usr_vars, calcF)."""
+    if C:
+        raise NotImplementedError("A99ForceDriving_Compressible! belongs to the compressible solver (outside SURVEY 8)")
+    return A99_vars(L.A99_HOST, T, seed), A99ForceDriving
+
+
+def _a99_integral(grid, kf, sigma2):
+    """sum(exp(-(k-kf)^2/sigma2) / (k+1)^2) over the whole (nkr, nl, nm) array, one z plane at a time."""
+    kr = grid.kr.astype(np.float64).reshape(1, -1)
+    l = grid.l.astype(np.float64).reshape(-1, 1)
+    tot = 0.0
+    for m in grid.m.astype(np.float64).ravel():
+        k = np.sqrt(kr * kr + l * l + m * m)
+        tot += float(np.sum(np.exp(-(k - kf) ** 2 / sigma2) / (k + 1.0) ** 2))
+    return tot
+
+
+def SetUpFk(prob, kf=2, P=1, σ2=1, **greek):
+    """SetUpFk(prob; kf, P, σ²) (pgen/A99ForceDriving.jl:93-127): A = sqrt(3 P (Lx/dx)(Ly/dy)(Lz/dz) / ∫Fk dk / dV),
+    Fk = A sqrt(exp(-(k-kf)²/σ²)/2π)/k with the kr = 0 plane zeroed.  (`σ²` is accepted as a keyword too.)"""
+    σ2 = greek.pop("σ²", σ2)
+    if greek:
+        raise TypeError(f"SetUpFk() got unexpected keyword arguments {sorted(greek)}")
+    uv = prob.vars.usr_vars
+    if not isinstance(uv, A99_vars) or uv.variant != L.A99_HOST or prob.params.calcF is not A99ForceDriving:
+        raise ValueError("construct the problem with the usr_vars and calcF of GetA99vars_And_function")
+    g = prob.grid
+    integral = _a99_integral(g, float(kf), float(σ2))
+    uv.Fk_A = math.sqrt(P * 3 * (g.Lx / g.dx) * (g.Ly / g.dy) * (g.Lz / g.dz) / integral * (1 / g.dx / g.dy / g.dz))
+    uv.kf, uv.σ2 = uv.T(kf), uv.T(σ2)
+    prob._sync_forcing(force=True)
+
+
+class A99GPU:
+    """module A99GPU (pgen/A99ForceDriving_GPU.jl): the same driving with its own basis vectors, a real Φ, |g_i|
+    clipped to 1, Im N_u = 0 on the kr = 0 plane; `SetUpFk!` stores kf = b (:45) and the kernel multiplies A twice
+    (:60-61, :89) -- both restated."""
+
+    @staticmethod
+    def A99ForceDriving(*args, **kw):
+        raise RuntimeError("A99GPU.A99ForceDriving is applied by the library; it is not called from the host")
+
+    @staticmethod
+    def GetA99vars_And_function(dev=None, nx=None, ny=None, nz=None, T=np.float32, seed=0):
+        """-> (usr_vars, calcF, SetUpFk!) (pgen/A99ForceDriving_GPU.jl:14-23)."""
+        return A99_vars(L.A99_GPU, T, seed), A99GPU.A99ForceDriving, A99GPU.SetUpFk
+
+    @staticmethod
+    def SetUpFk(prob, kf=2.0, P=1.0, σ=1.0, b=1.0):
+        """SetUpFk!(prob; kf, P, σ, b) (pgen/A99ForceDriving_GPU.jl:25-48)."""
+        uv = prob.vars.usr_vars
+        if not isinstance(uv, A99_vars) or uv.variant != L.A99_GPU or prob.params.calcF is not A99GPU.A99ForceDriving:
+            raise ValueError("construct the problem with the usr_vars and calcF of A99GPU.GetA99vars_And_function")
+        g = prob.grid
+        integral = _a99_integral(g, float(kf), float(σ) ** 2)
+        A = math.sqrt(P * 3 * (g.Lx / g.dx) * (g.Ly / g.dy) * (g.Lz / g.dz) / integral * (1 / g.dx / g.dy / g.dz))
+        uv.A, uv.σ2, uv.b = uv.T(A), uv.T(σ ** 2), uv.T(b)
+        uv.kf = uv.T(b)              # sic: `prob.vars.usr_vars.kf = T(b)` (:45)
+        uv.Fk_A = float(uv.A)        # Fk = A sqrt(...) k⁻¹ inside the kernel, then N += A Fk ... (:89, :106)
+        prob._sync_forcing(force=True)
+
+
 class _Clock:
     """FourierFlows.Clock{T}(dt, t, step) (Problems.jl:120) backed by the library's clock."""
 
@@ -191,9 +274,11 @@ class Problem:
             raise NotImplementedError("Compressibility / VP_method / Dye_Module are outside the B200 hot path (SURVEY 8)")
         if calcF is None:
             calcF = nothingfunction
-        if calcF is not nothingfunction and calcF is not N97ForceDriving:
-            raise NotImplementedError("arbitrary forcing callbacks cannot run on the device; constant forcings go through "
-                                      "set_forcing / N97ForceDriving (SURVEY 8b, 8f)")
+        if calcF not in (nothingfunction, N97ForceDriving, A99ForceDriving, A99GPU.A99ForceDriving):
+            raise NotImplementedError("arbitrary forcing callbacks cannot run on the device; the built-in forcings are "
+                                      "set_forcing / N97ForceDriving (constant) and A99ForceDriving (random driving)")
+        if calcF in (A99ForceDriving, A99GPU.A99ForceDriving) and not isinstance(usr_vars, A99_vars):
+            raise ValueError("A99ForceDriving needs usr_vars = the A99_vars of GetA99vars_And_function")
         if EMHD and not B_field:
             raise ValueError("EMHD requires B_field=true (datastructure.jl:78-88)")
         if stepper == "HM89":
@@ -232,6 +317,7 @@ class Problem:
         self.params = p
         self._names = names
         self.vars = _Vars(self, names)
+        object.__setattr__(self.vars, "usr_vars", usr_vars)
         # slab decomposition over `nranks` processes (ours: the reference is single-device, README.md:40-41)
         self.rank, self.nranks = int(rank), int(nranks)
         self._idbuf = None
@@ -292,6 +378,28 @@ class Problem:
             raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
         L.check(self._h, L.lib().mhdf_set_forcing(self._h, self._field_id(f), a.ctypes.data))
 
+    def _sync_forcing(self, force=False):
+        """Push the A99 parameters (usr_vars.A, b, kf, σ², seed) to the library when they changed -- the reference reads
+        usr_vars on every forcing call, so user code may retune A or b between steps."""
+        uv = getattr(self.vars, "usr_vars", None)
+        if not isinstance(uv, A99_vars) or uv.Fk_A is None:
+            return
+        key = (uv.variant, float(uv.A) * float(uv.Fk_A), float(uv.kf), float(uv.σ2), float(uv.b), uv.seed)
+        if not force and key == uv._pushed:
+            return
+        a = L.A99(variant=key[0], amp=key[1], kf=key[2], sigma2=key[3], b=key[4], seed=key[5], call=self.a99_calls())
+        L.check(self._h, L.lib().mhdf_set_forcing_a99(self._h, C.byref(a)))
+        uv._pushed = key
+
+    def a99_calls(self):
+        """Forcing evaluations so far (the counter word of the device random-number stream)."""
+        n = C.c_ulonglong()
+        L.check(self._h, L.lib().mhdf_forcing_a99_calls(self._h, C.byref(n)))
+        return n.value
+
+    def div_correction(self, group):
+        L.check(self._h, L.lib().mhdf_div_correction(self._h, int(group)))
+
     def get_real(self, f, which=L.FRESH, out=None):
         """Real-space field (c2r on demand).  `out`: optional preallocated (e.g. pinned) array to receive it."""
         if out is None:
@@ -324,6 +432,7 @@ class Problem:
 
     def calcN(self):
         """eqn.calcN!(N, sol, t, clock, vars, params, grid) on the current sol -> N (host copy)."""
+        self._sync_forcing()
         out = np.empty((self.Nl,) + self._spec_shape, dtype=self.CT)
         L.check(self._h, L.lib().mhdf_calcN(self._h, out.ctypes.data))
         return out
@@ -352,6 +461,7 @@ class Problem:
         return dict(nfields=v[0].value, Kx=v[1].value, Kxp=v[2].value, Ky=v[3].value, Kz=v[4].value, bytes_device=b.value)
 
     def step_timed(self, nsteps):
+        self._sync_forcing()
         ms = C.c_double()
         L.check(self._h, L.lib().mhdf_step_timed(self._h, int(nsteps), C.byref(ms)))
         return ms.value
@@ -398,7 +508,18 @@ def SetUpProblemIC(prob, *, ux=None, uy=None, uz=None, bx=None, by=None, bz=None
 def stepforward(prob, nsteps=1):
     """stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)
     (timestepper/timestepper.jl:4-6)."""
+    prob._sync_forcing()
     L.check(prob._h, L.lib().mhdf_step(prob._h, int(nsteps)))
+
+
+def DivVCorrection(prob):
+    """DivVCorrection!(prob) (Solver/VPSolver.jl:101-137): sol_u -= k (k·sol_u)/k², vars.u* refreshed."""
+    prob.div_correction(0)
+
+
+def DivBCorrection(prob):
+    """DivBCorrection!(prob) (Solver/VPSolver.jl:61-99): sol_b -= k (k·sol_b)/k², vars.b* refreshed."""
+    prob.div_correction(1)
 
 
 def getCFL(prob, t_diff, Coef=0.3):

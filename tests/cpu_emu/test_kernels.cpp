@@ -497,6 +497,128 @@ template <int PHYS> void test_spectral(int mode, bool forced, int P = 1, int ran
          worst < 1e-11, worst);
 }
 
+// ---- D2. A99 random driving: Philox known answers, forcing of every retained mode against std::complex formulas ---
+static void test_philox_kat() {
+  // Random123 known-answer vectors of philox4x32-10
+  struct V { unsigned c[4], k[2], out[4]; };
+  const V kat[3] = {{{0, 0, 0, 0}, {0, 0}, {0x6627e8d5u, 0xe169c58du, 0xbc57ac4cu, 0x9b00dbd8u}},
+                    {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, {0xffffffffu, 0xffffffffu}, {0x408f276du, 0x41c83b0eu, 0xa20bc7c6u, 0x6d5451fdu}},
+                    {{0x243f6a88u, 0x85a308d3u, 0x13198a2eu, 0x03707344u}, {0xa4093822u, 0x299f31d0u}, {0xd16cfe09u, 0x94fdccebu, 0x5001e420u, 0x24126ea1u}}};
+  bool ok = true;
+  for (const V& v : kat) {
+    Philox4 c; for (int i = 0; i < 4; ++i) c.v[i] = v.c[i];
+    const Philox4 o = philox4x32_10(c, v.k[0], v.k[1]);
+    for (int i = 0; i < 4; ++i) ok = ok && o.v[i] == v.out[i];
+  }
+  report("philox4x32-10 known answers", ok, ok ? 0.0 : 1.0);
+}
+template <typename T> void test_a99(int variant, int P, int rank) {
+  using C = Cx<T>;
+  const int nx = 16, ny = 16, nz = 32, nkr = nx / 2 + 1;
+  const Band bx = band_of(nx), by = band_of(ny), bz = band_of(nz);
+  const int Kx = bx.lo, Kxp = 8, Ky = by.count(), Kz = bz.count(), Kyl = (Ky + P - 1) / P, ky0 = rank * Kyl, F = 6;
+  const long long cf = (long long)Kxp * Kyl * Kz;
+  std::vector<T> kx(Kx), ky(Kyl), kz(Kz);
+  for (int i = 0; i < Kx; ++i) kx[i] = (T)i;
+  for (int j = 0; j < Kyl; ++j) ky[j] = (ky0 + j < Ky) ? (T)(by.wave(ky0 + j) * 0.5) : (T)0;
+  for (int k = 0; k < Kz; ++k) kz[k] = (T)(bz.wave(k) * 2.0);
+  std::vector<C> Sin = randc<T>((size_t)F * cf, 41), Pp = randc<T>((size_t)9 * cf, 42);
+  std::vector<C> mirror = randc<T>((size_t)P * F * Kz * Kyl, 43), N0((size_t)F * cf, mk<C>(0, 0)), N1 = N0, N2 = N0;
+  SpecArgs<T> a; std::memset(&a, 0, sizeof a);
+  a.g.Kx = Kx; a.g.Kxp = Kxp; a.g.by = by; a.g.bz = bz; a.g.Kyl = Kyl; a.g.ky0 = ky0; a.g.F = F;
+  a.g.kx = kx.data(); a.g.ky = ky.data(); a.g.kz = kz.data(); a.g.field = cf; a.g.mirror = (P > 1) ? mirror.data() : nullptr;
+  a.P = Pp.data(); a.Sin = Sin.data(); a.nu = (T)0.01; a.eta = (T)0.02; a.mode = STEP_CALCN;
+  a.Nout = N0.data();
+  emu::launch(k_spectral<T, PHYS_MHD>, dim3(3, 1, 1), 256, a);
+  A99Args<T>& q = a.a99;
+  q.variant = variant; q.nkr = nkr; q.amp = (T)1.7; q.kf = (T)2.5; q.sig2 = (T)1.3; q.b = (T)0.9; q.itanh = (T)(1.0 / std::tanh(0.9 * M_PI / 2));
+  q.seed_lo = 0x1234567u; q.seed_hi = 0x9abcdefu; q.call_lo = 77u; q.call_hi = 3u;
+  a.Nout = N1.data();
+  emu::launch(k_spectral<T, PHYS_MHD>, dim3(3, 1, 1), 256, a);
+  a.Nout = N2.data();
+  emu::launch(k_spectral2<T, PHYS_MHD, STEP_CALCN>, dim3((Kxp * Kyl + 255) / 256, Kz, 1), 256, a);
+  const bool same = std::memcmp(N1.data(), N2.data(), N1.size() * sizeof(C)) == 0;
+  double worst = 0, fmax = 0;
+  long forced = 0;
+  bool bfields_untouched = true, plane_ok = true;
+  for (int k = 0; k < Kz; ++k) for (int j = 0; j < Kyl; ++j) for (int x = 0; x < Kx; ++x) {
+    if (ky0 + j >= Ky) continue;
+    const size_t e = ((size_t)k * Kyl + j) * Kxp + x;
+    for (int f = 3; f < 6; ++f) bfields_untouched = bfields_untouched && std::memcmp(&N0[f * cf + e], &N1[f * cf + e], sizeof(C)) == 0;
+    const int jg = ky0 + j, iy = jg < by.lo ? jg : jg + (by.hi0 - by.lo), iz = k < bz.lo ? k : k + (bz.hi0 - bz.lo);
+    const unsigned long long mode = (unsigned long long)x + (unsigned long long)nkr * (iy + (unsigned long long)ny * iz);
+    T r[4];
+    a99_uniforms<T>(q, mode, r);
+    const double K[3] = {(double)kx[x], (double)ky[j], (double)kz[k]};
+    const double kk = std::sqrt(K[0] * K[0] + K[1] * K[1] + K[2] * K[2]), ik = kk > 0 ? 1 / kk : 0;
+    const double Fk = 1.7 * std::sqrt(std::exp(-(kk - 2.5) * (kk - 2.5) / 1.3) / 2 / M_PI) * ik;
+    const cd ph1 = std::polar(1.0, 2 * M_PI * (double)r[0]), ph2 = std::polar(1.0, 2 * M_PI * (double)r[3]);
+    cd gi, gj, exp3[3];
+    double e1[3], e2[3];
+    if (variant == A99_HOST) {
+      const double kp = std::sqrt(K[0] * K[0] + K[1] * K[1]);
+      e1[0] = (kp > 0 && iz == 0) ? K[1] / kp : 0; e1[1] = (kp > 0 && iz == 0) ? -K[0] / kp : 0; e1[2] = 0;   // e1 tables: first z plane only
+      e2[0] = kp > 0 ? K[0] * K[2] / kp * ik : 0; e2[1] = kp > 0 ? K[1] * K[2] / kp * ik : 0; e2[2] = -kp * ik;
+      const cd Phi = M_PI * cd((double)r[1], (double)r[2]);
+      gi = -std::tanh(0.9 * (Phi - M_PI / 2)) / std::tanh(0.9 * M_PI / 2);
+      gj = std::sqrt(1.0 - gi * gi);
+    } else {
+      const double kp = std::sqrt(K[0] * K[0] + K[2] * K[2]);
+      e1[0] = kp > 0 ? K[2] / kp : 0; e1[1] = 0; e1[2] = kp > 0 ? -K[0] / kp : 0;
+      e2[0] = kp > 0 ? K[0] * K[1] / kp * ik : 0; e2[1] = -kp * ik; e2[2] = kp > 0 ? K[2] * K[1] / kp * ik : 0;
+      double g = -std::tanh(0.9 * ((double)r[1] * M_PI - M_PI / 2)) / std::tanh(0.9 * M_PI / 2);
+      if (std::fabs(g) >= 1) g = g < 0 ? -1 : 1;
+      gi = g; gj = std::sqrt(1 - g * g);
+    }
+    for (int c = 0; c < 3; ++c) {
+      exp3[c] = Fk * (ph1 * gi * e1[c] + ph2 * gj * e2[c]);
+      if (variant == A99_HOST && x == 0) exp3[c] = 0;
+      cd want = cd(N0[c * cf + e].x, N0[c * cf + e].y) + exp3[c];
+      if (variant == A99_GPU && x == 0) want = cd(want.real(), 0.0);
+      const cd got(N1[c * cf + e].x, N1[c * cf + e].y);
+      worst = std::max(worst, std::abs(got - want));
+      fmax = std::max(fmax, std::abs(exp3[c]));
+      forced += std::abs(exp3[c]) > 1e-6;
+      if (variant == A99_GPU && x == 0) plane_ok = plane_ok && N1[c * cf + e].y == (T)0;
+    }
+  }
+  const double tol = sizeof(T) == 4 ? 2e-5 : 1e-12;
+  const std::string nm = std::string("A99 forcing ") + (variant == A99_HOST ? "host" : "gpu") + " variant " + (sizeof(T) == 4 ? "f32" : "f64") + " P=" + std::to_string(P) + " rank=" + std::to_string(rank);
+  report(nm, same && bfields_untouched && plane_ok && forced > 100 && fmax > 0.1 && worst < tol, worst);
+}
+// DivVCorrection! / DivBCorrection!: k . f^ = 0 afterwards, solenoidal part untouched
+template <typename T> void test_divclean() {
+  using C = Cx<T>;
+  const int n = 16;
+  const Band b = band_of(n);
+  const int Kx = b.lo, Kxp = 8, Ky = b.count(), Kz = b.count();
+  const long long cf = (long long)Kxp * Ky * Kz;
+  std::vector<T> kx(Kx), ky(Ky), kz(Kz);
+  for (int i = 0; i < Kx; ++i) kx[i] = (T)i;
+  for (int j = 0; j < Ky; ++j) ky[j] = (T)(b.wave(j) * 0.5);
+  for (int k = 0; k < Kz; ++k) kz[k] = (T)(b.wave(k) * 2.0);
+  std::vector<C> S = randc<T>((size_t)4 * cf, 51);
+  const std::vector<C> S0 = S;
+  SpecGeom<T> g; std::memset(&g, 0, sizeof g);
+  g.Kx = Kx; g.Kxp = Kxp; g.by = b; g.bz = b; g.Kyl = Ky; g.ky0 = 0; g.F = 4; g.kx = kx.data(); g.ky = ky.data(); g.kz = kz.data(); g.field = cf;
+  struct DC { SpecGeom<T> g; C* S; } dc{g, S.data() + cf};   // fields 1..3
+  emu::launch([](const DC& d) { k_divclean<T>(d.g, d.S); }, dim3(2, 1, 1), 256, dc);
+  double worst = 0;
+  for (int k = 0; k < Kz; ++k) for (int j = 0; j < Ky; ++j) for (int x = 0; x < Kx; ++x) {
+    const size_t e = ((size_t)k * Ky + j) * Kxp + x;
+    const double K[3] = {(double)kx[x], (double)ky[j], (double)kz[k]};
+    const double k2 = K[0] * K[0] + K[1] * K[1] + K[2] * K[2];
+    cd f[3], kd = 0;
+    for (int i = 0; i < 3; ++i) { f[i] = cd(S0[(1 + i) * cf + e].x, S0[(1 + i) * cf + e].y); kd += K[i] * f[i]; }
+    for (int i = 0; i < 3; ++i) {
+      const cd want = k2 > 0 ? f[i] - K[i] * kd / k2 : f[i];
+      worst = std::max(worst, std::abs(cd(S[(1 + i) * cf + e].x, S[(1 + i) * cf + e].y) - want));
+    }
+  }
+  const bool f0_same = std::memcmp(S.data(), S0.data(), cf * sizeof(C)) == 0;
+  report(std::string("divclean ") + (sizeof(T) == 4 ? "f32" : "f64"), f0_same && worst < (sizeof(T) == 4 ? 1e-5 : 1e-13), worst);
+}
+
 // EMHD derived spectra and the full <-> compact packing
 static void test_derive_and_pack() {
   using T = double; using C = Cx<T>;
@@ -563,6 +685,10 @@ int main() {
   for (int mode : {STEP_CALCN, STEP_RK4_1, STEP_RK4_2, STEP_RK4_4, STEP_LSRK}) test_spectral<PHYS_MHD>(mode, mode == STEP_RK4_2);
   test_spectral<PHYS_HD>(STEP_RK4_3, true); test_spectral<PHYS_EMHD>(STEP_LSRK, false);
   test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 0); test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 1);   // slab ranks: gathered mirror plane
+  test_philox_kat();
+  test_a99<float>(A99_HOST, 1, 0); test_a99<float>(A99_GPU, 1, 0); test_a99<double>(A99_HOST, 1, 0); test_a99<double>(A99_GPU, 2, 1);
+  test_a99<float>(A99_HOST, 2, 1);
+  test_divclean<float>(); test_divclean<double>();
   test_derive_and_pack();
   std::printf("%s: %d failure(s)\n", g_fail ? "FAILED" : "ALL PASS", g_fail);
   return g_fail ? 1 : 0;

@@ -1,0 +1,190 @@
+"""GPU parity tests of the SURVEY 8f rows added after the round's GPU budget was spent: A99 random driving (both reference
+implementations) and DivVCorrection! / DivBCorrection!, through the C ABI against oracle/forcing_oracle.py.
+
+The kernels were verified on the CPU emulator (tests/cpu_emu: Philox known answers, forcing of every mode, k_divclean), but
+this file has NOT RUN ON HARDWARE yet -- hence the non-strict xfail guard: a pass shows up as XPASS, a failure does not
+hide the verified suite that runs before it.  Remove the guard after the first green hardware run."""
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written without GPU access; first hardware run pending")]
+
+F32_TOL = 1e-5
+F64_TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mhdflows_jl_b200 as M
+    return M
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import mhdflows_oracle as O
+    return O
+
+
+@pytest.fixture(scope="module")
+def FO():
+    from oracle import forcing_oracle as FO
+    return FO
+
+
+def _forced_pair(M, O, FO, variant, T, dims=(32, 32, 32), stepper="RK4", seed=4242):
+    nx, ny, nz = dims
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True, stepper=stepper)
+    if variant == "host":
+        op = O.Problem(calcF=FO.A99ForceDriving, **kw)
+        op.vars.usr_vars = FO.A99Vars(op.grid)
+        FO.SetUpFk(op, kf=3, P=2, sigma2=1)
+        uv, fn = M.GetA99vars_And_function(M.GPU(), nx, ny, nz, T=T, seed=seed)
+        gp = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw)
+        M.SetUpFk(gp, kf=3, P=2, σ2=1)
+    else:
+        op = O.Problem(calcF=FO.A99ForceDriving_GPU, **kw)
+        op.vars.usr_vars = FO.A99GPUVars(op.grid)
+        FO.SetUpFk_GPU(op, kf=2.0, P=2.0, sigma=1.5, b=0.8)
+        uv, fn, setup = M.A99GPU.GetA99vars_And_function(M.GPU(), nx, ny, nz, T=T, seed=seed)
+        gp = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw)
+        setup(gp, kf=2.0, P=2.0, σ=1.5, b=0.8)
+    op.vars.usr_vars.rng = FO.PhiloxField(seed, op.grid)
+    u, b = O.random_phase_ic(op.grid, 21), O.random_phase_ic(op.grid, 22)
+    O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+    M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+    return op, gp
+
+
+@pytest.mark.parametrize("variant", ["host", "gpu"])
+@pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
+def test_a99_calcN_and_steps(M, O, FO, variant, T, tol):
+    op, gp = _forced_pair(M, O, FO, variant, T, dims=(32, 16, 64))
+    g = op.grid
+    # one RHS evaluation (forcing call 0 on both sides)
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+    Nd = gp.calcN()
+    ref = g.dealias(N.copy())
+    assert O.rel_l2(Nd, ref) < tol
+    # the forcing is a visible part of N
+    q = O.Problem(nx=g.nx, ny=g.ny, nz=g.nz, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+    q.sol[...] = op.sol
+    N0 = np.zeros_like(op.sol)
+    q.calcN(N0, q.sol.copy(), 0.0, q.clock, q.vars, q.params, g)
+    assert O.rel_l2(ref[:3], g.dealias(N0.copy())[:3]) > 1e-3
+    assert gp.a99_calls() == 1
+    # five steps: forcing calls 1..20
+    for _ in range(5):
+        O.stepforward(op)
+    M.stepforward(gp, 5)
+    assert gp.a99_calls() == 21 and op.vars.usr_vars.calls == 21
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < tol
+    gp.close()
+
+
+def test_a99_lsrk54_and_retuned_amplitude(M, O, FO):
+    op, gp = _forced_pair(M, O, FO, "host", np.float32, stepper="LSRK54")
+    for _ in range(3):
+        O.stepforward(op)
+    M.stepforward(gp, 3)
+    assert gp.a99_calls() == 15
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < F32_TOL
+    # usr_vars.A / b are read on every forcing call by the reference: retune between steps
+    op.vars.usr_vars.A = np.float32(2.5)
+    op.vars.usr_vars.b = np.float32(0.6)
+    gp.vars.usr_vars.A = np.float32(2.5)
+    gp.vars.usr_vars.b = np.float32(0.6)
+    for _ in range(2):
+        O.stepforward(op)
+    M.stepforward(gp, 2)
+    assert gp.a99_calls() == 25
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < F32_TOL
+    gp.close()
+
+
+def test_a99_is_reproducible_and_hd_forcing_is_lost(M, O, FO):
+    sols = []
+    for _ in range(2):
+        _, gp = _forced_pair(M, O, FO, "gpu", np.float32)
+        M.stepforward(gp, 3)
+        sols.append(gp.sol)
+        gp.close()
+    assert np.array_equal(sols[0], sols[1])                # same seed, same stream
+    # HD: the forcing is added before the advection zeroes N (pgen.jl:176-178, HDSolver.jl:55)
+    kw = dict(nx=32, T=np.float32, nu=2e-2, dt=4e-3)
+    uv, fn = M.GetA99vars_And_function(M.GPU(), 32, 32, 32)
+    forced, plain = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw), M.Problem(M.GPU(), **kw)
+    M.SetUpFk(forced)
+    u = O.random_phase_ic(O.Grid(32, T=np.float32), 3)
+    for p in (forced, plain):
+        M.SetUpProblemIC(p, ux=u[0], uy=u[1], uz=u[2])
+        M.stepforward(p, 2)
+    assert np.array_equal(forced.sol, plain.sol)
+    forced.close()
+    plain.close()
+
+
+@pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
+def test_div_corrections(M, O, FO, T, tol):
+    kw = dict(nx=32, ny=16, nz=64, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    g = op.grid
+    rng = np.random.default_rng(8)
+    # band-limited but not solenoidal fields (band-limited: the library stores the dealiased band only)
+    f = []
+    for _ in range(6):
+        h = g.dealias(g.rfft(rng.standard_normal((64, 16, 32)).astype(T)))
+        f.append(g.irfft(h))
+    O.SetUpProblemIC(op, *f[:3], bx=f[3], by=f[4], bz=f[5])
+    M.SetUpProblemIC(gp, ux=f[0], uy=f[1], uz=f[2], bx=f[3], by=f[4], bz=f[5])
+    FO.DivBCorrection(op)
+    M.DivBCorrection(gp)
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < tol
+    assert O.rel_l2(gp.vars.bx, op.vars.bx) < 10 * tol and O.rel_l2(gp.vars.ux, op.vars.ux) < 10 * tol
+    FO.DivVCorrection(op)
+    M.DivVCorrection(gp)
+    sol = gp.sol
+    assert O.rel_l2(sol, g.dealias(op.sol.copy())) < tol
+    for base in (0, 3):
+        div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
+        assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < (1e-5 if T is np.float32 else 1e-13)
+    # dashboard energies and CFL maxima follow the refreshed vars
+    ke, me = gp.energy(M.STALE)
+    dV = float(T(g.dx)) * float(T(g.dy)) * float(T(g.dz))
+    ke_ref = sum(float(np.sum(getattr(op.vars, n).astype(np.float64) ** 2)) for n in ("ux", "uy", "uz")) * dV
+    me_ref = sum(float(np.sum(getattr(op.vars, n).astype(np.float64) ** 2)) for n in ("bx", "by", "bz")) * dV
+    assert abs(ke - ke_ref) < 1e-4 * ke_ref and abs(me - me_ref) < 1e-4 * me_ref
+    mx, _ = gp.stale_stats()
+    assert abs(mx[4] - float(np.max(op.vars.by.astype(np.float64) ** 2))) < 1e-4 * mx[4]
+    # the corrections stay consistent with stepping afterwards
+    for _ in range(3):
+        O.stepforward(op)
+    M.stepforward(gp, 3)
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < tol
+    with pytest.raises(M.MHDFlowsError):
+        gp.div_correction(2)
+    gp.close()
+    hd = M.Problem(M.GPU(), nx=16, T=T)
+    with pytest.raises(M.MHDFlowsError):
+        M.DivBCorrection(hd)
+    hd.close()
+
+
+def test_div_b_correction_emhd(M, O, FO):
+    kw = dict(nx=32, T=np.float32, B_field=True, EMHD=True, dt=2e-4)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    g = op.grid
+    rng = np.random.default_rng(9)
+    f = [g.irfft(g.dealias(g.rfft(rng.standard_normal((32, 32, 32)).astype(np.float32)))) for _ in range(3)]
+    O.SetUpProblemIC(op, bx=f[0], by=f[1], bz=f[2])
+    M.SetUpProblemIC(gp, bx=f[0], by=f[1], bz=f[2])
+    FO.DivBCorrection(op)
+    M.DivBCorrection(gp)
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < F32_TOL
+    # EMHD's (B.grad)A term reads the stale real-space vars.b*: they were refreshed by the correction
+    for _ in range(3):
+        O.stepforward(op)
+    M.stepforward(gp, 3)
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < F32_TOL
+    gp.close()

@@ -116,3 +116,20 @@ def test_savefile_restart_roundtrip(tmp_path, b, e):
     assert q.clock.t == 1.25 and q.clock.step == 0
     for k in p.fields:
         assert np.array_equal(q.fields[k], p.fields[k])
+
+
+def test_a99_normalisation_matches_the_oracle_setup():
+    """SetUpFk's amplitude A (pgen/A99ForceDriving.jl:104-105): the host mirror sums the shell weights plane by plane in
+    Float64, the oracle evaluates the reference's array expressions in T."""
+    import math
+
+    from mhdflows_jl_b200.problem import _a99_integral, _Grid
+    from oracle import forcing_oracle as FO
+    from oracle import mhdflows_oracle as O
+    for T, tol in ((np.float32, 2e-6), (np.float64, 1e-13)):
+        op = O.Problem(nx=16, ny=32, nz=8, Lx=2 * math.pi, Ly=4 * math.pi, T=T, B_field=True)
+        op.vars.usr_vars = FO.A99Vars(op.grid)
+        A_ref = FO.SetUpFk(op, kf=3, P=2, sigma2=1.5)
+        g = _Grid(16, 32, 8, 2 * math.pi, 4 * math.pi, 2 * math.pi, T)
+        A = math.sqrt(2 * 3 * (g.Lx / g.dx) * (g.Ly / g.dy) * (g.Lz / g.dz) / _a99_integral(g, 3.0, 1.5) * (1 / g.dx / g.dy / g.dz))
+        assert abs(A - A_ref) < tol * A_ref
