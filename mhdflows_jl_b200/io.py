@@ -1,10 +1,11 @@
 """Checkpoint / restart of the reference (`savefile`, `Restart!`, `readMHDFlows`: src/integrator.jl:208-288,
 src/utils/IC.jl:245-257) over the C ABI.
 
-Same dataset names and contents as the reference's HDF5 files -- the real-space `vars` fields (i.e. the STALE
-fields) and `time` -- but stored as NumPy `.npz` archives: no HDF5 library exists in this environment
-(h5py / HDF5.jl are not installable offline), so the container format is the one documented deviation.
-Array layout inside the archive is the Julia one transposed to C order, `(nz, ny, nx)`.
+Same files as the reference: HDF5, `<path>_t_NNNN.h5`, datasets `i_velocity ... k_mag_field` = the real-space `vars`
+fields (i.e. the STALE fields) in the element type of the problem and the scalar `time`.  HDF5.jl stores a
+Julia `(nx, ny, nz)` array with dataspace dimensions `(nz, ny, nx)`, which is exactly our C-order array.  No HDF5 library
+exists in this environment (h5py / HDF5.jl are not installable offline): the files are written and read by the small
+format implementation in h5lite.py.  `.npz` dumps of earlier builds are still readable.
 Host-side only; nothing here touches the hot path.
 """
 from __future__ import annotations
@@ -12,13 +13,14 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib as L
+from . import h5lite
 
 _U = (("i_velocity", "ux"), ("j_velocity", "uy"), ("k_velocity", "uz"))
 _B = (("i_mag_field", "bx"), ("j_mag_field", "by"), ("k_mag_field", "bz"))
 
 
 def _filename(file_path_and_name: str, file_number: int) -> str:
-    return f"{file_path_and_name}_t_{int(file_number):04d}.npz"       # "<path>_t_NNNN" like integrator.jl:260-262
+    return f"{file_path_and_name}_t_{int(file_number):04d}.h5"        # integrator.jl:260-262
 
 
 def savefile(prob, file_number, file_path_and_name=""):
@@ -30,16 +32,25 @@ def savefile(prob, file_number, file_path_and_name=""):
     if prob.flag.b:
         for ds, f in _B:
             data[ds] = prob.get_real(f, L.STALE)
-    data["time"] = np.float64(prob.clock.t)
+    T = next((a.dtype.type for a in data.values()), np.float64)
+    data["time"] = T(prob.clock.t)                                    # write(fw, "time", prob.clock.t): a scalar of type T
     path = _filename(file_path_and_name, file_number)
-    np.savez(path, **data)
+    h5lite.write(path, data)
     return path
 
 
-def readMHDFlows(path):
-    """readMHDFlows (utils/IC.jl:245-257): the datasets of one dump as a dict."""
-    with np.load(path) as f:
-        return {k: f[k] for k in f.files}
+def readMHDFlows(path, as_tuple=False):
+    """readMHDFlows(FileName) (utils/IC.jl:245-257).  Default: the datasets of one dump as a dict (works for HD and EMHD
+    dumps too); `as_tuple=True` gives the reference's `(iv, jv, kv, ib, jb, kb, t)` with Float32 fields."""
+    if str(path).endswith(".npz"):
+        with np.load(path) as f:
+            d = {k: f[k] for k in f.files}
+    else:
+        f = h5lite.File(path)
+        d = {k: f.read(k) for k in f.names()}
+    if not as_tuple:
+        return d
+    return tuple(d[ds].astype(np.float32) for ds, _ in _U + _B) + (d["time"],)
 
 
 def Restart(prob, file_path_and_name):

@@ -597,8 +597,8 @@ def TimeIntegrator(prob, t0, N0, *, usr_dt=0.0, CFL_Coef=0.25, CFL_function=noth
                    dump_dt=0, quiet=True):
     """TimeIntegrator!(prob, t0, N0; ...) (integrator.jl:31-156): CFL -> stepforward! -> diagnostics per step.
     Keeps the reference's quirks: clock.step is reset to 0 (:76) and the loop runs while
-    N0 >= step && t0 >= t, i.e. N0+1 steps (:104).  `save=True` dumps through mhdflows_jl_b200.io.savefile (.npz with the
-    reference's dataset names; no HDF5 library exists here)."""
+    N0 >= step && t0 >= t, i.e. N0+1 steps (:104).  `save=True` dumps through mhdflows_jl_b200.io.savefile (HDF5 files with the
+    reference's names and datasets)."""
     file_path_and_name = ""
     if save:
         from .io import savefile

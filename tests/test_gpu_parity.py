@@ -300,7 +300,7 @@ def test_time_integrator_save_and_restart(M, O, tmp_path):
     op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float32, turb=False)
     M.TimeIntegrator(gp, 1e9, 3, usr_dt=1e-3, save=True, save_loc=str(tmp_path) + "/", filename="run", dump_dt=2e-3)
     files = sorted(p.name for p in tmp_path.iterdir())
-    assert files[0] == "run_t_0000.npz" and len(files) >= 2
+    assert files[0] == "run_t_0000.h5" and len(files) >= 2
     last = str(tmp_path / files[-1])
     d = M.readMHDFlows(last)
     assert set(d) == {"i_velocity", "j_velocity", "k_velocity", "i_mag_field", "j_mag_field", "k_mag_field", "time"}

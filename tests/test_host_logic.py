@@ -105,7 +105,7 @@ def test_savefile_restart_roundtrip(tmp_path, b, e):
     p = _FakeFieldProb(b, e)
     p.clock.t, p.clock.step = 1.25, 7
     path = M.savefile(p, 3, file_path_and_name=str(tmp_path / "run"))
-    assert path.endswith("run_t_0003.npz") and set(p.which) == {M.STALE}
+    assert path.endswith("run_t_0003.h5") and set(p.which) == {M.STALE}
     d = M.readMHDFlows(path)
     want = {"time"} | ({"i_mag_field", "j_mag_field", "k_mag_field"} if b else set()) | (set() if e else {"i_velocity", "j_velocity", "k_velocity"})
     assert set(d) == want and float(d["time"]) == 1.25
