@@ -204,6 +204,43 @@ def cpu_oracle_sample(kind, n, stepper, nu, eta, dt, nsamples=1, warm=0):
     return times
 
 
+def cufft_reference_point(kind, dims, reps=5):
+    """cuFFT timed alongside (north_star): the 3D transforms of one RHS evaluation through torch.fft (= cuFFT plans), without
+    any of the products / spectral work -- (a) the fused formulation's count (MHD 6 c2r + 9 r2c), (b) the reference's own
+    count (MHD 36: 6 c2r + 30 r2c incl. the rfft(irfft()) diffusion operands).  A library reference point, never the product
+    path.  Returns None when torch/cuFFT is unavailable."""
+    try:
+        import torch
+        nx, ny, nz = dims
+        n_c2r, n_r2c = {"mhd": (6, 9), "hd": (3, 6), "emhd": (24, 3)}[kind]
+        ref_total = {"mhd": 36, "hd": 24, "emhd": 51}[kind]
+        x = torch.randn((nz, ny, nx), device="cuda", dtype=torch.float32)
+        xh = torch.fft.rfftn(x)
+        for _ in range(2):
+            torch.fft.irfftn(xh, s=x.shape)
+            torch.fft.rfftn(x)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for _ in range(reps):
+            torch.fft.irfftn(xh, s=x.shape)
+        ev[1].record()
+        for _ in range(reps):
+            torch.fft.rfftn(x)
+        ev[2].record()
+        torch.cuda.synchronize()
+        c2r_ms, r2c_ms = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        fused = n_c2r * c2r_ms + n_r2c * r2c_ms
+        n_c2r_ref = {"mhd": 6, "hd": 3, "emhd": 7}[kind]
+        literal = n_c2r_ref * c2r_ms + (ref_total - n_c2r_ref) * r2c_ms
+        return {"library": "cuFFT via torch.fft (out-of-place, full (N/2+1)N^2 spectra, no pruning)", "c2r_ms": c2r_ms, "r2c_ms": r2c_ms,
+                "ffts_per_rhs_fused_form": n_c2r + n_r2c, "fft_only_ms_per_rhs_fused_form": fused,
+                "ffts_per_rhs_reference_form": ref_total, "fft_only_ms_per_rhs_reference_form": literal,
+                "what": "transforms only; our ms_per_step / stages also contains the products, the spectral assembly and the RK update"}
+    except Exception as e:      # a reference point must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's CPU path.  Julia + FFTW cannot run here (not installed, no network), so the
     oracle port (same 36-FFT op sequence, scipy pocketfft, all host threads) is timed; each "step" is a bounded
@@ -389,6 +426,13 @@ def main():
         "gpu_launches": int(l1 - l0),
         "clocks": clocks,
     }
+    if world == 1:
+        q.close()
+        stages_ = 4 if stepper == "RK4" else 5
+        cf = cufft_reference_point(kind, dims)
+        if cf and "fft_only_ms_per_rhs_fused_form" in cf:
+            cf["ours_ms_per_rhs_everything_included"] = ms_per_step / stages_
+        line["cufft_ref"] = cf
     if not args.no_cpu_baseline and world == 1:
         times = cpu_oracle_sample(kind, n, stepper, nu, eta, dt, nsamples=1, warm=0)
         stages = 4 if stepper == "RK4" else 5

@@ -871,7 +871,7 @@ __device__ __forceinline__ Cx<T> sym_apply(const SymSrc<T>& r, int fi, Cx<T> v) 
 
 // RHS of one retained mode e = (ix, jc, kc): N[] and the stage input sin[] at that mode.  V2: the mirror operand is
 // resolved once for all fields and the stage input is loaded once (same values, same arithmetic as the V1 form).
-template <typename T, int PHYS, bool V2, typename IDX>
+template <typename T, int PHYS, bool V2, bool A99, typename IDX>
 __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, int jc, int kc,
                                          Cx<T> (&N)[PHYS == PHYS_MHD ? 6 : 3], Cx<T> (&sin)[PHYS == PHYS_MHD ? 6 : 3]) {
   using C = Cx<T>;
@@ -934,7 +934,7 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
         for (int f = 0; f < F; ++f)
           if ((a.fmask >> f) & 1u) { const C w = a.force[f * g.field + e]; N[f].x += w.x; N[f].y += w.y; }
       }
-      if (a.a99.variant != A99_OFF) {
+      if constexpr (A99) {   // its own instantiation: the undriven kernels keep their register budget and instruction stream
         const int jg = g.ky0 + jc;
         const unsigned iy = (unsigned)(jg < g.by.lo ? jg : jg + (g.by.hi0 - g.by.lo));
         const unsigned iz = (unsigned)(kc < g.bz.lo ? kc : kc + (g.bz.hi0 - g.bz.lo));
@@ -949,7 +949,7 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
   }
 }
 
-template <typename T, int PHYS>
+template <typename T, int PHYS, bool A99 = false>
 __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a) {
   using C = Cx<T>;
   const SpecGeom<T>& g = a.g;
@@ -963,7 +963,7 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a)
     if (g.ky0 + jc >= g.by.count()) continue;   // padding rows of the last slab
     constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
     C N[F], sin[F];
-    spec_rhs<T, PHYS, false>(a, e, ix, jc, kc, N, sin);
+    spec_rhs<T, PHYS, false, A99>(a, e, ix, jc, kc, N, sin);
     spec_commit<T, F>(a, e, N, sin);
   }
 }
@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a)
 // Y / A operands of the stage update are requested before the RHS arithmetic instead of after it.  Same arithmetic in the
 // same order: results are bit-identical to k_spectral.  Opt-in (MHDF_SPEC2=1) until measured on hardware.
 // Needs F_total * field < 2^32 elements (true up to 1024^3 with 9 product fields).
-template <typename T, int PHYS, int MODE>
+template <typename T, int PHYS, int MODE, bool A99 = false>
 __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral2(SpecArgs<T> a) {
   using C = Cx<T>;
   const SpecGeom<T>& g = a.g;
@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral2(SpecArgs<T> a
     if constexpr (MODE == STEP_LSRK) ac[f] = a.first ? mk<C>(0, 0) : a.A[f * fld + e];
   }
   C N[F], sin[F];
-  spec_rhs<T, PHYS, true>(a, e, (int)ix, (int)jc, kc, N, sin);
+  spec_rhs<T, PHYS, true, A99>(a, e, (int)ix, (int)jc, kc, N, sin);
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     const unsigned o = f * fld + e;

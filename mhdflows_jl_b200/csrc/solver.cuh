@@ -886,27 +886,30 @@ struct Solver : mhdf_handle {
     wait_mirror();
     launch_spectral(sa);
   }
-  template <int PHYS> void launch_spectral2(const SpecArgs<T>& sa) {
+  template <int PHYS, bool A99> void launch_spectral2(const SpecArgs<T>& sa) {
     const unsigned plane = (unsigned)Kxp * (unsigned)Kyl;
     const dim3 grid((plane + 255u) / 256u, (unsigned)Kz);
     switch (sa.mode) {
-      case STEP_CALCN: k_spectral2<T, PHYS, STEP_CALCN><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_1: k_spectral2<T, PHYS, STEP_RK4_1><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_2: k_spectral2<T, PHYS, STEP_RK4_2><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_3: k_spectral2<T, PHYS, STEP_RK4_3><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_4: k_spectral2<T, PHYS, STEP_RK4_4><<<grid, 256, 0, st>>>(sa); break;
-      default:         k_spectral2<T, PHYS, STEP_LSRK><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_CALCN: k_spectral2<T, PHYS, STEP_CALCN, A99><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_1: k_spectral2<T, PHYS, STEP_RK4_1, A99><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_2: k_spectral2<T, PHYS, STEP_RK4_2, A99><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_3: k_spectral2<T, PHYS, STEP_RK4_3, A99><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_RK4_4: k_spectral2<T, PHYS, STEP_RK4_4, A99><<<grid, 256, 0, st>>>(sa); break;
+      default:         k_spectral2<T, PHYS, STEP_LSRK, A99><<<grid, 256, 0, st>>>(sa); break;
     }
   }
   void launch_spectral(SpecArgs<T>& sa) {
     prof_begin(KC_SPEC);
+    const bool driven = (phys == MHDF_MHD) && sa.a99.variant != A99_OFF;   // A99ForceDriving! acts on the MHD path only
     if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
-      if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD>(sa);
-      else if (phys == MHDF_HD) launch_spectral2<PHYS_HD>(sa);
-      else launch_spectral2<PHYS_EMHD>(sa);
+      if (driven) launch_spectral2<PHYS_MHD, true>(sa);
+      else if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD, false>(sa);
+      else if (phys == MHDF_HD) launch_spectral2<PHYS_HD, false>(sa);
+      else launch_spectral2<PHYS_EMHD, false>(sa);
     } else {
       const int grid = spec_grid();
-      if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
+      if (driven) k_spectral<T, PHYS_MHD, true><<<grid, 256, 0, st>>>(sa);
+      else if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
       else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<grid, 256, 0, st>>>(sa);
       else k_spectral<T, PHYS_EMHD><<<grid, 256, 0, st>>>(sa);
     }

@@ -534,9 +534,9 @@ template <typename T> void test_a99(int variant, int P, int rank) {
   q.variant = variant; q.nkr = nkr; q.amp = (T)1.7; q.kf = (T)2.5; q.sig2 = (T)1.3; q.b = (T)0.9; q.itanh = (T)(1.0 / std::tanh(0.9 * M_PI / 2));
   q.seed_lo = 0x1234567u; q.seed_hi = 0x9abcdefu; q.call_lo = 77u; q.call_hi = 3u;
   a.Nout = N1.data();
-  emu::launch(k_spectral<T, PHYS_MHD>, dim3(3, 1, 1), 256, a);
+  emu::launch(k_spectral<T, PHYS_MHD, true>, dim3(3, 1, 1), 256, a);
   a.Nout = N2.data();
-  emu::launch(k_spectral2<T, PHYS_MHD, STEP_CALCN>, dim3((Kxp * Kyl + 255) / 256, Kz, 1), 256, a);
+  emu::launch(k_spectral2<T, PHYS_MHD, STEP_CALCN, true>, dim3((Kxp * Kyl + 255) / 256, Kz, 1), 256, a);
   const bool same = std::memcmp(N1.data(), N2.data(), N1.size() * sizeof(C)) == 0;
   double worst = 0, fmax = 0;
   long forced = 0;

@@ -53,3 +53,21 @@ def test_pipelined_slab_run_equals_single_gpu():
     for l in lines:
         m = re.search(r"spectral max rel diff ([0-9.e+-]+)\s+real ([0-9.e+-]+)", l)
         assert m and float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l
+
+
+@pytest.mark.xfail(strict=False, reason="A99 driving and the divergence corrections were written after round 1's GPU budget was "
+                                        "spent (kernels verified on the CPU emulator); first hardware run pending")
+def test_driven_slab_run_equals_single_gpu():
+    """A99 random driving + DivVCorrection!/DivBCorrection! on 2 GPUs: the Philox counter is the global mode index, so the
+    slab run draws the same random numbers as the single-GPU run and the state stays bit-identical."""
+    if _ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29545", os.path.join(ROOT, "tools", "dist_check.py"), "forcing64"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, MHDF_PEER="1"), cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("dist-vs-single driven")]
+    assert len(lines) == 2
+    for l in lines:
+        m = re.search(r"spectral max rel diff ([0-9.e+-]+)\s+real ([0-9.e+-]+)", l)
+        assert m and float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l

@@ -14,8 +14,14 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 r, P = dist.get_rank(), dist.get_world_size()
 
 
-def run(kind, n, stepper, T, nsteps, timing=False):
+def run(kind, n, stepper, T, nsteps, timing=False, driven=False):
     kw = dict(nx=n, T=T, stepper=stepper, dt=2e-3)
+    uvs = []
+    if driven:      # A99 random driving: the Philox counter is the global mode index, so slabs draw the single-GPU numbers
+        for _ in range(2):
+            uv, fn = M.GetA99vars_And_function(M.GPU(local), n, n, n, T=T, seed=77)
+            uvs.append(uv)
+        kw.update(calcF=fn)
     if kind == "mhd":
         kw.update(nu=2e-2, eta=3e-2, B_field=True)
     elif kind == "hd":
@@ -26,12 +32,16 @@ def run(kind, n, stepper, T, nsteps, timing=False):
     u, b = O.random_phase_ic(g, 1234), O.random_phase_ic(g, 5678)
     ic = dict(bx=b[0], by=b[1], bz=b[2]) if kind == "emhd" else (dict(ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2]) if kind == "mhd" else dict(ux=u[0], uy=u[1], uz=u[2]))
     nid = nccl_id_via_torch()
-    dp = M.Problem(M.GPU(local), rank=r, nranks=P, nccl_id=nid, **kw)
+    dp = M.Problem(M.GPU(local), rank=r, nranks=P, nccl_id=nid, **(dict(kw, usr_vars=uvs[0]) if driven else kw))
     lay = dp.layout
     if os.environ.get("MHDF_PEER", "1") == "1":
         from mhdflows_jl_b200.dist import enable_peer_exchange
         enable_peer_exchange(dp)
     M.SetUpProblemIC(dp, **{k: lay.scatter_real(v) for k, v in ic.items()})
+    if driven:
+        M.SetUpFk(dp, kf=3, P=2)
+        M.DivVCorrection(dp)
+        M.DivBCorrection(dp)
     M.stepforward(dp, nsteps)
     slabs = [dp.get_spectral(i) for i in range(dp.Nl)]
     reals = dp.get_real(0, M.STALE)
@@ -39,8 +49,12 @@ def run(kind, n, stepper, T, nsteps, timing=False):
     gathered = [None] * P
     dist.all_gather_object(gathered, (slabs, reals))
     if r == 0:
-        sp = M.Problem(M.GPU(local), **kw)
+        sp = M.Problem(M.GPU(local), **(dict(kw, usr_vars=uvs[1]) if driven else kw))
         M.SetUpProblemIC(sp, **ic)
+        if driven:
+            M.SetUpFk(sp, kf=3, P=2)
+            M.DivVCorrection(sp)
+            M.DivBCorrection(sp)
         M.stepforward(sp, nsteps)
         worst = 0.0
         for i in range(sp.Nl):
@@ -53,7 +67,7 @@ def run(kind, n, stepper, T, nsteps, timing=False):
         e1 = sp.energy(M.STALE), sp.energy(M.FRESH), sp.helicity(), sp.stale_stats()
         ediff = max(abs(a - b) / (abs(b) + 1e-30) for x, y in zip(en[:3], e1[:3]) for a, b in zip(x, y))
         sdiff = float(max(np.abs(en[3][0] - e1[3][0]).max(), 0))
-        print(f"dist-vs-single {kind} {n}^3 {stepper} {np.dtype(T).name} P={P}: spectral max rel diff {worst:.2e}  real {rerr:.2e}  diag rel {ediff:.2e}  maxsq abs {sdiff:.2e}", flush=True)
+        print(f"dist-vs-single {'driven ' if driven else ''}{kind} {n}^3 {stepper} {np.dtype(T).name} P={P}: spectral max rel diff {worst:.2e}  real {rerr:.2e}  diag rel {ediff:.2e}  maxsq abs {sdiff:.2e}", flush=True)
         sp.close()
     if timing:
         dp.step_timed(2)
@@ -73,6 +87,9 @@ if which == "check64":
     run("mhd", 64, "RK4", np.float32, 3)
     run("hd", 64, "LSRK54", np.float32, 2)
     run("emhd", 64, "RK4", np.float64, 2)
+elif which == "forcing64":
+    run("mhd", 64, "RK4", np.float32, 3, driven=True)
+    run("mhd", 64, "LSRK54", np.float64, 2, driven=True)
 elif which == "check":
     run("mhd", 64, "RK4", np.float32, 3)
     run("hd", 64, "LSRK54", np.float32, 2)
