@@ -710,6 +710,8 @@ __host__ __device__ __forceinline__ void a99_uniforms(const A99Args<T>& q, unsig
     r[0] = u01(a.v[0], a.v[1], T()); r[1] = u01(a.v[2], a.v[3], T()); r[2] = u01(b.v[0], b.v[1], T()); r[3] = u01(b.v[2], b.v[3], T());
   }
 }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }     // a product that is never contracted into an FMA
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ void sincos2pi(float r, float& s, float& c) { sincospif(2.f * r, &s, &c); }
 __device__ __forceinline__ void sincos2pi(double r, double& s, double& c) { sincospi(2.0 * r, &s, &c); }
 // The forcing of one mode: f[0..2] += amp Fk (e^{i th1} g_i e1 + e^{i th2} g_j e2), Fk = sqrt(exp(-(k-kf)^2/sig2)/2pi)/k.
@@ -742,10 +744,14 @@ __device__ __forceinline__ void a99_force(const A99Args<T>& q, unsigned long lon
     const bool ok = kp > (T)0;
     e1[0] = (ok && e1_plane) ? ky / kp : (T)0; e1[1] = (ok && e1_plane) ? -kx / kp : (T)0; e1[2] = (T)0;
     e2[0] = ok ? kx * kz / kp * ik : (T)0; e2[1] = ok ? ky * kz / kp * ik : (T)0; e2[2] = -kp * ik;
-    // tanh(x + i y) = (sinh 2x + i sin 2y) / (cosh 2x + cos 2y),  x + i y = b (Phi - pi/2),  Phi = pi (r1 + i r2)
-    const T x2 = (T)2 * q.b * (PI * r[1] - PI / (T)2), y2 = (T)2 * q.b * (PI * r[2]);
-    const T den = cosh(x2) + cos(y2);
-    gi = mk<C>(-sinh(x2) / den * q.itanh, -sin(y2) / den * q.itanh);
+    // tanh(x + i y) by Kahan's formula (no cancellation next to the poles x = 0, y = pi/2 + n pi, where |g_i| reaches 1e3):
+    //   t = tan y, beta = 1 + t^2, s = sinh x, rho = sqrt(1 + s^2):  tanh = (beta rho s + i t) / (1 + beta s^2)
+    // x + i y = b (Phi - pi/2), Phi = pi (r1 + i r2); the products are rounded separately (no FMA contraction), like the
+    // reference's broadcast `Phi *= pi; b*(Phi - pi/2)` -- next to a pole the result amplifies argument rounding 1e3-fold
+    const T x = q.b * (mul_rn(PI, r[1]) - PI / (T)2), y = q.b * mul_rn(PI, r[2]);
+    const T tn = tan(y), beta = (T)1 + tn * tn, sh = sinh(x), rho = sqrt((T)1 + sh * sh);
+    const T den = (T)1 + beta * sh * sh;
+    gi = mk<C>(-(beta * rho * sh / den) * q.itanh, -(tn / den) * q.itanh);
     // principal sqrt(1 - gi^2)
     const T u = (T)1 - (gi.x * gi.x - gi.y * gi.y), v = -(T)2 * gi.x * gi.y;
     const T m = sqrt(u * u + v * v);
@@ -757,7 +763,7 @@ __device__ __forceinline__ void a99_force(const A99Args<T>& q, unsigned long lon
     const bool ok = kp > (T)0;
     e1[0] = ok ? kz / kp : (T)0; e1[1] = (T)0; e1[2] = ok ? -kx / kp : (T)0;
     e2[0] = ok ? kx * ky / kp * ik : (T)0; e2[1] = -kp * ik; e2[2] = ok ? kz * ky / kp * ik : (T)0;
-    T g = -tanh(q.b * (r[1] * PI - PI / (T)2)) * q.itanh;
+    T g = -tanh(q.b * (mul_rn(r[1], PI) - PI / (T)2)) * q.itanh;
     if (fabs(g) >= (T)1) g = g < (T)0 ? (T)-1 : (T)1;
     gi = mk<C>(g, 0);
     gj = mk<C>(sqrt((T)1 - g * g), 0);

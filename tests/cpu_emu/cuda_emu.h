@@ -80,6 +80,8 @@ inline double atomicAdd(double* p, double v) { std::lock_guard<std::mutex> g(emu
 inline unsigned atomicMax(unsigned* p, unsigned v) { std::lock_guard<std::mutex> g(emu::atomic_mu); unsigned o = *p; *p = std::max(o, v); return o; }
 using std::fmaxf;
 using std::rint;
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
 inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
 inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 

@@ -45,10 +45,10 @@ def _forced_pair(M, O, FO, variant, T, dims=(32, 32, 32), stepper="RK4", seed=42
     else:
         op = O.Problem(calcF=FO.A99ForceDriving_GPU, **kw)
         op.vars.usr_vars = FO.A99GPUVars(op.grid)
-        FO.SetUpFk_GPU(op, kf=2.0, P=2.0, sigma=1.5, b=0.8)
+        FO.SetUpFk_GPU(op, kf=2.0, P=2e-3, sigma=1.5, b=0.8)      # the amplitude enters squared in this variant
         uv, fn, setup = M.A99GPU.GetA99vars_And_function(M.GPU(), nx, ny, nz, T=T, seed=seed)
         gp = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw)
-        setup(gp, kf=2.0, P=2.0, σ=1.5, b=0.8)
+        setup(gp, kf=2.0, P=2e-3, σ=1.5, b=0.8)
     op.vars.usr_vars.rng = FO.PhiloxField(seed, op.grid)
     u, b = O.random_phase_ic(op.grid, 21), O.random_phase_ic(op.grid, 22)
     O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
