@@ -350,6 +350,26 @@ def main():
     alg_step = ALG_S_PER_STEP[(kind, stepper)] * S
     step_ach = alg_step / world / (ms_per_step * 1e-3) / 1e9   # per GPU
     shares = {k: v[0] / max(sum(x[0] for x in prof.values()), 1e-12) for k, v in prof.items() if v[1]}
+    nvlink = None
+    if world > 1:
+        # NVLink roofline of the global transposes: contract bytes sent per GPU per step (unpruned reference-layout
+        # fields) and the bytes the pruned exchange really pushes, over the exchange time measured with CUDA events on the
+        # communication stream (includes the two cross-rank barriers of every exchange); peak = 900 GB/s per direction per GPU.
+        try:
+            stages = 4 if stepper == "RK4" else 5
+            nf_x = XPASS_S_PER_LAUNCH[kind]
+            contract = stages * nf_x * (S / world) * (world - 1) / world
+            inf = p.info()
+            real = stages * nf_x * (dims[2] // world) * p.layout.Kyl * inf["Kxp"] * 8 * (world - 1)
+            ex_ms, ex_cnt = prof["exchange"]
+            ex_s_per_step = ex_ms * 1e-3 / K
+            nvlink = {"peak": 900.0, "unit": "GB/s", "contract_bytes_per_step_per_gpu": contract, "pushed_bytes_per_step_per_gpu": real,
+                      "exchange_ms_per_step": ex_s_per_step * 1e3, "exchanges_per_step": ex_cnt / K,
+                      "achieved_contract": contract / ex_s_per_step / 1e9, "frac_contract": contract / ex_s_per_step / 1e9 / 900.0,
+                      "achieved_pushed": real / ex_s_per_step / 1e9, "frac_pushed": real / ex_s_per_step / 1e9 / 900.0,
+                      "note": "exchange time is on the communication stream and overlaps the FFT passes; it is not additive to the step"}
+        except Exception as e:
+            nvlink = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     traffic = None
     tp = os.path.join(ROOT, "profiles", "xfused_traffic.json")
     if os.path.exists(tp):
@@ -426,6 +446,8 @@ def main():
         "gpu_launches": int(l1 - l0),
         "clocks": clocks,
     }
+    if nvlink is not None:
+        line["nvlink"] = nvlink
     if world == 1:
         q.close()
         stages_ = 4 if stepper == "RK4" else 5

@@ -12,6 +12,7 @@ tail -15 ${O}_pytest.log
 # 2. the forcing file alone with the guard lifted: real failure messages
 timeout 300 python -m pytest tests/test_gpu_zforcing.py -m gpu -q --runxfail -x > ${O}_forcing.log 2>&1; echo "forcing rc=$?" >> ${O}_forcing.log
 tail -5 ${O}_forcing.log
+timeout 200 python tools/time_forcing.py 256 > ${O}_time_forcing.log 2>&1; cat ${O}_time_forcing.log
 # 3. opt-in spectral kernel: bit-identity on hardware, then its A/B
 timeout 200 python tools/spec2_check.py > ${O}_spec2_check.log 2>&1; tail -3 ${O}_spec2_check.log
 timeout 300 bash tools/ab_env.sh MHDF_SPEC2=0 MHDF_SPEC2=1 > ${O}_ab_spec2.log 2>&1; cat ${O}_ab_spec2.log
