@@ -55,6 +55,7 @@ typedef struct {
   /* slab decomposition over `nranks` processes (one GPU each); rank 0..nranks-1.  nranks = 1: single GPU. */
   int rank, nranks;
   const void* nccl_id;     /* 128-byte ncclUniqueId from mhdf_nccl_unique_id on rank 0, shared by the host; NULL if nranks == 1 */
+  int vp;                  /* VP_method (pgen.jl:84): volume-penalisation terms in the HD / MHD right-hand side (VPSolver.jl:21-59) */
 } mhdf_config;
 
 /* Problem(...) constructor / finaliser (pgen.jl:64-127, Problems.jl:118-140). */
@@ -104,6 +105,12 @@ typedef struct {
 } mhdf_a99;
 int mhdf_set_forcing_a99(mhdf_handle* h, const mhdf_a99* p);
 int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls);
+
+/* Volume penalisation (Problem(...; VP_method = true)): the real fields params.χ (which = 0), params.U₀x,U₀y,U₀z (1..3) and, for
+ * MHD, params.B₀x,B₀y,B₀z (4..6) (datastructure.jl:80-81,94-95; SetUpProblemIC! keywords U₀x ..., IC.jl:93-106).  Every RHS
+ * evaluation then adds  N_a += -sum_j (delta_aj - k_j k_a / k^2) F[chi/eta (u_j - U0_j)],  eta = clock.dt * 13/7, to the
+ * velocity equation and the same with (b, B0) to the induction equation (VPSolver.jl:21-59).  All fields start as zero. */
+int mhdf_set_vp_field(mhdf_handle* h, int which, const void* host_real);
 
 /* DivVCorrection! (group 0) / DivBCorrection! (group 1) (Solver/VPSolver.jl:61-137): sol_i -= k_i (k . sol) / k^2 on the
  * three fields of the group, then the real-space `vars` of that group are refreshed from the corrected sol (stale view,

@@ -10,7 +10,7 @@ module MHDFlowsB200
 export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDiagnostic, Diagnostic,
        increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum,
        N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!,
-       A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!
+       A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!, setvpfield!
 
 const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
 
@@ -29,6 +29,7 @@ struct MhdfConfig
   physics::Cint; stepper::Cint; dtype::Cint; device::Cint
   rank::Cint; nranks::Cint
   nccl_id::Ptr{Cvoid}
+  vp::Cint
 end
 
 const MHDF_HD, MHDF_MHD, MHDF_EMHD = 0, 1, 2
@@ -87,18 +88,19 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   dev isa CPU && error("this build is the B200 path only: Problem(GPU(); ...)")
   câ‚› == 0.0 && Compressibility && error("You should define câ‚›")
   Shear && error("Shear haven't fully implemented yet!")
-  (Compressibility || VP_method || Dye_Module) && error("outside the B200 hot path")
+  (Compressibility || Dye_Module) && error("outside the B200 hot path")
+  VP_method && EMHD && error("VP_method: the EMHD equation has no volume-penalisation terms")
   (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! || calcF === A99GPU.A99ForceDriving!) ||
     error("arbitrary forcing callbacks cannot run on the device; constant forcings go through setforcing! / N97ForceDriving!")
   stepper in ("RK4", "LSRK54") || error("stepper must be \"RK4\" or \"LSRK54\" on the B200 path")
   physics = EMHD ? MHDF_EMHD : (B_field ? MHDF_MHD : MHDF_HD)
   cfg = MhdfConfig(nx, ny, nz, Lx, Ly, Lz, Î½, Î·, nÎ½, dt, physics, stepper == "RK4" ? 0 : 1,
-                   T === Float32 ? 0 : 1, dev.device, 0, 1, C_NULL)
+                   T === Float32 ? 0 : 1, dev.device, 0, 1, C_NULL, VP_method ? 1 : 0)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   code = ccall((:mhdf_create, lib), Cint, (Ref{MhdfConfig}, Ref{Ptr{Cvoid}}), cfg, h)
   code == 0 || check(C_NULL, code)
   prob = MHDFlowsProblem{T}(h[], Clock{T}(h[]), Grid{T}(nx, ny, nz, Lx, Ly, Lz, Lx/nx, Ly/ny, Lz/nz),
-                            Params(Î½, Î·, nÎ½, 0), Flag(B_field, EMHD, false, false, false),
+                            Params(Î½, Î·, nÎ½, 0), Flag(B_field, EMHD, VP_method, false, false),
                             physics == MHDF_MHD ? 6 : 3, isempty(usr_func) ? Any[nothingfunction] : collect(Any, usr_func),
                             Vars(usr_vars))
   finalizer(p -> ccall((:mhdf_destroy, lib), Cint, (Ptr{Cvoid},), p.h), prob)
@@ -210,6 +212,13 @@ module A99GPU
   end
 end
 
+"params.Ï‡, Uâ‚€x â€¦ Bâ‚€z of a VP_method problem: setvpfield!(prob, :Ï‡, mask)   (datastructure.jl:80-81,94-95; IC.jl:93-106)"
+function setvpfield!(prob, s::Symbol, A)
+  T = typeof(prob).parameters[1]
+  which = Dict(:Ï‡=>0, :Uâ‚€x=>1, :Uâ‚€y=>2, :Uâ‚€z=>3, :Bâ‚€x=>4, :Bâ‚€y=>5, :Bâ‚€z=>6)[s]
+  check(prob.h, ccall((:mhdf_set_vp_field, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, which, Array{T,3}(A)))
+end
+
 "DivVCorrection!(prob) / DivBCorrection!(prob)   (Solver/VPSolver.jl:61-137)"
 DivVCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, 0))
 DivBCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, 1))
@@ -266,10 +275,16 @@ function TimeIntegrator!(prob, tâ‚€::Number, Nâ‚€::Int; usr_dt = 0.0, CFL_Coef =
   t_diff = nv > 1 ? CFL_Coef * dl^nv / vi : CFL_Coef * dl^2 / vi
   prob.clock.step = 0
   usr_dt != 0.0 && (prob.clock.dt = usr_dt)
+  if prob.flag.vp                                   # integrator.jl:85-88
+    DivVCorrection!(prob); prob.flag.b && DivBCorrection!(prob)
+  end
   time = @elapsed while (Nâ‚€ >= prob.clock.step) && (tâ‚€ >= prob.clock.t)
     usr_dt == 0.0 && updateCFL!(prob, t_diff; Coef = CFL_Coef)
     stepforward!(prob)
     increment!(diags)
+    if prob.flag.vp                                 # integrator.jl:118-122
+      DivVCorrection!(prob); prob.flag.b && DivBCorrection!(prob)
+    end
     for foo! in prob.usr_func; foo!(prob); end
   end
   n = prob.grid.nx * prob.grid.ny * prob.grid.nz

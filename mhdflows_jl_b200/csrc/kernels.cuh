@@ -331,6 +331,10 @@ struct XArgs {
   int Kx, Kxp;
   T scale;             // 1/(nx ny nz)
   XRed* red;           // may be null
+  // volume penalisation (VP kernels only): real fields [1 + NF][rows][nx] = chi, then U0x,U0y,U0z[,B0x,B0y,B0z]
+  const T* vp;
+  long long vp_field;
+  T vp_eta;            // eta = clock.dt * 13/7 (VPSolver.jl:23,45)
 };
 
 template <typename T> __device__ __forceinline__ void warp_red_sum(double& x) {
@@ -388,7 +392,10 @@ enum { PHYS_HD = 0, PHYS_MHD = 1, PHYS_EMHD = 2 };
 // the reference's stale `vars` correspond to needs them; the other stages skip the work and the registers)
 // Register budget: measured on B200 (256^3 / 1024-wide rows), forcing more resident blocks (5, 6, 8 per SM) or 4
 // elements per thread was 2-23 % slower than letting the kernel keep the whole row set in 255 registers.
-template <typename T, int N, int E, int RB, int PHYS, bool RED>
+//   VP  : HD / MHD with the volume-penalisation method: additionally out V_j = chi/eta (f_j - W_j), W = U0 (and B0 for the
+//         magnetic field), j = x,y,z, appended after the tensor / E fields (reference: VPSolver.jl:21-59); its own
+//         instantiation, the plain kernels are unchanged
+template <typename T, int N, int E, int RB, int PHYS, bool RED, bool VP = false>
 __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
@@ -488,6 +495,26 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
           for (int m = 0; m < E; ++m)
             v[m] = lmulsub(f[j][m], f[3 + k][m], f[k][m], f[3 + j][m]);
           row_r2c<T, N, E, SYNC>(v, out + (6 + i) * a.out_field, a.Kx, t, sm, twt);
+        }
+      }
+      if constexpr (VP) {
+        constexpr int NT = (PHYS == PHYS_MHD) ? 9 : 6;
+        const T* vrow = a.vp + row * (long long)N;
+        C ce[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+          const C c = reinterpret_cast<const C*>(vrow)[t + Tm * m];
+          ce[m] = mk<C>(c.x / a.vp_eta, c.y / a.vp_eta);                       // chi/eta
+        }
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+          C v[E];
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            const C w = reinterpret_cast<const C*>(vrow + (1 + i) * a.vp_field)[t + Tm * m];
+            v[m] = lmul(ce[m], lsub(f[i][m], w));                               // chi/eta * (u_j - U_j)
+          }
+          row_r2c<T, N, E, SYNC>(v, out + (NT + i) * a.out_field, a.Kx, t, sm, twt);
         }
       }
     } else {
@@ -795,6 +822,9 @@ struct SpecArgs {
   unsigned fmask;        // bit f set: field f is forced
   A99Args<T> a99;        // random driving (variant = A99_OFF: none)
 };
+// Volume penalisation in the spectral kernel (VP instantiations): the penalisation spectra V^_j follow the tensor / E fields
+// in P;  N_a += -sum_j (delta_aj - k_j k_a / k^2) V^_j  for the velocity and, in MHD, the same with the B0 set for the
+// magnetic field (reference: VPSolver.jl:36, :56, called from HDSolver.jl:77-79, MHDSolver.jl:86-88, 161-163).
 
 template <typename T, int F>
 __device__ __forceinline__ void spec_commit(const SpecArgs<T>& a, long long e, const Cx<T> (&N)[F], const Cx<T> (&sin)[F]) {
@@ -877,7 +907,7 @@ __device__ __forceinline__ Cx<T> sym_apply(const SymSrc<T>& r, int fi, Cx<T> v) 
 
 // RHS of one retained mode e = (ix, jc, kc): N[] and the stage input sin[] at that mode.  V2: the mirror operand is
 // resolved once for all fields and the stage input is loaded once (same values, same arithmetic as the V1 form).
-template <typename T, int PHYS, bool V2, bool A99, typename IDX>
+template <typename T, int PHYS, bool V2, bool A99, bool VP, typename IDX>
 __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, int jc, int kc,
                                          Cx<T> (&N)[PHYS == PHYS_MHD ? 6 : 3], Cx<T> (&sin)[PHYS == PHYS_MHD ? 6 : 3]) {
   using C = Cx<T>;
@@ -934,6 +964,21 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
         N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
       }
     }
+    if constexpr (VP) {
+      constexpr int NT = (PHYS == PHYS_MHD) ? 9 : 6, NG = (PHYS == PHYS_MHD) ? 2 : 1;
+#pragma unroll
+      for (int gp = 0; gp < NG; ++gp) {
+        C V[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) V[j] = a.P[(NT + 3 * gp + j) * g.field + e];
+        const C kV = mk<C>((kx * V[0].x + ky * V[1].x + kz * V[2].x) * ik2, (kx * V[0].y + ky * V[1].y + kz * V[2].y) * ik2);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          N[3 * gp + c].x -= V[c].x - kk[c] * kV.x;
+          N[3 * gp + c].y -= V[c].y - kk[c] * kV.y;
+        }
+      }
+    }
     if constexpr (PHYS == PHYS_MHD) {   // addforcing! after the advection (pgen.jl:159); HD / EMHD: no effect, like the reference
       if (a.force != nullptr) {
 #pragma unroll
@@ -955,7 +1000,7 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
   }
 }
 
-template <typename T, int PHYS, bool A99 = false>
+template <typename T, int PHYS, bool A99 = false, bool VP = false>
 __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a) {
   using C = Cx<T>;
   const SpecGeom<T>& g = a.g;
@@ -969,7 +1014,7 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a)
     if (g.ky0 + jc >= g.by.count()) continue;   // padding rows of the last slab
     constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
     C N[F], sin[F];
-    spec_rhs<T, PHYS, false, A99>(a, e, ix, jc, kc, N, sin);
+    spec_rhs<T, PHYS, false, A99, VP>(a, e, ix, jc, kc, N, sin);
     spec_commit<T, F>(a, e, N, sin);
   }
 }
@@ -1001,7 +1046,7 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral2(SpecArgs<T> a
     if constexpr (MODE == STEP_LSRK) ac[f] = a.first ? mk<C>(0, 0) : a.A[f * fld + e];
   }
   C N[F], sin[F];
-  spec_rhs<T, PHYS, true, A99>(a, e, (int)ix, (int)jc, kc, N, sin);
+  spec_rhs<T, PHYS, true, A99, false>(a, e, (int)ix, (int)jc, kc, N, sin);
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     const unsigned o = f * fld + e;

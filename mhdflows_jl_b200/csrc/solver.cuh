@@ -106,6 +106,7 @@ struct mhdf_handle {
   virtual void set_forcing_a99(const mhdf_a99* p) = 0;
   virtual unsigned long long a99_calls() const = 0;
   virtual void div_correction(int group) = 0;
+  virtual void set_vp_field(int which, const void* p) = 0;
   virtual void ipc_export(void* blob) = 0;
   virtual void ipc_import(const void* blobs) = 0;
 };
@@ -157,6 +158,8 @@ struct Solver : mhdf_handle {
   T* bst = nullptr;   // EMHD stale real b [3][nz][ny][nx]
   C* force = nullptr; // constant spectral forcing [F][compact] (calcF! hook)
   unsigned fmask = 0;
+  bool vp_on = false;  // volume-penalisation method (Problem(...; VP_method = true))
+  T* vp_d = nullptr;   // [1 + F][nzl][ny][nx] real: chi, U0x, U0y, U0z[, B0x, B0y, B0z]  (params.χ, params.U₀x ...)
   A99Args<T> a99{};   // random driving (A99ForceDriving!), variant = A99_OFF: none
   unsigned long long a99_call = 0;   // forcing evaluations so far = the Philox counter word
   C *twx = nullptr, *twy = nullptr, *twz = nullptr;
@@ -220,6 +223,9 @@ struct Solver : mhdf_handle {
     F = (phys == MHDF_MHD) ? 6 : 3;
     nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 24);
     nout = (phys == MHDF_MHD) ? 9 : (phys == MHDF_HD ? 6 : 3);
+    vp_on = c.vp != 0;
+    if (vp_on && phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "VP_method: the EMHD equation has no volume-penalisation terms (MHDSolver.jl:183-270)"};
+    if (vp_on) nout += F;   // the penalisation products chi/eta (f_j - W_j) ride along the forward transforms
     cf = (long long)Kxp * Kyl * Kz;
     t_ = (T)0; dt_ = (T)c.dt;
     for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
@@ -258,6 +264,7 @@ struct Solver : mhdf_handle {
       D = dalloc<C>(szD);
       bst = dalloc<T>((size_t)3 * nx * ny * nzl);
     }
+    if (vp_on) vp_d = dalloc<T>((size_t)(1 + F) * nx * ny * nzl);   // zero: chi = 0 means "no solid anywhere"
     twx = make_tw(nx); twy = make_tw(ny); twz = make_tw(nz);
     // wavenumbers: built in Float64 then converted to T (FourierFlows ThreeDGrid; mirror utils/utils.jl:60-64)
     std::vector<T> hx(Kx), hy(Kyl), hz(Kz);
@@ -306,7 +313,7 @@ struct Solver : mhdf_handle {
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
-    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
+    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(vp_d); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
     cudaFree(plane_loc); cudaFree(plane_all);
@@ -317,7 +324,7 @@ struct Solver : mhdf_handle {
     if (st) cudaStreamDestroy(st);
     st = sc = nullptr; comm = nullptr; ipc_on = false; red_h = nullptr; diag_h = nullptr;
     for (int i = 0; i < 4; ++i) reg[i] = nullptr;
-    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
+    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; vp_d = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
     red_d = nullptr; diag_d = nullptr; spec_d = nullptr; plane_loc = plane_all = nullptr; bar_d = nullptr;
     dep_ev.clear(); evs.clear(); ev_free.clear();
     for (int i = 0; i < NCS_MAX; ++i) cs[i] = nullptr;
@@ -438,7 +445,11 @@ struct Solver : mhdf_handle {
       if (red) k_xfused<T, N, E, RB, PH, true><<<grid, threads, x_smem<N>(), st>>>(a);       \
       else k_xfused<T, N, E, RB, PH, false><<<grid, threads, x_smem<N>(), st>>>(a);          \
     } while (0)
-    if (phys == MHDF_MHD) XLAUNCH(PHYS_MHD);
+    if (vp_on && a.vp != nullptr) {   // penalised runs: one instantiation per physics (reductions always compiled in)
+      if (phys == MHDF_MHD) k_xfused<T, N, E, RB, PHYS_MHD, true, true><<<grid, threads, x_smem<N>(), st>>>(a);
+      else k_xfused<T, N, E, RB, PHYS_HD, true, true><<<grid, threads, x_smem<N>(), st>>>(a);
+    }
+    else if (phys == MHDF_MHD) XLAUNCH(PHYS_MHD);
     else if (phys == MHDF_HD) XLAUNCH(PHYS_HD);
     else XLAUNCH(PHYS_EMHD);
 #undef XLAUNCH
@@ -490,6 +501,8 @@ struct Solver : mhdf_handle {
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
@@ -708,7 +721,15 @@ struct Solver : mhdf_handle {
     a.Kx = Kx; a.Kxp = Kxp;
     a.scale = (T)(1.0 / ((double)nx * ny * nz));
     a.red = nullptr;
+    a.vp = nullptr; a.vp_field = 0; a.vp_eta = (T)1;
     return a;
+  }
+  // penalised RHS evaluations: the x kernel reads chi, U0 (B0) next to the row set; eta = clock.dt * 13/7 (VPSolver.jl:23)
+  void set_vp(XArgs<T>& xa, size_t real_off) const {
+    if (!vp_on) return;
+    xa.vp = vp_d + real_off;
+    xa.vp_field = (long long)nx * ny * nzl;
+    xa.vp_eta = dt_ * (T)13 / (T)7;
   }
 
   // ---- z-chunk pipelined slab path (opt-in: MHDF_ZCHUNKS = 2, 4, ...) ---------------------------------------------
@@ -801,6 +822,7 @@ struct Solver : mhdf_handle {
       XArgs<T> xa = xargs();
       xa.in = Xin + zoff; xa.out = Xout + zoff;
       xa.real_io = bst ? bst + (size_t)c * zc * ny * nx : nullptr;
+      set_vp(xa, (size_t)c * zc * ny * nx);
       xa.rows = (long long)ny * zc;
       xa.red = want_red ? red_d : nullptr;
       prof_begin(KC_XFUSED);
@@ -875,6 +897,7 @@ struct Solver : mhdf_handle {
     to_xlayout(zin, nin);
     XArgs<T> xa = xargs();
     xa.real_io = bst;
+    set_vp(xa, 0);
     if (want_red) xa.red = red_d;
     prof_begin(KC_XFUSED);
     launch_xfused(xa);
@@ -901,7 +924,12 @@ struct Solver : mhdf_handle {
   void launch_spectral(SpecArgs<T>& sa) {
     prof_begin(KC_SPEC);
     const bool driven = (phys == MHDF_MHD) && sa.a99.variant != A99_OFF;   // A99ForceDriving! acts on the MHD path only
-    if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
+    if (vp_on) {   // penalised runs: the product buffer carries the penalisation spectra as well
+      const int grid = spec_grid();
+      if (driven) k_spectral<T, PHYS_MHD, true, true><<<grid, 256, 0, st>>>(sa);
+      else if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD, false, true><<<grid, 256, 0, st>>>(sa);
+      else k_spectral<T, PHYS_HD, false, true><<<grid, 256, 0, st>>>(sa);
+    } else if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
       if (driven) launch_spectral2<PHYS_MHD, true>(sa);
       else if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD, false>(sa);
       else if (phys == MHDF_HD) launch_spectral2<PHYS_HD, false>(sa);
@@ -1079,6 +1107,15 @@ struct Solver : mhdf_handle {
     a99_call = p->call;
   }
   unsigned long long a99_calls() const override { return a99_call; }
+  // params.χ / params.U₀x ... / params.B₀x ... (datastructure.jl:80-81,94-95): which = 0 chi, 1..3 U0, 4..6 B0 (MHD)
+  void set_vp_field(int which, const void* p) override {
+    if (!vp_on) throw Err{MHDF_ERR_STATE, "the problem was created without VP_method"};
+    if (which < 0 || which > F) throw Err{MHDF_ERR_INVALID, "VP field index out of range (0 chi, 1..3 U0, 4..6 B0)"};
+    CK(cudaSetDevice(cfg.device));
+    const size_t n = (size_t)nx * ny * nzl;
+    CK(cudaMemcpyAsync(vp_d + (size_t)which * n, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    sync_all();
+  }
   // DivVCorrection! (group 0) / DivBCorrection! (group 1), Solver/VPSolver.jl:61-137: project sol, then refresh the
   // real-space vars of that group (ldiv!(vars.bx, rfftplan, deepcopy(bxh)) ...) = the stale view and its statistics.
   void div_correction(int group) override {

@@ -223,8 +223,22 @@ class _Grid:
         return msk
 
 
-class _Params:  # MHDParams / HDParams / EMHDParams (MHDParams.jl:42-94, HDParams.jl:30-51); 1-based indices
-    pass
+_VP_FIELDS = {"χ": 0, "chi": 0, "U₀x": 1, "U₀y": 2, "U₀z": 3, "B₀x": 4, "B₀y": 5, "B₀z": 6,
+              "U0x": 1, "U0y": 2, "U0z": 3, "B0x": 4, "B0y": 5, "B0z": 6}
+
+
+class _Params:
+    """MHDParams / HDParams / EMHDParams (MHDParams.jl:42-94, HDParams.jl:30-51); 1-based indices.  With VP_method the
+    reference's params also hold the real fields χ, U₀x, U₀y, U₀z (, B₀x, B₀y, B₀z) (datastructure.jl:80-81,94-95): assigning
+    one (`prob.params.χ = mask`, the mirror of `copyto!(prob.params.χ, mask)`) sends it to the device."""
+
+    def __init__(self, prob=None):
+        object.__setattr__(self, "_p", prob)
+
+    def __setattr__(self, name, value):
+        if name in _VP_FIELDS:
+            object.__getattribute__(self, "_p").set_vp_field(name, value)
+        object.__setattr__(self, name, value)
 
 
 class _Vars:
@@ -270,8 +284,10 @@ class Problem:
             raise ValueError("You should define cₛ")                       # pgen.jl:98-100
         if Shear:
             raise ValueError("Shear haven't fully implemented yet!")        # pgen.jl:103-105
-        if Compressibility or VP_method or Dye_Module:
-            raise NotImplementedError("Compressibility / VP_method / Dye_Module are outside the B200 hot path (SURVEY 8)")
+        if Compressibility or Dye_Module:
+            raise NotImplementedError("Compressibility / Dye_Module are outside the B200 hot path (SURVEY 8)")
+        if VP_method and EMHD:
+            raise ValueError("VP_method: the EMHD equation has no volume-penalisation terms (MHDSolver.jl:183-270)")
         if calcF is None:
             calcF = nothingfunction
         if calcF not in (nothingfunction, N97ForceDriving, A99ForceDriving, A99GPU.A99ForceDriving):
@@ -295,10 +311,10 @@ class Problem:
         self.T = T
         self.CT = np.complex64 if T is np.float32 else np.complex128
         self.grid = _Grid(nx, ny, nz, Lx, Ly, Lz, T)
-        self.flag = _Flag(B_field, EMHD)
+        self.flag = _Flag(B_field, EMHD, vp=bool(VP_method))
         self.stepper = stepper
         self.usr_func = list(usr_func) if usr_func else [nothingfunction]
-        p = _Params()
+        p = _Params(self)
         if EMHD:
             p.η, p.nη, p.bx_ind, p.by_ind, p.bz_ind = eta, 0, 1, 2, 3
             names = {"bx": 0, "by": 1, "bz": 2}
@@ -337,7 +353,8 @@ class Problem:
                        dt=float(dt), physics=physics, stepper=L.RK4 if stepper == "RK4" else L.LSRK54,
                        dtype=L.F32 if T is np.float32 else L.F64,
                        device=dev.device if isinstance(dev, GPU) else 0, rank=self.rank, nranks=self.nranks,
-                       nccl_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None)
+                       nccl_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None,
+                       vp=1 if VP_method else 0)
         h = C.c_void_p()
         code = L.lib().mhdf_create(C.byref(cfg), C.byref(h))
         if code != L.OK:
@@ -396,6 +413,14 @@ class Problem:
         n = C.c_ulonglong()
         L.check(self._h, L.lib().mhdf_forcing_a99_calls(self._h, C.byref(n)))
         return n.value
+
+    def set_vp_field(self, name, arr):
+        """params.χ / U₀x ... / B₀x ... of a VP_method problem (real fields of the problem's shape)."""
+        which = _VP_FIELDS[name] if isinstance(name, str) else int(name)
+        a = np.ascontiguousarray(arr, dtype=self.T)
+        if a.shape != self._real_shape:
+            raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
+        L.check(self._h, L.lib().mhdf_set_vp_field(self._h, which, a.ctypes.data))
 
     def div_correction(self, group):
         L.check(self._h, L.lib().mhdf_div_correction(self._h, int(group)))
@@ -490,8 +515,13 @@ class Problem:
 
 
 def SetUpProblemIC(prob, *, ux=None, uy=None, uz=None, bx=None, by=None, bz=None, **unsupported):
-    """SetUpProblemIC!(prob; ux, uy, uz, bx, by, bz) (utils/IC.jl:41-109): copy each given real field in and
-    r2c it into sol; no dealias, no projection; velocity is skipped for EMHD (:69)."""
+    """SetUpProblemIC!(prob; ux, uy, uz, bx, by, bz, U₀x, U₀y, U₀z, B₀x, B₀y, B₀z) (utils/IC.jl:41-109): copy each given real
+    field in and r2c it into sol; no dealias, no projection; velocity is skipped for EMHD (:69); with VP_method the wall
+    velocities / fields go to params (:93-106)."""
+    for k in [k for k in unsupported if k in _VP_FIELDS and k not in ("χ", "chi")]:
+        v = unsupported.pop(k)
+        if prob.flag.vp and v is not None and np.size(v) and (_VP_FIELDS[k] <= 3 or prob.flag.b):
+            setattr(prob.params, k, v)
     if any(v is not None and len(np.shape(v)) for v in unsupported.values()):
         raise NotImplementedError(f"unsupported IC fields on this path: {sorted(unsupported)}")
     if not prob.flag.e:
@@ -627,12 +657,20 @@ def TimeIntegrator(prob, t0, N0, *, usr_dt=0.0, CFL_Coef=0.25, CFL_function=noth
     usr_declared_dt = usr_dt != 0.0
     if usr_declared_dt:
         prob.clock.dt = usr_dt
+    if prob.flag.vp:                                                                                   # :85-88
+        DivVCorrection(prob)
+        if prob.flag.b:
+            DivBCorrection(prob)
     t_start = time.perf_counter()
     while N0 >= prob.clock.step and t0 >= prob.clock.t:
         if not usr_declared_dt:
             updateCFL(prob, t_diff, Coef=CFL_Coef)
         stepforward(prob)
         increment(list(diags))
+        if prob.flag.vp:                                                                               # :118-122
+            DivVCorrection(prob)
+            if prob.flag.b:
+                DivBCorrection(prob)
         for foo in prob.usr_func:
             foo(prob)
         if save and prob.clock.t >= t_next_save:                                                       # :136-141

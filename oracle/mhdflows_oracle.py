@@ -163,6 +163,7 @@ class Params:
     n_nu: int = 0
     n_eta: int = 0  # never forwarded by Problem (pgen.jl:114-116) -> always 0
     calcF: object = None
+    vp: object = None   # VPParams when Problem(VP_method=True): chi, U0x.., B0x.. (datastructure.jl:80-81,94-95)
     ux_ind: int = 0
     uy_ind: int = 1
     uz_ind: int = 2
@@ -176,6 +177,31 @@ class Params:
 # --------------------------------------------------------------------------
 def _delta(a, b):
     return 1 if a == b else 0
+
+
+class VPParams:
+    """The volume-penalisation members of MHDParams_VP / HDParams_VP (datastructure.jl:80-81,94-95): real fields chi,
+    U0x, U0y, U0z (, B0x, B0y, B0z), all zero after construction; `clock` is the problem's clock (VP_*Update! receive it)."""
+
+    def __init__(self, grid, B, clock):
+        z = lambda: np.zeros((grid.nz, grid.ny, grid.nx), dtype=grid.T)
+        self.chi, self.U0x, self.U0y, self.U0z = z(), z(), z(), z()
+        if B:
+            self.B0x, self.B0y, self.B0z = z(), z(), z()
+        self.clock = clock
+
+
+def _vp_update(dfdt, ka_kinv2, a, fs, Ws, vars, params, grid):
+    """VPSolver.VP_UiUpdate! / VP_BiUpdate! (VPSolver.jl:21-59): for j = x,y,z:
+    tmp = chi/eta*(f_j - W_j), eta = clock.dt*13/7;  df_a/dt += -(delta(a,j) - k_j*(k_a k^-2)) * rfft(tmp)."""
+    T = grid.T
+    ks = (grid.kr, grid.l, grid.m)
+    chi = params.vp.chi
+    eta = T(params.vp.clock.dt) * T(13) / T(7)
+    for j in range(3):
+        vars.nonlin1[...] = chi / eta * (fs[j] - Ws[j])
+        vars.nonlinh1[...] = grid.rfft(vars.nonlin1)
+        dfdt += -(T(_delta(a, j)) - ks[j] * ka_kinv2) * vars.nonlinh1
 
 
 def _hd_Ui_update(N, sol, vars, params, grid, a):
@@ -196,6 +222,9 @@ def _hd_Ui_update(N, sol, vars, params, grid, a):
                 dudt += (CT(-1j) * ks[i] * (T(_delta(a, j)) - ka * ks[j] * kinv2)) * uuh       # :68
                 if i != j:
                     dudt += (CT(-1j) * ks[j] * (T(_delta(a, i)) - ka * ks[i] * kinv2)) * uuh   # :70
+    if params.vp is not None:                                   # :76-79
+        vp = params.vp
+        _vp_update(dudt, ka * kinv2, a, us, (vp.U0x, vp.U0y, vp.U0z), vars, params, grid)
     uh = vars.nonlinh1
     uh[...] = grid.rfft(us[a])                                  # :84
     # -Krsq*nu*uh with nu Float64 -> evaluated in Float64, rounded on store
@@ -246,6 +275,9 @@ def _mhd_Ui_update(N, sol, vars, params, grid, a):
                 dudt += (CT(1j) * ks[i] * (T(_delta(a, j)) - ka * ks[j] * kinv2)) * Th       # :77
                 if i != j:
                     dudt += (CT(1j) * ks[j] * (T(_delta(a, i)) - ka * ks[i] * kinv2)) * Th   # :79
+    if params.vp is not None:                                   # :85-88
+        vp = params.vp
+        _vp_update(dudt, ka * kinv2, a, us, (vp.U0x, vp.U0y, vp.U0z), vars, params, grid)
     uh = vars.nonlinh1
     uh[...] = grid.rfft(us[a])                                  # :93
     dudt += (-(grid.Krsq.astype(np.float64)) * params.nu * uh).astype(CT)   # :94
@@ -266,6 +298,9 @@ def _mhd_Bi_update(N, sol, vars, params, grid, a):
             vars.nonlin1[...] = us[a] * bs[j] - bs[a] * us[j]   # :150
             vars.nonlinh1[...] = grid.rfft(vars.nonlin1)        # :152
             dbdt += (CT(1j) * ks[j]) * vars.nonlinh1            # :155
+    if params.vp is not None:                                   # :160-163
+        vp = params.vp
+        _vp_update(dbdt, ks[a] * grid.invKrsq, a, bs, (vp.B0x, vp.B0y, vp.B0z), vars, params, grid)
     bh = vars.nonlinh1
     bh[...] = grid.rfft(bs[a])                                  # :167
     dbdt += (-(grid.Krsq.astype(np.float64)) * params.eta * bh).astype(CT)  # :168
@@ -416,7 +451,7 @@ def stepforward(prob):
 class Problem:
     def __init__(self, nx=64, ny=None, nz=None, Lx=2 * math.pi, Ly=None, Lz=None, dt=0.0,
                  nu=0.0, n_nu=0, eta=0.0, n_eta=0, B_field=False, EMHD=False,
-                 stepper="RK4", calcF=None, T=np.float32, aliased_fraction=1 / 3):
+                 stepper="RK4", calcF=None, T=np.float32, aliased_fraction=1 / 3, VP_method=False):
         # aliased_fraction is accepted but NOT forwarded to the grid (pgen.jl:107)
         self.grid = Grid(nx, ny, nz, Lx, Ly, Lz, T)
         self.flag = Flag(b=B_field, e=EMHD)
@@ -437,6 +472,11 @@ class Problem:
         g = self.grid
         self.sol = np.zeros((self.Nl, g.nm, g.nl, g.nkr), dtype=g.CT)
         self.clock = Clock(dt=float(g.T(dt)))
+        self.flag.vp = bool(VP_method)
+        if VP_method:
+            if EMHD:
+                raise ValueError("VP_method: the EMHD equation has no volume-penalisation terms")
+            self.params.vp = VPParams(g, B_field, self.clock)
         if stepper == "RK4":
             self.timestepper = RK4TimeStepper(self.sol)
         elif stepper == "LSRK54":
@@ -527,12 +567,22 @@ def TimeIntegrator(prob, t0, N0, usr_dt=0.0, CFL_Coef=0.25, diags=(), on_step=No
     prob.clock.step = 0
     if usr_dt != 0.0:
         prob.clock.dt = float(g.T(usr_dt))
+
+    def vp_corrections():                                       # integrator.jl:85-88, 118-122
+        if prob.flag.vp:
+            from . import forcing_oracle as FO
+            FO.DivVCorrection(prob)
+            if prob.flag.b:
+                FO.DivBCorrection(prob)
+
+    vp_corrections()
     while N0 >= prob.clock.step and t0 >= prob.clock.t:
         if usr_dt == 0.0:
             getCFL(prob, t_diff, Coef=CFL_Coef)
         stepforward(prob)
         for d in diags:
             d.increment()
+        vp_corrections()
         if on_step is not None:
             on_step(prob)
 

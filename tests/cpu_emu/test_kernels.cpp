@@ -388,6 +388,97 @@ template <int N> void test_xplain() {
   report("xplain c2r N=" + std::to_string(N), std::sqrt(num / den) < 2e-6, std::sqrt(num / den));
 }
 
+// ---- C2. volume penalisation: the VP instantiations of the fused x kernel and of the spectral kernel -------------------
+template <int N, int PHYS, typename T> void test_xfused_vp() {
+  using C = Cx<T>;
+  constexpr int E = 8, Tm = N / 2 / E, RB = (64 / Tm > 0) ? 64 / Tm : 1;
+  constexpr int NF = (PHYS == PHYS_MHD) ? 6 : 3, NT = (PHYS == PHYS_MHD) ? 9 : 6, NOUT = NT + NF;
+  const Band bx = band_of(N);
+  const int Kx = bx.lo, Kxp = (Kx + 7) / 8 * 8;
+  const long long rows = 2 * RB;
+  auto tw = make_tw<T>(N);
+  auto in = randc<T>((size_t)NF * rows * Kxp, 61);
+  for (size_t i = 0; i < in.size(); ++i) if ((int)(i % Kxp) >= Kx) in[i] = mk<C>(0, 0);
+  std::vector<C> out((size_t)NOUT * rows * Kxp, mk<C>(0, 0)), plain((size_t)NT * rows * Kxp, mk<C>(0, 0));
+  std::vector<T> vp((size_t)(1 + NF) * rows * N);
+  std::mt19937 g(6); std::uniform_real_distribution<double> u01(-1, 1);
+  for (size_t i = 0; i < vp.size(); ++i) vp[i] = (i < (size_t)rows * N) ? (T)(u01(g) > 0.2 ? 1.0 : 0.0) : (T)u01(g);   // chi is a 0/1 mask
+  XRed red; std::memset(&red, 0, sizeof red);
+  XArgs<T> a;
+  a.in = in.data(); a.out = out.data(); a.tw = tw.data(); a.real_io = nullptr;
+  a.in_field = a.out_field = rows * Kxp; a.real_field = 0; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp; a.scale = (T)(1.0 / N); a.red = &red;
+  a.vp = vp.data(); a.vp_field = rows * N; a.vp_eta = (T)(2e-3 * 13 / 7);
+  emu::launch(k_xfused<T, N, E, RB, PHYS, true, true>, dim3(2, 1, 1), Tm * RB, a);
+  XArgs<T> b = a;
+  b.out = plain.data(); b.red = nullptr; b.vp = nullptr;
+  emu::launch(k_xfused<T, N, E, RB, PHYS, false>, dim3(2, 1, 1), Tm * RB, b);
+  // the tensor / E fields are exactly those of the plain kernel
+  const bool same = std::memcmp(out.data(), plain.data(), plain.size() * sizeof(C)) == 0;
+  std::vector<cd> ref((size_t)NF * rows * Kxp, 0);
+  std::vector<C> got((size_t)NF * rows * Kxp);
+  for (long long r = 0; r < rows; ++r)
+    for (int q = 0; q < NF; ++q) {
+      std::vector<double> f(N), pr(N);
+      for (int n = 0; n < N; ++n) {
+        double s = 0;
+        for (int k = 0; k < Kx; ++k) {
+          const C v = in[((size_t)q * rows + r) * Kxp + k];
+          const cd X = (k == 0) ? cd(v.x, 0) : cd(v.x, v.y);
+          const cd term = X * std::polar(1.0, 2 * M_PI * k * n / N);
+          s += (k == 0) ? term.real() : 2 * term.real();
+        }
+        f[n] = s / N;
+        pr[n] = (double)vp[(size_t)r * N + n] / (double)a.vp_eta * (f[n] - (double)vp[((size_t)(1 + q) * rows + r) * N + n]);
+      }
+      for (int k = 0; k < Kx; ++k) {
+        cd s = 0;
+        for (int n = 0; n < N; ++n) s += pr[n] * std::polar(1.0, -2 * M_PI * k * n / N);
+        ref[((size_t)q * rows + r) * Kxp + k] = s;
+      }
+      for (int k = 0; k < Kxp; ++k) got[((size_t)q * rows + r) * Kxp + k] = out[((size_t)(NT + q) * rows + r) * Kxp + k];
+    }
+  const double e = rel_err<T>(got, ref);
+  report(std::string("xfused VP ") + (PHYS == PHYS_MHD ? "MHD" : "HD") + " N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64"),
+         same && e < (sizeof(T) == 4 ? 3e-6 : 1e-13), e);
+}
+template <int PHYS> void test_spectral_vp() {
+  using T = double; using C = Cx<T>;
+  const int n = 16;
+  const Band b = band_of(n);
+  const int Kx = b.lo, Kxp = 8, Ky = b.count(), Kz = b.count();
+  constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3, NT = (PHYS == PHYS_MHD) ? 9 : 6, NOUT = NT + F;
+  const long long cf = (long long)Kxp * Ky * Kz;
+  std::vector<T> kx(Kx), ky(Ky), kz(Kz);
+  for (int i = 0; i < Kx; ++i) kx[i] = i * 1.0;
+  for (int j = 0; j < Ky; ++j) ky[j] = b.wave(j) * 0.5;
+  for (int k = 0; k < Kz; ++k) kz[k] = b.wave(k) * 2.0;
+  std::vector<C> Sin = randc<T>((size_t)F * cf, 71), Pp = randc<T>((size_t)NOUT * cf, 72), N0((size_t)F * cf, mk<C>(0, 0)), N1 = N0;
+  SpecArgs<T> a; std::memset(&a, 0, sizeof a);
+  a.g.Kx = Kx; a.g.Kxp = Kxp; a.g.by = b; a.g.bz = b; a.g.Kyl = Ky; a.g.ky0 = 0; a.g.F = F;
+  a.g.kx = kx.data(); a.g.ky = ky.data(); a.g.kz = kz.data(); a.g.field = cf;
+  a.P = Pp.data(); a.Sin = Sin.data(); a.nu = 0.01; a.eta = 0.02; a.mode = STEP_CALCN;
+  a.Nout = N0.data();
+  emu::launch(k_spectral<T, PHYS>, dim3(3, 1, 1), 256, a);
+  a.Nout = N1.data();
+  emu::launch(k_spectral<T, PHYS, false, true>, dim3(3, 1, 1), 256, a);
+  double worst = 0, vmax = 0;
+  for (int k = 0; k < Kz; ++k) for (int j = 0; j < Ky; ++j) for (int x = 0; x < Kx; ++x) {
+    const size_t e = ((size_t)k * Ky + j) * Kxp + x;
+    const double K[3] = {kx[x], ky[j], kz[k]};
+    const double k2 = K[0] * K[0] + K[1] * K[1] + K[2] * K[2], ik2 = k2 > 0 ? 1 / k2 : 0;
+    for (int gp = 0; gp < F / 3; ++gp) {
+      cd V[3], kV = 0;
+      for (int q = 0; q < 3; ++q) { const C v = Pp[(NT + 3 * gp + q) * cf + e]; V[q] = cd(v.x, v.y); kV += K[q] * V[q]; }
+      for (int c = 0; c < 3; ++c) {
+        const cd want = cd(N0[(3 * gp + c) * cf + e].x, N0[(3 * gp + c) * cf + e].y) - (V[c] - K[c] * kV * ik2);
+        worst = std::max(worst, std::abs(cd(N1[(3 * gp + c) * cf + e].x, N1[(3 * gp + c) * cf + e].y) - want));
+        vmax = std::max(vmax, std::abs(V[c]));
+      }
+    }
+  }
+  report(std::string("spectral VP phys=") + std::to_string(PHYS), vmax > 0.5 && worst < 1e-12, worst);
+}
+
 // ---- D. spectral kernel: RHS assembly + stage updates against the formulas in double ----------------------------
 template <typename T, int PHYS> void launch_spec2(const SpecArgs<T>& a, dim3 grid) {
   switch (a.mode) {
@@ -685,6 +776,8 @@ int main() {
   for (int mode : {STEP_CALCN, STEP_RK4_1, STEP_RK4_2, STEP_RK4_4, STEP_LSRK}) test_spectral<PHYS_MHD>(mode, mode == STEP_RK4_2);
   test_spectral<PHYS_HD>(STEP_RK4_3, true); test_spectral<PHYS_EMHD>(STEP_LSRK, false);
   test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 0); test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 1);   // slab ranks: gathered mirror plane
+  test_xfused_vp<32, PHYS_HD, float>(); test_xfused_vp<128, PHYS_MHD, float>(); test_xfused_vp<64, PHYS_MHD, double>(); test_xfused_vp<1024, PHYS_HD, float>();
+  test_spectral_vp<PHYS_HD>(); test_spectral_vp<PHYS_MHD>();
   test_philox_kat();
   test_a99<float>(A99_HOST, 1, 0); test_a99<float>(A99_GPU, 1, 0); test_a99<double>(A99_HOST, 1, 0); test_a99<double>(A99_GPU, 2, 1);
   test_a99<float>(A99_HOST, 2, 1);

@@ -52,7 +52,7 @@ def test_config_struct_layout_matches_header():
         stmt = re.sub(r"^(const\s+)?(int|double|void\s*\*)\s*", "", stmt)
         decl += [x.strip().lstrip("*").strip() for x in stmt.split(",")]
     assert names == decl
-    assert ctypes.sizeof(_lib.Config) == 104
+    assert ctypes.sizeof(_lib.Config) == 112
 
 
 def test_invalid_arguments_are_status_codes_not_crashes(lib):

@@ -117,3 +117,38 @@ def test_div_corrections(T, tol):
     sol_part = before[:3] - np.stack([[g.kr, g.l, g.m][i] * div(before[:3]) * g.invKrsq for i in range(3)])
     assert O.rel_l2(p.sol[:3], sol_part.astype(g.CT)) < 10 * tol
     assert k2.shape == (16, 16, 9)
+
+
+@pytest.mark.parametrize("B", [False, True])
+def test_volume_penalisation_terms(B):
+    """VP_method (VPSolver.jl:21-59 via HDSolver.jl:77-79 / MHDSolver.jl:86-88,161-163): chi = 0 leaves the equations
+    untouched; a solid region damps the velocity towards the wall velocity; the added term equals
+    -P[F(chi/eta (u - U0))] with P the solenoidal projector and eta = dt 13/7."""
+    kw = dict(nx=16, T=np.float64, nu=1e-2, eta=1e-2, dt=1e-3, B_field=B)
+    plain, zero, pen = O.Problem(**kw), O.Problem(VP_method=True, **kw), O.Problem(VP_method=True, **kw)
+    g = plain.grid
+    ic = O.taylor_green_ic(g)
+    for p in (plain, zero, pen):
+        O.SetUpProblemIC(p, *ic[:3], **(dict(bx=ic[3], by=ic[4], bz=ic[5]) if B else {}))
+    chi = ((g.x.reshape(1, 1, -1) ** 2 + g.y.reshape(1, -1, 1) ** 2) < 1.0) * np.ones((16, 16, 16))
+    pen.params.vp.chi[...] = chi
+    pen.params.vp.U0x[...] = 0.25
+    # the term itself, on one RHS evaluation
+    N0, N1 = np.zeros_like(plain.sol), np.zeros_like(pen.sol)
+    plain.calcN(N0, plain.sol.copy(), 0.0, plain.clock, plain.vars, plain.params, g)
+    pen.calcN(N1, pen.sol.copy(), 0.0, pen.clock, pen.vars, pen.params, g)
+    eta = 1e-3 * 13 / 7
+    u = [g.irfft(g.dealias(plain.sol[i].copy())) for i in range(3)]
+    W = [0.25, 0.0, 0.0]
+    V = np.stack([g.rfft(chi / eta * (u[j] - W[j])) for j in range(3)])
+    kV = (g.kr * V[0] + g.l * V[1] + g.m * V[2]) * g.invKrsq
+    for a_, k in enumerate((g.kr, g.l, g.m)):
+        assert O.rel_l2(N1[a_] - N0[a_], -(V[a_] - k * kV)) < 1e-12
+    if B:
+        assert O.rel_l2(N1[3:], N0[3:]) > 1e-3          # B0 = 0 walls: the induction equation is penalised as well
+    for _ in range(5):
+        for p in (plain, zero, pen):
+            O.stepforward(p)
+    assert O.rel_l2(zero.sol, plain.sol) == 0.0
+    inside = lambda p: float(np.sum((chi * (p.vars.ux - 0.25)) ** 2))
+    assert inside(pen) < 0.2 * inside(plain)

@@ -188,3 +188,69 @@ def test_div_b_correction_emhd(M, O, FO):
     M.stepforward(gp, 3)
     assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < F32_TOL
     gp.close()
+
+
+def _vp_pair(M, O, B, T, dims=(32, 16, 64)):
+    nx, ny, nz = dims
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, nu=2e-2, dt=2e-3, VP_method=True)
+    if B:
+        kw.update(eta=3e-2, B_field=True)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    g = op.grid
+    u, b = O.random_phase_ic(g, 31), O.random_phase_ic(g, 32)
+    # a cylinder of solid around the z axis, rotating like a rigid body, with a uniform field frozen into it
+    X, Y = g.x.astype(np.float64).reshape(1, 1, -1), g.y.astype(np.float64).reshape(1, -1, 1)
+    chi = (((X ** 2 + Y ** 2) < 1.5) * np.ones((nz, ny, nx))).astype(T)
+    U0 = [(-0.3 * Y * chi).astype(T), (0.3 * X * chi).astype(T), np.zeros((nz, ny, nx), T)]
+    B0 = [np.zeros((nz, ny, nx), T), np.zeros((nz, ny, nx), T), (0.2 * chi).astype(T)]
+    op.params.vp.chi[...] = chi
+    op.params.vp.U0x[...], op.params.vp.U0y[...], op.params.vp.U0z[...] = U0
+    gp.params.χ = chi
+    if B:
+        op.params.vp.B0x[...], op.params.vp.B0y[...], op.params.vp.B0z[...] = B0
+        O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2],
+                         U0x=U0[0], U0y=U0[1], U0z=U0[2], B0x=B0[0], B0y=B0[1], B0z=B0[2])     # Python cannot spell U₀x
+    else:
+        O.SetUpProblemIC(op, *u)
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], U0x=U0[0], U0y=U0[1], U0z=U0[2])
+    return op, gp
+
+
+@pytest.mark.parametrize("B", [False, True])
+@pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
+def test_volume_penalisation(M, O, B, T, tol):
+    """Problem(...; VP_method = true): the penalisation terms of VPSolver.jl:21-59 inside every RHS evaluation."""
+    op, gp = _vp_pair(M, O, B, T)
+    g = op.grid
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+    assert O.rel_l2(gp.calcN(), g.dealias(N.copy())) < tol
+    q = O.Problem(nx=g.nx, ny=g.ny, nz=g.nz, T=T, nu=2e-2, dt=2e-3, **(dict(eta=3e-2, B_field=True) if B else {}))
+    q.sol[...] = op.sol
+    N0 = np.zeros_like(op.sol)
+    q.calcN(N0, q.sol.copy(), 0.0, q.clock, q.vars, q.params, g)
+    assert O.rel_l2(g.dealias(N.copy()), g.dealias(N0.copy())) > 1e-2          # the penalisation is a visible part of N
+    for _ in range(5):
+        O.stepforward(op)
+    M.stepforward(gp, 5)
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < tol
+    gp.close()
+
+
+def test_volume_penalisation_time_integrator(M, O):
+    """TimeIntegrator! with flag.vp: DivVCorrection! / DivBCorrection! before the loop and after every step
+    (integrator.jl:85-88, 118-122); eta follows clock.dt."""
+    op, gp = _vp_pair(M, O, True, np.float32, dims=(32, 32, 32))
+    O.TimeIntegrator(op, 1e9, 3, usr_dt=1.5e-3)
+    M.TimeIntegrator(gp, 1e9, 3, usr_dt=1.5e-3)
+    g = op.grid
+    assert gp.clock.step == op.clock.step == 4
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < F32_TOL
+    sol = gp.sol
+    for base in (0, 3):
+        div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
+        assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < 1e-5
+    gp.close()
+    with pytest.raises(ValueError):
+        M.Problem(M.GPU(), nx=16, B_field=True, EMHD=True, VP_method=True)

@@ -133,3 +133,31 @@ def test_a99_normalisation_matches_the_oracle_setup():
         g = _Grid(16, 32, 8, 2 * math.pi, 4 * math.pi, 2 * math.pi, T)
         A = math.sqrt(2 * 3 * (g.Lx / g.dx) * (g.Ly / g.dy) * (g.Lz / g.dz) / _a99_integral(g, 3.0, 1.5) * (1 / g.dx / g.dy / g.dz))
         assert abs(A - A_ref) < tol * A_ref
+
+
+def test_vp_fields_are_routed_to_the_library():
+    """Problem(...; VP_method=true): params.χ and the U₀ / B₀ keywords of SetUpProblemIC! (IC.jl:93-106) end up in
+    set_vp_field with the header's numbering (0 chi, 1..3 U0, 4..6 B0); B₀ is ignored without a magnetic field."""
+    from mhdflows_jl_b200.problem import _Flag, _Params
+
+    class Fake:
+        def __init__(self, b):
+            self.flag = _Flag(b, False, vp=True)
+            self.sent = []
+            self.params = _Params(self)
+
+        def set_vp_field(self, name, arr):
+            self.sent.append((P._VP_FIELDS[name], float(np.asarray(arr).ravel()[0])))
+
+        def set_real(self, f, arr):
+            self.sent.append((f, None))
+
+    for b in (False, True):
+        p = Fake(b)
+        p.params.χ = np.full((2, 2, 2), 7.0)
+        p.params.ν = 0.1                                   # ordinary members stay ordinary
+        M.SetUpProblemIC(p, ux=np.ones((2, 2, 2)), U0y=np.full((2, 2, 2), 2.0), B0z=np.full((2, 2, 2), 3.0), **{"U₀x": np.full((2, 2, 2), 1.0)})
+        want = [(0, 7.0), (2, 2.0)] + ([(6, 3.0)] if b else []) + [(1, 1.0), ("ux", None)]
+        assert sorted(map(str, p.sent)) == sorted(map(str, want)) and p.params.ν == 0.1
+    with pytest.raises(NotImplementedError):
+        M.SetUpProblemIC(Fake(True), rho=np.ones((2, 2, 2)))
