@@ -535,6 +535,19 @@ def SetUpProblemIC(prob, *, ux=None, uy=None, uz=None, bx=None, by=None, bz=None
     return None
 
 
+def Cylindrical_Mask_Function(grid, R2=0.82 * math.pi, R1=0.0, **greek):
+    """Cylindrical_Mask_Function(grid; R₂, R₁) (utils/IC.jl:5-27): the VP mask χ -- 0 in the fluid R₁ <= sqrt(x²+y²) <= R₂,
+    1 in the solid -- as a (nz, ny, nx) array for `prob.params.χ`.  (`R₂` / `R₁` are accepted as keywords via **{...}.)"""
+    R2, R1 = greek.pop("R₂", R2), greek.pop("R₁", R1)
+    if greek:
+        raise TypeError(f"Cylindrical_Mask_Function() got unexpected keyword arguments {sorted(greek)}")
+    x = grid.x.reshape(1, 1, -1)
+    y = grid.y.reshape(1, -1, 1)
+    R = np.sqrt(x * x + y * y)                       # evaluated in the grid's element type like √(xᵢ^2+yᵢ^2)
+    S = np.where((R2 >= R) & (R >= R1), 0, 1).astype(grid.T)
+    return np.broadcast_to(S, (grid.nz, grid.ny, grid.nx)).copy()
+
+
 def stepforward(prob, nsteps=1):
     """stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)
     (timestepper/timestepper.jl:4-6)."""

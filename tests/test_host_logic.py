@@ -161,3 +161,17 @@ def test_vp_fields_are_routed_to_the_library():
         assert sorted(map(str, p.sent)) == sorted(map(str, want)) and p.params.ν == 0.1
     with pytest.raises(NotImplementedError):
         M.SetUpProblemIC(Fake(True), rho=np.ones((2, 2, 2)))
+
+
+def test_cylindrical_mask_function():
+    """Cylindrical_Mask_Function (utils/IC.jl:5-27): 0 inside the annulus R1 <= R <= R2, 1 in the solid, constant along z."""
+    g = P._Grid(32, 32, 8, 2 * math.pi, 2 * math.pi, 2 * math.pi, np.float32)
+    S = M.Cylindrical_Mask_Function(g)
+    assert S.shape == (8, 32, 32) and S.dtype == np.float32 and set(np.unique(S)) == {0.0, 1.0}
+    assert np.array_equal(S[0], S[5])
+    for j in (0, 7, 16, 31):
+        for i in (0, 3, 16, 30):
+            R = math.sqrt(float(g.x[i]) ** 2 + float(g.y[j]) ** 2)
+            assert S[0, j, i] == (0.0 if R <= 0.82 * math.pi else 1.0)
+    S2 = M.Cylindrical_Mask_Function(g, R1=1.0, **{"R₂": 2.0})
+    assert S2[0, 16, 16] == 1.0 and S2[0, 16, 16 + 8] == 0.0     # R = 0 is solid, R = 8 dx = 1.57 is fluid
