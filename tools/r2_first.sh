@@ -1,6 +1,6 @@
 #!/bin/bash
 # First gpurun call of round 2: everything that was written after round 1's GPU budget was spent, in one batch.
-#   (here, before the call)  python -m mhdflows_jl_b200.build --variant=f32x2
+#   (here, before the call)  python -m mhdflows_jl_b200.build --variant=f32x2 --variant=emhd_unroll
 #   gpurun --timeout 1500 -- 'bash tools/r2_first.sh'
 # Writes gpurun_out/r2_first_*.log.  Order: the cheap correctness checks first, then the A/B timings.
 set -u
@@ -22,6 +22,27 @@ if [ -f mhdflows_jl_b200/libmhdflows_b200_f32x2.so ]; then
   MHDF_LIB=$PWD/mhdflows_jl_b200/libmhdflows_b200_f32x2.so timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > ${O}_pytest_f32x2.log 2>&1
   tail -3 ${O}_pytest_f32x2.log
 fi
+# 4b. EMHD x kernel: rolled component loop (default, ~105 KB of SASS) vs the round-1 fully unrolled shape (194 KB), 256^3 and 512^3;
+#     then one full ncu capture of the default EMHD x kernel (round 1 has none)
+cat > /tmp/emhd_time.py <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+import bench
+for n in (256, 512):
+    M, p = bench.make_problem("emhd", n, "RK4", 0.0, 0.0, 1e-5)
+    bench.set_ic(M, p, "emhd", bench.tg_fields(n))
+    p.step_timed(2)
+    ms = p.step_timed(5) / 5
+    p.profile(True); p.step_timed(5); pr = p.profile_get(); p.profile(False)
+    print(os.environ.get("MHDF_LIB", "default"), "emhd", n, f"{ms:.3f} ms/step |", " ".join(f"{k}={v[0]/5:.3f}" for k, v in pr.items() if v[1]), flush=True)
+    p.close()
+PY
+timeout 300 python /tmp/emhd_time.py > ${O}_emhd.log 2>&1
+if [ -f mhdflows_jl_b200/libmhdflows_b200_emhd_unroll.so ]; then
+  MHDF_LIB=$PWD/mhdflows_jl_b200/libmhdflows_b200_emhd_unroll.so timeout 300 python /tmp/emhd_time.py >> ${O}_emhd.log 2>&1
+fi
+cat ${O}_emhd.log
+timeout 600 bash tools/gpu_ncu1.sh emhd_x_r2 emhd512 k_xfused 2 1
 # 5. bench line (carries the cuFFT reference point)
 timeout 400 python bench.py --steps 20 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; cut -c1-800 ${O}_bench.json; tail -3 ${O}_bench.err
 ls gpurun_out | head -30
