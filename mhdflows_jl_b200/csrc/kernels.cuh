@@ -594,6 +594,120 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   }
 }
 
+// EMHD fused x pass, second form (opt-in: MHDF_EMHD2=1).  Same arithmetic in the same order as the EMHD branch of k_xfused --
+// results are bit-identical -- but the six multiplier fields (A_j and the stale b_j in real space) wait in thread-private
+// shared-memory slots instead of 96 registers, so every loop can stay rolled: 5 inlined row transforms instead of 13 (27
+// before round 1's last change), a 168-register budget (6 instead of 4 resident blocks per SM) and 58-71 KB of SASS instead of
+// 103-118 KB (180-203 KB).  Slot of (field f, element m) of a thread: mult[(f * E + m) * Tm] with mult already offset by the
+// thread's (row, t): consecutive threads hit consecutive banks; only the owning thread ever touches a slot, no barrier.
+#ifndef MHDF_EMHD2_MINB
+#define MHDF_EMHD2_MINB 6   // 168 registers: 16 bytes of spills at 512-point rows (128 registers: 108-224 bytes); 6 blocks x 33 KB of shared memory fill an SM
+#endif
+template <typename T, int N, int E, int RB, bool RED>
+__global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD2_MINB <= 1024 ? MHDF_EMHD2_MINB : 1) k_xfused_emhd2(XArgs<T> a) {
+  using C = Cx<T>;
+  constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
+  using SYNC = typename XSync<(Tm <= 32), RB>::type;
+  MHDF_DYN_SMEM(unsigned char, smem_raw);
+  const int r = threadIdx.x / Tm;
+  const int t = threadIdx.x % Tm;
+  constexpr int RS = RowIdx<M, R1>::SIZE;
+  RowSmem<C> sm;
+  sm.a = reinterpret_cast<C*>(smem_raw) + (size_t)(2 * r) * RS;
+  sm.b = sm.a + RS;
+  C* mult = reinterpret_cast<C*>(smem_raw) + (size_t)2 * RB * RS + (size_t)r * 6 * M + t;
+  const C* twt = a.tw;
+  MHDF_KEEP_PTR(twt);
+  double rs[7];
+  float rm[6];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) rs[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) rm[i] = 0.f;
+  // reductions with a run-time slot: predicated adds keep rs / rm in registers
+  auto red_add = [&](int slot, T s, float mx) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      if (q == slot) { rs[q] += (double)s; rm[q] = fmaxf(rm[q], mx); }
+  };
+  const long long nsets = a.rows / RB;
+  for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
+    const long long row = set * RB + r;
+    const C* in = a.in + row * a.Kxp;
+    C* out = a.out + row * a.Kxp;
+    C* breal = reinterpret_cast<C*>(a.real_io + row * (long long)N);
+    {
+      const long long nset = set + gridDim.x;
+      if (nset < nsets) {
+        const char* nb = reinterpret_cast<const char*>(a.in + (nset * RB + r) * a.Kxp);
+        const int bytes = a.Kx * (int)sizeof(C);
+        for (int f = 0; f < 24; ++f)
+          for (int o = t * 128; o < bytes; o += Tm * 128)
+#ifndef MHDF_CPU_EMU
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(nb + (long long)f * a.in_field * (long long)sizeof(C) + o));
+#else
+            (void)nb;
+#endif
+      }
+    }
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {   // A_i = c2r(A^_i) and the stale b_i -> multiplier slots
+      C g[E];
+      row_c2r<T, N, E, SYNC>(g, in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
+      T s = 0;
+      float mx = 0.f;
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        if constexpr (RED) {
+          const C sq = lmul(g[m], g[m]);
+          s += sq.x + sq.y;
+          mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+        }
+        mult[(i * E + m) * Tm] = g[m];
+        mult[((3 + i) * E + m) * Tm] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
+      }
+      if constexpr (RED) red_add(i, s, mx);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {   // G_i = sum_j A_j d_j B_i - b^stale_j d_j A_i
+      C acc[E];
+#pragma unroll
+      for (int m = 0; m < E; ++m) acc[m] = mk<C>(0, 0);
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        C g[E];
+        row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
+#pragma unroll
+        for (int m = 0; m < E; ++m) acc[m] = lfma(mult[(j * E + m) * Tm], g[m], acc[m]);
+        row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
+#pragma unroll
+        for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(mult[((3 + j) * E + m) * Tm]), g[m], acc[m]);
+      }
+      row_r2c<T, N, E, SYNC>(acc, out + i * a.out_field, a.Kx, t, sm, twt);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {   // refresh the real-space b (vars.b*) from the current stage input
+      C g[E];
+      row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
+      T s = 0;
+      float mx = 0.f;
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        if constexpr (RED) {
+          const C sq = lmul(g[m], g[m]);
+          s += sq.x + sq.y;
+          mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+        }
+        reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
+      }
+      if constexpr (RED) red_add(3 + i, s, mx);
+    }
+  }
+  if constexpr (RED) {
+    if (a.red != nullptr) block_reduce_commit<7, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
+  }
+}
+
 // Plain x passes for the API boundary (set_real / get_real): real rows <-> spectral rows.
 template <typename T, int N, int E, int RB, int DIR>
 __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {

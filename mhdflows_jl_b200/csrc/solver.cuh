@@ -445,7 +445,12 @@ struct Solver : mhdf_handle {
       if (red) k_xfused<T, N, E, RB, PH, true><<<grid, threads, x_smem<N>(), st>>>(a);       \
       else k_xfused<T, N, E, RB, PH, false><<<grid, threads, x_smem<N>(), st>>>(a);          \
     } while (0)
-    if (vp_on && a.vp != nullptr) {   // penalised runs: one instantiation per physics (reductions always compiled in)
+    if (phys == MHDF_EMHD && emhd2) {   // opt-in second form of the EMHD kernel (MHDF_EMHD2=1): bit-identical results
+      const size_t smem = x_smem<N>() + (size_t)RB * 6 * (N / 2) * sizeof(C);
+      if (red) k_xfused_emhd2<T, N, E, RB, true><<<grid, threads, smem, st>>>(a);
+      else k_xfused_emhd2<T, N, E, RB, false><<<grid, threads, smem, st>>>(a);
+    }
+    else if (vp_on && a.vp != nullptr) {   // penalised runs: one instantiation per physics (reductions always compiled in)
       if (phys == MHDF_MHD) k_xfused<T, N, E, RB, PHYS_MHD, true, true><<<grid, threads, x_smem<N>(), st>>>(a);
       else k_xfused<T, N, E, RB, PHYS_HD, true, true><<<grid, threads, x_smem<N>(), st>>>(a);
     }
@@ -501,6 +506,13 @@ struct Solver : mhdf_handle {
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_EMHD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    const int smem2 = smem + (int)((size_t)RB * 6 * (N / 2) * sizeof(C));
+    if (smem2 > 48 * 1024) {
+      CK(cudaFuncSetAttribute(k_xfused_emhd2<T, N, E, RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      CK(cudaFuncSetAttribute(k_xfused_emhd2<T, N, E, RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    }
+    if (smem > 48 * 1024) {
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -742,6 +754,7 @@ struct Solver : mhdf_handle {
   //   P2 forward send, Q forward receive.
   // NOT YET VERIFIED ON HARDWARE (written after the round's GPU budget was spent); off unless MHDF_ZCHUNKS is set.
   bool spec2 = [] { const char* e = getenv("MHDF_SPEC2"); return e && atoi(e) != 0; }();
+  bool emhd2 = [] { const char* e = getenv("MHDF_EMHD2"); return e && atoi(e) != 0; }();
   int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
   C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
   bool pipe_ok() const {

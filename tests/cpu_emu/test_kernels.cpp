@@ -388,6 +388,36 @@ template <int N> void test_xplain() {
   report("xplain c2r N=" + std::to_string(N), std::sqrt(num / den) < 2e-6, std::sqrt(num / den));
 }
 
+// ---- C1b. EMHD second form (multipliers in shared memory, rolled loops) must reproduce the first form bit for bit ---
+template <int N, typename T> void test_xfused_emhd2() {
+  using C = Cx<T>;
+  constexpr int E = 8, M = N / 2, Tm = M / E, RB = (64 / Tm > 0) ? 64 / Tm : 1, R1 = imin(E, M);
+  const Band bx = band_of(N);
+  const int Kx = bx.lo, Kxp = (Kx + 7) / 8 * 8;
+  const long long rows = 3 * RB;
+  auto tw = make_tw<T>(N);
+  auto in = randc<T>((size_t)24 * rows * Kxp, 81);
+  for (size_t i = 0; i < in.size(); ++i) if ((int)(i % Kxp) >= Kx) in[i] = mk<C>(0, 0);
+  std::vector<T> bst((size_t)3 * rows * N);
+  std::mt19937 g(7); std::uniform_real_distribution<double> u01(-1, 1);
+  for (auto& x : bst) x = (T)u01(g);
+  std::vector<C> out1((size_t)3 * rows * Kxp, mk<C>(0, 0)), out2 = out1;
+  std::vector<T> b1 = bst, b2 = bst;
+  XRed red1, red2; std::memset(&red1, 0, sizeof red1); std::memset(&red2, 0, sizeof red2);
+  XArgs<T> a;
+  a.in = in.data(); a.tw = tw.data(); a.in_field = a.out_field = rows * Kxp; a.real_field = rows * N; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp;
+  a.scale = (T)(1.0 / N); a.vp = nullptr; a.vp_field = 0; a.vp_eta = 1;
+  a.out = out1.data(); a.real_io = b1.data(); a.red = &red1;
+  emu::launch(k_xfused<T, N, E, RB, PHYS_EMHD, true>, dim3(2, 1, 1), Tm * RB, a);
+  a.out = out2.data(); a.real_io = b2.data(); a.red = &red2;
+  static_assert((size_t)2 * RB * RowIdx<M, R1>::SIZE * sizeof(C) + (size_t)RB * 6 * M * sizeof(C) <= 256 * 1024, "emulator shared memory");
+  emu::launch(k_xfused_emhd2<T, N, E, RB, true>, dim3(2, 1, 1), Tm * RB, a);
+  bool same = std::memcmp(out1.data(), out2.data(), out1.size() * sizeof(C)) == 0 && std::memcmp(b1.data(), b2.data(), b1.size() * sizeof(T)) == 0;
+  for (int q = 0; q < 6; ++q) same = same && red1.maxsq[q] == red2.maxsq[q] && std::fabs(red1.sumsq[q] - red2.sumsq[q]) <= 1e-12 * std::fabs(red1.sumsq[q]);
+  bool changed = std::memcmp(b1.data(), bst.data(), b1.size() * sizeof(T)) != 0;
+  report("xfused EMHD second form == first form N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64"), same && changed && red1.sumsq[4] > 0, same ? 0.0 : 1.0);
+}
+
 // ---- C2. volume penalisation: the VP instantiations of the fused x kernel and of the spectral kernel -------------------
 template <int N, int PHYS, typename T> void test_xfused_vp() {
   using C = Cx<T>;
@@ -778,6 +808,7 @@ int main() {
   test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 0); test_spectral<PHYS_MHD>(STEP_CALCN, false, 2, 1);   // slab ranks: gathered mirror plane
   test_xfused_vp<32, PHYS_HD, float>(); test_xfused_vp<128, PHYS_MHD, float>(); test_xfused_vp<64, PHYS_MHD, double>(); test_xfused_vp<1024, PHYS_HD, float>();
   test_spectral_vp<PHYS_HD>(); test_spectral_vp<PHYS_MHD>();
+  test_xfused_emhd2<32, float>(); test_xfused_emhd2<128, float>(); test_xfused_emhd2<512, float>(); test_xfused_emhd2<1024, float>(); test_xfused_emhd2<64, double>();
   test_philox_kat();
   test_a99<float>(A99_HOST, 1, 0); test_a99<float>(A99_GPU, 1, 0); test_a99<double>(A99_HOST, 1, 0); test_a99<double>(A99_GPU, 2, 1);
   test_a99<float>(A99_HOST, 2, 1);

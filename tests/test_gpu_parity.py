@@ -333,3 +333,22 @@ def test_optin_spectral_variant_is_bit_identical():
         m = re.search(r"max abs diff ([0-9.e+-]+) norm ([0-9.e+-]+)", l)
         assert m and float(m.group(1)) == 0.0 and float(m.group(2)) > 0.0, l
 
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in second form of the EMHD x kernel (MHDF_EMHD2=1) was written without GPU access: "
+                                        "bit-identical to the default kernel on the CPU emulator, not yet run on hardware")
+def test_optin_emhd_kernel_is_bit_identical():
+    """k_xfused_emhd2 (multipliers in shared memory, rolled loops) against the EMHD branch of k_xfused, in a subprocess."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "emhd2_check.py")], capture_output=True, text=True,
+                         timeout=300, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("emhd2-vs-default")]
+    assert len(lines) == 4
+    for l in lines:
+        m = re.search(r"max abs diff ([0-9.e+-]+) norm ([0-9.e+-]+)", l)
+        assert m and float(m.group(1)) == 0.0 and float(m.group(2)) > 0.0, l

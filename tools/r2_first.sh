@@ -42,7 +42,9 @@ if [ -f mhdflows_jl_b200/libmhdflows_b200_emhd_unroll.so ]; then
   MHDF_LIB=$PWD/mhdflows_jl_b200/libmhdflows_b200_emhd_unroll.so timeout 300 python /tmp/emhd_time.py >> ${O}_emhd.log 2>&1
 fi
 cat ${O}_emhd.log
+timeout 400 python tools/emhd2_check.py --time > ${O}_emhd2.log 2>&1; cat ${O}_emhd2.log
 timeout 600 bash tools/gpu_ncu1.sh emhd_x_r2 emhd512 k_xfused 2 1
+MHDF_EMHD2=1 timeout 600 bash tools/gpu_ncu1.sh emhd2_x_r2 emhd512 k_xfused_emhd2 2 1
 # 5. bench line (carries the cuFFT reference point)
 timeout 400 python bench.py --steps 20 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; cut -c1-800 ${O}_bench.json; tail -3 ${O}_bench.err
 ls gpurun_out | head -30
