@@ -45,6 +45,11 @@ cat ${O}_emhd.log
 timeout 400 python tools/emhd2_check.py --time > ${O}_emhd2.log 2>&1; cat ${O}_emhd2.log
 timeout 600 bash tools/gpu_ncu1.sh emhd_x_r2 emhd512 k_xfused 2 1
 MHDF_EMHD2=1 timeout 600 bash tools/gpu_ncu1.sh emhd2_x_r2 emhd512 k_xfused_emhd2 2 1
+# 4c. compute-sanitizer over every kernel family on tiny grids (memcheck / racecheck in the test plan)
+for tool in memcheck racecheck synccheck; do
+  timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python tools/sanitize_target.py > ${O}_sanitize_$tool.log 2>&1
+  echo "compute-sanitizer $tool rc=$?" | tee -a ${O}_sanitize_$tool.log; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize-target done" ${O}_sanitize_$tool.log | tail -3
+done
 # 5. bench line (carries the cuFFT reference point)
 timeout 400 python bench.py --steps 20 --warmup 3 > ${O}_bench.json 2> ${O}_bench.err; cut -c1-800 ${O}_bench.json; tail -3 ${O}_bench.err
 ls gpurun_out | head -30
