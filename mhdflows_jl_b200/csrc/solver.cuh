@@ -7,9 +7,16 @@
 //   -> forward y pass -> forward z pass -> spectral assembly + Runge-Kutta stage update
 // on a compact state that stores only the modes FourierFlows' dealias!() keeps.
 #pragma once
+#ifdef MHDF_CPU_EMU
+#include "cuda_host_emu.h"   // tests/cpu_emu: the library compiled as plain C++ for the CPU test-suite (never shipped)
+#define MHDF_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch_call(dim3(grid), (int)(block), [&] { kernel(__VA_ARGS__); })
+#else
 #include <cuda_runtime.h>
-#include <dlfcn.h>
 #include <nccl.h>
+// one spelling for every kernel launch (the kernel name is parenthesised because template argument lists contain commas)
+#define MHDF_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -405,11 +412,11 @@ struct Solver : mhdf_handle {
     dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
     // the blocked side is the z side of the z passes and the ky side of the y passes: output of inverse-z / forward-y,
     // input of inverse-y / forward-z
-    if (a.blk_rows == 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 0><<<grid, (N / E) * TX, smem, st>>>(a);
-    else if (a.blk2_rows > 0 && blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 4><<<grid, (N / E) * TX, smem, st>>>(a);
-    else if (a.blk2_rows > 0) k_pass<T, N, E, TX, DIR, (DIR > 0), 3><<<grid, (N / E) * TX, smem, st>>>(a);
-    else if (blk_out) k_pass<T, N, E, TX, DIR, (DIR > 0), 2><<<grid, (N / E) * TX, smem, st>>>(a);
-    else k_pass<T, N, E, TX, DIR, (DIR > 0), 1><<<grid, (N / E) * TX, smem, st>>>(a);
+    if (a.blk_rows == 0) MHDF_LAUNCH((k_pass<T, N, E, TX, DIR, (DIR > 0), 0>), grid, (N / E) * TX, smem, st, a);
+    else if (a.blk2_rows > 0 && blk_out) MHDF_LAUNCH((k_pass<T, N, E, TX, DIR, (DIR > 0), 4>), grid, (N / E) * TX, smem, st, a);
+    else if (a.blk2_rows > 0) MHDF_LAUNCH((k_pass<T, N, E, TX, DIR, (DIR > 0), 3>), grid, (N / E) * TX, smem, st, a);
+    else if (blk_out) MHDF_LAUNCH((k_pass<T, N, E, TX, DIR, (DIR > 0), 2>), grid, (N / E) * TX, smem, st, a);
+    else MHDF_LAUNCH((k_pass<T, N, E, TX, DIR, (DIR > 0), 1>), grid, (N / E) * TX, smem, st, a);
     ++launches;
   }
   template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
@@ -442,17 +449,17 @@ struct Solver : mhdf_handle {
     const bool red = a.red != nullptr;
 #define XLAUNCH(PH)                                                                          \
     do {                                                                                     \
-      if (red) k_xfused<T, N, E, RB, PH, true><<<grid, threads, x_smem<N>(), st>>>(a);       \
-      else k_xfused<T, N, E, RB, PH, false><<<grid, threads, x_smem<N>(), st>>>(a);          \
+      if (red) MHDF_LAUNCH((k_xfused<T, N, E, RB, PH, true>), grid, threads, x_smem<N>(), st, a);       \
+      else MHDF_LAUNCH((k_xfused<T, N, E, RB, PH, false>), grid, threads, x_smem<N>(), st, a);          \
     } while (0)
     if (phys == MHDF_EMHD && emhd2) {   // opt-in second form of the EMHD kernel (MHDF_EMHD2=1): bit-identical results
       const size_t smem = x_smem<N>() + (size_t)RB * 6 * (N / 2) * sizeof(C);
-      if (red) k_xfused_emhd2<T, N, E, RB, true><<<grid, threads, smem, st>>>(a);
-      else k_xfused_emhd2<T, N, E, RB, false><<<grid, threads, smem, st>>>(a);
+      if (red) MHDF_LAUNCH((k_xfused_emhd2<T, N, E, RB, true>), grid, threads, smem, st, a);
+      else MHDF_LAUNCH((k_xfused_emhd2<T, N, E, RB, false>), grid, threads, smem, st, a);
     }
     else if (vp_on && a.vp != nullptr) {   // penalised runs: one instantiation per physics (reductions always compiled in)
-      if (phys == MHDF_MHD) k_xfused<T, N, E, RB, PHYS_MHD, true, true><<<grid, threads, x_smem<N>(), st>>>(a);
-      else k_xfused<T, N, E, RB, PHYS_HD, true, true><<<grid, threads, x_smem<N>(), st>>>(a);
+      if (phys == MHDF_MHD) MHDF_LAUNCH((k_xfused<T, N, E, RB, PHYS_MHD, true, true>), grid, threads, x_smem<N>(), st, a);
+      else MHDF_LAUNCH((k_xfused<T, N, E, RB, PHYS_HD, true, true>), grid, threads, x_smem<N>(), st, a);
     }
     else if (phys == MHDF_MHD) XLAUNCH(PHYS_MHD);
     else if (phys == MHDF_HD) XLAUNCH(PHYS_HD);
@@ -462,7 +469,7 @@ struct Solver : mhdf_handle {
   }
   template <int N, int DIR> void launch_xplain_n(XArgs<T>& a) {
     constexpr int E = xE(N), RB = xRB(N);
-    k_xplain<T, N, E, RB, DIR><<<x_grid(a.rows, RB), (N / 2 / E) * RB, x_smem<N>(), st>>>(a);
+    MHDF_LAUNCH((k_xplain<T, N, E, RB, DIR>), x_grid(a.rows, RB), (N / 2 / E) * RB, x_smem<N>(), st, a);
     ++launches;
   }
   void launch_xfused(XArgs<T>& a) {
@@ -703,7 +710,7 @@ struct Solver : mhdf_handle {
   void gather_mirror(const C* S) {
     if (P_ == 1) return;
     const long long n = (long long)F * Kz * Kyl;
-    k_plane<T><<<(int)((n + 255) / 256), 256, 0, st>>>(geom(), S, plane_loc);
+    MHDF_LAUNCH((k_plane<T>), (int)((n + 255) / 256), 256, 0, st, geom(), S, plane_loc);
     ++launches;
     CK(cudaGetLastError());
     order(st, sc);
@@ -782,7 +789,7 @@ struct Solver : mhdf_handle {
     if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {
       prof_begin(KC_DERIVE);
-      k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
+      MHDF_LAUNCH((k_emhd_derive<T>), spec_grid(), 256, 0, st, geom(), Sin, D);
       ++launches;
       CK(cudaGetLastError());
       prof_end();
@@ -895,7 +902,7 @@ struct Solver : mhdf_handle {
     if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {
       prof_begin(KC_DERIVE);
-      k_emhd_derive<T><<<spec_grid(), 256, 0, st>>>(geom(), Sin, D);
+      MHDF_LAUNCH((k_emhd_derive<T>), spec_grid(), 256, 0, st, geom(), Sin, D);
       ++launches;
       CK(cudaGetLastError());
       prof_end();
@@ -926,12 +933,12 @@ struct Solver : mhdf_handle {
     const unsigned plane = (unsigned)Kxp * (unsigned)Kyl;
     const dim3 grid((plane + 255u) / 256u, (unsigned)Kz);
     switch (sa.mode) {
-      case STEP_CALCN: k_spectral2<T, PHYS, STEP_CALCN, A99><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_1: k_spectral2<T, PHYS, STEP_RK4_1, A99><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_2: k_spectral2<T, PHYS, STEP_RK4_2, A99><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_3: k_spectral2<T, PHYS, STEP_RK4_3, A99><<<grid, 256, 0, st>>>(sa); break;
-      case STEP_RK4_4: k_spectral2<T, PHYS, STEP_RK4_4, A99><<<grid, 256, 0, st>>>(sa); break;
-      default:         k_spectral2<T, PHYS, STEP_LSRK, A99><<<grid, 256, 0, st>>>(sa); break;
+      case STEP_CALCN: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_CALCN, A99>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_1: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_1, A99>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_2: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_2, A99>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_3: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_3, A99>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_4: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_4, A99>), grid, 256, 0, st, sa); break;
+      default:         MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_LSRK, A99>), grid, 256, 0, st, sa); break;
     }
   }
   void launch_spectral(SpecArgs<T>& sa) {
@@ -939,9 +946,9 @@ struct Solver : mhdf_handle {
     const bool driven = (phys == MHDF_MHD) && sa.a99.variant != A99_OFF;   // A99ForceDriving! acts on the MHD path only
     if (vp_on) {   // penalised runs: the product buffer carries the penalisation spectra as well
       const int grid = spec_grid();
-      if (driven) k_spectral<T, PHYS_MHD, true, true><<<grid, 256, 0, st>>>(sa);
-      else if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD, false, true><<<grid, 256, 0, st>>>(sa);
-      else k_spectral<T, PHYS_HD, false, true><<<grid, 256, 0, st>>>(sa);
+      if (driven) MHDF_LAUNCH((k_spectral<T, PHYS_MHD, true, true>), grid, 256, 0, st, sa);
+      else if (phys == MHDF_MHD) MHDF_LAUNCH((k_spectral<T, PHYS_MHD, false, true>), grid, 256, 0, st, sa);
+      else MHDF_LAUNCH((k_spectral<T, PHYS_HD, false, true>), grid, 256, 0, st, sa);
     } else if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
       if (driven) launch_spectral2<PHYS_MHD, true>(sa);
       else if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD, false>(sa);
@@ -949,10 +956,10 @@ struct Solver : mhdf_handle {
       else launch_spectral2<PHYS_EMHD, false>(sa);
     } else {
       const int grid = spec_grid();
-      if (driven) k_spectral<T, PHYS_MHD, true><<<grid, 256, 0, st>>>(sa);
-      else if (phys == MHDF_MHD) k_spectral<T, PHYS_MHD><<<grid, 256, 0, st>>>(sa);
-      else if (phys == MHDF_HD) k_spectral<T, PHYS_HD><<<grid, 256, 0, st>>>(sa);
-      else k_spectral<T, PHYS_EMHD><<<grid, 256, 0, st>>>(sa);
+      if (driven) MHDF_LAUNCH((k_spectral<T, PHYS_MHD, true>), grid, 256, 0, st, sa);
+      else if (phys == MHDF_MHD) MHDF_LAUNCH((k_spectral<T, PHYS_MHD>), grid, 256, 0, st, sa);
+      else if (phys == MHDF_HD) MHDF_LAUNCH((k_spectral<T, PHYS_HD>), grid, 256, 0, st, sa);
+      else MHDF_LAUNCH((k_spectral<T, PHYS_EMHD>), grid, 256, 0, st, sa);
     }
     ++launches;
     CK(cudaGetLastError());
@@ -1138,7 +1145,7 @@ struct Solver : mhdf_handle {
     else if (group == 1) { if (phys == MHDF_HD) throw Err{MHDF_ERR_INVALID, "DivBCorrection!: the HD state has no magnetic field"}; f0 = (phys == MHDF_EMHD) ? 0 : 3; }
     else throw Err{MHDF_ERR_INVALID, "group must be 0 (velocity) or 1 (magnetic field)"};
     C* Y = reg[iY] + (size_t)f0 * cf;
-    k_divclean<T><<<spec_grid(), 256, 0, st>>>(geom(), Y);
+    MHDF_LAUNCH((k_divclean<T>), spec_grid(), 256, 0, st, geom(), Y);
     ++launches;
     CK(cudaGetLastError());
     if (iStale >= 0 && iStale != iY)
@@ -1183,7 +1190,7 @@ struct Solver : mhdf_handle {
     const int nyh = (P_ > 1) ? Kyl : ny;     // slab runs exchange the local compact ky rows directly
     const size_t n = (size_t)nkr * nyh * nz;
     CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyHostToDevice, st));
-    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, reg[iY] + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
+    MHDF_LAUNCH((k_pack<T>), pack_grid(), 256, 0, st, R, reg[iY] + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
     sync_all();
@@ -1196,7 +1203,7 @@ struct Solver : mhdf_handle {
   void unpack_to_host(const C* comp, C* host) {
     const int nyh = (P_ > 1) ? Kyl : ny;
     const size_t n = (size_t)nkr * nyh * nz;
-    k_pack<T><<<pack_grid(), 256, 0, st>>>(R, const_cast<C*>(comp), nkr, nyh, nz, Kx, Kxp, by, bz, 1, P_ > 1);
+    MHDF_LAUNCH((k_pack<T>), pack_grid(), 256, 0, st, R, const_cast<C*>(comp), nkr, nyh, nz, Kx, Kxp, by, bz, 1, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDeviceToHost, st));
@@ -1241,7 +1248,7 @@ struct Solver : mhdf_handle {
     CK(cudaMemsetAsync(diag_d, 0, 8 * sizeof(double), st));
     const int has_u = (phys != MHDF_EMHD), has_b = (phys != MHDF_HD), boff = (phys == MHDF_EMHD) ? 0 : 3;
     wait_mirror();
-    k_diag<T><<<spec_grid(), 256, 0, st>>>(geom(), src, has_u, has_b, boff, 1.0 / ((double)nx * ny * nz), diag_d);
+    MHDF_LAUNCH((k_diag<T>), spec_grid(), 256, 0, st, geom(), src, has_u, has_b, boff, 1.0 / ((double)nx * ny * nz), diag_d);
     ++launches;
     CK(cudaGetLastError());
     if (P_ > 1) { order(st, sc); NK(g_nccl.AllReduce(diag_d, diag_d, 8, ncclFloat64, ncclSum, comm, sc)); order(sc, st); }
@@ -1284,7 +1291,7 @@ struct Solver : mhdf_handle {
     CK(cudaMemsetAsync(spec_d, 0, nbins * sizeof(double), st));
     gather_mirror(reg[iY]);
     wait_mirror();
-    k_spectrum<T><<<spec_grid(), 256, nbins * sizeof(double), st>>>(geom(), reg[iY], field, spec_d, nbins);
+    MHDF_LAUNCH((k_spectrum<T>), spec_grid(), 256, nbins * sizeof(double), st, geom(), reg[iY], field, spec_d, nbins);
     ++launches;
     CK(cudaGetLastError());
     if (P_ > 1) { order(st, sc); NK(g_nccl.AllReduce(spec_d, spec_d, nbins, ncclFloat64, ncclSum, comm, sc)); order(sc, st); }

@@ -86,9 +86,9 @@ inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI *
 inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 
 namespace emu {
-// run kernel(args) on a (gx, gy, gz) grid of 1-D blocks of `nthreads` threads
-template <typename K, typename A>
-void launch(K kernel, dim3 grid, int nthreads, const A& args) {
+// run body() once per CUDA thread of a (gx, gy, gz) grid of 1-D blocks of `nthreads` threads, blocks one after another
+template <typename F>
+void launch_call(dim3 grid, int nthreads, F&& body) {
   const int nw = (nthreads + 31) / 32;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
@@ -108,12 +108,17 @@ void launch(K kernel, dim3 grid, int nthreads, const A& args) {
             blockIdx = uint3{bx, by, bz};
             blockDim = dim3(nthreads, 1, 1);
             gridDim = grid;
-            kernel(args);
+            body();
             // a thread that has left the kernel no longer takes part in barriers (CUDA semantics)
             blk.bar->arrive_and_drop();
             blk.warps[warp_id].bar->arrive_and_drop();
           });
         for (auto& x : th) x.join();
       }
+}
+// run kernel(args) on a grid
+template <typename K, typename A>
+void launch(K kernel, dim3 grid, int nthreads, const A& args) {
+  launch_call(grid, nthreads, [&] { kernel(args); });
 }
 }  // namespace emu

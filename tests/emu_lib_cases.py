@@ -1,0 +1,368 @@
+"""End-to-end cases run against the CPU-EMULATED build of the library (tests/cpu_emu/cuda_host_emu.h): the real api.cu +
+solver.cuh orchestration and the real kernel sources, compiled as plain C++, on 16-point grids.  Executed by
+tests/test_emulated_library.py in a subprocess with MHDF_LIB pointing at the emulated library; prints one PASS / FAIL line
+per case.  This is how features written without GPU access (A99 driving, volume penalisation, divergence corrections, the
+second EMHD kernel form, HDF5 dumps) get their host-side logic exercised before their first hardware run -- the emulated
+library is test infrastructure, never a fallback of the product (mhdflows_jl_b200 only ever loads it through MHDF_LIB).
+
+Not collected by pytest (no test_ prefix)."""
+import os
+import sys
+import tempfile
+import time
+import traceback
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mhdflows_jl_b200 as M  # noqa: E402
+from oracle import forcing_oracle as FO  # noqa: E402
+from oracle import mhdflows_oracle as O  # noqa: E402
+from tests.test_gpu_zforcing import _forced_pair, _vp_pair  # noqa: E402
+
+F32_TOL, F64_TOL = 1e-5, 1e-12
+DIMS = (16, 16, 32)
+CASES = []
+
+
+def case(fn):
+    CASES.append(fn)
+    return fn
+
+
+def _band_limited(g, x):
+    """A real field whose spectrum lies strictly inside the band both implementations carry: dealias!() keeps the waves
+    -n/3 .. n/3-1, so the unpaired wave -n/3 is dropped too (its Hermitian partner +n/3 is aliased: the reference keeps it in
+    `vars` until the next dealias!, the library never stores it)."""
+    h = g.dealias(g.rfft(x))
+    h[:, g.ny - g.ny // 3, :] = 0
+    h[g.nz - g.nz // 3, :, :] = 0
+    return g.irfft(h)
+
+
+def _dealiased(op):
+    return op.grid.dealias(op.sol.copy())
+
+
+@case
+def smoke_mhd_rk4_against_the_oracle():
+    kw = dict(nx=16, T=np.float32, nu=1e-2, eta=1e-2, dt=5e-3, B_field=True)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    ic = O.taylor_green_ic(op.grid)
+    O.SetUpProblemIC(op, *ic[:3], bx=ic[3], by=ic[4], bz=ic[5])
+    M.SetUpProblemIC(gp, ux=ic[0], uy=ic[1], uz=ic[2], bx=ic[3], by=ic[4], bz=ic[5])
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    gp.close()
+
+
+@case
+def a99_host_variant_calcN_steps_counter():
+    op, gp = _forced_pair(M, O, FO, "host", np.float32, dims=DIMS)
+    g = op.grid
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+    Nd = gp.calcN()
+    ref = g.dealias(N.copy())
+    assert O.rel_l2(Nd, ref) < F32_TOL, O.rel_l2(Nd, ref)
+    q = O.Problem(nx=g.nx, ny=g.ny, nz=g.nz, T=np.float32, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+    q.sol[...] = op.sol
+    N0 = np.zeros_like(op.sol)
+    q.calcN(N0, q.sol.copy(), 0.0, q.clock, q.vars, q.params, g)
+    assert O.rel_l2(ref[:3], g.dealias(N0.copy())[:3]) > 1e-3
+    assert gp.a99_calls() == 1
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert gp.a99_calls() == 5 and op.vars.usr_vars.calls == 5
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    gp.close()
+
+
+@case
+def a99_gpu_variant_calcN_and_step():
+    op, gp = _forced_pair(M, O, FO, "gpu", np.float32, dims=DIMS)
+    g = op.grid
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+    assert O.rel_l2(gp.calcN(), g.dealias(N.copy())) < F32_TOL
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    gp.close()
+
+
+@case
+def a99_float64_both_variants_calcN():
+    for variant in ("host", "gpu"):
+        op, gp = _forced_pair(M, O, FO, variant, np.float64, dims=(16, 16, 16))
+        g = op.grid
+        N = np.zeros_like(op.sol)
+        op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+        err = O.rel_l2(gp.calcN(), g.dealias(N.copy()))
+        assert err < F64_TOL, (variant, err)
+        gp.close()
+
+
+@case
+def a99_lsrk54_and_retuned_amplitude():
+    op, gp = _forced_pair(M, O, FO, "host", np.float32, dims=(16, 16, 16), stepper="LSRK54")
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert gp.a99_calls() == 5
+    op.vars.usr_vars.A = np.float32(2.5)
+    op.vars.usr_vars.b = np.float32(0.6)
+    gp.vars.usr_vars.A = np.float32(2.5)
+    gp.vars.usr_vars.b = np.float32(0.6)
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert gp.a99_calls() == 10
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    gp.close()
+
+
+@case
+def a99_reproducible_and_lost_in_hd():
+    sols = []
+    for _ in range(2):
+        _, gp = _forced_pair(M, O, FO, "gpu", np.float32, dims=(16, 16, 16))
+        M.stepforward(gp)
+        sols.append(gp.sol)
+        gp.close()
+    assert np.array_equal(sols[0], sols[1])
+    kw = dict(nx=16, T=np.float32, nu=2e-2, dt=4e-3)
+    uv, fn = M.GetA99vars_And_function(M.GPU(), 16, 16, 16)
+    forced, plain = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw), M.Problem(M.GPU(), **kw)
+    M.SetUpFk(forced)
+    u = O.random_phase_ic(O.Grid(16, T=np.float32), 3)
+    for p in (forced, plain):
+        M.SetUpProblemIC(p, ux=u[0], uy=u[1], uz=u[2])
+        M.stepforward(p)
+    assert np.array_equal(forced.sol, plain.sol)
+    forced.close()
+    plain.close()
+
+
+def _div_case(T, tol):
+    nx, ny, nz = DIMS
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    g = op.grid
+    rng = np.random.default_rng(8)
+    f = [_band_limited(g, rng.standard_normal((nz, ny, nx)).astype(T)) for _ in range(6)]
+    O.SetUpProblemIC(op, *f[:3], bx=f[3], by=f[4], bz=f[5])
+    M.SetUpProblemIC(gp, ux=f[0], uy=f[1], uz=f[2], bx=f[3], by=f[4], bz=f[5])
+    FO.DivBCorrection(op)
+    M.DivBCorrection(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < tol
+    assert O.rel_l2(gp.vars.bx, op.vars.bx) < 10 * tol and O.rel_l2(gp.vars.ux, op.vars.ux) < 10 * tol
+    FO.DivVCorrection(op)
+    M.DivVCorrection(gp)
+    sol = gp.sol
+    assert O.rel_l2(sol, _dealiased(op)) < tol
+    for base in (0, 3):
+        div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
+        assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < (1e-5 if T is np.float32 else 1e-13)
+    ke, me = gp.energy(M.STALE)
+    dV = float(T(g.dx)) * float(T(g.dy)) * float(T(g.dz))
+    ke_ref = sum(float(np.sum(getattr(op.vars, n).astype(np.float64) ** 2)) for n in ("ux", "uy", "uz")) * dV
+    me_ref = sum(float(np.sum(getattr(op.vars, n).astype(np.float64) ** 2)) for n in ("bx", "by", "bz")) * dV
+    assert abs(ke - ke_ref) < 1e-4 * ke_ref and abs(me - me_ref) < 1e-4 * me_ref
+    mx, _ = gp.stale_stats()
+    assert abs(mx[4] - float(np.max(op.vars.by.astype(np.float64) ** 2))) < 1e-4 * mx[4]
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < tol
+    # after a step the stale view is a different register: the correction must reach it too
+    FO.DivBCorrection(op)
+    M.DivBCorrection(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < tol
+    assert O.rel_l2(gp.get_real("bz", M.STALE), g.irfft(_dealiased(op)[5])) < 10 * tol
+    for bad in (2, -1):
+        try:
+            gp.div_correction(bad)
+            raise AssertionError("group out of range was accepted")
+        except M.MHDFlowsError:
+            pass
+    gp.close()
+
+
+@case
+def div_corrections_float32():
+    _div_case(np.float32, F32_TOL)
+
+
+@case
+def div_corrections_float64():
+    _div_case(np.float64, F64_TOL)
+
+
+@case
+def div_b_correction_emhd_and_hd_refusal():
+    kw = dict(nx=16, T=np.float32, B_field=True, EMHD=True, dt=2e-4)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    g = op.grid
+    rng = np.random.default_rng(9)
+    f = [_band_limited(g, rng.standard_normal((16, 16, 16)).astype(np.float32)) for _ in range(3)]
+    O.SetUpProblemIC(op, bx=f[0], by=f[1], bz=f[2])
+    M.SetUpProblemIC(gp, bx=f[0], by=f[1], bz=f[2])
+    FO.DivBCorrection(op)
+    M.DivBCorrection(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL      # the (B.grad)A term read the refreshed stale b
+    try:
+        M.DivVCorrection(gp)
+        raise AssertionError("DivVCorrection! on an EMHD problem was accepted")
+    except M.MHDFlowsError:
+        pass
+    gp.close()
+    hd = M.Problem(M.GPU(), nx=16)
+    try:
+        M.DivBCorrection(hd)
+        raise AssertionError("DivBCorrection! on an HD problem was accepted")
+    except M.MHDFlowsError:
+        pass
+    hd.close()
+
+
+def _vp_case(B, T, tol, steps):
+    op, gp = _vp_pair(M, O, B, T, dims=DIMS)
+    g = op.grid
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+    err = O.rel_l2(gp.calcN(), g.dealias(N.copy()))
+    assert err < tol, err
+    q = O.Problem(nx=g.nx, ny=g.ny, nz=g.nz, T=T, nu=2e-2, dt=2e-3, **(dict(eta=3e-2, B_field=True) if B else {}))
+    q.sol[...] = op.sol
+    N0 = np.zeros_like(op.sol)
+    q.calcN(N0, q.sol.copy(), 0.0, q.clock, q.vars, q.params, g)
+    assert O.rel_l2(g.dealias(N.copy()), g.dealias(N0.copy())) > 1e-2
+    for _ in range(steps):
+        O.stepforward(op)
+    M.stepforward(gp, steps)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < tol
+    gp.close()
+
+
+@case
+def volume_penalisation_hd_float32():
+    _vp_case(False, np.float32, F32_TOL, 2)
+
+
+@case
+def volume_penalisation_mhd_float32():
+    _vp_case(True, np.float32, F32_TOL, 1)
+
+
+@case
+def volume_penalisation_mhd_float64():
+    _vp_case(True, np.float64, F64_TOL, 1)
+
+
+@case
+def volume_penalisation_time_integrator_and_refusals():
+    op, gp = _vp_pair(M, O, True, np.float32, dims=(16, 16, 16))
+    O.TimeIntegrator(op, 1e9, 1, usr_dt=1.5e-3)
+    M.TimeIntegrator(gp, 1e9, 1, usr_dt=1.5e-3)
+    g = op.grid
+    assert gp.clock.step == op.clock.step == 2
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    sol = gp.sol
+    for base in (0, 3):
+        div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
+        assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < 1e-5
+    gp.close()
+    try:
+        M.Problem(M.GPU(), nx=16, B_field=True, EMHD=True, VP_method=True)
+        raise AssertionError("VP_method + EMHD was accepted")
+    except ValueError:
+        pass
+    plain = M.Problem(M.GPU(), nx=16)
+    try:
+        plain.set_vp_field("χ", np.zeros((16, 16, 16), np.float32))
+        raise AssertionError("set_vp_field without VP_method was accepted")
+    except M.MHDFlowsError:
+        pass
+    plain.close()
+
+
+def _emhd_run(flag, stepper, T):
+    os.environ["MHDF_EMHD2"] = flag
+    p = M.Problem(M.GPU(), nx=16, ny=16, nz=16 if stepper == "LSRK54" else 32, T=T, stepper=stepper, B_field=True, EMHD=True, dt=1e-4)
+    rng = np.random.default_rng(11)
+    f = [rng.standard_normal(p._real_shape).astype(T) for _ in range(3)]
+    M.SetUpProblemIC(p, bx=f[0], by=f[1], bz=f[2])
+    M.stepforward(p)
+    out = (p.sol, p.get_real("by", M.STALE), p.stale_stats()[0])
+    p.close()
+    os.environ["MHDF_EMHD2"] = "0"
+    return out
+
+
+@case
+def second_emhd_kernel_form_is_bit_identical():
+    for stepper, T in (("RK4", np.float32), ("LSRK54", np.float64)):
+        a, b = _emhd_run("0", stepper, T), _emhd_run("1", stepper, T)
+        assert np.linalg.norm(a[0]) > 0
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), stepper
+
+
+@case
+def optin_spectral_kernel_is_bit_identical_with_forcing_and_driving():
+    sols = []
+    for flag in ("0", "1"):
+        os.environ["MHDF_SPEC2"] = flag
+        _, gp = _forced_pair(M, O, FO, "host", np.float32, dims=(16, 16, 16))
+        g = O.Grid(16, T=np.float32)
+        gp.set_forcing("uy", (0.3 * np.sin(2 * g.x.reshape(1, 1, -1)) * np.ones((16, 16, 16))).astype(np.float32))
+        M.stepforward(gp)
+        sols.append(gp.sol)
+        gp.close()
+    os.environ["MHDF_SPEC2"] = "0"
+    assert np.array_equal(sols[0], sols[1]) and np.linalg.norm(sols[0]) > 0
+
+
+@case
+def hdf5_dump_and_restart_through_the_library():
+    kw = dict(nx=16, T=np.float32, nu=2e-2, eta=3e-2, dt=2e-3, B_field=True)
+    gp = M.Problem(M.GPU(), **kw)
+    ic = O.taylor_green_ic(O.Grid(16, T=np.float32))
+    M.SetUpProblemIC(gp, ux=ic[0], uy=ic[1], uz=ic[2], bx=ic[3], by=ic[4], bz=ic[5])
+    with tempfile.TemporaryDirectory() as d:
+        M.TimeIntegrator(gp, 1e9, 1, usr_dt=2e-3, save=True, save_loc=d + "/", filename="run", dump_dt=2e-3)
+        files = sorted(os.listdir(d))
+        assert files[0] == "run_t_0000.h5" and len(files) >= 2, files
+        last = os.path.join(d, files[-1])
+        dump = M.readMHDFlows(last)
+        assert set(dump) == {"i_velocity", "j_velocity", "k_velocity", "i_mag_field", "j_mag_field", "k_mag_field", "time"}
+        assert dump["i_velocity"].dtype == np.float32 and dump["time"].dtype == np.float32
+        tup = M.readMHDFlows(last, as_tuple=True)
+        assert len(tup) == 7 and np.array_equal(tup[3], dump["i_mag_field"])
+        rp = M.Problem(M.GPU(), **kw)
+        M.Restart(rp, last)
+        assert abs(rp.clock.t - float(dump["time"])) < 1e-9 and rp.clock.step == 0
+        assert O.rel_l2(rp.get_real("ux", M.FRESH), dump["i_velocity"]) < 1e-6
+        assert O.rel_l2(rp.get_real("bz", M.FRESH), dump["k_mag_field"]) < 1e-6
+        rp.close()
+    gp.close()
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    failed = 0
+    for fn in CASES:
+        if only and not any(o in fn.__name__ for o in only):
+            continue
+        t0 = time.time()
+        try:
+            fn()
+            print(f"PASS {fn.__name__} ({time.time() - t0:.1f} s)", flush=True)
+        except Exception:
+            failed += 1
+            print(f"FAIL {fn.__name__} ({time.time() - t0:.1f} s)\n{traceback.format_exc()}", flush=True)
+    print(f"emu-lib cases done: {failed} failure(s)", flush=True)
+    sys.exit(1 if failed else 0)

@@ -1,0 +1,71 @@
+"""The whole library on the CPU emulator: api.cu + solver.cuh (buffer sizing, launch arguments, register rotation, the API
+boundary) and the kernel sources are compiled as plain C++ against tests/cpu_emu/cuda_host_emu.h (heap = device memory,
+inert streams, kernel launches = one OS thread per CUDA thread) into a throw-away libmhdflows_b200_emu.so; the end-to-end
+cases of tests/emu_lib_cases.py then run through the ordinary Python mirror with MHDF_LIB pointing at it, against the oracle,
+on 16-point grids.  This is what exercises the HOST side of features written without GPU access (A99 driving, volume
+penalisation, divergence corrections, second EMHD kernel form, k_spectral2, HDF5 dumps) before their first hardware run.
+
+The emulated library is test infrastructure: it is built into a temporary directory, never by mhdflows_jl_b200.build, and
+the product has no path to it other than the MHDF_LIB tuning variable (tests/test_abi.py checks the no-GPU failure of the
+real library)."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "mhdflows_jl_b200", "csrc")
+
+# case-name filters of the four concurrent workers (balanced by measured run time)
+GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5"],
+          ["a99_gpu", "a99_lsrk54", "a99_reproducible", "div_b_correction_emhd"],
+          ["div_corrections", "volume_penalisation_hd", "optin_spectral"],
+          ["volume_penalisation_mhd", "volume_penalisation_time", "second_emhd"]]
+
+
+@pytest.fixture(scope="module")
+def emu_library(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    d = tmp_path_factory.mktemp("emu_lib")
+    objs, procs = [], []
+    for src in ("api.cu", "solver_f32.cu", "solver_f64.cu"):
+        obj = str(d / (src[:-3] + ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-fPIC", "-pthread", "-DMHDF_CPU_EMU", "-I", os.path.join(ROOT, "tests", "cpu_emu"),
+                                       "-I", "/usr/local/cuda/include", "-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=900)
+        assert p.returncode == 0, out[-4000:]
+    lib = str(d / "libmhdflows_b200_emu.so")
+    res = subprocess.run([gxx, "-shared", "-pthread", "-o", lib] + objs + ["-ldl"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    return lib
+
+
+def test_end_to_end_cases_on_the_emulated_library(emu_library):
+    env = dict(os.environ, MHDF_LIB=emu_library, MHDF_EMHD2="0", MHDF_SPEC2="0")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu_lib_cases.py")] + g, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for g in GROUPS]
+    outs = []
+    for p in procs:
+        out, _ = p.communicate(timeout=2400)
+        outs.append(out)
+    text = "\n".join(outs)
+    fails = [l for l in text.splitlines() if l.startswith("FAIL")]
+    assert not fails and all(p.returncode == 0 for p in procs), text[-6000:]
+    passed = [l.split()[1] for l in text.splitlines() if l.startswith("PASS")]
+    # every case ran exactly once
+    sys.path.insert(0, ROOT)
+    import ast
+    src = open(os.path.join(ROOT, "tests", "emu_lib_cases.py")).read()
+    names = []
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and any(getattr(d, "id", "") == "case" for d in node.decorator_list):
+            names.append(node.name)
+    assert sorted(passed) == sorted(names), (sorted(passed), sorted(names))
