@@ -21,28 +21,41 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PARAMS = ["scalar", "f32x2", "asan"] + (["tsan"] if os.environ.get("MHDF_EMU_TSAN") == "1" else [])
 
 
-@pytest.fixture(scope="module", params=PARAMS)
-def emu_binary(request, tmp_path_factory):
+@pytest.fixture(scope="module")
+def emu_runs(tmp_path_factory):
+    """Build every variant concurrently, then run them concurrently: {variant: CompletedProcess-like (returncode, stdout, stderr)}."""
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    out = str(tmp_path_factory.mktemp("emu") / "emu_test")
-    extra = {"f32x2": ["-DMHDF_F32X2"], "asan": ["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"],
-             "tsan": ["-g", "-fsanitize=thread"]}.get(request.param, [])
-    cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *extra, "-I", os.path.join(ROOT, "tests", "cpu_emu"),
-           "-I", os.path.join(ROOT, "mhdflows_jl_b200", "csrc"), "-I", "/usr/local/cuda/include",
-           "-o", out, os.path.join(ROOT, "tests", "cpu_emu", "test_kernels.cpp")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stderr[-4000:]
-    return out
+    d = tmp_path_factory.mktemp("emu")
+    flags = {"scalar": [], "f32x2": ["-DMHDF_F32X2"], "asan": ["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"],
+             "tsan": ["-g", "-fsanitize=thread"]}
+    builds = {}
+    for v in PARAMS:
+        out = str(d / f"emu_test_{v}")
+        cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *flags[v], "-I", os.path.join(ROOT, "tests", "cpu_emu"),
+               "-I", os.path.join(ROOT, "mhdflows_jl_b200", "csrc"), "-I", "/usr/local/cuda/include",
+               "-o", out, os.path.join(ROOT, "tests", "cpu_emu", "test_kernels.cpp")]
+        builds[v] = (out, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for v, (out, p) in builds.items():
+        log, _ = p.communicate(timeout=900)
+        assert p.returncode == 0, f"{v}: " + log[-4000:]
+    runs = {v: subprocess.Popen([out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+            for v, (out, _) in builds.items()}
+    res = {}
+    for v, p in runs.items():
+        so, se = p.communicate(timeout=3000)
+        res[v] = (p.returncode, so, se)
+    return res
 
 
-def test_kernels_on_the_cpu_emulator(emu_binary):
-    res = subprocess.run([emu_binary], capture_output=True, text=True, timeout=3000, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
-    assert "ERROR: AddressSanitizer" not in res.stderr and "runtime error:" not in res.stderr and "WARNING: ThreadSanitizer" not in res.stderr, res.stderr[-4000:]
-    lines = res.stdout.strip().splitlines()
+@pytest.mark.parametrize("variant", PARAMS)
+def test_kernels_on_the_cpu_emulator(emu_runs, variant):
+    rc, stdout, stderr = emu_runs[variant]
+    assert "ERROR: AddressSanitizer" not in stderr and "runtime error:" not in stderr and "WARNING: ThreadSanitizer" not in stderr, stderr[-4000:]
+    lines = stdout.strip().splitlines()
     fails = [l for l in lines if l.startswith("FAIL")]
-    assert res.returncode == 0 and not fails, "\n".join(fails) + res.stderr[-2000:]
+    assert rc == 0 and not fails, "\n".join(fails) + stderr[-2000:]
     assert lines[-1].startswith("ALL PASS")
     names = " ".join(lines)
     for needle in ("pass forward N=128", "slab inverse leg bit-identical, NZC=4", "xfused MHD N=1024", "xfused EMHD N=128",
