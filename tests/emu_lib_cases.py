@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 import mhdflows_jl_b200 as M  # noqa: E402
 from oracle import forcing_oracle as FO  # noqa: E402
 from oracle import mhdflows_oracle as O  # noqa: E402
+from tests.test_gpu_parity import _pair  # noqa: E402
 from tests.test_gpu_zforcing import _forced_pair, _vp_pair  # noqa: E402
 
 F32_TOL, F64_TOL = 1e-5, 1e-12
@@ -348,6 +349,110 @@ def hdf5_dump_and_restart_through_the_library():
         assert O.rel_l2(rp.get_real("ux", M.FRESH), dump["i_velocity"]) < 1e-6
         assert O.rel_l2(rp.get_real("bz", M.FRESH), dump["k_mag_field"]) < 1e-6
         rp.close()
+    gp.close()
+
+
+# ---- regression guard for the hardware-verified paths (tiny versions of tests/test_gpu_parity.py) -------------------
+@case
+def regress_calcN_hd_emhd_noncubic():
+    for kind, dims in (("hd", (16, 16, 16)), ("emhd", (16, 16, 16)), ("mhd", (32, 16, 16))):
+        op, gp = _pair(M, O, kind, dims, np.float32)
+        N = np.zeros_like(op.sol)
+        op.calcN(N, op.sol, 0.0, op.clock, op.vars, op.params, op.grid)
+        op.grid.dealias(N)
+        got = gp.calcN()
+        for i in range(op.Nl):
+            assert O.rel_l2(got[i], N[i]) < F32_TOL, (kind, i)
+        gp.close()
+
+
+@case
+def regress_per_step_parity_lsrk54_f64_and_emhd():
+    for kind, stepper, T, tol in (("hd", "LSRK54", np.float64, F64_TOL), ("emhd", "RK4", np.float32, F32_TOL), ("mhd", "LSRK54", np.float32, F32_TOL)):
+        op, gp = _pair(M, O, kind, (16, 16, 16), T, stepper=stepper)
+        for s in range(2):
+            O.stepforward(op)
+            M.stepforward(gp)
+            assert O.rel_l2(gp.sol, _dealiased(op)) < tol, (kind, s)
+        assert abs(gp.clock.t - op.clock.t) < 1e-6 and gp.clock.step == op.clock.step
+        gp.close()
+
+
+@case
+def regress_cfl_path_stale_vars_spectrum_helicity():
+    op, gp = _pair(M, O, "mhd", (16, 16, 16), np.float32, turb=False)
+    O.TimeIntegrator(op, 1e9, 1, CFL_Coef=0.25)
+    M.TimeIntegrator(gp, 1e9, 1, CFL_Coef=0.25)
+    assert gp.clock.step == op.clock.step == 2
+    assert abs(gp.clock.dt - op.clock.dt) / op.clock.dt < 1e-5
+    assert O.rel_l2(gp.sol, _dealiased(op)) < 5e-5
+    assert O.rel_l2(gp.vars.ux, op.vars.ux) < 1e-5 and O.rel_l2(gp.vars.bz, op.vars.bz) < 1e-5
+    Pk, kr = M.spectralline(gp, "bx")
+    Pk_ref, kr_ref = O.spectralline(op.grid.irfft(_dealiased(op)[3]), op.grid)
+    assert len(Pk) == len(Pk_ref) and np.abs(Pk - Pk_ref).max() / Pk_ref.max() < 1e-4
+    gp.close()
+    # helicities / energies on a broadband field, reference evaluated in Float64 from the oracle's state
+    op, gp = _pair(M, O, "mhd", (16, 16, 16), np.float32, turb=True)
+    O.stepforward(op)
+    M.stepforward(gp)
+    g64 = O.Grid(16, T=np.float64)
+    sol = _dealiased(op).astype(np.complex128)
+    u = [g64.irfft(sol[i].copy()) for i in range(3)]
+    b = [g64.irfft(sol[3 + i].copy()) for i in range(3)]
+    hk_ref, hm_ref = float(np.sum(O.h_k(*u, g64))), float(np.sum(O.h_m(*b, g64)))
+    hm_scale = float(np.sum(np.abs(O.h_m(*b, g64))))
+    hk, hm, hc = gp.helicity()
+    dv = g64.dx * g64.dy * g64.dz
+    hc_ref = float(np.sum(u[0] * b[0] + u[1] * b[1] + u[2] * b[2])) * dv
+    assert abs(hc - hc_ref) < 1e-5 * abs(hc_ref) and abs(hk - hk_ref) < 1e-4 * abs(hk_ref), (hk, hk_ref, hc, hc_ref)
+    assert abs(hm - hm_ref) < 1e-5 * hm_scale, (hm, hm_ref, hm_scale)
+    ke, me = gp.energy(M.FRESH)
+    assert abs(ke - float(sum(np.sum(x ** 2) for x in u)) * dv) < 1e-5 * ke and abs(me - float(sum(np.sum(x ** 2) for x in b)) * dv) < 1e-5 * me
+    gp.close()
+
+
+@case
+def regress_errors_and_n97_forcing():
+    try:
+        M.Problem(M.GPU(), nx=48)
+        raise AssertionError("nx = 48 was accepted")
+    except M.MHDFlowsError:
+        pass
+    p = M.Problem(M.GPU(), nx=16)
+    try:
+        p.get_spectral(5)
+        raise AssertionError("field 5 of an HD problem was accepted")
+    except M.MHDFlowsError:
+        pass
+    p.set_real(0, np.full((16, 16, 16), np.nan, dtype=np.float32))
+    p.clock.dt = 1e-3
+    try:
+        M.stepforward(p)
+        raise AssertionError("NaN went unnoticed")
+    except M.MHDFlowsError as e:
+        assert e.code == -4
+    p.close()
+    kw = dict(nx=16, T=np.float32, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+    g0 = O.Grid(16, T=np.float32)
+    X, Y, Z = (g0.x.astype(np.float64).reshape(1, 1, -1), g0.y.astype(np.float64).reshape(1, -1, 1), g0.z.astype(np.float64).reshape(-1, 1, 1))
+    fxh = g0.rfft((0.5 * np.sin(2 * X) * np.cos(2 * Y) * np.cos(2 * Z)).astype(np.float32))
+    fyh = g0.rfft((-0.5 * np.cos(2 * X) * np.sin(2 * Y) * np.cos(2 * Z)).astype(np.float32))
+
+    def calcF(N, sol, t, clock, vars, params, grid):
+        N[params.ux_ind] += fxh
+        N[params.uy_ind] += fyh
+
+    op = O.Problem(calcF=calcF, **kw)
+    uv, fn = M.GetN97vars_And_function(M.GPU(), 16, 16, 16)
+    gp = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw)
+    u, b = O.random_phase_ic(op.grid, 11), O.random_phase_ic(op.grid, 12)
+    O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+    M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+    M.SetUpN97(gp, F0=0.5, kf=2)
+    for _ in range(2):
+        O.stepforward(op)
+    M.stepforward(gp, 2)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
     gp.close()
 
 

@@ -29,7 +29,10 @@ def run(flag, n, stepper, T, steps=3, timing=False):
 
 
 if __name__ == "__main__":
-    for n, stepper, T in ((32, "RK4", np.float32), (64, "LSRK54", np.float32), (128, "RK4", np.float32), (32, "RK4", np.float64)):
+    cases = ((32, "RK4", np.float32), (64, "LSRK54", np.float32), (128, "RK4", np.float32), (32, "RK4", np.float64))
+    if "--small" in sys.argv:     # dry run on the CPU-emulated library
+        cases = ((16, "RK4", np.float32),)
+    for n, stepper, T in cases:
         (a, _), (b, _) = run("0", n, stepper, T), run("1", n, stepper, T)
         d = max(float(np.max(np.abs(a[0] - b[0]))), float(np.max(np.abs(a[1] - b[1]))), float(np.max(np.abs(a[2] - b[2]))))
         print(f"emhd2-vs-default n={n} {stepper} {np.dtype(T).name} max abs diff {d:.3e} norm {np.linalg.norm(a[0]):.3e}", flush=True)
