@@ -1,0 +1,87 @@
+// Driver for sanitizer runs of the WHOLE library on the CPU emulator (api.cu + solver.cuh + kernels compiled with
+// -DMHDF_CPU_EMU -fsanitize=address,undefined or -fsanitize=thread and linked with this file): device buffers are heap blocks
+// of exactly the sizes the solver computes, so any kernel or copy that leaves a buffer is a heap-buffer-overflow.
+// Drives the C ABI only (no oracle): HD / MHD / EMHD, RK4 / LSRK54, both EMHD x-kernel forms, k_spectral2, constant forcing,
+// A99 driving, volume penalisation, divergence corrections, calcN, get/set real and spectral, diagnostics, spectrum.
+// Built and run by tests/test_emulated_library.py when MHDF_EMU_SANITIZE_LIB=1.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/mhdflows_b200.h"
+
+static int g_fail = 0;
+#define OK(call)                                                                            \
+  do {                                                                                      \
+    const int rc_ = (call);                                                                 \
+    if (rc_ != 0) { std::printf("FAIL %s -> %d (%s)\n", #call, rc_, mhdf_last_error(h)); ++g_fail; } \
+  } while (0)
+
+template <typename T>
+static void run(const char* label, int physics, int stepper, int nx, int ny, int nz, bool vp, bool a99, bool forcing) {
+  mhdf_config c;
+  std::memset(&c, 0, sizeof c);
+  c.nx = nx; c.ny = ny; c.nz = nz; c.Lx = c.Ly = c.Lz = 2 * M_PI;
+  c.nu = 1e-2; c.eta = 1e-2; c.n_nu = physics == MHDF_MHD ? 2 : 0; c.dt = physics == MHDF_EMHD ? 1e-4 : 1e-3;
+  c.physics = physics; c.stepper = stepper; c.dtype = sizeof(T) == 4 ? MHDF_F32 : MHDF_F64; c.nranks = 1; c.vp = vp;
+  mhdf_handle* h = nullptr;
+  if (mhdf_create(&c, &h) != 0) { std::printf("FAIL create %s: %s\n", label, mhdf_last_error(nullptr)); ++g_fail; return; }
+  const size_t n = (size_t)nx * ny * nz, ns = (size_t)(nx / 2 + 1) * ny * nz;
+  const int F = physics == MHDF_MHD ? 6 : 3;
+  std::vector<T> re(n), back(n);
+  std::vector<T> spec(2 * ns * F);
+  for (int f = 0; f < F; ++f) {
+    for (size_t i = 0; i < n; ++i) re[i] = (T)(0.1 * std::sin(0.37 * (double)i + f) + 0.05 * std::cos(0.011 * (double)i * (f + 1)));
+    OK(mhdf_set_real(h, f, re.data()));
+  }
+  if (forcing) OK(mhdf_set_forcing(h, 1, re.data()));
+  if (a99) { mhdf_a99 q{MHDF_A99_HOST, 0.5, 2.0, 1.0, 1.0, 42ull, 0ull}; OK(mhdf_set_forcing_a99(h, &q)); }
+  if (vp) for (int w = 0; w <= F; ++w) {
+    for (size_t i = 0; i < n; ++i) re[i] = w == 0 ? (T)((i / 7) % 2) : (T)(0.01 * w);
+    OK(mhdf_set_vp_field(h, w, re.data()));
+  }
+  OK(mhdf_step(h, 1));
+  OK(mhdf_calcN(h, spec.data()));
+  if (physics != MHDF_EMHD) OK(mhdf_div_correction(h, 0));
+  if (physics != MHDF_HD) OK(mhdf_div_correction(h, 1));
+  OK(mhdf_step(h, 1));
+  double dt = 0, ke = 0, me = 0, hk, hm, hc;
+  OK(mhdf_cfl_dt(h, 0.25, 1e-3, &dt));
+  OK(mhdf_energy(h, MHDF_FRESH, &ke, &me));
+  OK(mhdf_energy(h, MHDF_STALE, &ke, &me));
+  OK(mhdf_helicity(h, &hk, &hm, &hc));
+  std::vector<double> Pk(32);
+  OK(mhdf_spectrum(h, 0, Pk.data(), 32));
+  for (int f = 0; f < F; ++f) {
+    OK(mhdf_get_real(h, f, MHDF_STALE, back.data()));
+    OK(mhdf_get_spectral(h, f, MHDF_FRESH, spec.data()));
+    OK(mhdf_set_spectral(h, f, spec.data()));
+  }
+  OK(mhdf_step(h, 1));
+  const bool finite = std::isfinite(ke) && std::isfinite(me) && std::isfinite((double)back[n / 2]);
+  std::printf("%s %s (KE %.3e ME %.3e, %lld launches)\n", finite ? "PASS" : "FAIL", label, ke, me, mhdf_launch_count(h));
+  if (!finite) ++g_fail;
+  OK(mhdf_destroy(h));
+}
+
+int main() {
+  run<float>("hd rk4 16x32x16", MHDF_HD, MHDF_RK4, 16, 32, 16, false, false, false);
+  run<float>("mhd rk4 32x16x16 forcing + a99", MHDF_MHD, MHDF_RK4, 32, 16, 16, false, true, true);
+  run<float>("mhd lsrk54 16^3", MHDF_MHD, MHDF_LSRK54, 16, 16, 16, false, false, false);
+  run<double>("mhd rk4 f64 16x16x32", MHDF_MHD, MHDF_RK4, 16, 16, 32, false, false, false);
+  run<float>("emhd rk4 16x16x32", MHDF_EMHD, MHDF_RK4, 16, 16, 32, false, false, false);
+  setenv("MHDF_EMHD2", "1", 1);
+  run<float>("emhd lsrk54 second x-kernel form 16^3", MHDF_EMHD, MHDF_LSRK54, 16, 16, 16, false, false, false);
+  run<double>("emhd rk4 f64 second x-kernel form 16^3", MHDF_EMHD, MHDF_RK4, 16, 16, 16, false, false, false);
+  setenv("MHDF_EMHD2", "0", 1);
+  setenv("MHDF_SPEC2", "1", 1);
+  run<float>("mhd rk4 k_spectral2 a99 16^3", MHDF_MHD, MHDF_RK4, 16, 16, 16, false, true, false);
+  setenv("MHDF_SPEC2", "0", 1);
+  run<float>("hd rk4 volume penalisation 16x16x32", MHDF_HD, MHDF_RK4, 16, 16, 32, true, false, false);
+  run<float>("mhd rk4 volume penalisation + a99 16^3", MHDF_MHD, MHDF_RK4, 16, 16, 16, true, true, false);
+  run<double>("mhd lsrk54 f64 volume penalisation 16^3", MHDF_MHD, MHDF_LSRK54, 16, 16, 16, true, false, false);
+  std::printf("library sanitize driver done: %d failure(s)\n", g_fail);
+  return g_fail ? 1 : 0;
+}

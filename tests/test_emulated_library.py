@@ -70,3 +70,35 @@ def test_end_to_end_cases_on_the_emulated_library(emu_library):
         if isinstance(node, ast.FunctionDef) and any(getattr(d, "id", "") == "case" for d in node.decorator_list):
             names.append(node.name)
     assert sorted(passed) == sorted(names), (sorted(passed), sorted(names))
+
+
+@pytest.mark.skipif(os.environ.get("MHDF_EMU_SANITIZE_LIB") != "1", reason="18 min: the whole library under ASan + UBSan + LeakSanitizer "
+                    "(set MHDF_EMU_SANITIZE_LIB=1); last result in profiles/r01_emulator_sanitizers.txt")
+def test_whole_library_under_address_sanitizer(tmp_path):
+    """api.cu + solver.cuh + kernels + the C-ABI driver tests/cpu_emu/test_library_sanitize.cpp, all with -fsanitize=address,undefined:
+    the solver's device buffers are heap blocks of exactly the computed sizes, so any overrun is reported."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    san = ["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+    objs, procs = [], []
+    for src in ("api.cu", "solver_f32.cu", "solver_f64.cu"):
+        obj = str(tmp_path / (src[:-3] + ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *san, "-I", os.path.join(ROOT, "tests", "cpu_emu"),
+                                       "-I", "/usr/local/cuda/include", "-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    drv = str(tmp_path / "drv.o")
+    res = subprocess.run([gxx, "-std=c++20", "-O1", *san, "-c", os.path.join(ROOT, "tests", "cpu_emu", "test_library_sanitize.cpp"), "-o", drv],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    for p in procs:
+        out, _ = p.communicate(timeout=1800)
+        assert p.returncode == 0, out[-4000:]
+    exe = str(tmp_path / "libsan")
+    res = subprocess.run([gxx, "-fsanitize=address,undefined", "-pthread", "-o", exe, drv] + objs + ["-ldl"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=7200, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+    assert res.returncode == 0 and "ERROR: AddressSanitizer" not in res.stderr and "runtime error:" not in res.stderr \
+        and "LeakSanitizer" not in res.stderr, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("PASS") == 11 and "0 failure(s)" in res.stdout
