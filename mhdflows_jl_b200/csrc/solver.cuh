@@ -63,6 +63,15 @@ struct NcclApi {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string& why) {
     if (so) return true;
+#ifdef MHDF_CPU_EMU   // CPU test-suite: the in-process stand-ins of tests/cpu_emu/cuda_host_emu.h (ranks = threads)
+    (void)why;
+    so = this;
+    GetUniqueId = emu_nccl::GetUniqueId; CommInitRank = emu_nccl::CommInitRank; CommDestroy = emu_nccl::CommDestroy;
+    Send = emu_nccl::Send; Recv = emu_nccl::Recv; GroupStart = emu_nccl::GroupStart; GroupEnd = emu_nccl::GroupEnd;
+    AllReduce = emu_nccl::AllReduce; AllGather = emu_nccl::AllGather;
+    GetErrorString = emu_nccl::GetErrorString;
+    return true;
+#endif
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) { so = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (so) break; }
     if (!so) { why = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }

@@ -47,6 +47,7 @@ struct Block {
 inline thread_local Block* cur_block = nullptr;
 inline thread_local int lane_id = 0, warp_id = 0;
 inline std::mutex atomic_mu;
+inline std::mutex launch_mu;   // one kernel launch at a time, process-wide (not per launch_call instantiation)
 }  // namespace emu
 
 inline thread_local uint3 threadIdx, blockIdx;
@@ -89,6 +90,9 @@ namespace emu {
 // run body() once per CUDA thread of a (gx, gy, gz) grid of 1-D blocks of `nthreads` threads, blocks one after another
 template <typename F>
 void launch_call(dim3 grid, int nthreads, F&& body) {
+  // blocks run one at a time and share smem_raw / the function-local __shared__ arrays: launches of concurrent host threads
+  // (the rank threads of the multi-rank driver) take turns
+  std::lock_guard<std::mutex> launch_guard(launch_mu);
   const int nw = (nthreads + 31) / 32;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)

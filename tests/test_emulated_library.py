@@ -26,50 +26,75 @@ GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5"],
           ["regress_"]]
 
 
+# slab-decomposed runs, ranks = threads of tests/cpu_emu/test_library_ranks.cpp: (ranks, environment)
+RANK_RUNS = {"P=2 peer pushes, z-chunk pipeline": (2, {"MHDF_ZCHUNKS": "2"}),
+             "P=4 send/recv": (4, {"MHDF_PEER": "0"})}
+
+
 @pytest.fixture(scope="module")
-def emu_library(tmp_path_factory):
+def emu_results(tmp_path_factory):
+    """Build the emulated library (+ the multi-rank driver) once, then run every case group and rank configuration concurrently."""
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
     d = tmp_path_factory.mktemp("emu_lib")
+    inc = ["-I", os.path.join(ROOT, "tests", "cpu_emu"), "-I", "/usr/local/cuda/include"]
     objs, procs = [], []
     for src in ("api.cu", "solver_f32.cu", "solver_f64.cu"):
         obj = str(d / (src[:-3] + ".o"))
         objs.append(obj)
-        procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-fPIC", "-pthread", "-DMHDF_CPU_EMU", "-I", os.path.join(ROOT, "tests", "cpu_emu"),
-                                       "-I", "/usr/local/cuda/include", "-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj],
+        procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-fPIC", "-pthread", "-DMHDF_CPU_EMU", *inc, "-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj],
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    drv = str(d / "ranks.o")
+    procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-fPIC", "-pthread", "-c", os.path.join(ROOT, "tests", "cpu_emu", "test_library_ranks.cpp"), "-o", drv],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
         out, _ = p.communicate(timeout=900)
         assert p.returncode == 0, out[-4000:]
-    lib = str(d / "libmhdflows_b200_emu.so")
-    res = subprocess.run([gxx, "-shared", "-pthread", "-o", lib] + objs + ["-ldl"], capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr[-4000:]
-    return lib
-
-
-def test_end_to_end_cases_on_the_emulated_library(emu_library):
-    env = dict(os.environ, MHDF_LIB=emu_library, MHDF_EMHD2="0", MHDF_SPEC2="0")
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu_lib_cases.py")] + g, stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for g in GROUPS]
-    outs = []
-    for p in procs:
+    lib, exe = str(d / "libmhdflows_b200_emu.so"), str(d / "ranks_emu")
+    for cmd in ([gxx, "-shared", "-pthread", "-o", lib] + objs + ["-ldl"], [gxx, "-pthread", "-o", exe, drv] + objs + ["-ldl"]):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-4000:]
+    env = dict(os.environ, MHDF_LIB=lib, MHDF_EMHD2="0", MHDF_SPEC2="0")
+    env.pop("MHDF_ZCHUNKS", None)
+    running = {("cases", i): subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu_lib_cases.py")] + g, stdout=subprocess.PIPE,
+                                              stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for i, g in enumerate(GROUPS)}
+    for name, (P, extra) in RANK_RUNS.items():
+        running[("ranks", name)] = subprocess.Popen([exe, str(P)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                                    env=dict(env, MHDF_RANKS_QUICK="1", **extra))
+    results = {}
+    for key, p in running.items():
         out, _ = p.communicate(timeout=2400)
-        outs.append(out)
-    text = "\n".join(outs)
+        results[key] = (p.returncode, out)
+    return results
+
+
+def test_end_to_end_cases_on_the_emulated_library(emu_results):
+    runs = [v for k, v in emu_results.items() if k[0] == "cases"]
+    text = "\n".join(out for _, out in runs)
     fails = [l for l in text.splitlines() if l.startswith("FAIL")]
-    assert not fails and all(p.returncode == 0 for p in procs), text[-6000:]
+    assert not fails and all(rc == 0 for rc, _ in runs), text[-6000:]
     passed = [l.split()[1] for l in text.splitlines() if l.startswith("PASS")]
     # every case ran exactly once
-    sys.path.insert(0, ROOT)
     import ast
-    src = open(os.path.join(ROOT, "tests", "emu_lib_cases.py")).read()
-    names = []
-    tree = ast.parse(src)
-    for node in tree.body:
-        if isinstance(node, ast.FunctionDef) and any(getattr(d, "id", "") == "case" for d in node.decorator_list):
-            names.append(node.name)
+    tree = ast.parse(open(os.path.join(ROOT, "tests", "emu_lib_cases.py")).read())
+    names = [n.name for n in tree.body if isinstance(n, ast.FunctionDef) and any(getattr(d, "id", "") == "case" for d in n.decorator_list)]
     assert sorted(passed) == sorted(names), (sorted(passed), sorted(names))
+
+
+@pytest.mark.parametrize("config", list(RANK_RUNS))
+def test_slab_runs_on_the_emulated_library_equal_the_single_rank_run(emu_results, config):
+    """Ranks as threads, NCCL / CUDA IPC replaced by in-process stand-ins (cuda_host_emu.h): the spectral state of the P-rank run is
+    bit-identical to the single-rank run -- EMHD Float64 and MHD with A99 driving + volume penalisation + DivVCorrection!, through
+    the copy-push transport with the z-chunk pipelined path (MHDF_ZCHUNKS, not yet run on hardware) and through send/recv on 4
+    ranks.  Streams are synchronous here: this checks layouts, offsets, slab bounds and reductions, not event ordering."""
+    rc, out = emu_results[("ranks", config)]
+    lines = [l for l in out.splitlines() if "ranks-vs-single" in l]
+    assert rc == 0 and len(lines) == 2 and all(l.startswith("PASS") for l in lines), out[-4000:]
+    if "pipeline" in config:     # the pipelined path really ran: it launches its passes once per z chunk
+        for l in lines:
+            a, b = l.split("launches ")[1].rstrip(")").split(" -> ")
+            assert int(b) > int(a), l
 
 
 @pytest.mark.skipif(os.environ.get("MHDF_EMU_SANITIZE_LIB") != "1", reason="18 min: the whole library under ASan + UBSan + LeakSanitizer "
