@@ -1,7 +1,7 @@
 #!/bin/bash
 # First gpurun call of round 2: everything that was written after round 1's GPU budget was spent, in one batch.
 #   (here, before the call)  python -m mhdflows_jl_b200.build --variant=f32x2 --variant=emhd_unroll
-#   gpurun --timeout 1500 -- 'bash tools/r2_first.sh'
+#   gpurun --timeout 2400 -- 'bash tools/r2_first.sh'
 # Writes gpurun_out/r2_first_*.log.  Order: the cheap correctness checks first, then the A/B timings.
 set -u
 mkdir -p gpurun_out
