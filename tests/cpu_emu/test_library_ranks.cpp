@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -120,6 +121,14 @@ int main(int argc, char** argv) {
   const int P = argc > 1 ? std::atoi(argv[1]) : 2;
   const char* e = std::getenv("MHDF_PEER");
   const bool peer = !(e && std::atoi(e) == 0);
+  if (argc >= 5) {   // custom shape: test_library_ranks P nx ny nz [hd|mhd|emhd]
+    const int nx = std::atoi(argv[2]), ny = std::atoi(argv[3]), nz = std::atoi(argv[4]);
+    const std::string ph = argc > 5 ? argv[5] : "mhd";
+    const int phys = ph == "hd" ? MHDF_HD : (ph == "emhd" ? MHDF_EMHD : MHDF_MHD);
+    compare<float>((ph + " rk4 custom " + std::to_string(nx) + "x" + std::to_string(ny) + "x" + std::to_string(nz)).c_str(), P, peer, phys, MHDF_RK4, nx, ny, nz, false, false);
+    std::printf("library ranks driver done: %d failure(s)\n", g_fail);
+    return g_fail ? 1 : 0;
+  }
   const bool quick = std::getenv("MHDF_RANKS_QUICK") != nullptr;   // CI: two cases; the full set takes ~90 s per configuration
   if (!quick) compare<float>("mhd rk4 16x16x32", P, peer, MHDF_MHD, MHDF_RK4, 16, 16, 32, false, false);
   if (!quick) compare<float>("hd lsrk54 16x32x16", P, peer, MHDF_HD, MHDF_LSRK54, 16, 32, 16, false, false);
