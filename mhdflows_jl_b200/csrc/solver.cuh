@@ -235,6 +235,10 @@ struct Solver : mhdf_handle {
     ky0 = rank_ * Kyl;
     if (P_ > 1 && (nz % P_ != 0 || (P_ - 1) * Kyl >= Ky))
       throw Err{MHDF_ERR_INVALID, "grid too small for this many ranks (need nz % nranks == 0 and a non-empty ky slab per rank)"};
+    // the blocked exchange addressing divides row indices by nzl / Kyl with a 32-bit multiply-high (magic = ceil(2^32 / d)),
+    // which cannot represent d = 1 (found on the CPU emulator with ranks as threads, tests/cpu_emu/test_library_ranks.cpp)
+    if (P_ > 1 && (nzl < 2 || Kyl < 2))
+      throw Err{MHDF_ERR_INVALID, "grid too small for this many ranks (need at least 2 z planes and 2 retained ky rows per rank)"};
     phys = c.physics;
     F = (phys == MHDF_MHD) ? 6 : 3;
     nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 24);
@@ -776,6 +780,7 @@ struct Solver : mhdf_handle {
   bool pipe_ok() const {
     if (P_ == 1 || zchunks <= 1 || nzl % zchunks != 0) return false;
     const int zc = nzl / zchunks, rb = 1024 / nx > 1 ? 1024 / nx : 1;
+    if (zc < 2) return false;   // one plane per chunk: the second-level divisor would be 1 (see init)
     if ((long long)(nin > nout ? nin : nout) * nz * Kyl * Kxp >= (1LL << 31)) return false;   // 32-bit row offsets
     return ((long long)ny * zc) % rb == 0;
   }

@@ -40,8 +40,9 @@ class SlabLayout:
             raise ValueError("nz must be divisible by the number of ranks")
         self.nzl = nz // nranks
         self.Kyl = -(-self.Ky // nranks)
-        if nranks > 1 and (nranks - 1) * self.Kyl >= self.Ky:
-            raise ValueError("grid too small for this many ranks")
+        if nranks > 1 and ((nranks - 1) * self.Kyl >= self.Ky or self.nzl < 2 or self.Kyl < 2):
+            raise ValueError("grid too small for this many ranks (every rank needs a non-empty ky slab, "
+                             "at least 2 z planes and 2 retained ky rows)")
         self.ky0 = rank * self.Kyl
 
     # full index of every compact row (ky and kz)
