@@ -15,6 +15,8 @@ import sys
 
 import pytest
 
+from tests import emu_build
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mhdflows_jl_b200", "csrc")
 
@@ -34,26 +36,17 @@ RANK_RUNS = {"P=2 peer pushes, z-chunk pipeline": (2, {"MHDF_ZCHUNKS": "2"}),
 
 
 @pytest.fixture(scope="module")
-def emu_results(tmp_path_factory):
-    """Build the emulated library (+ the multi-rank driver) once, then run every case group and rank configuration concurrently."""
+def emu_results():
+    """Build the emulated library (+ the multi-rank driver) once (compiles started at session start by tests/conftest.py), then run
+    every case group and rank configuration concurrently."""
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    d = tmp_path_factory.mktemp("emu_lib")
-    inc = ["-I", os.path.join(ROOT, "tests", "cpu_emu"), "-I", "/usr/local/cuda/include"]
-    objs, procs = [], []
-    for src in ("api.cu", "solver_f32.cu", "solver_f64.cu"):
-        obj = str(d / (src[:-3] + ".o"))
-        objs.append(obj)
-        procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-fPIC", "-pthread", "-DMHDF_CPU_EMU", *inc, "-x", "c++", "-c", os.path.join(CSRC, src), "-o", obj],
-                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    drv = str(d / "ranks.o")
-    procs.append(subprocess.Popen([gxx, "-std=c++20", "-O1", "-fPIC", "-pthread", "-c", os.path.join(ROOT, "tests", "cpu_emu", "test_library_ranks.cpp"), "-o", drv],
-                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    d, objs, drv, procs = emu_build.start("library")
     for p in procs:
         out, _ = p.communicate(timeout=900)
         assert p.returncode == 0, out[-4000:]
-    lib, exe = str(d / "libmhdflows_b200_emu.so"), str(d / "ranks_emu")
+    lib, exe = os.path.join(d, "libmhdflows_b200_emu.so"), os.path.join(d, "ranks_emu")
     for cmd in ([gxx, "-shared", "-pthread", "-o", lib] + objs + ["-ldl"], [gxx, "-pthread", "-o", exe, drv] + objs + ["-ldl"]):
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-4000:]

@@ -15,28 +15,20 @@ import subprocess
 
 import pytest
 
+from tests import emu_build
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-
-PARAMS = ["scalar", "f32x2", "asan"] + (["tsan"] if os.environ.get("MHDF_EMU_TSAN") == "1" else [])
+PARAMS = emu_build.KERNEL_PARAMS
 
 
 @pytest.fixture(scope="module")
-def emu_runs(tmp_path_factory):
-    """Build every variant concurrently, then run them concurrently: {variant: CompletedProcess-like (returncode, stdout, stderr)}."""
-    gxx = shutil.which("g++")
-    if gxx is None:
+def emu_runs():
+    """Build every variant concurrently (started at session start by tests/conftest.py), then run them concurrently:
+    {variant: CompletedProcess-like (returncode, stdout, stderr)}."""
+    if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    d = tmp_path_factory.mktemp("emu")
-    flags = {"scalar": [], "f32x2": ["-DMHDF_F32X2"], "asan": ["-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"],
-             "tsan": ["-g", "-fsanitize=thread"]}
-    builds = {}
-    for v in PARAMS:
-        out = str(d / f"emu_test_{v}")
-        cmd = [gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *flags[v], "-I", os.path.join(ROOT, "tests", "cpu_emu"),
-               "-I", os.path.join(ROOT, "mhdflows_jl_b200", "csrc"), "-I", "/usr/local/cuda/include",
-               "-o", out, os.path.join(ROOT, "tests", "cpu_emu", "test_kernels.cpp")]
-        builds[v] = (out, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    builds = emu_build.start("kernels")
     for v, (out, p) in builds.items():
         log, _ = p.communicate(timeout=900)
         assert p.returncode == 0, f"{v}: " + log[-4000:]
