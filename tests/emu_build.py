@@ -7,6 +7,7 @@ import os
 import shutil
 import subprocess
 import tempfile
+import threading
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mhdflows_jl_b200", "csrc")
@@ -29,15 +30,33 @@ def _popen(cmd):
     return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
 
 
+class KernelJob(threading.Thread):
+    """Compile one code shape of tests/cpu_emu/test_kernels.cpp, then run it straight away (the runs of the variants overlap
+    with whatever the suite is doing meanwhile).  After join(): build_rc / build_log, result = (returncode, stdout, stderr)."""
+
+    def __init__(self, cmd, exe):
+        super().__init__(daemon=True)
+        self.cmd, self.exe = cmd, exe
+        self.build_rc, self.build_log, self.result = None, "", None
+
+    def run(self):
+        b = subprocess.run(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        self.build_rc, self.build_log = b.returncode, b.stdout
+        if b.returncode == 0:
+            r = subprocess.run([self.exe], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+            self.result = (r.returncode, r.stdout, r.stderr)
+
+
 def _start_kernels(gxx):
-    """One executable per code shape of tests/cpu_emu/test_kernels.cpp: {variant: (path, Popen)}."""
+    """{variant: KernelJob (started)}."""
     d = _tmpdir("emu")
-    builds = {}
+    jobs = {}
     for v in KERNEL_PARAMS:
         out = os.path.join(d, f"emu_test_{v}")
-        builds[v] = (out, _popen([gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *KERNEL_FLAGS[v], "-I", EMU, "-I", CSRC,
-                                  "-I", "/usr/local/cuda/include", "-o", out, os.path.join(EMU, "test_kernels.cpp")]))
-    return builds
+        jobs[v] = KernelJob([gxx, "-std=c++20", "-O1", "-pthread", "-DMHDF_CPU_EMU", *KERNEL_FLAGS[v], "-I", EMU, "-I", CSRC,
+                             "-I", "/usr/local/cuda/include", "-o", out, os.path.join(EMU, "test_kernels.cpp")], out)
+        jobs[v].start()
+    return jobs
 
 
 def _start_library(gxx):

@@ -9,35 +9,28 @@ sm_100 add/mul/fma.f32x2 instructions, with the packed primitives emulated lane 
 AddressSanitizer + UBSan -- every global array of the harness is a host vector of exactly the size the solver would
 allocate, so an out-of-bounds index in a kernel is a heap-buffer-overflow here (the CPU stand-in for compute-sanitizer
 memcheck; MHDF_EMU_TSAN=1 adds a ThreadSanitizer run = racecheck between the emulated CUDA threads, ~10 min)."""
-import os
 import shutil
-import subprocess
 
 import pytest
 
 from tests import emu_build
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PARAMS = emu_build.KERNEL_PARAMS
 
 
 @pytest.fixture(scope="module")
 def emu_runs():
-    """Build every variant concurrently (started at session start by tests/conftest.py), then run them concurrently:
-    {variant: CompletedProcess-like (returncode, stdout, stderr)}."""
+    """Every variant is built and then run by its own background job, started at session start by tests/conftest.py:
+    {variant: (returncode, stdout, stderr)}."""
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    builds = emu_build.start("kernels")
-    for v, (out, p) in builds.items():
-        log, _ = p.communicate(timeout=900)
-        assert p.returncode == 0, f"{v}: " + log[-4000:]
-    runs = {v: subprocess.Popen([out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
-            for v, (out, _) in builds.items()}
+    jobs = emu_build.start("kernels")
     res = {}
-    for v, p in runs.items():
-        so, se = p.communicate(timeout=3000)
-        res[v] = (p.returncode, so, se)
+    for v, job in jobs.items():
+        job.join(timeout=3900)
+        assert not job.is_alive(), f"{v}: emulator run did not finish"
+        assert job.build_rc == 0, f"{v}: " + job.build_log[-4000:]
+        res[v] = job.result
     return res
 
 
