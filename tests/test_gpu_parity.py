@@ -294,6 +294,8 @@ def test_n97_taylor_green_forcing(M, O):
         gp.close()
 
 
+@pytest.mark.xfail(strict=False, reason="written after round 1's last hardware run (same policy as tests/test_gpu_zforcing.py): the same "
+                   "path passes on the emulated library (tests/emu_lib_cases.py::hdf5); a pass shows up as XPASS")
 def test_time_integrator_save_and_restart(M, O, tmp_path):
     """save=true path of TimeIntegrator! (integrator.jl:44-51,136-141) and Restart! (:208-257): dumps hold the stale vars
     and the time; a restarted problem starts from exactly those fields."""
