@@ -12,8 +12,11 @@
  * Field ids follow params.*_ind - 1 (src/Structure/datastructure.jl:88-90):
  *   HD: ux,uy,uz = 0,1,2   MHD: ux,uy,uz,bx,by,bz = 0..5   EMHD: bx,by,bz = 0,1,2
  *
- * The handle owns all device memory, streams and communicators; host pointers are borrowed
+ * The handle owns all device memory, streams and communicators; caller pointers are borrowed
  * for the duration of a call.  One host thread per handle.
+ * Field pointers (`host_real`, `host_spec`) may be host memory OR device memory of the handle's GPU
+ * (unified addressing, cudaMemcpyDefault): a Julia host passes `pointer(A)` of an Array or of a CuArray
+ * alike -- the reference's `vars.*` / `sol` live on the device (datastructure.jl:58-108).
  *
  * file:line citations are into the reference tree (MHDFlows.jl).
  */
@@ -116,6 +119,15 @@ int mhdf_set_vp_field(mhdf_handle* h, int which, const void* host_real);
  * three fields of the group, then the real-space `vars` of that group are refreshed from the corrected sol (stale view,
  * CFL maxima, energies). */
 int mhdf_div_correction(mhdf_handle* h, int group);
+
+/* DivFreeSpectraMap(grid; k_peak, P, k0) (utils/IC.jl:130-179) + SetUpProblemIC! (IC.jl:41-109) for the velocity (group 0) or
+ * the magnetic field (group 1), entirely on the device (the reference builds the map on grid.device too):
+ *   F^_i = A k^k0 e^{2 pi i theta(k)} e2_i(k),  e2 = (kx kz, ky kz, -kp^2) / (kp k),  zero on the kr = 0 plane and for k < k_peak,
+ *   A = sqrt(3 P (Lx/dx)(Ly/dy)(Lz/dz) / sum(k^k0 / (k+1)^2) / dV),  then dealias!, and sol / vars.* of the group are set from it.
+ * theta: Julia's rand stream cannot be reproduced; it is word 0 of the Philox4x32-10 block with key = seed and counter = index
+ * of the mode in the (nx/2+1, ny, nz) array (independent of the number of GPUs; regenerated bit for bit by
+ * oracle/forcing_oracle.py::PhiloxField for the parity tests). */
+int mhdf_set_random_phase(mhdf_handle* h, int group, unsigned long long seed, double k0, double P, double k_peak);
 
 /* stepforward! (timestepper/timestepper.jl:4-6): nsteps steps of clock.dt. */
 int mhdf_step(mhdf_handle* h, int nsteps);

@@ -22,6 +22,7 @@ SYMBOLS = [
     "mhdf_step_timed", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
     "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
     "mhdf_set_forcing_a99", "mhdf_forcing_a99_calls", "mhdf_div_correction", "mhdf_set_vp_field",
+    "mhdf_set_random_phase",
 ]
 A99_HOST, A99_GPU = 1, 2
 
@@ -90,6 +91,7 @@ def lib():
         "mhdf_forcing_a99_calls": (i, [vp, C.POINTER(C.c_ulonglong)]),
         "mhdf_div_correction": (i, [vp, i]),
         "mhdf_set_vp_field": (i, [vp, i, vp]),
+        "mhdf_set_random_phase": (i, [vp, i, C.c_ulonglong, d, d, d]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(L, name) and os.environ.get("MHDF_LIB"):

@@ -102,6 +102,9 @@ int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls) {
 }
 int mhdf_set_vp_field(mhdf_handle* h, int which, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_vp_field(which, p); }); }
 int mhdf_div_correction(mhdf_handle* h, int group) { return guard(h, [&] { h->div_correction(group); }); }
+int mhdf_set_random_phase(mhdf_handle* h, int group, unsigned long long seed, double k0, double P, double k_peak) {
+  return guard(h, [&] { h->set_random_phase(group, seed, k0, P, k_peak); });
+}
 int mhdf_ipc_blob_size(const mhdf_handle*) { return (int)sizeof(IpcBlob); }
 int mhdf_ipc_export(mhdf_handle* h, void* blob) { return guard(h, [&] { if (!blob) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_export(blob); }); }
 int mhdf_ipc_import(mhdf_handle* h, const void* blobs) { return guard(h, [&] { if (!blobs) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->ipc_import(blobs); }); }

@@ -864,6 +864,9 @@ __host__ __device__ __forceinline__ void a99_uniforms(const A99Args<T>& q, unsig
     r[0] = u01(a.v[0], a.v[1], T()); r[1] = u01(a.v[2], a.v[3], T()); r[2] = u01(b.v[0], b.v[1], T()); r[3] = u01(b.v[2], b.v[3], T());
   }
 }
+// c * x + y per component as ONE fused multiply-add (the same rounding whatever the compiler would contract)
+__device__ __forceinline__ float2 axpy(float c, float2 x, float2 y) { return mk<float2>(fmaf(c, x.x, y.x), fmaf(c, x.y, y.y)); }
+__device__ __forceinline__ double2 axpy(double c, double2 x, double2 y) { return mk<double2>(fma(c, x.x, y.x), fma(c, x.y, y.y)); }
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }     // a product that is never contracted into an FMA
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ void sincos2pi(float r, float& s, float& c) { sincospif(2.f * r, &s, &c); }
@@ -953,40 +956,6 @@ struct SpecArgs {
 // in P;  N_a += -sum_j (delta_aj - k_j k_a / k^2) V^_j  for the velocity and, in MHD, the same with the B0 set for the
 // magnetic field (reference: VPSolver.jl:36, :56, called from HDSolver.jl:77-79, MHDSolver.jl:86-88, 161-163).
 
-template <typename T, int F>
-__device__ __forceinline__ void spec_commit(const SpecArgs<T>& a, long long e, const Cx<T> (&N)[F], const Cx<T> (&sin)[F]) {
-  using C = Cx<T>;
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    const long long o = f * a.g.field + e;
-    switch (a.mode) {
-      case STEP_CALCN: a.Nout[o] = N[f]; break;
-      case STEP_RK4_1: {   // Sin == Y
-        const C y = a.Y[o];
-        a.A[o] = mk<C>(y.x + a.ca * N[f].x, y.y + a.ca * N[f].y);
-        a.Sout[o] = mk<C>(y.x + a.cs * N[f].x, y.y + a.cs * N[f].y);
-      } break;
-      case STEP_RK4_2:
-      case STEP_RK4_3: {
-        const C y = a.Y[o];
-        const C ac = a.A[o];
-        a.A[o] = mk<C>(ac.x + a.ca * N[f].x, ac.y + a.ca * N[f].y);
-        a.Sout[o] = mk<C>(y.x + a.cs * N[f].x, y.y + a.cs * N[f].y);
-      } break;
-      case STEP_RK4_4: {   // sol = A + dt/6 k4, written to Sout (= Y)
-        const C ac = a.A[o];
-        a.Sout[o] = mk<C>(ac.x + a.ca * N[f].x, ac.y + a.ca * N[f].y);
-      } break;
-      default: {           // LSRK54: S2 = A_i S2 + dt N ; sol += B_i S2
-        C s2 = mk<C>(a.dt * N[f].x, a.dt * N[f].y);
-        if (!a.first) { const C o2 = a.A[o]; s2.x += a.ca * o2.x; s2.y += a.ca * o2.y; }
-        a.A[o] = s2;
-        a.Sout[o] = mk<C>(sin[f].x + a.cs * s2.x, sin[f].y + a.cs * s2.y);
-      } break;
-    }
-  }
-}
-
 // RHS assembly + Runge-Kutta stage update, one thread per retained mode.
 //   MHD/HD: N_a = D_a - k_a (k.D)/k^2 - nu k^2 u^sym_a [- nu k^(2 n_nu) u^sym_a],  D_j = sum_i i k_i T^_ij
 //           N_{3+a} = i (k x E^)_a - eta k^2 b^sym_a
@@ -995,7 +964,7 @@ __device__ __forceinline__ void spec_commit(const SpecArgs<T>& a, long long e, c
 #ifndef MHDF_SPEC_MINB
 #define MHDF_SPEC_MINB 4   // <= 64 registers: a streaming kernel wants the occupancy, not the registers
 #endif
-// Mirror operand of the kr = 0 symmetrisation, resolved once per mode for all fields (k_spectral2): base pointer of
+// Mirror operand of the kr = 0 symmetrisation, resolved once per mode for all fields: base pointer of
 // field 0 and the field stride, or null when the mode is off the plane / its mirror is dealiased.
 template <typename T> struct SymSrc {
   const Cx<T>* base;
@@ -1032,9 +1001,9 @@ __device__ __forceinline__ Cx<T> sym_apply(const SymSrc<T>& r, int fi, Cx<T> v) 
   return v;
 }
 
-// RHS of one retained mode e = (ix, jc, kc): N[] and the stage input sin[] at that mode.  V2: the mirror operand is
-// resolved once for all fields and the stage input is loaded once (same values, same arithmetic as the V1 form).
-template <typename T, int PHYS, bool V2, bool A99, bool VP, typename IDX>
+// RHS of one retained mode e = (ix, jc, kc): N[] and the stage input sin[] at that mode.  The mirror operand of the kr = 0
+// symmetrisation is resolved once for all fields and the stage input is loaded once.
+template <typename T, int PHYS, bool A99, bool VP, typename IDX>
 __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, int jc, int kc,
                                          Cx<T> (&N)[PHYS == PHYS_MHD ? 6 : 3], Cx<T> (&sin)[PHYS == PHYS_MHD ? 6 : 3]) {
   using C = Cx<T>;
@@ -1057,20 +1026,15 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
     D[2] = mk<C>(kx * Tt[2].x + ky * Tt[4].x + kz * Tt[5].x, kx * Tt[2].y + ky * Tt[4].y + kz * Tt[5].y);
     const C kD = mk<C>((kx * D[0].x + ky * D[1].x + kz * D[2].x) * ik2, (kx * D[0].y + ky * D[1].y + kz * D[2].y) * ik2);
     const T kk[3] = {kx, ky, kz};
-    SymSrc<T> sy;
-    if constexpr (V2) {
-      sy = sym_src<T>(a.Sin, g, ix, jc, kc);
+    const SymSrc<T> sy = sym_src<T>(a.Sin, g, ix, jc, kc);
 #pragma unroll
-      for (int f = 0; f < F; ++f) sin[f] = a.Sin[f * g.field + e];
-    }
+    for (int f = 0; f < F; ++f) sin[f] = a.Sin[f * g.field + e];
     T hyper = (T)0;
     if (a.n_nu > 1) { hyper = (T)1; for (int q = 0; q < a.n_nu; ++q) hyper *= k2; }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const C pr = mk<C>(D[c].x - kk[c] * kD.x, D[c].y - kk[c] * kD.y);   // still missing the factor i
-      C us;
-      if constexpr (V2) us = sym_apply<T>(sy, c, sin[c]);
-      else { us = load_sym<T>(a.Sin, c, g, ix, jc, kc); sin[c] = a.Sin[c * g.field + e]; }
+      const C us = sym_apply<T>(sy, c, sin[c]);
       const T dc = -(a.nu * k2) - a.nu * hyper;
       N[c] = mk<C>(-pr.y + dc * us.x, pr.x + dc * us.y);
     }
@@ -1085,9 +1049,7 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
       const T dc = -(a.eta * k2);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        C bsym;
-        if constexpr (V2) bsym = sym_apply<T>(sy, 3 + c, sin[3 + c]);
-        else { bsym = load_sym<T>(a.Sin, 3 + c, g, ix, jc, kc); sin[3 + c] = a.Sin[(3 + c) * g.field + e]; }
+        const C bsym = sym_apply<T>(sy, 3 + c, sin[3 + c]);
         N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
       }
     }
@@ -1127,32 +1089,14 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
   }
 }
 
-template <typename T, int PHYS, bool A99 = false, bool VP = false>
+// The stage mode is a template parameter, the grid is (plane, kz) and element indices are 32-bit: no 64-bit division per
+// mode and no run-time switch, and the Y / A operands of the stage update are requested before the RHS arithmetic.
+// (Round 1 shipped a grid-stride form with three 64-bit divisions per mode and a run-time stage switch; on B200 this form
+// is 23 % faster -- 0.713 -> 0.550 ms at 256^3, 36.0 -> 27.6 ms per step at 1024^3, profiles/README.md -- and replaced it.
+// The stage updates are written with explicit fused multiply-adds so the result does not depend on the compiler's
+// contraction choices.)  Needs n_fields * field < 2^32 elements (true up to 1024^3 with 15 product fields).
+template <typename T, int PHYS, int MODE, bool A99 = false, bool VP = false>
 __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a) {
-  using C = Cx<T>;
-  const SpecGeom<T>& g = a.g;
-  const int Ky = g.Kyl, Kz = g.bz.count();
-  const long long total = (long long)g.Kxp * Ky * Kz;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int ix = (int)(e % g.Kxp);
-    if (ix >= g.Kx) continue;
-    const long long rowi = e / g.Kxp;
-    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
-    if (g.ky0 + jc >= g.by.count()) continue;   // padding rows of the last slab
-    constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
-    C N[F], sin[F];
-    spec_rhs<T, PHYS, false, A99, VP>(a, e, ix, jc, kc, N, sin);
-    spec_commit<T, F>(a, e, N, sin);
-  }
-}
-
-// Variant with the stage mode as a template parameter, a (plane, kz) grid and 32-bit element indices: no 64-bit
-// division per mode (three in k_spectral, about a third of its 650 instructions per mode), no run-time switch, and the
-// Y / A operands of the stage update are requested before the RHS arithmetic instead of after it.  Same arithmetic in the
-// same order: results are bit-identical to k_spectral.  Opt-in (MHDF_SPEC2=1) until measured on hardware.
-// Needs F_total * field < 2^32 elements (true up to 1024^3 with 9 product fields).
-template <typename T, int PHYS, int MODE, bool A99 = false>
-__global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral2(SpecArgs<T> a) {
   using C = Cx<T>;
   const SpecGeom<T>& g = a.g;
   constexpr int F = (PHYS == PHYS_MHD) ? 6 : 3;
@@ -1173,25 +1117,25 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral2(SpecArgs<T> a
     if constexpr (MODE == STEP_LSRK) ac[f] = a.first ? mk<C>(0, 0) : a.A[f * fld + e];
   }
   C N[F], sin[F];
-  spec_rhs<T, PHYS, true, A99, false>(a, e, (int)ix, (int)jc, kc, N, sin);
+  spec_rhs<T, PHYS, A99, VP>(a, e, (int)ix, (int)jc, kc, N, sin);
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     const unsigned o = f * fld + e;
     if constexpr (MODE == STEP_CALCN) {
       a.Nout[o] = N[f];
     } else if constexpr (MODE == STEP_RK4_1) {   // Sin == Y
-      a.A[o] = mk<C>(y[f].x + a.ca * N[f].x, y[f].y + a.ca * N[f].y);
-      a.Sout[o] = mk<C>(y[f].x + a.cs * N[f].x, y[f].y + a.cs * N[f].y);
+      a.A[o] = axpy(a.ca, N[f], y[f]);
+      a.Sout[o] = axpy(a.cs, N[f], y[f]);
     } else if constexpr (MODE == STEP_RK4_2 || MODE == STEP_RK4_3) {
-      a.A[o] = mk<C>(ac[f].x + a.ca * N[f].x, ac[f].y + a.ca * N[f].y);
-      a.Sout[o] = mk<C>(y[f].x + a.cs * N[f].x, y[f].y + a.cs * N[f].y);
+      a.A[o] = axpy(a.ca, N[f], ac[f]);
+      a.Sout[o] = axpy(a.cs, N[f], y[f]);
     } else if constexpr (MODE == STEP_RK4_4) {
-      a.Sout[o] = mk<C>(ac[f].x + a.ca * N[f].x, ac[f].y + a.ca * N[f].y);
+      a.Sout[o] = axpy(a.ca, N[f], ac[f]);
     } else {                                     // LSRK54: S2 = A_i S2 + dt N ; sol += B_i S2
       C s2 = mk<C>(a.dt * N[f].x, a.dt * N[f].y);
-      if (!a.first) { s2.x += a.ca * ac[f].x; s2.y += a.ca * ac[f].y; }
+      if (!a.first) s2 = axpy(a.ca, ac[f], s2);
       a.A[o] = s2;
-      a.Sout[o] = mk<C>(sin[f].x + a.cs * s2.x, sin[f].y + a.cs * s2.y);
+      a.Sout[o] = axpy(a.cs, s2, sin[f]);
     }
   }
 }
@@ -1252,6 +1196,92 @@ __global__ void __launch_bounds__(256) k_divclean(SpecGeom<T> g, Cx<T>* __restri
     const C s = mk<C>((k[0] * f[0].x + k[1] * f[1].x + k[2] * f[2].x) * ik2, (k[0] * f[0].y + k[1] * f[1].y + k[2] * f[2].y) * ik2);
 #pragma unroll
     for (int i = 0; i < 3; ++i) S[i * g.field + e] = mk<C>(f[i].x - k[i] * s.x, f[i].y - k[i] * s.y);
+  }
+}
+
+// ---- DivFreeSpectraMap (utils/IC.jl:130-179) on the device ---------------------------------------------------------------
+// Random-phase power-law solenoidal field:  F^_i = A k^k0 e^{2 pi i theta} e2_i(k),  e2 = (kx kz, ky kz, -kp^2) / (kp k),
+// kp^2 = kx^2 + ky^2, 0/0 -> 0, zero on the kr = 0 plane and for k < k_peak;  A = sqrt(3 P (Lx/dx)(Ly/dy)(Lz/dz) / sum(Fk/(k+1)^2)
+// / dV) with the sum over the WHOLE (nkr, nl, nm) array (taken before dealias!, like the reference).  The reference draws
+// theta = rand(T, nkr, nl, nm) from Julia's stream, which cannot be reproduced: theta is word 0 of the Philox4x32-10 block
+// (key = seed, counter = index of the mode in the (nkr, nl, nm) array, tag word), the generator of the A99 driving.
+// Arithmetic in T (k, Fk, the e2 basis as T broadcasts like IC.jl:139-159, evaluated left to right); e^{i theta 2 pi} in
+// Float64 then rounded (IC.jl:163: `im .* rand(T, ...) * 2pi` promotes to Float64).
+template <typename T>
+struct DfsmArgs {
+  int nkr, ny, nz;
+  double dkx, dky, dkz;    // 2 pi / L per axis
+  T k0, kpeak, amp;
+  unsigned seed_lo, seed_hi;
+};
+enum : unsigned { DFSM_CALL_LO = 0x44465350u, DFSM_CALL_HI = 0x7FFFFFFFu };   // counter tag: never a forcing-call number
+template <typename T>
+__device__ __forceinline__ T dfsm_fk(T kx, T ky, T kz, int ix, T k0, T kpeak, T& k) {
+  const T k2 = kx * kx + ky * ky + kz * kz;
+  k = sqrt(k2);
+  if (ix == 0 || !(k2 > (T)0) || k < kpeak) return (T)0;   // Fk[1,1,1] = 0; Fk[1,:,:] .= 0; Fk[k .< k_peak] .= 0
+  return pow(k, k0);
+}
+// sum over every mode of the (nkr, ny, nz) array of Fk / (k + 1)^2  ->  out[0]  (Float64 accumulation)
+template <typename T>
+__global__ void __launch_bounds__(256) k_dfsm_norm(DfsmArgs<T> q, double* __restrict__ out) {
+  const long long total = (long long)q.nkr * q.ny * q.nz;
+  double s = 0.0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % q.nkr);
+    const long long r = e / q.nkr;
+    const int j = (int)(r % q.ny), kk = (int)(r / q.ny);
+    const T kx = (T)(ix * q.dkx), ky = (T)((j < q.ny / 2 ? j : j - q.ny) * q.dky), kz = (T)((kk < q.nz / 2 ? kk : kk - q.nz) * q.dkz);
+    T k;
+    const T Fk = dfsm_fk<T>(kx, ky, kz, ix, q.k0, q.kpeak, k);
+    const T k1 = k + (T)1;
+    s += (double)(Fk * ((T)1 / (k1 * k1)));
+  }
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  warp_red_sum<double>(s);
+  if (lane == 0) sh[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    double x = lane < nw ? sh[lane] : 0.0;
+    warp_red_sum<double>(x);
+    if (lane == 0) atomicAdd(out, x);
+  }
+}
+// the three components on the retained modes of a compact state (fields S, S + field, S + 2 field)
+template <typename T>
+__global__ void __launch_bounds__(256) k_dfsm_fill(SpecGeom<T> g, DfsmArgs<T> q, Cx<T>* __restrict__ S) {
+  using C = Cx<T>;
+  const int Ky = g.Kyl, Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  A99Args<T> rq;
+  rq.seed_lo = q.seed_lo; rq.seed_hi = q.seed_hi; rq.call_lo = DFSM_CALL_LO; rq.call_hi = DFSM_CALL_HI;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    const int jg = g.ky0 + jc;
+    if (jg >= g.by.count()) continue;
+    const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
+    T k;
+    const T Fk = dfsm_fk<T>(kx, ky, kz, ix, q.k0, q.kpeak, k) * q.amp;
+    const T k2 = kx * kx + ky * ky + kz * kz;
+    const T kinv = sqrt((k2 > (T)0) ? (T)1 / k2 : (T)0);
+    const T kp = sqrt(kx * kx + ky * ky);
+    T e2[3] = {kx * kz / kp * kinv, ky * kz / kp * kinv, -kp * kinv};
+    if (e2[0] != e2[0]) e2[0] = (T)0;
+    if (e2[1] != e2[1]) e2[1] = (T)0;
+    const unsigned iy = (unsigned)(jg < g.by.lo ? jg : jg + (g.by.hi0 - g.by.lo));
+    const unsigned iz = (unsigned)(kc < g.bz.lo ? kc : kc + (g.bz.hi0 - g.bz.lo));
+    const unsigned long long mode = (unsigned)ix + (unsigned long long)q.nkr * (iy + (unsigned long long)g.by.n * iz);
+    T r[4];
+    a99_uniforms<T>(rq, mode, r);
+    double sn, cs;
+    sincospi(2.0 * (double)r[0], &sn, &cs);
+    const T er = (T)cs, ei = (T)sn;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) S[c * g.field + e] = mk<C>((Fk * er) * e2[c], (Fk * ei) * e2[c]);
   }
 }
 

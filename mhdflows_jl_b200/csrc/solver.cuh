@@ -122,6 +122,7 @@ struct mhdf_handle {
   virtual void set_forcing_a99(const mhdf_a99* p) = 0;
   virtual unsigned long long a99_calls() const = 0;
   virtual void div_correction(int group) = 0;
+  virtual void set_random_phase(int group, unsigned long long seed, double k0, double P, double k_peak) = 0;
   virtual void set_vp_field(int which, const void* p) = 0;
   virtual void ipc_export(void* blob) = 0;
   virtual void ipc_import(const void* blobs) = 0;
@@ -773,8 +774,9 @@ struct Solver : mhdf_handle {
   //   P inverse send, R inverse receive, Xin x-pass input (later the product spectra), Xout x-pass output,
   //   P2 forward send, Q forward receive.
   // NOT YET VERIFIED ON HARDWARE (written after the round's GPU budget was spent); off unless MHDF_ZCHUNKS is set.
-  bool spec2 = [] { const char* e = getenv("MHDF_SPEC2"); return e && atoi(e) != 0; }();
-  bool emhd2 = [] { const char* e = getenv("MHDF_EMHD2"); return e && atoi(e) != 0; }();
+  // EMHD x kernel: the shared-memory-multiplier form (k_xfused_emhd2) is the default -- 32.6 ms against 45.3 ms per 512^3 step
+  // for the register form on B200 (profiles/README.md); MHDF_EMHD2=0 selects the register form (bit-identical results)
+  bool emhd2 = [] { const char* e = getenv("MHDF_EMHD2"); return !e || atoi(e) != 0; }();
   int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
   C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
   bool pipe_ok() const {
@@ -943,37 +945,30 @@ struct Solver : mhdf_handle {
     wait_mirror();
     launch_spectral(sa);
   }
-  template <int PHYS, bool A99> void launch_spectral2(const SpecArgs<T>& sa) {
+  template <int PHYS, bool A99, bool VP> void launch_spectral_m(const SpecArgs<T>& sa) {
     const unsigned plane = (unsigned)Kxp * (unsigned)Kyl;
     const dim3 grid((plane + 255u) / 256u, (unsigned)Kz);
     switch (sa.mode) {
-      case STEP_CALCN: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_CALCN, A99>), grid, 256, 0, st, sa); break;
-      case STEP_RK4_1: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_1, A99>), grid, 256, 0, st, sa); break;
-      case STEP_RK4_2: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_2, A99>), grid, 256, 0, st, sa); break;
-      case STEP_RK4_3: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_3, A99>), grid, 256, 0, st, sa); break;
-      case STEP_RK4_4: MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_RK4_4, A99>), grid, 256, 0, st, sa); break;
-      default:         MHDF_LAUNCH((k_spectral2<T, PHYS, STEP_LSRK, A99>), grid, 256, 0, st, sa); break;
+      case STEP_CALCN: MHDF_LAUNCH((k_spectral<T, PHYS, STEP_CALCN, A99, VP>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_1: MHDF_LAUNCH((k_spectral<T, PHYS, STEP_RK4_1, A99, VP>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_2: MHDF_LAUNCH((k_spectral<T, PHYS, STEP_RK4_2, A99, VP>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_3: MHDF_LAUNCH((k_spectral<T, PHYS, STEP_RK4_3, A99, VP>), grid, 256, 0, st, sa); break;
+      case STEP_RK4_4: MHDF_LAUNCH((k_spectral<T, PHYS, STEP_RK4_4, A99, VP>), grid, 256, 0, st, sa); break;
+      default:         MHDF_LAUNCH((k_spectral<T, PHYS, STEP_LSRK, A99, VP>), grid, 256, 0, st, sa); break;
     }
   }
   void launch_spectral(SpecArgs<T>& sa) {
     prof_begin(KC_SPEC);
     const bool driven = (phys == MHDF_MHD) && sa.a99.variant != A99_OFF;   // A99ForceDriving! acts on the MHD path only
     if (vp_on) {   // penalised runs: the product buffer carries the penalisation spectra as well
-      const int grid = spec_grid();
-      if (driven) MHDF_LAUNCH((k_spectral<T, PHYS_MHD, true, true>), grid, 256, 0, st, sa);
-      else if (phys == MHDF_MHD) MHDF_LAUNCH((k_spectral<T, PHYS_MHD, false, true>), grid, 256, 0, st, sa);
-      else MHDF_LAUNCH((k_spectral<T, PHYS_HD, false, true>), grid, 256, 0, st, sa);
-    } else if (spec2) {   // opt-in variant (MHDF_SPEC2=1): same arithmetic, cheaper indexing; see k_spectral2
-      if (driven) launch_spectral2<PHYS_MHD, true>(sa);
-      else if (phys == MHDF_MHD) launch_spectral2<PHYS_MHD, false>(sa);
-      else if (phys == MHDF_HD) launch_spectral2<PHYS_HD, false>(sa);
-      else launch_spectral2<PHYS_EMHD, false>(sa);
+      if (driven) launch_spectral_m<PHYS_MHD, true, true>(sa);
+      else if (phys == MHDF_MHD) launch_spectral_m<PHYS_MHD, false, true>(sa);
+      else launch_spectral_m<PHYS_HD, false, true>(sa);
     } else {
-      const int grid = spec_grid();
-      if (driven) MHDF_LAUNCH((k_spectral<T, PHYS_MHD, true>), grid, 256, 0, st, sa);
-      else if (phys == MHDF_MHD) MHDF_LAUNCH((k_spectral<T, PHYS_MHD>), grid, 256, 0, st, sa);
-      else if (phys == MHDF_HD) MHDF_LAUNCH((k_spectral<T, PHYS_HD>), grid, 256, 0, st, sa);
-      else MHDF_LAUNCH((k_spectral<T, PHYS_EMHD>), grid, 256, 0, st, sa);
+      if (driven) launch_spectral_m<PHYS_MHD, true, false>(sa);
+      else if (phys == MHDF_MHD) launch_spectral_m<PHYS_MHD, false, false>(sa);
+      else if (phys == MHDF_HD) launch_spectral_m<PHYS_HD, false, false>(sa);
+      else launch_spectral_m<PHYS_EMHD, false, false>(sa);
     }
     ++launches;
     CK(cudaGetLastError());
@@ -1087,6 +1082,7 @@ struct Solver : mhdf_handle {
     rhs(reg[iY], sa, true);
     sync_all();
     absorb_red();
+    iStale = iY;   // calcN! left vars.* = irfft(sol): the stale view is the state itself now
     const size_t fe = (P_ > 1) ? (size_t)nkr * Kyl * nz : (size_t)nkr * ny * nz;
     for (int f = 0; f < F; ++f) unpack_to_host(reg[o] + f * cf, (C*)p + (size_t)f * fe);
   }
@@ -1099,7 +1095,7 @@ struct Solver : mhdf_handle {
   void real_to_compact(const void* p, C* dst, int emhd_slot) {
     T* re = reinterpret_cast<T*>(R);
     const size_t n = (size_t)nx * ny * nzl;
-    CK(cudaMemcpyAsync(re, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(re, p, n * sizeof(T), cudaMemcpyDefault, st));
     if (emhd_slot >= 0)   // vars.b* <- the (undealiased) IC real field (IC.jl:86-90)
       CK(cudaMemcpyAsync(bst + (size_t)emhd_slot * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     XArgs<T> xa = xargs();
@@ -1115,7 +1111,11 @@ struct Solver : mhdf_handle {
     check_field(field);
     CK(cudaSetDevice(cfg.device));
     real_to_compact(p, reg[iY] + field * cf, phys == MHDF_EMHD ? field : -1);
-    // vars.* statistics of the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88)
+    // vars.* <- the copied-in field (copyto!(prob_ui, ui), IC.jl:74,88): the stale view follows sol, and so do its statistics
+    if (iStale >= 0 && iStale != iY) {
+      CK(cudaMemcpyAsync(reg[iStale] + field * cf, reg[iY] + field * cf, (size_t)cf * sizeof(C), cudaMemcpyDeviceToDevice, st));
+      sync_all();
+    }
     const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
     st_sum[slot] = red_h->sumsq[0];
     float f;
@@ -1147,7 +1147,7 @@ struct Solver : mhdf_handle {
     if (which < 0 || which > F) throw Err{MHDF_ERR_INVALID, "VP field index out of range (0 chi, 1..3 U0, 4..6 B0)"};
     CK(cudaSetDevice(cfg.device));
     const size_t n = (size_t)nx * ny * nzl;
-    CK(cudaMemcpyAsync(vp_d + (size_t)which * n, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(vp_d + (size_t)which * n, p, n * sizeof(T), cudaMemcpyDefault, st));
     sync_all();
   }
   // DivVCorrection! (group 0) / DivBCorrection! (group 1), Solver/VPSolver.jl:61-137: project sol, then refresh the
@@ -1162,6 +1162,12 @@ struct Solver : mhdf_handle {
     MHDF_LAUNCH((k_divclean<T>), spec_grid(), 256, 0, st, geom(), Y);
     ++launches;
     CK(cudaGetLastError());
+    refresh_vars(f0);
+  }
+  // vars.* of the three fields starting at state field f0 <- c2r of sol (ldiv!(vars.bx, rfftplan, deepcopy(bxh)) ...,
+  // VPSolver.jl:95-97,133-135): the stale register, EMHD's real-space b, and the CFL maxima / energies of those fields.
+  void refresh_vars(int f0) {
+    C* Y = reg[iY] + (size_t)f0 * cf;
     if (iStale >= 0 && iStale != iY)
       CK(cudaMemcpyAsync(reg[iStale] + (size_t)f0 * cf, Y, 3 * (size_t)cf * sizeof(C), cudaMemcpyDeviceToDevice, st));
     T* re = reinterpret_cast<T*>(R);
@@ -1183,6 +1189,36 @@ struct Solver : mhdf_handle {
       st_max[slot] = (double)f;
     }
   }
+  // DivFreeSpectraMap (utils/IC.jl:130-179) followed by SetUpProblemIC! (IC.jl:41-109) for one vector field, on the device:
+  // the random-phase power-law spectra go straight onto the retained modes of sol (the reference's irfft -> copy -> rfft round
+  // trip is the identity on them: the map is zero on the kr = 0 plane and dealiased), then vars.* are refreshed from sol.
+  void set_random_phase(int group, unsigned long long seed, double k0, double Pw, double k_peak) override {
+    CK(cudaSetDevice(cfg.device));
+    int f0;
+    if (group == 0) { if (phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "random-phase field: the EMHD state has no velocity (IC.jl:69)"}; f0 = 0; }
+    else if (group == 1) { if (phys == MHDF_HD) throw Err{MHDF_ERR_INVALID, "random-phase field: the HD state has no magnetic field"}; f0 = (phys == MHDF_EMHD) ? 0 : 3; }
+    else throw Err{MHDF_ERR_INVALID, "group must be 0 (velocity) or 1 (magnetic field)"};
+    if (!(Pw > 0) || !std::isfinite(k0) || !std::isfinite(k_peak)) throw Err{MHDF_ERR_INVALID, "random-phase field: need P > 0 and finite k0, k_peak"};
+    DfsmArgs<T> q;
+    q.nkr = nkr; q.ny = ny; q.nz = nz;
+    q.dkx = 2.0 * M_PI / cfg.Lx; q.dky = 2.0 * M_PI / cfg.Ly; q.dkz = 2.0 * M_PI / cfg.Lz;
+    q.k0 = (T)k0; q.kpeak = (T)k_peak; q.amp = (T)0;
+    q.seed_lo = (unsigned)seed; q.seed_hi = (unsigned)(seed >> 32);
+    CK(cudaMemsetAsync(diag_d, 0, 8 * sizeof(double), st));
+    MHDF_LAUNCH((k_dfsm_norm<T>), pack_grid(), 256, 0, st, q, diag_d);   // every rank sums the whole array: no collective needed
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(diag_h, diag_d, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    sync_all();
+    const double intF = diag_h[0];
+    if (!(intF > 0) || !std::isfinite(intF)) throw Err{MHDF_ERR_INVALID, "random-phase field: the spectrum k^k0 (k >= k_peak) is empty on this grid"};
+    const double dx = cfg.Lx / nx, dy = cfg.Ly / ny, dz = cfg.Lz / nz;
+    q.amp = (T)std::sqrt(Pw * 3 * (cfg.Lx / dx) * (cfg.Ly / dy) * (cfg.Lz / dz) / intF * (1 / dx / dy / dz));   // IC.jl:150
+    MHDF_LAUNCH((k_dfsm_fill<T>), spec_grid(), 256, 0, st, geom(), q, reg[iY] + (size_t)f0 * cf);
+    ++launches;
+    CK(cudaGetLastError());
+    refresh_vars(f0);
+  }
   const C* source(int which) const {
     if (which == MHDF_STALE && iStale >= 0) return reg[iStale];
     return reg[iY];
@@ -1195,7 +1231,7 @@ struct Solver : mhdf_handle {
     XArgs<T> xa = xargs();
     xa.real_io = re; xa.in = Q; xa.out = nullptr;
     launch_xplain<+1>(xa);
-    CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nzl * sizeof(T), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p, re, (size_t)nx * ny * nzl * sizeof(T), cudaMemcpyDefault, st));
     sync_all();
   }
   void set_spectral(int field, const void* p) override {
@@ -1203,7 +1239,7 @@ struct Solver : mhdf_handle {
     CK(cudaSetDevice(cfg.device));
     const int nyh = (P_ > 1) ? Kyl : ny;     // slab runs exchange the local compact ky rows directly
     const size_t n = (size_t)nkr * nyh * nz;
-    CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyDefault, st));
     MHDF_LAUNCH((k_pack<T>), pack_grid(), 256, 0, st, R, reg[iY] + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
@@ -1220,7 +1256,7 @@ struct Solver : mhdf_handle {
     MHDF_LAUNCH((k_pack<T>), pack_grid(), 256, 0, st, R, const_cast<C*>(comp), nkr, nyh, nz, Kx, Kxp, by, bz, 1, P_ > 1);
     ++launches;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(host, R, n * sizeof(C), cudaMemcpyDefault, st));
     sync_all();
   }
   void get_spectral(int field, int which, void* p) override {

@@ -379,11 +379,27 @@ class Problem:
     def _field_id(self, f):
         return self._names[f] if isinstance(f, str) else int(f)
 
-    def set_real(self, f, arr):
+    def _real_ptr(self, arr, writable=False):
+        """Address of a real field for the C ABI: a NumPy array (host) or any object with `data_ptr()` -- a torch tensor,
+        host or CUDA: the library copies with cudaMemcpyDefault, so device-resident fields (the reference's CuArray
+        `vars.*`) never bounce through the host.  Returns (pointer, keep-alive object)."""
+        if hasattr(arr, "data_ptr"):
+            want = "float32" if self.T is np.float32 else "float64"
+            if tuple(arr.shape) != self._real_shape or str(arr.dtype).split(".")[-1] != want or not arr.is_contiguous():
+                raise ValueError(f"expected a contiguous {want} tensor of shape {self._real_shape}")
+            return arr.data_ptr(), arr
+        if writable:
+            if arr.shape != self._real_shape or arr.dtype != self.T or not arr.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
+            return arr.ctypes.data, arr
         a = np.ascontiguousarray(arr, dtype=self.T)
         if a.shape != self._real_shape:
             raise ValueError(f"expected shape {self._real_shape}, got {a.shape}")
-        L.check(self._h, L.lib().mhdf_set_real(self._h, self._field_id(f), a.ctypes.data))
+        return a.ctypes.data, a
+
+    def set_real(self, f, arr):
+        ptr, keep = self._real_ptr(arr)
+        L.check(self._h, L.lib().mhdf_set_real(self._h, self._field_id(f), ptr))
 
     def set_forcing(self, f, arr):
         """Constant real-space forcing of field `f` (the calcF! hook for time-independent forcings); None removes it."""
@@ -429,9 +445,8 @@ class Problem:
         """Real-space field (c2r on demand).  `out`: optional preallocated (e.g. pinned) array to receive it."""
         if out is None:
             out = np.empty(self._real_shape, dtype=self.T)
-        elif out.shape != self._real_shape or out.dtype != self.T or not out.flags.c_contiguous:
-            raise ValueError("out must be a C-contiguous array of the field's shape and dtype")
-        L.check(self._h, L.lib().mhdf_get_real(self._h, self._field_id(f), which, out.ctypes.data))
+        ptr, keep = self._real_ptr(out, writable=True)
+        L.check(self._h, L.lib().mhdf_get_real(self._h, self._field_id(f), which, ptr))
         return out
 
     def set_spectral(self, f, arr):
@@ -713,40 +728,28 @@ def spectralline(prob, field, nbins=None):
     return Pk.astype(prob.T), kr
 
 
-def DivFreeSpectraMap(grid, *, k_peak=0.0, P=1, k0=-5 / 3 / 2, b=1, theta=None, seed=None):
-    """DivFreeSpectraMap(grid; k_peak, P, k0, b) (utils/IC.jl:130-179): random-phase power-law solenoidal field.
-    Host-side initial-condition generator (one-off, not on the hot path).  The uniform random numbers are either
-    injected (`theta`, shape (nz, ny, nkr) in [0,1)) or drawn from numpy's default_rng(seed) -- Julia's RNG stream
-    cannot be reproduced."""
-    import scipy.fft as sfft
+DFSM_CALL = 0x7FFFFFFF44465350      # counter tag of the device random-phase stream (csrc/kernels.cuh: DFSM_CALL_HI/LO)
 
-    T = grid.T
-    CT = np.complex64 if T is np.float32 else np.complex128
-    if theta is None:
-        theta = np.random.default_rng(seed).random((grid.nm, grid.nl, grid.nkr), dtype=np.float64).astype(T)
-    kx, ky, kz = grid.kr, grid.l, grid.m
-    Krsq = grid.Krsq
-    with np.errstate(divide="ignore", invalid="ignore"):
-        inv = (T(1) / Krsq).astype(T)
-        inv[0, 0, 0] = 0
-        kinv, k = np.sqrt(inv), np.sqrt(Krsq)
-        kperp = np.sqrt(kx ** 2 + ky ** 2) + 0 * kz
-        dkm2 = 1 / (k + 1) ** 2
-        Fk = k ** T(k0)
-        Fk[0, 0, 0] = 0
-        Fk[..., 0] = 0
-        Fk[k < k_peak] = 0
-        intF = float(np.sum((Fk * dkm2).astype(np.float64)))
-        A = math.sqrt(P * 3 * (grid.Lx / grid.dx) * (grid.Ly / grid.dy) * (grid.Lz / grid.dz) / intF / grid.dx / grid.dy / grid.dz)
-        Fk = (Fk * T(A)).astype(T)
-        e2x, e2y, e2z = kx * kz / kperp * kinv, ky * kz / kperp * kinv, -kperp * kinv
-    e2x[np.isnan(e2x)] = 0
-    e2y[np.isnan(e2y)] = 0
-    eith = np.exp(1j * theta.astype(np.float64) * 2 * math.pi).astype(CT)
-    msk = grid.retained_mask()
-    out = []
-    for e2 in (e2x, e2y, e2z):
-        Fh = (Fk * eith * e2).astype(CT)
-        Fh[~msk] = 0
-        out.append(sfft.irfftn(Fh, s=(grid.nz, grid.ny, grid.nx), axes=(0, 1, 2)).astype(T))
-    return tuple(out)
+
+def SetUpRandomPhaseIC(prob, *, seed_u=None, seed_b=None, k_peak=0.0, P=1, k0=-5 / 3 / 2):
+    """`Fx, Fy, Fz = DivFreeSpectraMap(grid; ...)` followed by `SetUpProblemIC!(prob; ux = Fx, ...)` (utils/IC.jl:130-179, 41-109)
+    without leaving the device: the velocity (seed_u) and / or the magnetic field (seed_b) of `prob` are set to random-phase
+    power-law solenoidal fields (mhdf_set_random_phase).  Works on slab-decomposed problems (every rank fills its modes)."""
+    if seed_u is not None and not prob.flag.e:
+        L.check(prob._h, L.lib().mhdf_set_random_phase(prob._h, 0, int(seed_u), float(k0), float(P), float(k_peak)))
+    if seed_b is not None and prob.flag.b:
+        L.check(prob._h, L.lib().mhdf_set_random_phase(prob._h, 1, int(seed_b), float(k0), float(P), float(k_peak)))
+
+
+def DivFreeSpectraMap(grid, *, k_peak=0.0, P=1, k0=-5 / 3 / 2, b=1, seed=0, dev=None):
+    """DivFreeSpectraMap(grid; k_peak, P, k0, b) (utils/IC.jl:130-179): random-phase power-law solenoidal field, returned as
+    the three real arrays Fx, Fy, Fz like the reference.  Built on the device (the reference builds it on grid.device): a
+    scratch HD problem on `grid` runs mhdf_set_random_phase and the fields are read back.  `seed` keys the Philox stream of the
+    phases (Julia's rand stream cannot be reproduced); `b` is unused by the reference as well.  To initialise a problem
+    directly, without the host round trip, use SetUpRandomPhaseIC."""
+    p = Problem(dev if dev is not None else GPU(), nx=grid.nx, ny=grid.ny, nz=grid.nz, Lx=grid.Lx, Ly=grid.Ly, Lz=grid.Lz, T=grid.T)
+    try:
+        SetUpRandomPhaseIC(p, seed_u=seed, k_peak=k_peak, P=P, k0=k0)
+        return tuple(p.get_real(i, L.FRESH) for i in range(3))
+    finally:
+        p.close()

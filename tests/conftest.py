@@ -21,11 +21,3 @@ def pytest_collection_finish(session):
     for name, f in (("library", "test_emulated_library.py"), ("kernels", "test_kernel_emulation.py")):
         if f in files and any(os.path.basename(str(i.fspath)) == f and not i.get_closest_marker("skip") for i in session.items):
             emu_build.start(name)
-
-
-def pytest_collection_modifyitems(config, items):
-    """GPU runs use -x: keep the cases whose kernels were measured on hardware in front.  The EMHD x kernel changed shape after the
-    last hardware run, so the EMHD-parametrised GPU cases move behind the HD / MHD ones (stable otherwise)."""
-    def late(item):
-        return item.get_closest_marker("gpu") is not None and "emhd" in item.nodeid.lower() and "zforcing" not in item.nodeid
-    items[:] = [i for i in items if not late(i)] + [i for i in items if late(i)]

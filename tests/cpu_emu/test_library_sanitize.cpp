@@ -1,7 +1,7 @@
 // Driver for sanitizer runs of the WHOLE library on the CPU emulator (api.cu + solver.cuh + kernels compiled with
 // -DMHDF_CPU_EMU -fsanitize=address,undefined or -fsanitize=thread and linked with this file): device buffers are heap blocks
 // of exactly the sizes the solver computes, so any kernel or copy that leaves a buffer is a heap-buffer-overflow.
-// Drives the C ABI only (no oracle): HD / MHD / EMHD, RK4 / LSRK54, both EMHD x-kernel forms, k_spectral2, constant forcing,
+// Drives the C ABI only (no oracle): HD / MHD / EMHD, RK4 / LSRK54, both EMHD x-kernel forms, constant forcing,
 // A99 driving, volume penalisation, divergence corrections, calcN, get/set real and spectral, diagnostics, spectrum.
 // Built and run by tests/test_emulated_library.py when MHDF_EMU_SANITIZE_LIB=1.
 #include <cmath>
@@ -71,14 +71,13 @@ int main() {
   run<float>("mhd rk4 32x16x16 forcing + a99", MHDF_MHD, MHDF_RK4, 32, 16, 16, false, true, true);
   run<float>("mhd lsrk54 16^3", MHDF_MHD, MHDF_LSRK54, 16, 16, 16, false, false, false);
   run<double>("mhd rk4 f64 16x16x32", MHDF_MHD, MHDF_RK4, 16, 16, 32, false, false, false);
-  run<float>("emhd rk4 16x16x32", MHDF_EMHD, MHDF_RK4, 16, 16, 32, false, false, false);
+  setenv("MHDF_EMHD2", "0", 1);
+  run<float>("emhd rk4 register-form x kernel 16x16x32", MHDF_EMHD, MHDF_RK4, 16, 16, 32, false, false, false);
   setenv("MHDF_EMHD2", "1", 1);
   run<float>("emhd lsrk54 second x-kernel form 16^3", MHDF_EMHD, MHDF_LSRK54, 16, 16, 16, false, false, false);
   run<double>("emhd rk4 f64 second x-kernel form 16^3", MHDF_EMHD, MHDF_RK4, 16, 16, 16, false, false, false);
-  setenv("MHDF_EMHD2", "0", 1);
-  setenv("MHDF_SPEC2", "1", 1);
-  run<float>("mhd rk4 k_spectral2 a99 16^3", MHDF_MHD, MHDF_RK4, 16, 16, 16, false, true, false);
-  setenv("MHDF_SPEC2", "0", 1);
+  unsetenv("MHDF_EMHD2");
+  run<float>("mhd rk4 a99 16^3", MHDF_MHD, MHDF_RK4, 16, 16, 16, false, true, false);
   run<float>("hd rk4 volume penalisation 16x16x32", MHDF_HD, MHDF_RK4, 16, 16, 32, true, false, false);
   run<float>("mhd rk4 volume penalisation + a99 16^3", MHDF_MHD, MHDF_RK4, 16, 16, 16, true, true, false);
   run<double>("mhd lsrk54 f64 volume penalisation 16^3", MHDF_MHD, MHDF_LSRK54, 16, 16, 16, true, false, false);

@@ -59,6 +59,43 @@ def smoke_mhd_rk4_against_the_oracle():
     gp.close()
 
 
+def _random_phase_case(M, O, FO, T, tol, dims, nranks_note=""):
+    """mhdf_set_random_phase against oracle.DivFreeSpectraMap with the device's Philox phases injected (IC.jl:130-179)."""
+    nx, ny, nz = dims
+    L3 = dict(Lx=2 * np.pi, Ly=3.0, Lz=5.0)
+    gp = M.Problem(M.GPU(), nx=nx, ny=ny, nz=nz, T=T, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, **L3)
+    M.SetUpRandomPhaseIC(gp, seed_u=1234, seed_b=(5 << 32) + 678, k0=-5 / 6, P=2.0, k_peak=1.5)
+    g = O.Grid(nx, ny, nz, L3["Lx"], L3["Ly"], L3["Lz"], T)
+    worst = 0.0
+    for names, seed in ((("ux", "uy", "uz"), 1234), (("bx", "by", "bz"), (5 << 32) + 678)):
+        theta = FO.PhiloxField(seed, g).uniforms(M.DFSM_CALL)[0]
+        ref = O.DivFreeSpectraMap(g, theta, k_peak=1.5, P=2.0, k0=-5 / 6)
+        for nm, r in zip(names, ref):
+            assert np.linalg.norm(r) > 0
+            worst = max(worst, O.rel_l2(gp.get_real(nm, M.FRESH), r), O.rel_l2(gp.get_real(nm, M.STALE), r))
+    assert worst < tol, worst
+    # SetUpProblemIC! semantics: sol = rfft(F), vars.* = F  ->  the stale statistics are those of F
+    op = O.Problem(nx=nx, ny=ny, nz=nz, T=T, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, **L3)
+    u = O.DivFreeSpectraMap(g, FO.PhiloxField(1234, g).uniforms(M.DFSM_CALL)[0], k_peak=1.5, P=2.0, k0=-5 / 6)
+    b = O.DivFreeSpectraMap(g, FO.PhiloxField((5 << 32) + 678, g).uniforms(M.DFSM_CALL)[0], k_peak=1.5, P=2.0, k0=-5 / 6)
+    O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+    ke, me = gp.energy(M.STALE)
+    ko, mo = O.ProbDiagnostic(op, rounded=False)
+    assert abs(ke - ko) < 1e-4 * abs(ko) and abs(me - mo) < 1e-4 * abs(mo)
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
+    gp.close()
+    return worst
+
+
+@case
+def random_phase_ic_on_device_matches_the_oracle():
+    _random_phase_case(M, O, FO, np.float32, F32_TOL, (16, 32, 16))
+    _random_phase_case(M, O, FO, np.float64, F64_TOL, (16, 16, 16))
+
+
 @case
 def a99_host_variant_calcN_steps_counter():
     op, gp = _forced_pair(M, O, FO, "host", np.float32, dims=DIMS)
@@ -299,7 +336,7 @@ def _emhd_run(flag, stepper, T):
     M.stepforward(p)
     out = (p.sol, p.get_real("by", M.STALE), p.stale_stats()[0])
     p.close()
-    os.environ["MHDF_EMHD2"] = "0"
+    os.environ.pop("MHDF_EMHD2", None)
     return out
 
 
@@ -310,21 +347,6 @@ def second_emhd_kernel_form_is_bit_identical():
         assert np.linalg.norm(a[0]) > 0
         for x, y in zip(a, b):
             assert np.array_equal(x, y), stepper
-
-
-@case
-def optin_spectral_kernel_is_bit_identical_with_forcing_and_driving():
-    sols = []
-    for flag in ("0", "1"):
-        os.environ["MHDF_SPEC2"] = flag
-        _, gp = _forced_pair(M, O, FO, "host", np.float32, dims=(16, 16, 16))
-        g = O.Grid(16, T=np.float32)
-        gp.set_forcing("uy", (0.3 * np.sin(2 * g.x.reshape(1, 1, -1)) * np.ones((16, 16, 16))).astype(np.float32))
-        M.stepforward(gp)
-        sols.append(gp.sol)
-        gp.close()
-    os.environ["MHDF_SPEC2"] = "0"
-    assert np.array_equal(sols[0], sols[1]) and np.linalg.norm(sols[0]) > 0
 
 
 @case

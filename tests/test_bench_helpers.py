@@ -47,4 +47,41 @@ def test_cufft_reference_point_never_takes_the_bench_down():
     # counts used for the per-RHS extrapolation
     import inspect
     src = inspect.getsource(bench.cufft_reference_point)
-    assert '"mhd": (6, 9)' in src and '"mhd": 36' in src and '"emhd": 51' in src
+    assert bench.XPASS_FIELDS["mhd"] == (6, 9) and '"mhd": 36' in src and '"emhd": 51' in src
+
+
+def test_taylor_green_fields_equal_the_direct_formula():
+    """The plane-by-plane builder must reproduce (sin x cos y) cos z ... evaluated in Float64 and rounded, bit for bit."""
+    n, dims = 16, (16, 32, 16)
+    nx, ny, nz = dims
+    dx = 2 * math.pi / n
+    X = (np.float32(-math.pi * nx / n) + np.float32(dx) * np.arange(nx)).astype(np.float64).reshape(1, 1, -1)
+    Y = (np.float32(-math.pi * ny / n) + np.float32(dx) * np.arange(ny)).astype(np.float64).reshape(1, -1, 1)
+    Z = (np.float32(-math.pi * nz / n) + np.float32(dx) * np.arange(nz)).astype(np.float64).reshape(-1, 1, 1)
+    want = [np.sin(X) * np.cos(Y) * np.cos(Z), -np.cos(X) * np.sin(Y) * np.cos(Z), np.zeros((nz, ny, nx)),
+            np.cos(X) * np.sin(Y) * np.sin(Z), np.sin(X) * np.cos(Y) * np.sin(Z), -2 * np.sin(X) * np.sin(Y) * np.cos(Z)]
+    got = bench.tg_fields(n, dims=dims)
+    for w, (g, _) in zip(want, got):
+        assert np.array_equal(w.astype(np.float32), g)
+    import torch
+    for i in range(6):
+        assert np.array_equal(bench.tg_field_device(n, dims, i, "cpu").numpy(), got[i][0])
+
+
+def test_defaults_are_the_north_star_configuration_and_both_arms_share_the_config():
+    assert bench.DEFAULT_WORKLOAD == "mhd1024" and bench.WORKLOADS["mhd1024"][:3] == ("mhd", 1024, "RK4")
+    a = bench.config_for("mhd1024", (1024, 1024, 1024), 8, True)
+    b = bench.config_for("mhd1024", (1024, 1024, 1024), 8, True)
+    assert a == b and a["workload"] == "mhd1024" and a["grid"] == [1024, 1024, 1024]
+    (kind, ns, stepper, *_), text = bench.ref_sample("mhd1024")
+    assert (kind, ns, stepper) == ("mhd", bench.REF_SAMPLE_N, "RK4") and "bounded sample" in text
+
+
+def test_pruned_byte_model_counts_every_pass_once():
+    info = {"Kxp": 344, "Ky": 682, "Kz": 682}
+    step, x = bench.pruned_bytes("mhd", "RK4", info, (1024, 1024, 1024), 1, 6)
+    cf, zf, xf = 344 * 682 * 682 * 8, 1024 * 682 * 344 * 8, 1024 * 1024 * 344 * 8
+    assert x == 15 * xf
+    stage = 6 * (cf + zf) + 6 * (zf + xf) + 15 * xf + 9 * (xf + zf) + 9 * (zf + cf)
+    assert step == 4 * stage + (4 * 9 + 16 * 6) * cf
+    assert 0.75e12 < step < 0.95e12          # ~0.85 TB per 1024^3 step

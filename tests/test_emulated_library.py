@@ -3,7 +3,7 @@ boundary) and the kernel sources are compiled as plain C++ against tests/cpu_emu
 inert streams, kernel launches = one OS thread per CUDA thread) into a throw-away libmhdflows_b200_emu.so; the end-to-end
 cases of tests/emu_lib_cases.py then run through the ordinary Python mirror with MHDF_LIB pointing at it, against the oracle,
 on 16-point grids.  This is what exercises the HOST side of features written without GPU access (A99 driving, volume
-penalisation, divergence corrections, second EMHD kernel form, k_spectral2, HDF5 dumps) before their first hardware run.
+penalisation, divergence corrections, second EMHD kernel form, HDF5 dumps) before their first hardware run.
 
 The emulated library is test infrastructure: it is built into a temporary directory, never by mhdflows_jl_b200.build, and
 the product has no path to it other than the MHDF_LIB tuning variable (tests/test_abi.py checks the no-GPU failure of the
@@ -23,7 +23,7 @@ CSRC = os.path.join(ROOT, "mhdflows_jl_b200", "csrc")
 # case-name filters of the concurrent workers (balanced by measured run time)
 GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5"],
           ["a99_gpu", "a99_lsrk54", "a99_reproducible", "div_b_correction_emhd"],
-          ["div_corrections", "volume_penalisation_hd", "optin_spectral"],
+          ["div_corrections", "volume_penalisation_hd", "random_phase"],
           ["volume_penalisation_mhd", "volume_penalisation_time", "second_emhd"],
           ["regress_"]]
 
@@ -50,7 +50,8 @@ def emu_results():
     for cmd in ([gxx, "-shared", "-pthread", "-o", lib] + objs + ["-ldl"], [gxx, "-pthread", "-o", exe, drv] + objs + ["-ldl"]):
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-4000:]
-    env = dict(os.environ, MHDF_LIB=lib, MHDF_EMHD2="0", MHDF_SPEC2="0")
+    env = dict(os.environ, MHDF_LIB=lib)
+    env.pop("MHDF_EMHD2", None)
     env.pop("MHDF_ZCHUNKS", None)
     running = {("cases", i): subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "emu_lib_cases.py")] + g, stdout=subprocess.PIPE,
                                               stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT) for i, g in enumerate(GROUPS)}

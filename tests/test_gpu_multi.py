@@ -37,9 +37,6 @@ def test_slab_run_equals_single_gpu(peer):
         assert float(m.group(3)) < 1e-10, l                                 # reductions: summation order differs
 
 
-@pytest.mark.xfail(strict=False, reason="z-chunk pipelined slab path (MHDF_ZCHUNKS) was written after round 1's GPU budget "
-                                        "was spent: its kernel addressing is verified on the CPU emulator, its stream / event "
-                                        "orchestration has not run on hardware yet")
 def test_pipelined_slab_run_equals_single_gpu():
     if _ngpu() < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -55,8 +52,6 @@ def test_pipelined_slab_run_equals_single_gpu():
         assert m and float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l
 
 
-@pytest.mark.xfail(strict=False, reason="A99 driving and the divergence corrections were written after round 1's GPU budget was "
-                                        "spent (kernels verified on the CPU emulator); first hardware run pending")
 def test_driven_slab_run_equals_single_gpu():
     """A99 random driving + DivVCorrection!/DivBCorrection! on 2 GPUs: the Philox counter is the global mode index, so the
     slab run draws the same random numbers as the single-GPU run and the state stays bit-identical."""

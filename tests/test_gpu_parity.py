@@ -294,8 +294,6 @@ def test_n97_taylor_green_forcing(M, O):
         gp.close()
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's last hardware run (same policy as tests/test_gpu_zforcing.py): the same "
-                   "path passes on the emulated library (tests/emu_lib_cases.py::hdf5); a pass shows up as XPASS")
 def test_time_integrator_save_and_restart(M, O, tmp_path):
     """save=true path of TimeIntegrator! (integrator.jl:44-51,136-141) and Restart! (:208-257): dumps hold the stale vars
     and the time; a restarted problem starts from exactly those fields."""
@@ -316,31 +314,9 @@ def test_time_integrator_save_and_restart(M, O, tmp_path):
     gp.close()
 
 
-@pytest.mark.xfail(strict=False, reason="opt-in spectral kernel variant (MHDF_SPEC2=1) was written after round 1's GPU budget was "
-                                        "spent: bit-identical to the default kernel on the CPU emulator, not yet run on hardware")
-def test_optin_spectral_variant_is_bit_identical():
-    """k_spectral2 (32-bit indexing, stage mode as template parameter) against the default k_spectral, in a subprocess so
-    that a fault in the unverified variant cannot poison this process's CUDA context."""
-    import os
-    import re
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, os.path.join(root, "tools", "spec2_check.py")], capture_output=True, text=True,
-                         timeout=300, cwd=root)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    lines = [l for l in res.stdout.splitlines() if l.startswith("spec2-vs-default")]
-    assert len(lines) == 6
-    for l in lines:
-        m = re.search(r"max abs diff ([0-9.e+-]+) norm ([0-9.e+-]+)", l)
-        assert m and float(m.group(1)) == 0.0 and float(m.group(2)) > 0.0, l
-
-
-
-@pytest.mark.xfail(strict=False, reason="opt-in second form of the EMHD x kernel (MHDF_EMHD2=1) was written without GPU access: "
-                                        "bit-identical to the default kernel on the CPU emulator, not yet run on hardware")
-def test_optin_emhd_kernel_is_bit_identical():
-    """k_xfused_emhd2 (multipliers in shared memory, rolled loops) against the EMHD branch of k_xfused, in a subprocess."""
+def test_emhd_kernel_forms_are_bit_identical():
+    """k_xfused_emhd2 (multipliers in shared memory, rolled loops; the default) against the register form (the EMHD branch of
+    k_xfused, MHDF_EMHD2=0), in a subprocess."""
     import os
     import re
     import subprocess

@@ -1,14 +1,11 @@
-"""GPU parity tests of the SURVEY 8f rows added after the round's GPU budget was spent: A99 random driving (both reference
-implementations) and DivVCorrection! / DivBCorrection!, through the C ABI against oracle/forcing_oracle.py.
-
-The kernels were verified on the CPU emulator (tests/cpu_emu: Philox known answers, forcing of every mode, k_divclean), but
-this file has NOT RUN ON HARDWARE yet -- hence the non-strict xfail guard: a pass shows up as XPASS, a failure does not
-hide the verified suite that runs before it.  Remove the guard after the first green hardware run."""
+"""GPU parity tests of the SURVEY 8f rows: A99 random driving (both reference implementations), DivVCorrection! /
+DivBCorrection! and the volume-penalisation terms, through the C ABI against oracle/forcing_oracle.py.
+(First green hardware run: round 2, profiles/r02_c1_pytest.log; the kernels are also checked on the CPU emulator,
+tests/cpu_emu: Philox known answers, forcing of every mode, k_divclean.)"""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written without GPU access; first hardware run pending")]
+pytestmark = pytest.mark.gpu
 
 F32_TOL = 1e-5
 F64_TOL = 1e-12

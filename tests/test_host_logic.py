@@ -39,19 +39,6 @@ def test_grid_matches_oracle_grid(dims):
         assert g.aliased_range(n) == O.aliased_range(n)
 
 
-def test_divfree_spectra_map_matches_oracle():
-    g = P._Grid(24, 24, 24, 2 * math.pi, 2 * math.pi, 2 * math.pi, np.float64)
-    o = O.Grid(24, T=np.float64)
-    theta = np.random.default_rng(3).random((24, 24, 13))
-    a = M.DivFreeSpectraMap(g, theta=theta, k0=-5 / 6)
-    b = O.DivFreeSpectraMap(o, theta, k0=-5 / 6)
-    for x, y in zip(a, b):
-        assert O.rel_l2(x, y) < 1e-12
-    c = M.DivFreeSpectraMap(g, seed=1234, k0=-5 / 6)
-    d = O.random_phase_ic(o, 1234)
-    assert O.rel_l2(c[0], d[0]) < 1e-12
-
-
 class _FakeClock:
     def __init__(self):
         self.t, self.step, self.dt = 0.0, 0, 0.1

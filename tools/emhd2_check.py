@@ -1,6 +1,7 @@
-"""Opt-in second form of the EMHD x kernel (MHDF_EMHD2=1: multipliers in shared memory, rolled loops, 168 registers) vs the
-default one: spectral state, stale real b and CFL statistics after a few steps must be bit-identical (same arithmetic in
-the same order) for RK4 / LSRK54, Float32 / Float64, 32..128-point rows.  Run under gpurun; one line per case, then timings."""
+"""The two forms of the EMHD x kernel -- MHDF_EMHD2=1 (default since round 2: multipliers in shared memory, rolled loops, 168
+registers) and MHDF_EMHD2=0 (register form, the EMHD branch of k_xfused): spectral state, stale real b and CFL statistics after a
+few steps must be bit-identical (same arithmetic in the same order) for RK4 / LSRK54, Float32 / Float64, 32..128-point rows.
+Run under gpurun; one line per case, then timings."""
 import os
 import sys
 

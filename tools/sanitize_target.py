@@ -40,12 +40,9 @@ run("hd 32x64x32 rk4", nx=32, ny=64, nz=32, nu=1e-2, dt=1e-3)
 run("mhd 64x32x32 rk4", nx=64, ny=32, nz=32, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True)
 run("mhd 32^3 lsrk54 hyper", nx=32, nu=1e-2, eta=1e-2, n_nu=2, dt=1e-3, B_field=True, stepper="LSRK54")
 run("emhd 32^3 rk4", nx=32, dt=1e-4, B_field=True, EMHD=True)
-os.environ["MHDF_EMHD2"] = "1"
-run("emhd 32x32x64 rk4 second x-kernel form", nx=32, ny=32, nz=64, dt=1e-4, B_field=True, EMHD=True)
 os.environ["MHDF_EMHD2"] = "0"
-os.environ["MHDF_SPEC2"] = "1"
-run("mhd 32^3 rk4 k_spectral2", nx=32, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True)
-os.environ["MHDF_SPEC2"] = "0"
+run("emhd 32x32x64 rk4 register form of the x kernel", nx=32, ny=32, nz=64, dt=1e-4, B_field=True, EMHD=True)
+os.environ["MHDF_EMHD2"] = "1"
 uv, fn = M.GetA99vars_And_function(M.GPU(), 32, 32, 32)
 run("mhd 32^3 a99 driving", setup=lambda p: M.SetUpFk(p, kf=2, P=1e-3), nx=32, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, calcF=fn, usr_vars=uv)
 
