@@ -183,6 +183,42 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
   }
 }
 
+// ---- cross-rank flags of the slab exchange ----------------------------------------------------------------------
+// A rank announces "my piece for slot s has landed in your receive buffer" by storing the exchange's epoch into word
+// [s][sender] of the RECEIVER's flag array (peer memory mapped with CUDA IPC); the receiver's compute stream spins on its own
+// array before it reads the buffer.  k_flag_set runs on the copy stream right behind the copy-engine push (stream order: the
+// push has completed), k_flag_wait on the compute stream.  Replaces the two 1-element ncclAllReduce barriers per exchange of
+// round 1 (40 tiny collectives per step).  A wait that sees nothing for MHDF_FLAG_TIMEOUT_NS gives up and reports through
+// `err` (host-mapped): a lost peer becomes an error code, not a hung GPU.
+#ifndef MHDF_FLAG_TIMEOUT_NS
+#define MHDF_FLAG_TIMEOUT_NS 20000000000ULL
+#endif
+#ifdef MHDF_CPU_EMU
+inline void st_flag(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned ld_flag(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+#else
+__device__ __forceinline__ void st_flag(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__global__ void __launch_bounds__(32) k_flag_set(unsigned* flag, unsigned v) {
+  if (threadIdx.x == 0) { __threadfence_system(); st_flag(flag, v); }
+}
+// thread q < n (q != skip) waits until flags[q] has reached epoch v (wrap-safe comparison)
+__global__ void __launch_bounds__(32) k_flag_wait(const unsigned* flags, unsigned v, int n, int skip, int* err) {
+  const int q = threadIdx.x;
+  if (q < n && q != skip) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(ld_flag(flags + q) - v) < 0) {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > MHDF_FLAG_TIMEOUT_NS) { *((volatile int*)err) = 1 + q; break; }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // x pass: rows are contiguous.  Real rows of length N are handled as M = N/2 complex points.
 // ------------------------------------------------------------------------------------------------

@@ -127,7 +127,7 @@ struct mhdf_handle {
   virtual void ipc_export(void* blob) = 0;
   virtual void ipc_import(const void* blobs) = 0;
 };
-struct IpcBlob { cudaIpcMemHandle_t r, q; int device; int pad[15]; };
+struct IpcBlob { cudaIpcMemHandle_t r, q, f; int device; int pad[15]; };
 
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
@@ -166,6 +166,14 @@ struct Solver : mhdf_handle {
   int NCS = [] { const char* e = getenv("MHDF_COPY_STREAMS"); int n = e ? atoi(e) : 7; return n < 1 ? 1 : (n > NCS_MAX ? NCS_MAX : n); }();
   cudaStream_t cs[NCS_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copy streams (copy engines, no SMs)
   float* bar_d = nullptr;
+  // cross-rank flags (kernels.cuh: k_flag_set / k_flag_wait): word [slot][sender] of the receiver's array holds the epoch of the
+  // last exchange of that slot whose piece from `sender` has landed; slot = direction * 32 + z chunk
+  static constexpr int FSLOTS = 64;
+  unsigned* flags_d = nullptr;
+  std::vector<unsigned*> peerF;
+  unsigned epoch_[FSLOTS] = {};
+  int* ferr_h = nullptr;   // host-mapped: set by a wait that timed out
+  bool use_flags = [] { const char* e = getenv("MHDF_FLAGS"); return !e || atoi(e) != 0; }();
   // state registers (compact, F fields each)
   C* reg[4] = {nullptr, nullptr, nullptr, nullptr};
   int iY = 0;       // register holding sol
@@ -258,7 +266,8 @@ struct Solver : mhdf_handle {
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (P_ > 1) {
       CK(cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking));
-      dep_ev.resize(1024);   // cyclic pool; far more than one RHS evaluation can take between a record and its wait
+      dep_ev.resize(8192);   // cyclic pool; far more than one RHS evaluation can take between a record and its wait
+      CK(cudaEventCreateWithFlags(&red_own, cudaEventDisableTiming));
       for (auto& e : dep_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       std::string why;
       if (!g_nccl.load(why)) throw Err{MHDF_ERR_NCCL, why};
@@ -312,6 +321,9 @@ struct Solver : mhdf_handle {
   void build_tables() {   // slab runs: mirror-plane buffers, exchange-size check
     plane_loc = dalloc<C>((size_t)F * Kz * Kyl);
     plane_all = dalloc<C>((size_t)P_ * F * Kz * Kyl);
+    flags_d = dalloc<unsigned>((size_t)FSLOTS * P_);
+    CK(cudaMallocHost(&ferr_h, sizeof(int)));
+    *ferr_h = 0;
     check_blk(CHUNK > 0 ? CHUNK : (nin > nout ? nin : nout));
   }
   void check_blk(int nf) const {
@@ -326,10 +338,14 @@ struct Solver : mhdf_handle {
     if (ipc_on) {
       // peers may still be pushing into our buffers: close the mappings only after a final cross-rank barrier
       if (comm) { g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc); cudaStreamSynchronize(sc); }
-      for (int q = 0; q < P_; ++q) if (q != rank_) { cudaIpcCloseMemHandle(peerR[q]); cudaIpcCloseMemHandle(peerQ[q]); }
+      for (int q = 0; q < P_; ++q) if (q != rank_) { cudaIpcCloseMemHandle(peerR[q]); cudaIpcCloseMemHandle(peerQ[q]); cudaIpcCloseMemHandle(peerF[q]); }
     }
-    cudaFree(bar_d);
+    cudaFree(bar_d); cudaFree(flags_d);
+    if (ferr_h) cudaFreeHost(ferr_h);
+    flags_d = nullptr; ferr_h = nullptr;
     for (auto& e : dep_ev) cudaEventDestroy(e);
+    if (red_own) cudaEventDestroy(red_own);
+    red_own = red_ev = nullptr;
     if (sc) cudaStreamDestroy(sc);
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -620,36 +636,82 @@ struct Solver : mhdf_handle {
   // copy.  Two transports: (a) after mhdf_ipc_import, copy-engine pushes straight into the peers' receive buffer over
   // NVLink (no SMs, overlaps the axis passes), closed by a tiny all-reduce as the cross-rank barrier; (b) NCCL
   // send/recv.  `recv` must be R or Q (+ offset).
-  void exchange(const C* send, C* recv, int nf, bool first_of_leg = true, size_t block_elems = 0) {
+  // slot >= 0 (pipelined path, peer memory): no collective at all -- every push is followed by a flag store into the
+  // receiver's flag array (returns the epoch the receiver has to wait for with wait_flags); the buffers of that path are
+  // never aliased, so "the peer is done with its receive buffer" follows from the data dependencies of the step itself
+  // (see rhs_pipe).  slot < 0: two cross-rank barriers (before the first push of a leg, after the last push).
+  // `len` (default: the whole piece) = elements copied per piece, for pushing a field sub-range of the pieces: send / recv
+  // then point at the first field of the range inside piece 0.
+  unsigned exchange(const C* send, C* recv, int nf, bool first_of_leg = true, size_t block_elems = 0, int slot = -1, size_t len = 0) {
     const size_t B = block_elems ? block_elems : blk(nf);
+    const size_t L = len ? len : B;
     const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat32 : ncclFloat64;
+    const bool flagged = ipc_on && use_flags && slot >= 0;
+    unsigned ep = 0;
     prof_begin(KC_EXCH, sc);
     // pushes land in the peers' buffer without the peer posting a receive: before the first push of a leg every rank
     // must be past its last use of that buffer (stream order on each rank + this barrier)
-    if (ipc_on && first_of_leg) NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));
-    CK(cudaMemcpyAsync(recv + (size_t)rank_ * B, send + (size_t)rank_ * B, B * sizeof(C), cudaMemcpyDeviceToDevice, sc));
+    if (ipc_on && first_of_leg && !flagged) NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));
+    CK(cudaMemcpyAsync(recv + (size_t)rank_ * B, send + (size_t)rank_ * B, L * sizeof(C), cudaMemcpyDeviceToDevice, sc));
     if (ipc_on) {
       const bool inR = (recv >= R && recv < R + szR);
       const size_t off = inR ? (size_t)(recv - R) : (size_t)(recv - Q);
+      if (flagged) ep = ++epoch_[slot];
       for (int i = 0; i < NCS && i < P_ - 1; ++i) order(sc, cs[i]);
       int k = 0;
       for (int d = 1; d < P_; ++d, ++k) {
         const int q = (rank_ + d) % P_;   // stagger the targets so the pushes of all ranks spread over the links
         C* dst = (inR ? peerR[q] : peerQ[q]) + off + (size_t)rank_ * B;
-        CK(cudaMemcpyAsync(dst, send + (size_t)q * B, B * sizeof(C), cudaMemcpyDeviceToDevice, cs[k % NCS]));
+        CK(cudaMemcpyAsync(dst, send + (size_t)q * B, L * sizeof(C), cudaMemcpyDeviceToDevice, cs[k % NCS]));
+        if (flagged) flag_signal(peerF[q] + (size_t)slot * P_ + rank_, ep, cs[k % NCS]);
       }
       for (int i = 0; i < NCS && i < P_ - 1; ++i) order(cs[i], sc);
-      NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));   // every rank's pushes have landed
+      if (!flagged) NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));   // every rank's pushes have landed
     } else {
       NK(g_nccl.GroupStart());
       for (int q = 0; q < P_; ++q) {
         if (q == rank_) continue;
-        NK(g_nccl.Send(send + (size_t)q * B, 2 * B, dt, q, comm, sc));
-        NK(g_nccl.Recv(recv + (size_t)q * B, 2 * B, dt, q, comm, sc));
+        NK(g_nccl.Send(send + (size_t)q * B, 2 * L, dt, q, comm, sc));
+        NK(g_nccl.Recv(recv + (size_t)q * B, 2 * L, dt, q, comm, sc));
       }
       NK(g_nccl.GroupEnd());
     }
     prof_end(sc);
+    return ep;
+  }
+  void flag_signal(unsigned* peer_flag, unsigned v, cudaStream_t s) {
+#ifdef MHDF_CPU_EMU   // streams are synchronous and kernel launches take turns process-wide: store from the rank's host thread
+    (void)s;
+    st_flag(peer_flag, v);
+#else
+    k_flag_set<<<1, 32, 0, s>>>(peer_flag, v);
+    ++launches;
+#endif
+  }
+  // the compute stream waits until every peer's piece of (slot, epoch) has landed
+  void wait_flags(int slot, unsigned ep) {
+    if (ep == 0) return;
+#ifdef MHDF_CPU_EMU
+    for (int q = 0; q < P_; ++q) if (q != rank_) while ((int)(ld_flag(flags_d + (size_t)slot * P_ + q) - ep) < 0) std::this_thread::yield();
+#else
+    k_flag_wait<<<1, 32, 0, st>>>(flags_d + (size_t)slot * P_, ep, P_, rank_, ferr_h);
+    ++launches;
+#endif
+  }
+  // cross-rank barrier of the compute streams: separates API-level transforms (barrier-mode exchanges on aliased buffers)
+  // from the flag-mode pipeline of the time step
+  void rank_barrier() {
+    if (P_ == 1 || !ipc_on) return;
+    order(st, sc);
+    NK(g_nccl.AllReduce(bar_d, bar_d, 1, ncclFloat32, ncclSum, comm, sc));
+    order(sc, st);
+  }
+  void check_flags() {
+    if (ferr_h && *ferr_h) {
+      const int q = *ferr_h - 1;
+      *ferr_h = 0;
+      throw Err{MHDF_ERR_NCCL, "slab exchange: timed out waiting for the piece of rank " + std::to_string(q)};
+    }
   }
   void ipc_export(void* blob) override {
     if (P_ == 1) throw Err{MHDF_ERR_STATE, "peer exchange needs nranks > 1"};
@@ -658,22 +720,28 @@ struct Solver : mhdf_handle {
     CK(cudaSetDevice(cfg.device));
     CK(cudaIpcGetMemHandle(&b.r, R));
     CK(cudaIpcGetMemHandle(&b.q, Q));
+    CK(cudaIpcGetMemHandle(&b.f, flags_d));
     b.device = cfg.device;
     std::memcpy(blob, &b, sizeof b);
   }
   void ipc_import(const void* blobs) override {
     if (P_ == 1) throw Err{MHDF_ERR_STATE, "peer exchange needs nranks > 1"};
     CK(cudaSetDevice(cfg.device));
-    peerR.assign(P_, nullptr); peerQ.assign(P_, nullptr);
+    peerR.assign(P_, nullptr); peerQ.assign(P_, nullptr); peerF.assign(P_, nullptr);
     const IpcBlob* b = reinterpret_cast<const IpcBlob*>(blobs);
     for (int q = 0; q < P_; ++q) {
-      if (q == rank_) { peerR[q] = R; peerQ[q] = Q; continue; }
-      void *pr = nullptr, *pq = nullptr;
+      if (q == rank_) { peerR[q] = R; peerQ[q] = Q; peerF[q] = flags_d; continue; }
+      void *pr = nullptr, *pq = nullptr, *pf = nullptr;
       CK(cudaIpcOpenMemHandle(&pr, b[q].r, cudaIpcMemLazyEnablePeerAccess));
       CK(cudaIpcOpenMemHandle(&pq, b[q].q, cudaIpcMemLazyEnablePeerAccess));
-      peerR[q] = reinterpret_cast<C*>(pr); peerQ[q] = reinterpret_cast<C*>(pq);
+      CK(cudaIpcOpenMemHandle(&pf, b[q].f, cudaIpcMemLazyEnablePeerAccess));
+      peerR[q] = reinterpret_cast<C*>(pr); peerQ[q] = reinterpret_cast<C*>(pq); peerF[q] = reinterpret_cast<unsigned*>(pf);
     }
-    for (int i = 0; i < NCS; ++i) if (!cs[i]) CK(cudaStreamCreateWithFlags(&cs[i], cudaStreamNonBlocking));
+    // copy streams at the highest priority: the one-thread flag kernels behind the pushes must not queue behind the blocks of a
+    // big compute kernel
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int i = 0; i < NCS; ++i) if (!cs[i]) CK(cudaStreamCreateWithPriority(&cs[i], cudaStreamNonBlocking, prio_hi));
     if (!bar_d) bar_d = dalloc<float>(1);
     CK(cudaStreamSynchronize(st));
     ipc_on = true;
@@ -736,13 +804,20 @@ struct Solver : mhdf_handle {
     if (P_ > 1 && mirror_ready) { CK(cudaStreamWaitEvent(st, mirror_ready, 0)); mirror_ready = nullptr; }
   }
   // global sums / maxima of the x-kernel reductions, then the host copy
+  cudaEvent_t red_ev = nullptr, red_own = nullptr;   // red_own: dedicated event (it is waited for a whole step after its record)
   void finish_red() {
     if (P_ == 1) { CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st)); return; }
     order(st, sc);
     NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, sc));
     NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint32, ncclMax, comm, sc));
     CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, sc));
-    order(sc, st);   // the next memset of red_d must not overtake the copy
+    CK(cudaEventRecord(red_own, sc));
+    red_ev = red_own;    // the next reset of red_d must not overtake the copy (waited for in red_reset, not here: the compute
+                         // stream must not stall behind the pushes queued on the communication stream)
+  }
+  void red_reset() {
+    if (red_ev) { CK(cudaStreamWaitEvent(st, red_ev, 0)); red_ev = nullptr; }
+    CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
   }
 
   XArgs<T> xargs() const {
@@ -780,7 +855,7 @@ struct Solver : mhdf_handle {
   int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
   C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
   bool pipe_ok() const {
-    if (P_ == 1 || zchunks <= 1 || nzl % zchunks != 0) return false;
+    if (P_ == 1 || zchunks <= 1 || zchunks > 8 || nzl % zchunks != 0) return false;
     const int zc = nzl / zchunks, rb = 1024 / nx > 1 ? 1024 / nx : 1;
     if (zc < 2) return false;   // one plane per chunk: the second-level divisor would be 1 (see init)
     if ((long long)(nin > nout ? nin : nout) * nz * Kyl * Kxp >= (1LL << 31)) return false;   // 32-bit row offsets
@@ -796,11 +871,25 @@ struct Solver : mhdf_handle {
   void set_blk(PassArgs<T>& a, int rows, size_t stride) {
     a.blk_rows = rows; a.blk_stride = (int)stride; a.blk_magic = (unsigned)((0x100000000ULL + rows - 1) / rows);
   }
+  // field groups of the pipelined exchanges: the pieces of one (chunk, peer) are pushed group by group so that the z passes
+  // at both ends of an evaluation overlap the first / last pushes (MHDF_FGROUPS=0: one group)
+  bool fgroups_on = [] { const char* e = getenv("MHDF_FGROUPS"); return !e || atoi(e) != 0; }();
+  int groups_of(int nf) const {
+    if (!fgroups_on) return 1;
+    for (int g = 4; g > 1; --g) if (nf % g == 0 && nf / g >= 3) return g;
+    return 1;
+  }
+  cudaEvent_t mark(cudaStream_t s) {
+    cudaEvent_t e = dep_ev[dep_next++ % dep_ev.size()];
+    CK(cudaEventRecord(e, s));
+    return e;
+  }
   void rhs_pipe(const C* Sin, SpecArgs<T> sa, bool want_red) {
     pipe_alloc();
     const int NZC = zchunks, zc = nzl / NZC;
     const size_t Bi = (size_t)nin * zc * Kyl * Kxp, Bo = (size_t)nout * zc * Kyl * Kxp;   // one (chunk, peer) piece
     const long long fld = (long long)zc * Kyl * Kxp;                                      // field stride inside a piece
+    const int Gi = groups_of(nin), Go = groups_of(nout), fgi = nin / Gi, fgo = nout / Go;   // groups and fields per group
     const C* zin = Sin;
     if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {
@@ -816,10 +905,17 @@ struct Solver : mhdf_handle {
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
     sa.force = fmask ? force : nullptr; sa.fmask = fmask;
     next_a99(sa);
-    if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
-    {   // inverse z pass of every field into the two-level send layout
+    if (want_red) red_reset();
+    // Flag mode (peer memory): no collective in this function.  Why a peer's receive buffer is free when my push arrives:
+    //  R (inverse receive) of peer q is read by its inverse y passes; my next inverse push follows my spectral update, which
+    //    waited for q's forward pieces of ALL chunks, each sent after q's forward y pass of that chunk, i.e. after q read R;
+    //  Q (forward receive) of peer q is read by its forward z pass; my next forward push of chunk c follows my inverse y pass
+    //    of chunk c, which waited for q's inverse piece of the next evaluation, sent after q's spectral update, i.e. after
+    //    q's forward z pass read Q.
+    std::vector<cudaEvent_t> zdone(Gi);
+    for (int g = 0; g < Gi; ++g) {   // inverse z pass, one field group at a time, into the two-level send layout
       PassArgs<T> a;
-      a.in = zin; a.out = P; a.tw = twz;
+      a.in = zin + (size_t)g * fgi * cf; a.out = P + (size_t)g * fgi * fld; a.tw = twz;
       a.in_row = a.out_row = Kyl * Kxp;
       a.in_outer = a.out_outer = 0;
       a.in_field = cf; a.out_field = fld;
@@ -828,19 +924,24 @@ struct Solver : mhdf_handle {
       a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bi); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
       blk_out = true;
       prof_begin(KC_ZINV);
-      launch_pass<+1>(nz, a, 1, nin);
+      launch_pass<+1>(nz, a, 1, fgi);
       prof_end();
+      zdone[g] = mark(st);
     }
-    order(st, sc);
-    std::vector<cudaEvent_t> inv(NZC), fwd(NZC);
-    for (int c = 0; c < NZC; ++c) {
-      exchange(P + (size_t)c * P_ * Bi, R + (size_t)c * P_ * Bi, nin, c == 0, Bi);
-      inv[c] = dep_ev[dep_next++ % dep_ev.size()];
-      CK(cudaEventRecord(inv[c], sc));
+    std::vector<cudaEvent_t> inv(NZC), fwd((size_t)NZC * Go);
+    std::vector<unsigned> epi((size_t)NZC * Gi), epf((size_t)NZC * Go);
+    for (int c = 0; c < NZC; ++c) {   // pushes in the order the consumers need them: chunk by chunk, group by group
+      for (int g = 0; g < Gi; ++g) {
+        if (c == 0) CK(cudaStreamWaitEvent(sc, zdone[g], 0));
+        const size_t o = (size_t)c * P_ * Bi + (size_t)g * fgi * fld;
+        epi[c * Gi + g] = exchange(P + o, R + o, fgi, c == 0 && g == 0, Bi, c * 4 + g, (size_t)fgi * fld);
+      }
+      inv[c] = mark(sc);
     }
     for (int c = 0; c < NZC; ++c) {
       const size_t zoff = (size_t)c * zc * ny * Kxp;
       CK(cudaStreamWaitEvent(st, inv[c], 0));
+      for (int g = 0; g < Gi; ++g) wait_flags(c * 4 + g, epi[c * Gi + g]);
       {   // inverse y pass of chunk c: received pieces -> x-pass layout
         PassArgs<T> a;
         a.in = R + (size_t)c * P_ * Bi; a.out = Xin + zoff; a.tw = twy;
@@ -864,9 +965,10 @@ struct Solver : mhdf_handle {
       prof_begin(KC_XFUSED);
       launch_xfused(xa);
       prof_end();
-      {   // forward y pass of chunk c into the forward send layout
+      if (want_red && c == NZC - 1) finish_red();
+      for (int g = 0; g < Go; ++g) {   // forward y pass of chunk c, group by group, each followed by its push
         PassArgs<T> a;
-        a.in = Xout + zoff; a.out = P2 + (size_t)c * P_ * Bo; a.tw = twy;
+        a.in = Xout + zoff + (size_t)g * fgo * nzl * ny * Kxp; a.out = P2 + (size_t)c * P_ * Bo + (size_t)g * fgo * fld; a.tw = twy;
         a.in_row = a.out_row = Kxp;
         a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
         a.in_field = (long long)nzl * ny * Kxp; a.out_field = fld;
@@ -875,19 +977,18 @@ struct Solver : mhdf_handle {
         a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
         blk_out = true;
         prof_begin(KC_YFWD);
-        launch_pass<-1>(ny, a, zc, nout);
+        launch_pass<-1>(ny, a, zc, fgo);
         prof_end();
+        order(st, sc);
+        const size_t o = (size_t)c * P_ * Bo + (size_t)g * fgo * fld;
+        epf[c * Go + g] = exchange(P2 + o, Q + o, fgo, c == 0 && g == 0, Bo, 32 + c * 4 + g, (size_t)fgo * fld);
+        fwd[c * Go + g] = mark(sc);
       }
-      if (want_red && c == NZC - 1) finish_red();
-      order(st, sc);
-      exchange(P2 + (size_t)c * P_ * Bo, Q + (size_t)c * P_ * Bo, nout, c == 0, Bo);
-      fwd[c] = dep_ev[dep_next++ % dep_ev.size()];
-      CK(cudaEventRecord(fwd[c], sc));
     }
-    for (int c = 0; c < NZC; ++c) CK(cudaStreamWaitEvent(st, fwd[c], 0));
-    {   // forward z pass from the two-level receive layout to the compact product spectra (in Xin, free by now)
+    for (int g = 0; g < Go; ++g) {   // forward z pass of a field group as soon as its pieces of every chunk have landed
+      for (int c = 0; c < NZC; ++c) { CK(cudaStreamWaitEvent(st, fwd[c * Go + g], 0)); wait_flags(32 + c * 4 + g, epf[c * Go + g]); }
       PassArgs<T> a;
-      a.in = Q; a.out = Xin; a.tw = twz;
+      a.in = Q + (size_t)g * fgo * fld; a.out = Xin + (size_t)g * fgo * cf; a.tw = twz;   // compact product spectra go to Xin (free by now)
       a.in_row = a.out_row = Kyl * Kxp;
       a.in_outer = a.out_outer = 0;
       a.in_field = fld; a.out_field = cf;
@@ -896,7 +997,7 @@ struct Solver : mhdf_handle {
       a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bo); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
       blk_out = false;
       prof_begin(KC_ZFWD);
-      launch_pass<-1>(nz, a, 1, nout);
+      launch_pass<-1>(nz, a, 1, fgo);
       prof_end();
     }
     sa.P = Xin;
@@ -929,7 +1030,7 @@ struct Solver : mhdf_handle {
     sa.nu = (T)cfg.nu; sa.eta = (T)cfg.eta; sa.n_nu = cfg.n_nu;
     sa.force = fmask ? force : nullptr; sa.fmask = fmask;
     next_a99(sa);
-    if (want_red) CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+    if (want_red) red_reset();
     to_xlayout(zin, nin);
     XArgs<T> xa = xargs();
     xa.real_io = bst;
@@ -1044,8 +1145,10 @@ struct Solver : mhdf_handle {
 
   void step(int n) override {
     CK(cudaSetDevice(cfg.device));
+    rank_barrier();
     for (int i = 0; i < n; ++i) one_step();
     sync_all();
+    check_flags();
     if (n > 0) {
       absorb_red();
       check_finite();
@@ -1059,11 +1162,13 @@ struct Solver : mhdf_handle {
     CK(cudaSetDevice(cfg.device));
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    rank_barrier();
     sync_all();
     CK(cudaEventRecord(a, st));
     for (int i = 0; i < n; ++i) one_step();
     CK(cudaEventRecord(b, st));
     sync_all();
+    check_flags();
     float f = 0;
     CK(cudaEventElapsedTime(&f, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
@@ -1079,8 +1184,10 @@ struct Solver : mhdf_handle {
     for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
     SpecArgs<T> sa = blank_args();
     sa.mode = STEP_CALCN; sa.Nout = reg[o];
+    rank_barrier();
     rhs(reg[iY], sa, true);
     sync_all();
+    check_flags();
     absorb_red();
     iStale = iY;   // calcN! left vars.* = irfft(sol): the stale view is the state itself now
     const size_t fe = (P_ > 1) ? (size_t)nkr * Kyl * nz : (size_t)nkr * ny * nz;
@@ -1100,7 +1207,7 @@ struct Solver : mhdf_handle {
       CK(cudaMemcpyAsync(bst + (size_t)emhd_slot * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     XArgs<T> xa = xargs();
     xa.real_io = re; xa.out = Q; xa.in = nullptr;
-    CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+    red_reset();
     xa.red = red_d;
     launch_xplain<-1>(xa);
     finish_red();
@@ -1176,7 +1283,7 @@ struct Solver : mhdf_handle {
       to_xlayout(Y + (size_t)i * cf, 1);
       XArgs<T> xa = xargs();
       xa.real_io = re; xa.in = Q; xa.out = nullptr;
-      CK(cudaMemsetAsync(red_d, 0, sizeof(XRed), st));
+      red_reset();
       xa.red = red_d;
       launch_xplain<+1>(xa);
       if (phys == MHDF_EMHD) CK(cudaMemcpyAsync(bst + (size_t)i * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));

@@ -387,6 +387,9 @@ class Problem:
             want = "float32" if self.T is np.float32 else "float64"
             if tuple(arr.shape) != self._real_shape or str(arr.dtype).split(".")[-1] != want or not arr.is_contiguous():
                 raise ValueError(f"expected a contiguous {want} tensor of shape {self._real_shape}")
+            if getattr(arr, "is_cuda", False):      # the library copies on its own stream: the producer's stream must be done
+                import torch
+                torch.cuda.current_stream(arr.device).synchronize()
             return arr.data_ptr(), arr
         if writable:
             if arr.shape != self._real_shape or arr.dtype != self.T or not arr.flags.c_contiguous:
