@@ -199,11 +199,11 @@ inline unsigned ld_flag(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_
 #else
 __device__ __forceinline__ void st_flag(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned ld_flag(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__global__ void __launch_bounds__(32) k_flag_set(unsigned* flag, unsigned v) {
+static __global__ void __launch_bounds__(32) k_flag_set(unsigned* flag, unsigned v) {
   if (threadIdx.x == 0) { __threadfence_system(); st_flag(flag, v); }
 }
 // thread q < n (q != skip) waits until flags[q] has reached epoch v (wrap-safe comparison)
-__global__ void __launch_bounds__(32) k_flag_wait(const unsigned* flags, unsigned v, int n, int skip, int* err) {
+static __global__ void __launch_bounds__(32) k_flag_wait(const unsigned* flags, unsigned v, int n, int skip, int* err) {
   const int q = threadIdx.x;
   if (q < n && q != skip) {
     unsigned long long t0, t1;
@@ -356,8 +356,8 @@ template <> struct XSync<false, 1> { using type = SyncBlock; };
 struct XRed {
   double sumsq[6];   // sum f^2 per input field (ux,uy,uz,bx,by,bz | EMHD: Ax,Ay,Az,bx,by,bz)
   double cross;      // sum u.b
-  unsigned maxsq[6]; // max f^2 per field, float bit pattern (non-negative floats order as ints)
-  unsigned pad;
+  unsigned long long maxsq[6]; // max f^2 per field as the bit pattern of a non-negative T (orders like an unsigned integer):
+                               // Float32 in the low word, Float64 in the whole word -- getCFL!'s maximum in the problem's precision
 };
 
 template <typename T>
@@ -381,16 +381,20 @@ template <typename T> __device__ __forceinline__ void warp_red_sum(double& x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
 }
-__device__ __forceinline__ void warp_red_max(float& x) {
+__device__ __forceinline__ float max2(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max2(double a, double b) { return fmax(a, b); }
+template <typename TM> __device__ __forceinline__ void warp_red_max(TM& x) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  for (int o = 16; o > 0; o >>= 1) x = max2(x, __shfl_xor_sync(0xffffffffu, x, o));
 }
+__device__ __forceinline__ void atomic_max_bits(unsigned long long* p, float x) { atomicMax(reinterpret_cast<unsigned*>(p), __float_as_uint(x)); }   // little endian: low word
+__device__ __forceinline__ void atomic_max_bits(unsigned long long* p, double x) { atomicMax(p, (unsigned long long)__double_as_longlong(x)); }
 
 // Block reduction of NS sums + NM maxima followed by one atomic per quantity per block.
-template <int NS, int NM>
-__device__ __forceinline__ void block_reduce_commit(double (&s)[NS], float (&mx)[NM], double* gs, unsigned* gm) {
+template <int NS, int NM, typename TM>
+__device__ __forceinline__ void block_reduce_commit(double (&s)[NS], TM (&mx)[NM], double* gs, unsigned long long* gm) {
   __shared__ double sh_s[32][NS];
-  __shared__ float sh_m[32][NM];
+  __shared__ TM sh_m[32][NM];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int i = 0; i < NS; ++i) warp_red_sum<double>(s[i]);
@@ -412,9 +416,9 @@ __device__ __forceinline__ void block_reduce_commit(double (&s)[NS], float (&mx)
     }
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
-      float x = lane < nw ? sh_m[lane][i] : 0.f;
+      TM x = lane < nw ? sh_m[lane][i] : (TM)0;
       warp_red_max(x);
-      if (lane == 0) atomicMax(&gm[i], __float_as_uint(x));
+      if (lane == 0) atomic_max_bits(&gm[i], x);
     }
   }
 }
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   MHDF_KEEP_PTR(twt);
 
   double rs[7];
-  float rm[6];
+  T rm[6];
 #pragma unroll
   for (int i = 0; i < 7; ++i) rs[i] = 0.0;
 #pragma unroll
@@ -487,15 +491,15 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         row_c2r<T, N, E, SYNC>(f[i], in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
         if constexpr (RED) {
           T s = 0;
-          float mx = 0.f;
+          T mx = 0;
 #pragma unroll
           for (int m = 0; m < E; ++m) {
             const C sq = lmul(f[i][m], f[i][m]);
             s += sq.x + sq.y;
-            mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+            mx = max2(mx, max2(sq.x, sq.y));
           }
           rs[i] += (double)s;
-          rm[i] = fmaxf(rm[i], mx);
+          rm[i] = max2(rm[i], mx);
         }
       }
       if constexpr (PHYS == PHYS_MHD && RED) {
@@ -565,18 +569,18 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
       for (int i = 0; i < 3; ++i) {
         row_c2r<T, N, E, SYNC>(A[i], in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
         T s = 0;
-        float mx = 0.f;
+        T mx = 0;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           if constexpr (RED) {
             const C sq = lmul(A[i][m], A[i][m]);
             s += sq.x + sq.y;
-            mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+            mx = max2(mx, max2(sq.x, sq.y));
           }
           bs[i][m] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
         }
         rs[i] += (double)s;
-        rm[i] = fmaxf(rm[i], mx);
+        rm[i] = max2(rm[i], mx);
       }
       // One loop body for the three components (MHDF_EMHD_UNROLL_I = 1 restores the fully unrolled form): unrolled, the kernel
       // carries 27 inlined row transforms = 194 KB of SASS at 512-point rows against 103 KB for the MHD kernel, and ran 3.4x slower
@@ -610,18 +614,18 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         C g[E];
         row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
         T s = 0;
-        float mx = 0.f;
+        T mx = 0;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
           if constexpr (RED) {
             const C sq = lmul(g[m], g[m]);
             s += sq.x + sq.y;
-            mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+            mx = max2(mx, max2(sq.x, sq.y));
           }
           reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
         }
         rs[3 + i] += (double)s;
-        rm[3 + i] = fmaxf(rm[3 + i], mx);
+        rm[3 + i] = max2(rm[3 + i], mx);
       }
     }
   }
@@ -655,16 +659,16 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
   const C* twt = a.tw;
   MHDF_KEEP_PTR(twt);
   double rs[7];
-  float rm[6];
+  T rm[6];
 #pragma unroll
   for (int i = 0; i < 7; ++i) rs[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) rm[i] = 0.f;
   // reductions with a run-time slot: predicated adds keep rs / rm in registers
-  auto red_add = [&](int slot, T s, float mx) {
+  auto red_add = [&](int slot, T s, T mx) {
 #pragma unroll
     for (int q = 0; q < 6; ++q)
-      if (q == slot) { rs[q] += (double)s; rm[q] = fmaxf(rm[q], mx); }
+      if (q == slot) { rs[q] += (double)s; rm[q] = max2(rm[q], mx); }
   };
   const long long nsets = a.rows / RB;
   for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
@@ -691,13 +695,13 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
       C g[E];
       row_c2r<T, N, E, SYNC>(g, in + i * a.in_field, a.Kx, a.scale, t, sm, twt);
       T s = 0;
-      float mx = 0.f;
+      T mx = 0;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
         if constexpr (RED) {
           const C sq = lmul(g[m], g[m]);
           s += sq.x + sq.y;
-          mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+          mx = max2(mx, max2(sq.x, sq.y));
         }
         mult[(i * E + m) * Tm] = g[m];
         mult[((3 + i) * E + m) * Tm] = reinterpret_cast<const C*>(reinterpret_cast<const T*>(breal) + i * a.real_field)[t + Tm * m];
@@ -726,13 +730,13 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
       C g[E];
       row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
       T s = 0;
-      float mx = 0.f;
+      T mx = 0;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
         if constexpr (RED) {
           const C sq = lmul(g[m], g[m]);
           s += sq.x + sq.y;
-          mx = fmaxf(mx, fmaxf((float)sq.x, (float)sq.y));
+          mx = max2(mx, max2(sq.x, sq.y));
         }
         reinterpret_cast<C*>(reinterpret_cast<T*>(breal) + i * a.real_field)[t + Tm * m] = g[m];
       }
@@ -760,7 +764,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
   const C* twt = a.tw;
   MHDF_KEEP_PTR(twt);
   double rs[1] = {0.0};
-  float rm[1] = {0.f};
+  T rm[1] = {(T)0};
   const long long nsets = a.rows / RB;
   for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
     const long long row = set * RB + r;
@@ -768,30 +772,30 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xplain(XArgs<T> a) {
     C v[E];
     if constexpr (DIR < 0) {   // real -> spectral
       T s = 0;
-      float mx = 0.f;
+      T mx = 0;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
         v[m] = re[t + Tm * m];
         const T x2 = v[m].x * v[m].x, y2 = v[m].y * v[m].y;
         s += x2 + y2;
-        mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
+        mx = max2(mx, max2(x2, y2));
       }
       rs[0] += (double)s;
-      rm[0] = fmaxf(rm[0], mx);
+      rm[0] = max2(rm[0], mx);
       row_r2c<T, N, E, SYNC>(v, a.out + row * a.Kxp, a.Kx, t, sm, twt);
     } else {                   // spectral -> real
       row_c2r<T, N, E, SYNC>(v, a.in + row * a.Kxp, a.Kx, a.scale, t, sm, twt);
       T s = 0;
-      float mx = 0.f;
+      T mx = 0;
 #pragma unroll
       for (int m = 0; m < E; ++m) {
         re[t + Tm * m] = v[m];
         const T x2 = v[m].x * v[m].x, y2 = v[m].y * v[m].y;
         s += x2 + y2;
-        mx = fmaxf(mx, fmaxf((float)x2, (float)y2));
+        mx = max2(mx, max2(x2, y2));
       }
       rs[0] += (double)s;
-      rm[0] = fmaxf(rm[0], mx);
+      rm[0] = max2(rm[0], mx);
     }
   }
   if (a.red != nullptr) block_reduce_commit<1, 1>(rs, rm, a.red->sumsq, a.red->maxsq);

@@ -306,6 +306,7 @@ struct Solver : mhdf_handle {
     CK(cudaMemcpyAsync(kyv, hy.data(), Kyl * sizeof(T), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(kzv, hz.data(), Kz * sizeof(T), cudaMemcpyHostToDevice, st));
     if (P_ > 1) build_tables();
+    choose_chunks();
     red_d = dalloc<XRed>(1);
     diag_d = dalloc<double>(8);
     CK(cudaMallocHost(&red_h, sizeof(XRed)));
@@ -809,7 +810,7 @@ struct Solver : mhdf_handle {
     if (P_ == 1) { CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st)); return; }
     order(st, sc);
     NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, sc));
-    NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint32, ncclMax, comm, sc));
+    NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint64, ncclMax, comm, sc));
     CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, sc));
     CK(cudaEventRecord(red_own, sc));
     red_ev = red_own;    // the next reset of red_d must not overtake the copy (waited for in red_reset, not here: the compute
@@ -852,7 +853,20 @@ struct Solver : mhdf_handle {
   // EMHD x kernel: the shared-memory-multiplier form (k_xfused_emhd2) is the default -- 32.6 ms against 45.3 ms per 512^3 step
   // for the register form on B200 (profiles/README.md); MHDF_EMHD2=0 selects the register form (bit-identical results)
   bool emhd2 = [] { const char* e = getenv("MHDF_EMHD2"); return !e || atoi(e) != 0; }();
-  int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 1; return n < 1 ? 1 : n; }();
+  // z chunks of the pipelined slab path: MHDF_ZCHUNKS, or (unset) chosen from the size of the pushes -- 4 chunks when one
+  // chunk's inverse pushes still move >= 64 MB per round, else 2 (measured on B200s: 8 chunks lose to 4 at 512^3 and 1024^3,
+  // copy-engine pushes below ~30 MB run at less than half of the NVLink rate; profiles/r02_c3_*)
+  int zchunks = [] { const char* e = getenv("MHDF_ZCHUNKS"); const int n = e ? atoi(e) : 0; return n < 0 ? 0 : n; }();
+  void choose_chunks() {
+    if (P_ == 1) { zchunks = 1; return; }
+    if (zchunks > 0) return;
+    auto round_bytes = [&](int nzc) { return (double)nin * (nzl / nzc) * Kyl * Kxp * sizeof(C) * (P_ - 1); };
+    zchunks = (nzl % 4 == 0 && nzl / 4 >= 2 && round_bytes(4) >= 64e6) ? 4 : 2;
+  }
+  // field groups: worth their extra launches when a group's pushes of one round still move >= 100 MB
+  bool groups_pay(int nf, int g) const {
+    return (double)(nf / g) * (nzl / zchunks) * Kyl * Kxp * sizeof(C) * (P_ - 1) >= 100e6;
+  }
   C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
   bool pipe_ok() const {
     if (P_ == 1 || zchunks <= 1 || zchunks > 8 || nzl % zchunks != 0) return false;
@@ -873,10 +887,11 @@ struct Solver : mhdf_handle {
   }
   // field groups of the pipelined exchanges: the pieces of one (chunk, peer) are pushed group by group so that the z passes
   // at both ends of an evaluation overlap the first / last pushes (MHDF_FGROUPS=0: one group)
-  bool fgroups_on = [] { const char* e = getenv("MHDF_FGROUPS"); return !e || atoi(e) != 0; }();
+  int fgroups_env = [] { const char* e = getenv("MHDF_FGROUPS"); return e ? atoi(e) : -1; }();   // 0 off, 1 on, unset: by size
   int groups_of(int nf) const {
-    if (!fgroups_on) return 1;
-    for (int g = 4; g > 1; --g) if (nf % g == 0 && nf / g >= 3) return g;
+    if (fgroups_env == 0) return 1;
+    for (int g = 4; g > 1; --g)
+      if (nf % g == 0 && nf / g >= 3) return (fgroups_env == 1 || groups_pay(nf, g)) ? g : 1;
     return 1;
   }
   cudaEvent_t mark(cudaStream_t s) {
@@ -1081,12 +1096,15 @@ struct Solver : mhdf_handle {
     return (int)(b < cap ? b : cap);
   }
 
+  double red_max(int i) const {   // max f^2 in the problem's precision (XRed::maxsq holds the bit pattern of a T)
+    T v;
+    std::memcpy(&v, &red_h->maxsq[i], sizeof(T));
+    return (double)v;
+  }
   void absorb_red() {   // after a stream sync: stale vars statistics of the last RHS evaluation
     for (int i = 0; i < 6; ++i) {
       st_sum[i] = red_h->sumsq[i];
-      float f;
-      std::memcpy(&f, &red_h->maxsq[i], 4);
-      st_max[i] = (double)f;
+      st_max[i] = red_max(i);
     }
     st_cross = red_h->cross;
   }
@@ -1225,9 +1243,7 @@ struct Solver : mhdf_handle {
     }
     const int slot = (phys == MHDF_EMHD) ? 3 + field : field;
     st_sum[slot] = red_h->sumsq[0];
-    float f;
-    std::memcpy(&f, &red_h->maxsq[0], 4);
-    st_max[slot] = (double)f;
+    st_max[slot] = red_max(0);
   }
   void set_forcing(int field, const void* p) override {
     check_field(field);
@@ -1291,9 +1307,7 @@ struct Solver : mhdf_handle {
       sync_all();
       const int slot = (phys == MHDF_EMHD) ? 3 + i : f0 + i;
       st_sum[slot] = red_h->sumsq[0];
-      float f;
-      std::memcpy(&f, &red_h->maxsq[0], 4);
-      st_max[slot] = (double)f;
+      st_max[slot] = red_max(0);
     }
   }
   // DivFreeSpectraMap (utils/IC.jl:130-179) followed by SetUpProblemIC! (IC.jl:41-109) for one vector field, on the device:

@@ -46,8 +46,12 @@ class File:
     scalar), nested groups addressed as "a/b"."""
 
     def __init__(self, path):
-        with open(path, "rb") as f:
-            self.buf = f.read()
+        import mmap
+        with open(path, "rb") as f:       # mapped, not read: a restart of a large grid touches only the datasets it reads
+            try:
+                self.buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            except (ValueError, OSError):
+                self.buf = f.read()
         start = 0
         while True:                                   # the superblock may sit behind a user block of 512, 1024, ... bytes
             if self.buf[start:start + 8] == SIG:
@@ -103,7 +107,7 @@ class File:
         seg_addr = struct.unpack_from("<Q", b, h + 24)[0] + self.base
 
         def name_at(off):
-            e = b.index(b"\0", seg_addr + off)
+            e = b.find(b"\0", seg_addr + off)
             return b[seg_addr + off:e].decode()
 
         links = {}

@@ -23,19 +23,51 @@ def _filename(file_path_and_name: str, file_number: int) -> str:
     return f"{file_path_and_name}_t_{int(file_number):04d}.h5"        # integrator.jl:260-262
 
 
+def _dist(prob):
+    """torch.distributed of a slab-decomposed problem (one process per GPU): the dump / restart of such a problem is a
+    collective over the ranks."""
+    try:
+        import torch.distributed as dist
+        ok = dist.is_available() and dist.is_initialized() and dist.get_world_size() == prob.nranks and dist.get_rank() == prob.rank
+    except Exception:
+        ok = False
+    if not ok:
+        raise NotImplementedError("savefile / Restart of a slab-decomposed problem (nranks > 1) gathers / scatters the z slabs through "
+                                  "torch.distributed: initialise a process group whose ranks are the problem's ranks")
+    return dist
+
+
+def _gather_slabs(prob, slab):
+    """The z slabs (nz / P, ny, nx) of all ranks -> the full (nz, ny, nx) field on rank 0 (None on the other ranks)."""
+    import torch
+    dist = _dist(prob)
+    t = torch.from_numpy(np.ascontiguousarray(slab))
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    bufs = [torch.empty_like(t) for _ in range(prob.nranks)] if prob.rank == 0 else None
+    dist.gather(t, bufs, dst=0)
+    if prob.rank != 0:
+        return None
+    return np.concatenate([b.cpu().numpy() for b in bufs], axis=0)
+
+
 def savefile(prob, file_number, file_path_and_name=""):
-    """savefile(prob, file_number; file_path_and_name) (integrator.jl:259-288)."""
+    """savefile(prob, file_number; file_path_and_name) (integrator.jl:259-288).  Slab-decomposed problems (ours: the reference
+    is single-device) write ONE file with the full (nx, ny, nz) datasets: the z slabs are gathered field by field to rank 0,
+    which writes; every rank returns the path."""
     data = {}
-    if not prob.flag.e:
-        for ds, f in _U:
-            data[ds] = prob.get_real(f, L.STALE)
-    if prob.flag.b:
-        for ds, f in _B:
-            data[ds] = prob.get_real(f, L.STALE)
-    T = next((a.dtype.type for a in data.values()), np.float64)
-    data["time"] = T(prob.clock.t)                                    # write(fw, "time", prob.clock.t): a scalar of type T
+    T = np.float64
+    fields = (() if prob.flag.e else _U) + (_B if prob.flag.b else ())
+    for ds, f in fields:
+        a = prob.get_real(f, L.STALE)
+        T = a.dtype.type
+        data[ds] = _gather_slabs(prob, a) if prob.nranks > 1 else a
     path = _filename(file_path_and_name, file_number)
-    h5lite.write(path, data)
+    if prob.rank == 0:
+        data["time"] = T(prob.clock.t)                                # write(fw, "time", prob.clock.t): a scalar of type T
+        h5lite.write(path, data)
+    if prob.nranks > 1:
+        _dist(prob).barrier()                                         # the file is complete when any rank returns
     return path
 
 
@@ -57,11 +89,19 @@ def Restart(prob, file_path_and_name):
     """Restart!(prob, file_path_and_name) (integrator.jl:208-257): load the fields into vars, r2c them into sol and
     restore clock.t (the step counter and dt are not restored, like the reference)."""
     d = readMHDFlows(file_path_and_name)
+    nzl = prob._real_shape[0]
+
+    def mine(a):   # a dump holds the whole grid: a slab-decomposed problem takes its own z planes
+        if prob.nranks > 1:
+            if a.shape != (prob.grid.nz, prob.grid.ny, prob.grid.nx):
+                raise ValueError(f"restart file holds fields of shape {a.shape}, the problem's grid is {(prob.grid.nz, prob.grid.ny, prob.grid.nx)}")
+            return a[prob.rank * nzl:(prob.rank + 1) * nzl]
+        return a
     if not prob.flag.e:
         for ds, f in _U:
-            prob.set_real(f, d[ds])
+            prob.set_real(f, mine(d[ds]))
     if prob.flag.b:
         for ds, f in _B:
-            prob.set_real(f, d[ds])
+            prob.set_real(f, mine(d[ds]))
     prob.clock.t = float(d["time"])
     return None

@@ -79,7 +79,10 @@ inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned 
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline double atomicAdd(double* p, double v) { std::lock_guard<std::mutex> g(emu::atomic_mu); double o = *p; *p = o + v; return o; }
 inline unsigned atomicMax(unsigned* p, unsigned v) { std::lock_guard<std::mutex> g(emu::atomic_mu); unsigned o = *p; *p = std::max(o, v); return o; }
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { std::lock_guard<std::mutex> g(emu::atomic_mu); unsigned long long o = *p; *p = std::max(o, v); return o; }
+inline long long __double_as_longlong(double d) { long long u; std::memcpy(&u, &d, 8); return u; }
 using std::fmaxf;
+using std::fmax;
 using std::rint;
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline double __dmul_rn(double a, double b) { return a * b; }

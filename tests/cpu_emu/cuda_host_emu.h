@@ -60,7 +60,7 @@ inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 // rendezvous of the rank threads).
 struct ncclUniqueId { char internal[128]; };
 typedef enum { ncclSuccess = 0, ncclEmuError = 1 } ncclResult_t;
-typedef enum { ncclFloat32 = 7, ncclFloat64 = 8, ncclUint32 = 3 } ncclDataType_t;
+typedef enum { ncclFloat32 = 7, ncclFloat64 = 8, ncclUint32 = 3, ncclUint64 = 5 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclMax = 2 } ncclRedOp_t;
 namespace emu_nccl {
 struct SendOp { int peer; const void* p; size_t bytes; };
@@ -75,7 +75,7 @@ struct Comm { World* w; int rank; };
 inline std::mutex mu;
 inline std::vector<std::pair<long long, World*>> worlds;
 inline long long next_id = 1;
-inline size_t size_of(ncclDataType_t t) { return t == ncclFloat64 ? 8 : 4; }
+inline size_t size_of(ncclDataType_t t) { return (t == ncclFloat64 || t == ncclUint64) ? 8 : 4; }
 struct GroupState { bool open = false; std::vector<SendOp> sends; struct R { int peer; void* p; size_t bytes; Comm* c; }; std::vector<R> recvs; Comm* c = nullptr; };
 inline thread_local GroupState grp;
 inline ncclResult_t GetUniqueId(ncclUniqueId* id) { std::lock_guard<std::mutex> g(mu); std::memset(id, 0, sizeof *id); const long long v = next_id++; std::memcpy(id->internal, &v, sizeof v); return ncclSuccess; }
@@ -97,6 +97,7 @@ inline ncclResult_t AllReduce(const void* s, void* r, size_t count, ncclDataType
   for (size_t i = 0; i < count; ++i) {
     if (t == ncclFloat64) { double a = 0; for (int q = 0; q < w->n; ++q) { const double x = ((const double*)w->ptr[q])[i]; a = op == ncclSum ? (q ? a + x : x) : (q ? std::max(a, x) : x); } ((double*)tmp.data())[i] = a; }
     else if (t == ncclFloat32) { float a = 0; for (int q = 0; q < w->n; ++q) { const float x = ((const float*)w->ptr[q])[i]; a = op == ncclSum ? (q ? a + x : x) : (q ? std::max(a, x) : x); } ((float*)tmp.data())[i] = a; }
+    else if (t == ncclUint64) { unsigned long long a = 0; for (int q = 0; q < w->n; ++q) { const unsigned long long x = ((const unsigned long long*)w->ptr[q])[i]; a = op == ncclSum ? (q ? a + x : x) : (q ? std::max(a, x) : x); } ((unsigned long long*)tmp.data())[i] = a; }
     else { unsigned a = 0; for (int q = 0; q < w->n; ++q) { const unsigned x = ((const unsigned*)w->ptr[q])[i]; a = op == ncclSum ? (q ? a + x : x) : (q ? std::max(a, x) : x); } ((unsigned*)tmp.data())[i] = a; }
   }
   w->bar->arrive_and_wait();                       // everyone has read every send buffer (in-place calls)

@@ -56,7 +56,7 @@ def test_write_read_round_trip_and_structure(tmp_path):
     assert k0 == 0 and b[child:child + 4] == b"SNOD" and b[seg + k1:seg + k1 + 5] == b"time\0"
     assert struct.unpack_from("<H", b, child + 6)[0] == len(ds)
     offs = [struct.unpack_from("<Q", b, child + 8 + 40 * i)[0] for i in range(len(ds))]
-    names = [b[seg + o:b.index(b"\0", seg + o)].decode() for o in offs]
+    names = [b[seg + o:b.find(b"\0", seg + o)].decode() for o in offs]
     assert names == sorted(ds) and all(o % 8 == 0 for o in offs)
     # every object header: version 1, message sizes multiples of 8, data 8-byte aligned inside the file
     for k in ds:
