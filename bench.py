@@ -44,7 +44,7 @@ ALG_S_PER_STEP = {("mhd", "RK4"): 384, ("mhd", "LSRK54"): 450, ("hd", "RK4"): 21
 # 0.271 s per iteration on an RTX 3080 (README.md:78) = 6.19e7 grid-points*steps/s.  Nothing is published for other configs.
 PUBLISHED_PTS_STEPS_PER_S = {"mhd256": 256 ** 3 / 0.271}
 # fields through the fused x pass: (n_in, n_out); SURVEY 8(d): (n_in + n_out) S per launch
-XPASS_FIELDS = {"mhd": (6, 9), "hd": (3, 6), "emhd": (24, 3)}
+XPASS_FIELDS = {"mhd": (6, 9), "hd": (3, 6), "emhd": (18, 3)}
 XPASS_S_PER_LAUNCH = {"mhd": 15, "hd": 9, "emhd": 19}
 REF_SAMPLE_N = 128          # grid of the CPU-reference sample (full time steps of the same physics; see run_reference)
 
@@ -280,7 +280,7 @@ def cufft_reference_point(kind, dims, reps=3):
         nx, ny, nz = dims
         n_c2r, n_r2c = XPASS_FIELDS[kind]
         if kind == "emhd":
-            n_c2r = 24
+            n_c2r = 24          # row transforms of the gradient form (18 fields through the y / z passes)
         ref_total = {"mhd": 36, "hd": 24, "emhd": 51}[kind]
         x = torch.randn((nz, ny, nx), device="cuda", dtype=torch.float32)
         xh = torch.fft.rfftn(x)
@@ -367,7 +367,7 @@ def pruned_bytes(kind, stepper, info, dims, world, F):
         spec = 5 * (nout + 4 * F) * cf
         nst = 5
     if kind == "emhd":
-        stage += (3 + 24) * cf            # k_emhd_derive
+        stage += (3 + 18) * cf            # k_emhd_derive
     return nst * stage + spec, xpass
 
 

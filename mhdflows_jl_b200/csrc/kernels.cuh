@@ -286,9 +286,12 @@ __device__ __forceinline__ C r2c_post(C z1, C z2, C w) {
 #endif
 }
 
+// dkx != nullptr: the row is differentiated along x on the way in -- X[k] -> i kx[k] X[k] with the kr table of the grid
+// (the EMHD kernels get d/dx B_i and d/dx A_i from the rows of B_i and A_i themselves instead of from separately
+// transformed derivative fields: 6 of the 24 inverse-transformed fields of the gradient form disappear)
 template <typename T, int N, int E, typename SYNC>
 __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__ X, int Kx, T scale, int t,
-                                        RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw) {
+                                        RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw, const T* __restrict__ dkx = nullptr) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
   MHDF_KEEP_PTR(X);
@@ -297,7 +300,11 @@ __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__
     const int k = t + Tm * m;
     const int k2 = M - k;
     C x1 = ldg_pred(X + (unsigned)k, k < Kx);
-    const C x2 = ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx);
+    C x2 = ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx);
+    if (dkx != nullptr) {   // same expression as k_emhd_derive: i * (k_x * f)
+      x1 = cmuli(cscale(x1, k < Kx ? __ldg(dkx + k) : (T)0));
+      x2 = cmuli(cscale(x2, k2 < Kx ? __ldg(dkx + k2) : (T)0));
+    }
     if (k == 0) x1.y = 0;
     v[m] = c2r_pre(x1, x2, XTwSrc<T, N, E>::wn(tw, m, k), scale);
   }
@@ -375,6 +382,7 @@ struct XArgs {
   const T* vp;
   long long vp_field;
   T vp_eta;            // eta = clock.dt * 13/7 (VPSolver.jl:23,45)
+  const T* kxv;        // [Kx] kr of the grid (EMHD kernels: x derivatives are formed inside the row transform)
 };
 
 template <typename T> __device__ __forceinline__ void warp_red_sum(double& x) {
@@ -430,7 +438,7 @@ enum { PHYS_HD = 0, PHYS_MHD = 1, PHYS_EMHD = 2 };
 //   HD  : in u(3)              out T_ij = -u_i u_j (xx,xy,xz,yy,yz,zz)
 //   MHD : in u(3), b(3)        out T_ij = b_i b_j - u_i u_j (6), E = u x b (3)
 //         (reference: MHDSolver.jl:73 and :150; HDSolver.jl:62)
-//   EMHD: in A(3), dB(9), dA(9), B(3) spectral + stale b (3, real)   out G_i (3), fresh b -> real_io
+//   EMHD: in A(3), d_{y,z}B(6), d_{y,z}A(6), B(3) spectral + stale b (3, real)   out G_i (3), fresh b -> real_io
 //         G_i = sum_j A_j d_j B_i - b^stale_j d_j A_i   (reference: MHDSolver.jl:241-266, 323-325)
 // RED: accumulate the per-field sum f^2 / max f^2 / sum u.b reductions (only the launch whose real-space fields
 // the reference's stale `vars` correspond to needs them; the other stages skip the work and the registers)
@@ -463,7 +471,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   for (int i = 0; i < 6; ++i) rm[i] = 0.f;
 
   const long long nsets = a.rows / RB;
-  constexpr int NINF = (PHYS == PHYS_MHD) ? 6 : (PHYS == PHYS_HD ? 3 : 24);
+  constexpr int NINF = (PHYS == PHYS_MHD) ? 6 : (PHYS == PHYS_HD ? 3 : 18);
   for (long long set = blockIdx.x; set < nsets; set += gridDim.x) {
     const long long row = set * RB + r;
     const C* in = a.in + row * a.Kxp;
@@ -562,7 +570,8 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         }
       }
     } else {
-      // EMHD: field order in `in`: A(0..2), dB_ij at 3 + 3 i + j, dA_ij at 12 + 3 i + j, B(21..23)
+      // EMHD: field order in `in`: A(0..2), d_j B_i (j = y, z) at 3 + 2 i + (j - 1), d_j A_i (j = y, z) at 9 + 2 i + (j - 1),
+      // B(15..17); the x derivatives come from the rows of B_i / A_i (row_c2r with the kr table)
       C A[3][E], bs[3][E];
       C* breal = reinterpret_cast<C*>(a.real_io + row * (long long)N);
 #pragma unroll
@@ -599,10 +608,10 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           C g[E];
-          row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
+          row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? 15 + i : 3 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, j == 0 ? a.kxv : nullptr);
 #pragma unroll
           for (int m = 0; m < E; ++m) acc[m] = lfma(A[j][m], g[m], acc[m]);
-          row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
+          row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? i : 9 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, j == 0 ? a.kxv : nullptr);
 #pragma unroll
           for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(bs[j][m]), g[m], acc[m]);
         }
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
         C g[E];
-        row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
+        row_c2r<T, N, E, SYNC>(g, in + (15 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
         T s = 0;
         T mx = 0;
 #pragma unroll
@@ -681,7 +690,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
       if (nset < nsets) {
         const char* nb = reinterpret_cast<const char*>(a.in + (nset * RB + r) * a.Kxp);
         const int bytes = a.Kx * (int)sizeof(C);
-        for (int f = 0; f < 24; ++f)
+        for (int f = 0; f < 18; ++f)
           for (int o = t * 128; o < bytes; o += Tm * 128)
 #ifndef MHDF_CPU_EMU
             asm volatile("prefetch.global.L2 [%0];" :: "l"(nb + (long long)f * a.in_field * (long long)sizeof(C) + o));
@@ -716,10 +725,11 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
 #pragma unroll 1
       for (int j = 0; j < 3; ++j) {
         C g[E];
-        row_c2r<T, N, E, SYNC>(g, in + (3 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
+        const T* dk = (j == 0) ? a.kxv : nullptr;     // j = x: differentiate the rows of B_i / A_i on the way in
+        row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? 15 + i : 3 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, dk);
 #pragma unroll
         for (int m = 0; m < E; ++m) acc[m] = lfma(mult[(j * E + m) * Tm], g[m], acc[m]);
-        row_c2r<T, N, E, SYNC>(g, in + (12 + 3 * i + j) * a.in_field, a.Kx, a.scale, t, sm, twt);
+        row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? i : 9 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, dk);
 #pragma unroll
         for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(mult[((3 + j) * E + m) * Tm]), g[m], acc[m]);
       }
@@ -728,7 +738,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
 #pragma unroll 1
     for (int i = 0; i < 3; ++i) {   // refresh the real-space b (vars.b*) from the current stage input
       C g[E];
-      row_c2r<T, N, E, SYNC>(g, in + (21 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
+      row_c2r<T, N, E, SYNC>(g, in + (15 + i) * a.in_field, a.Kx, a.scale, t, sm, twt);
       T s = 0;
       T mx = 0;
 #pragma unroll
@@ -1180,8 +1190,9 @@ __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a)
   }
 }
 
-// EMHD: derive the 24 inverse-transform inputs from B^ (compact):
-//   A = i k x B (0..2), dB_ij = i k_j B_i (3+3i+j), dA_ij = i k_j A_i (12+3i+j), B (21..23)
+// EMHD: derive the 18 inverse-transform inputs from B^ (compact):
+//   A = i k x B (0..2), d_j B_i = i k_j B_i for j = y, z (3 + 2i + (j-1)), d_j A_i = i k_j A_i for j = y, z (9 + 2i + (j-1)),
+//   B (15..17); the x derivatives are formed inside the fused x kernel from the rows of B_i / A_i
 //   (reference: MHDSolver.jl:301-309 "way 2", :246, :257)
 template <typename T>
 __global__ void __launch_bounds__(256) k_emhd_derive(SpecGeom<T> g, const Cx<T>* __restrict__ B, Cx<T>* __restrict__ out) {
@@ -1205,11 +1216,11 @@ __global__ void __launch_bounds__(256) k_emhd_derive(SpecGeom<T> g, const Cx<T>*
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       out[i * g.field + e] = A[i];
-      out[(21 + i) * g.field + e] = b[i];
+      out[(15 + i) * g.field + e] = b[i];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        out[(3 + 3 * i + j) * g.field + e] = cmuli(cscale(b[i], k[j]));
-        out[(12 + 3 * i + j) * g.field + e] = cmuli(cscale(A[i], k[j]));
+      for (int j = 1; j < 3; ++j) {
+        out[(3 + 2 * i + (j - 1)) * g.field + e] = cmuli(cscale(b[i], k[j]));
+        out[(9 + 2 * i + (j - 1)) * g.field + e] = cmuli(cscale(A[i], k[j]));
       }
     }
   }

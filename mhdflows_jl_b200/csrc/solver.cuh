@@ -250,7 +250,7 @@ struct Solver : mhdf_handle {
       throw Err{MHDF_ERR_INVALID, "grid too small for this many ranks (need at least 2 z planes and 2 retained ky rows per rank)"};
     phys = c.physics;
     F = (phys == MHDF_MHD) ? 6 : 3;
-    nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 24);
+    nin = (phys == MHDF_MHD) ? 6 : (phys == MHDF_HD ? 3 : 18);
     nout = (phys == MHDF_MHD) ? 9 : (phys == MHDF_HD ? 6 : 3);
     vp_on = c.vp != 0;
     if (vp_on && phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "VP_method: the EMHD equation has no volume-penalisation terms (MHDSolver.jl:183-270)"};
@@ -290,7 +290,7 @@ struct Solver : mhdf_handle {
     if (P_ == 1) szQ = mx(szQ, (size_t)nout * (size_t)cf);
     P = dalloc<C>(szP); Q = dalloc<C>(szQ); R = dalloc<C>(szR);
     if (phys == MHDF_EMHD) {
-      szD = (size_t)24 * cf;
+      szD = (size_t)18 * cf;
       D = dalloc<C>(szD);
       bst = dalloc<T>((size_t)3 * nx * ny * nzl);
     }
@@ -399,6 +399,7 @@ struct Solver : mhdf_handle {
   void sync_all() {
     CK(cudaStreamSynchronize(st));
     if (sc) CK(cudaStreamSynchronize(sc));
+    for (int i = 0; i < NCS; ++i) if (cs[i]) CK(cudaStreamSynchronize(cs[i]));   // my own pushes out of the send buffers
   }
   void prof_begin(int cls, cudaStream_t s = nullptr) {
     if (!prof) return;
@@ -831,6 +832,7 @@ struct Solver : mhdf_handle {
     a.scale = (T)(1.0 / ((double)nx * ny * nz));
     a.red = nullptr;
     a.vp = nullptr; a.vp_field = 0; a.vp_eta = (T)1;
+    a.kxv = kxv;
     return a;
   }
   // penalised RHS evaluations: the x kernel reads chi, U0 (B0) next to the row set; eta = clock.dt * 13/7 (VPSolver.jl:23)
@@ -863,10 +865,6 @@ struct Solver : mhdf_handle {
     auto round_bytes = [&](int nzc) { return (double)nin * (nzl / nzc) * Kyl * Kxp * sizeof(C) * (P_ - 1); };
     zchunks = (nzl % 4 == 0 && nzl / 4 >= 2 && round_bytes(4) >= 64e6) ? 4 : 2;
   }
-  // field groups: worth their extra launches when a group's pushes of one round still move >= 100 MB
-  bool groups_pay(int nf, int g) const {
-    return (double)(nf / g) * (nzl / zchunks) * Kyl * Kxp * sizeof(C) * (P_ - 1) >= 100e6;
-  }
   C *Xin = nullptr, *Xout = nullptr, *P2 = nullptr;
   bool pipe_ok() const {
     if (P_ == 1 || zchunks <= 1 || zchunks > 8 || nzl % zchunks != 0) return false;
@@ -887,24 +885,73 @@ struct Solver : mhdf_handle {
   }
   // field groups of the pipelined exchanges: the pieces of one (chunk, peer) are pushed group by group so that the z passes
   // at both ends of an evaluation overlap the first / last pushes (MHDF_FGROUPS=0: one group)
-  int fgroups_env = [] { const char* e = getenv("MHDF_FGROUPS"); return e ? atoi(e) : -1; }();   // 0 off, 1 on, unset: by size
-  int groups_of(int nf) const {
-    if (fgroups_env == 0) return 1;
-    for (int g = 4; g > 1; --g)
-      if (nf % g == 0 && nf / g >= 3) return (fgroups_env == 1 || groups_pay(nf, g)) ? g : 1;
+  // Field groups of the pipelined exchanges: the pieces of a (chunk, peer) can be pushed group by group so that the z passes at
+  // both ends of an evaluation overlap the first / last pushes.  MHDF_FGROUPS: 0 never, 1 every chunk, 2 only where it shortens
+  // the critical path (the first inverse chunk and the last forward chunk); unset: 2 when a group's piece is still >= 16 MB,
+  // and every chunk when it is >= 100 MB (measured on B200s: copy-engine pushes of ~20 MB run at less than half of the rate of
+  // 100 MB pushes, so small pieces cost more than the overlap returns; profiles/r02_c3_*, r02_c4_*)
+  int fgroups_env = [] { const char* e = getenv("MHDF_FGROUPS"); return e ? atoi(e) : -1; }();
+  int group_mode(int nf, int g) const {
+    if (fgroups_env >= 0) return fgroups_env;
+    const double piece = (double)(nf / g) * (nzl / zchunks) * Kyl * Kxp * sizeof(C);
+    return piece >= 100e6 ? 1 : (piece >= 16e6 ? 2 : 0);
+  }
+  int groups_max(int nf) const {
+    for (int g = 4; g > 1; --g) if (nf % g == 0 && nf / g >= 3) return g;
     return 1;
   }
+  // pushes of one exchange without joining the copy streams: every peer's stream runs its pushes back to back, ordered only
+  // behind the kernel that produced the data (`ready`) -- no per-round rendezvous of the seven streams (MHDF_NOJOIN=0: joined)
+  bool nojoin = [] { const char* e = getenv("MHDF_NOJOIN"); return !e || atoi(e) != 0; }();
   cudaEvent_t mark(cudaStream_t s) {
     cudaEvent_t e = dep_ev[dep_next++ % dep_ev.size()];
     CK(cudaEventRecord(e, s));
     return e;
+  }
+  // One push round of the pipelined path: elements [0, L) of every (peer) piece (pieces B apart) from `send` to the same place in
+  // the peers' receive buffer `recv`; `ready` = the producing kernel has finished.  Returns the epoch to wait for.
+  unsigned push_round(const C* send, C* recv, size_t B, size_t L, int slot, cudaEvent_t ready) {
+    if (!(ipc_on && use_flags && nojoin)) {
+      CK(cudaStreamWaitEvent(sc, ready, 0));
+      return exchange(send, recv, 0, false, B, slot, L);
+    }
+    const unsigned ep = ++epoch_[slot];
+    const bool inR = (recv >= R && recv < R + szR);
+    const size_t off = inR ? (size_t)(recv - R) : (size_t)(recv - Q);
+    CK(cudaStreamWaitEvent(sc, ready, 0));
+    CK(cudaMemcpyAsync(recv + (size_t)rank_ * B, send + (size_t)rank_ * B, L * sizeof(C), cudaMemcpyDeviceToDevice, sc));
+    int k = 0;
+    for (int d = 1; d < P_; ++d, ++k) {
+      const int q = (rank_ + d) % P_;
+      cudaStream_t s = cs[k % NCS];
+      CK(cudaStreamWaitEvent(s, ready, 0));
+      if (k == 0) prof_begin(KC_EXCH, s);
+      C* dst = (inR ? peerR[q] : peerQ[q]) + off + (size_t)rank_ * B;
+      CK(cudaMemcpyAsync(dst, send + (size_t)q * B, L * sizeof(C), cudaMemcpyDeviceToDevice, s));
+      flag_signal(peerF[q] + (size_t)slot * P_ + rank_, ep, s);
+      if (k == 0) prof_end(s);
+    }
+    pushes_pending = true;
+    return ep;
+  }
+  bool pushes_pending = false;
+  // my own pushes out of the send buffers must have completed before the next evaluation overwrites those buffers
+  void drain_pushes() {
+    if (!pushes_pending) return;
+    for (int i = 0; i < NCS && i < P_ - 1; ++i) CK(cudaStreamWaitEvent(st, mark(cs[i]), 0));
+    pushes_pending = false;
   }
   void rhs_pipe(const C* Sin, SpecArgs<T> sa, bool want_red) {
     pipe_alloc();
     const int NZC = zchunks, zc = nzl / NZC;
     const size_t Bi = (size_t)nin * zc * Kyl * Kxp, Bo = (size_t)nout * zc * Kyl * Kxp;   // one (chunk, peer) piece
     const long long fld = (long long)zc * Kyl * Kxp;                                      // field stride inside a piece
-    const int Gi = groups_of(nin), Go = groups_of(nout), fgi = nin / Gi, fgo = nout / Go;   // groups and fields per group
+    const int Gim = groups_max(nin), Gom = groups_max(nout);
+    const int mi = Gim > 1 ? group_mode(nin, Gim) : 0, mo = Gom > 1 ? group_mode(nout, Gom) : 0;
+    auto Gi_of = [&](int c) { return (mi == 1 || (mi == 2 && c == 0)) ? Gim : 1; };          // groups of inverse chunk c
+    auto Go_of = [&](int c) { return (mo == 1 || (mo == 2 && c == NZC - 1)) ? Gom : 1; };    // groups of forward chunk c
+    const int Gz = mi ? Gim : 1, fgz = nin / Gz;      // the inverse z pass runs group by group whenever any chunk is grouped
+    const int Gf = mo ? Gom : 1, fgf = nout / Gf;     // ... and so does the forward z pass
     const C* zin = Sin;
     if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {
@@ -921,16 +968,17 @@ struct Solver : mhdf_handle {
     sa.force = fmask ? force : nullptr; sa.fmask = fmask;
     next_a99(sa);
     if (want_red) red_reset();
+    drain_pushes();
     // Flag mode (peer memory): no collective in this function.  Why a peer's receive buffer is free when my push arrives:
     //  R (inverse receive) of peer q is read by its inverse y passes; my next inverse push follows my spectral update, which
     //    waited for q's forward pieces of ALL chunks, each sent after q's forward y pass of that chunk, i.e. after q read R;
     //  Q (forward receive) of peer q is read by its forward z pass; my next forward push of chunk c follows my inverse y pass
     //    of chunk c, which waited for q's inverse piece of the next evaluation, sent after q's spectral update, i.e. after
     //    q's forward z pass read Q.
-    std::vector<cudaEvent_t> zdone(Gi);
-    for (int g = 0; g < Gi; ++g) {   // inverse z pass, one field group at a time, into the two-level send layout
+    std::vector<cudaEvent_t> zdone(Gz);
+    for (int g = 0; g < Gz; ++g) {   // inverse z pass, one field group at a time, into the two-level send layout
       PassArgs<T> a;
-      a.in = zin + (size_t)g * fgi * cf; a.out = P + (size_t)g * fgi * fld; a.tw = twz;
+      a.in = zin + (size_t)g * fgz * cf; a.out = P + (size_t)g * fgz * fld; a.tw = twz;
       a.in_row = a.out_row = Kyl * Kxp;
       a.in_outer = a.out_outer = 0;
       a.in_field = cf; a.out_field = fld;
@@ -939,24 +987,28 @@ struct Solver : mhdf_handle {
       a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bi); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
       blk_out = true;
       prof_begin(KC_ZINV);
-      launch_pass<+1>(nz, a, 1, fgi);
+      launch_pass<+1>(nz, a, 1, fgz);
       prof_end();
       zdone[g] = mark(st);
     }
-    std::vector<cudaEvent_t> inv(NZC), fwd((size_t)NZC * Go);
-    std::vector<unsigned> epi((size_t)NZC * Gi), epf((size_t)NZC * Go);
+    struct Round { int slot; unsigned ep; };
+    std::vector<std::vector<Round>> inv_r(NZC), fwd_r(NZC);
+    std::vector<cudaEvent_t> inv_local(NZC);
     for (int c = 0; c < NZC; ++c) {   // pushes in the order the consumers need them: chunk by chunk, group by group
-      for (int g = 0; g < Gi; ++g) {
-        if (c == 0) CK(cudaStreamWaitEvent(sc, zdone[g], 0));
-        const size_t o = (size_t)c * P_ * Bi + (size_t)g * fgi * fld;
-        epi[c * Gi + g] = exchange(P + o, R + o, fgi, c == 0 && g == 0, Bi, c * 4 + g, (size_t)fgi * fld);
+      const int G = Gi_of(c), fg = nin / G;
+      for (int g = 0; g < G; ++g) {
+        const size_t o = (size_t)c * P_ * Bi + (size_t)g * fg * fld;
+        // data of group g of this chunk is complete once the z passes of the field groups it spans are done
+        const cudaEvent_t ready = zdone[G == 1 ? Gz - 1 : g];
+        inv_r[c].push_back({c * 4 + g, push_round(P + o, R + o, Bi, (size_t)fg * fld, c * 4 + g, ready)});
       }
-      inv[c] = mark(sc);
+      inv_local[c] = mark(sc);
     }
+    std::vector<cudaEvent_t> fwd_local;
     for (int c = 0; c < NZC; ++c) {
       const size_t zoff = (size_t)c * zc * ny * Kxp;
-      CK(cudaStreamWaitEvent(st, inv[c], 0));
-      for (int g = 0; g < Gi; ++g) wait_flags(c * 4 + g, epi[c * Gi + g]);
+      CK(cudaStreamWaitEvent(st, inv_local[c], 0));
+      for (const Round& r : inv_r[c]) wait_flags(r.slot, r.ep);
       {   // inverse y pass of chunk c: received pieces -> x-pass layout
         PassArgs<T> a;
         a.in = R + (size_t)c * P_ * Bi; a.out = Xin + zoff; a.tw = twy;
@@ -981,9 +1033,10 @@ struct Solver : mhdf_handle {
       launch_xfused(xa);
       prof_end();
       if (want_red && c == NZC - 1) finish_red();
-      for (int g = 0; g < Go; ++g) {   // forward y pass of chunk c, group by group, each followed by its push
+      const int G = Go_of(c), fg = nout / G;
+      for (int g = 0; g < G; ++g) {   // forward y pass of chunk c (group by group where grouped), each followed by its push
         PassArgs<T> a;
-        a.in = Xout + zoff + (size_t)g * fgo * nzl * ny * Kxp; a.out = P2 + (size_t)c * P_ * Bo + (size_t)g * fgo * fld; a.tw = twy;
+        a.in = Xout + zoff + (size_t)g * fg * nzl * ny * Kxp; a.out = P2 + (size_t)c * P_ * Bo + (size_t)g * fg * fld; a.tw = twy;
         a.in_row = a.out_row = Kxp;
         a.in_outer = (long long)ny * Kxp; a.out_outer = (long long)Kyl * Kxp;
         a.in_field = (long long)nzl * ny * Kxp; a.out_field = fld;
@@ -992,18 +1045,21 @@ struct Solver : mhdf_handle {
         a.blk2_rows = 0; a.blk2_stride = 0; a.blk2_magic = 0;
         blk_out = true;
         prof_begin(KC_YFWD);
-        launch_pass<-1>(ny, a, zc, fgo);
+        launch_pass<-1>(ny, a, zc, fg);
         prof_end();
-        order(st, sc);
-        const size_t o = (size_t)c * P_ * Bo + (size_t)g * fgo * fld;
-        epf[c * Go + g] = exchange(P2 + o, Q + o, fgo, c == 0 && g == 0, Bo, 32 + c * 4 + g, (size_t)fgo * fld);
-        fwd[c * Go + g] = mark(sc);
+        const size_t o = (size_t)c * P_ * Bo + (size_t)g * fg * fld;
+        fwd_r[c].push_back({32 + c * 4 + g, push_round(P2 + o, Q + o, Bo, (size_t)fg * fld, 32 + c * 4 + g, mark(st))});
+        fwd_local.push_back(mark(sc));
       }
     }
-    for (int g = 0; g < Go; ++g) {   // forward z pass of a field group as soon as its pieces of every chunk have landed
-      for (int c = 0; c < NZC; ++c) { CK(cudaStreamWaitEvent(st, fwd[c * Go + g], 0)); wait_flags(32 + c * 4 + g, epf[c * Go + g]); }
+    for (cudaEvent_t e : fwd_local) CK(cudaStreamWaitEvent(st, e, 0));   // own pieces (local copies) are in place
+    for (int g = 0; g < Gf; ++g) {   // forward z pass of a field group as soon as its pieces of every chunk have landed
+      for (int c = 0; c < NZC; ++c) {
+        if ((int)fwd_r[c].size() == 1) { if (g == 0) wait_flags(fwd_r[c][0].slot, fwd_r[c][0].ep); }   // whole-chunk push: wait once
+        else wait_flags(fwd_r[c][g].slot, fwd_r[c][g].ep);
+      }
       PassArgs<T> a;
-      a.in = Q + (size_t)g * fgo * fld; a.out = Xin + (size_t)g * fgo * cf; a.tw = twz;   // compact product spectra go to Xin (free by now)
+      a.in = Q + (size_t)g * fgf * fld; a.out = Xin + (size_t)g * fgf * cf; a.tw = twz;   // compact product spectra go to Xin (free by now)
       a.in_row = a.out_row = Kyl * Kxp;
       a.in_outer = a.out_outer = 0;
       a.in_field = fld; a.out_field = cf;
@@ -1012,7 +1068,7 @@ struct Solver : mhdf_handle {
       a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bo); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
       blk_out = false;
       prof_begin(KC_ZFWD);
-      launch_pass<-1>(nz, a, 1, fgo);
+      launch_pass<-1>(nz, a, 1, fgf);
       prof_end();
     }
     sa.P = Xin;

@@ -321,8 +321,10 @@ template <int N> void test_xfused_hd_emhd() {
     report("xfused HD N=" + std::to_string(N), e < 3e-6, e);
   }
   {   // EMHD: G_i = sum_j A_j dB_ij - bst_j dA_ij ; fresh b written back
-    auto in = randc<T>((size_t)24 * rows * Kxp, 22);
+    auto in = randc<T>((size_t)18 * rows * Kxp, 22);
     for (size_t i = 0; i < in.size(); ++i) if ((int)(i % Kxp) >= Kx) in[i] = mk<C>(0, 0);
+    std::vector<T> krv(Kx);
+    for (int k = 0; k < Kx; ++k) krv[k] = (T)(0.75 * k);     // Lx = 8 pi / 3
     std::vector<C> out((size_t)3 * rows * Kxp, mk<C>(0, 0));
     std::vector<T> bst((size_t)3 * rows * N);
     std::mt19937 g(5); std::uniform_real_distribution<double> u01(-1, 1);
@@ -332,19 +334,33 @@ template <int N> void test_xfused_hd_emhd() {
     XArgs<T> a;
     a.in = in.data(); a.out = out.data(); a.tw = tw.data(); a.real_io = bst.data();
     a.in_field = a.out_field = rows * Kxp; a.real_field = rows * N; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp; a.scale = (T)(1.0 / N); a.red = &red;
+    a.kxv = krv.data();
     emu::launch(k_xfused<T, N, E, RB, PHYS_EMHD, true>, dim3(1, 1, 1), Tm * RB, a);
     std::vector<cd> ref(out.size(), 0);
     double eb = 0, nb = 0;
     for (long long r = 0; r < rows; ++r) {
-      std::vector<std::vector<double>> F(24);
-      for (int q = 0; q < 24; ++q) F[q] = c2r_ref(&in[((size_t)q * rows + r) * Kxp], Kx, N);
+      // layout: A (0..2), d_{y,z} B_i (3 + 2 i + j - 1), d_{y,z} A_i (9 + 2 i + j - 1), B (15..17); d_x rows = i kr X of the B_i / A_i rows
+      std::vector<std::vector<double>> F(18), DXB(3), DXA(3);
+      for (int q = 0; q < 18; ++q) F[q] = c2r_ref(&in[((size_t)q * rows + r) * Kxp], Kx, N);
+      for (int i = 0; i < 3; ++i) {
+        std::vector<C> db(Kxp, mk<C>(0, 0)), da(Kxp, mk<C>(0, 0));
+        for (int k = 0; k < Kx; ++k) {
+          const C xb = in[((size_t)(15 + i) * rows + r) * Kxp + k], xa = in[((size_t)i * rows + r) * Kxp + k];
+          db[k] = mk<C>(-krv[k] * xb.y, krv[k] * xb.x);
+          da[k] = mk<C>(-krv[k] * xa.y, krv[k] * xa.x);
+        }
+        DXB[i] = c2r_ref(db.data(), Kx, N);
+        DXA[i] = c2r_ref(da.data(), Kx, N);
+      }
       for (int i = 0; i < 3; ++i) {
         std::vector<double> acc(N, 0.0);
-        for (int j = 0; j < 3; ++j) for (int n = 0; n < N; ++n)
-          acc[n] += F[j][n] * F[3 + 3 * i + j][n] - (double)bst0[((size_t)j * rows + r) * N + n] * F[12 + 3 * i + j][n];
+        for (int j = 0; j < 3; ++j) for (int n = 0; n < N; ++n) {
+          const double dB = (j == 0) ? DXB[i][n] : F[3 + 2 * i + (j - 1)][n], dA = (j == 0) ? DXA[i][n] : F[9 + 2 * i + (j - 1)][n];
+          acc[n] += F[j][n] * dB - (double)bst0[((size_t)j * rows + r) * N + n] * dA;
+        }
         auto X = r2c_ref(acc, Kx);
         for (int k = 0; k < Kx; ++k) ref[((size_t)i * rows + r) * Kxp + k] = X[k];
-        for (int n = 0; n < N; ++n) { const double d = bst[((size_t)i * rows + r) * N + n] - F[21 + i][n]; eb += d * d; nb += F[21 + i][n] * F[21 + i][n]; }
+        for (int n = 0; n < N; ++n) { const double d = bst[((size_t)i * rows + r) * N + n] - F[15 + i][n]; eb += d * d; nb += F[15 + i][n] * F[15 + i][n]; }
       }
     }
     const double e = rel_err<T>(out, ref);
@@ -396,8 +412,10 @@ template <int N, typename T> void test_xfused_emhd2() {
   const int Kx = bx.lo, Kxp = (Kx + 7) / 8 * 8;
   const long long rows = 3 * RB;
   auto tw = make_tw<T>(N);
-  auto in = randc<T>((size_t)24 * rows * Kxp, 81);
+  auto in = randc<T>((size_t)18 * rows * Kxp, 81);
   for (size_t i = 0; i < in.size(); ++i) if ((int)(i % Kxp) >= Kx) in[i] = mk<C>(0, 0);
+  std::vector<T> krv(Kx);
+  for (int k = 0; k < Kx; ++k) krv[k] = (T)(0.75 * k);
   std::vector<T> bst((size_t)3 * rows * N);
   std::mt19937 g(7); std::uniform_real_distribution<double> u01(-1, 1);
   for (auto& x : bst) x = (T)u01(g);
@@ -406,7 +424,7 @@ template <int N, typename T> void test_xfused_emhd2() {
   XRed red1, red2; std::memset(&red1, 0, sizeof red1); std::memset(&red2, 0, sizeof red2);
   XArgs<T> a;
   a.in = in.data(); a.tw = tw.data(); a.in_field = a.out_field = rows * Kxp; a.real_field = rows * N; a.rows = rows; a.Kx = Kx; a.Kxp = Kxp;
-  a.scale = (T)(1.0 / N); a.vp = nullptr; a.vp_field = 0; a.vp_eta = 1;
+  a.scale = (T)(1.0 / N); a.vp = nullptr; a.vp_field = 0; a.vp_eta = 1; a.kxv = krv.data();
   a.out = out1.data(); a.real_io = b1.data(); a.red = &red1;
   emu::launch(k_xfused<T, N, E, RB, PHYS_EMHD, true>, dim3(2, 1, 1), Tm * RB, a);
   a.out = out2.data(); a.real_io = b2.data(); a.red = &red2;
@@ -743,7 +761,7 @@ static void test_derive_and_pack() {
   SpecGeom<T> g; std::memset(&g, 0, sizeof g);
   g.Kx = Kx; g.Kxp = Kxp; g.by = by; g.bz = bz; g.Kyl = Ky; g.ky0 = 0; g.F = 3; g.kx = kx.data(); g.ky = ky.data(); g.kz = kz.data(); g.field = cf;
   auto B = randc<T>((size_t)3 * cf, 41);
-  std::vector<C> out((size_t)24 * cf, mk<C>(0, 0));
+  std::vector<C> out((size_t)18 * cf, mk<C>(0, 0));
   struct DArgs { SpecGeom<T> g; const C* B; C* out; } da{g, B.data(), out.data()};
   emu::launch([](const DArgs& d) { k_emhd_derive<T>(d.g, d.B, d.out); }, dim3(2, 1, 1), 256, da);
   double worst = 0;
@@ -757,10 +775,10 @@ static void test_derive_and_pack() {
     auto got = [&](int f) { return cd(out[f * cf + e].x, out[f * cf + e].y); };
     for (int i = 0; i < 3; ++i) {
       worst = std::max(worst, std::abs(got(i) - A[i]));
-      worst = std::max(worst, std::abs(got(21 + i) - b[i]));
-      for (int jj = 0; jj < 3; ++jj) {
-        worst = std::max(worst, std::abs(got(3 + 3 * i + jj) - I * K[jj] * b[i]));
-        worst = std::max(worst, std::abs(got(12 + 3 * i + jj) - I * K[jj] * A[i]));
+      worst = std::max(worst, std::abs(got(15 + i) - b[i]));
+      for (int jj = 1; jj < 3; ++jj) {
+        worst = std::max(worst, std::abs(got(3 + 2 * i + (jj - 1)) - I * K[jj] * b[i]));
+        worst = std::max(worst, std::abs(got(9 + 2 * i + (jj - 1)) - I * K[jj] * A[i]));
       }
     }
   }

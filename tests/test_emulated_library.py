@@ -29,8 +29,8 @@ GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5"],
 
 
 # slab-decomposed runs, ranks = threads of tests/cpu_emu/test_library_ranks.cpp: (ranks, environment)
-RANK_RUNS = {"P=2 peer pushes, z-chunk pipeline": (2, {"MHDF_ZCHUNKS": "2"}),
-             "P=4 send/recv": (4, {"MHDF_PEER": "0"})}
+RANK_RUNS = {"P=2 peer pushes + flags, z-chunk pipeline, field groups at the ends": (2, {"MHDF_ZCHUNKS": "2", "MHDF_FGROUPS": "2"}),
+             "P=4 send/recv, field groups in every chunk": (4, {"MHDF_PEER": "0", "MHDF_FGROUPS": "1"})}
 # Found with this harness and fixed: the multiply-high division of the blocked exchange addressing cannot represent a divisor
 # of 1 -- one z plane per pipeline chunk (or per rank) silently scrambled the exchange; such shapes now fall back / are refused.
 
