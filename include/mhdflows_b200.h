@@ -149,6 +149,16 @@ int mhdf_spectrum(mhdf_handle* h, int field, double* Pk, int nbins);
 /* stale per-field maxima of f^2 and sums of f^2 (6 each; EMHD: curl B then b) as used by getCFL!/ProbDiagnostic. */
 int mhdf_stale_stats(const mhdf_handle* h, double* maxsq6, double* sumsq6);
 
+/* On-device analysis of the state (utils/MHDAnalysis.jl), three real fields (x, y, z components, consecutive) to `out3`
+ * (host or device memory):
+ *   ScaleDecomposition(B1, B2, B3, grid; kf = [k1, k2]) (MHDAnalysis.jl:54-82): the part of the velocity (group 0) or of the
+ *     magnetic field (group 1) with k1 <= |k| <= k2;
+ *   VectorPotential(B1, B2, B3) (MHDAnalysis.jl:129-174): a = curl^-1 b in the Coulomb gauge, a^ = i (k x b^) / k^2.
+ * which = MHDF_FRESH (sol) or MHDF_STALE (the reference's vars.*, what a user script would pass).  The reference applies these
+ * to arbitrary arrays; here the input is the (dealiased) state, i.e. equal whenever the argument is band-limited. */
+int mhdf_scale_decomposition(mhdf_handle* h, int group, int which, double k1, double k2, void* out3);
+int mhdf_vector_potential(mhdf_handle* h, int which, void* out3);
+
 /* Measurement helpers. */
 int mhdf_step_timed(mhdf_handle* h, int nsteps, double* ms_total);   /* CUDA events on the library stream */
 int mhdf_profile(mhdf_handle* h, int enable);                        /* per-kernel-class CUDA event timing */

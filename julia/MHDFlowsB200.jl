@@ -4,13 +4,15 @@
 # `using MHDFlows` to `using MHDFlowsB200` (reference: src/MHDFlows.jl:65-88, src/pgen.jl:64-127,
 # src/utils/IC.jl:41-109, src/integrator.jl:31-198, src/utils/UserInterface.jl:65-86,
 # src/DiagnosticWrapper.jl:14-105).  NOT EXECUTED in the build environment (Julia is not installed there);
-# the Python ctypes mirror mhdflows_jl_b200/ is the tested twin of this file -- keep them line-for-line.
+# the Python ctypes mirror mhdflows_jl_b200/ is the tested twin of this file -- keep them line-for-line
+# (tests/test_abi.py checks that every entry point bound here exists in the header with the same argument count).
 module MHDFlowsB200
 
 export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDiagnostic, Diagnostic,
        increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum,
        N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!,
-       A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!, setvpfield!
+       A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!, setvpfield!,
+       savefile, Restart!, readMHDFlows, DivFreeSpectraMap, SetUpRandomPhaseIC!
 
 const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
 
@@ -110,11 +112,21 @@ end
 fieldid(prob, s::Symbol) = prob.flag.e ? Dict(:bx=>0, :by=>1, :bz=>2)[s] :
                            Dict(:ux=>0, :uy=>1, :uz=>2, :bx=>3, :by=>4, :bz=>5)[s]
 
+# Field arguments may live on the host (Array) or on the device (CuArray): the library copies with cudaMemcpyDefault
+# (include/mhdflows_b200.h), so a device array is passed by its device pointer and never bounces through the host.
+_fieldarg(::Type{T}, A::Array) where {T} = Array{T,3}(A)
+_fieldarg(::Type{T}, A) where {T} = (eltype(A) === T || error("device fields must already have the problem's element type"); A)
+_fieldptr(A::Array) = Ptr{Cvoid}(pointer(A))
+_fieldptr(A) = Ptr{Cvoid}(UInt(pointer(A)))          # CuArray: CuPtr -> raw address (unified addressing)
+
 "SetUpProblemIC!(prob; ux, uy, uz, bx, by, bz)   (utils/IC.jl:41-109)"
 function SetUpProblemIC!(prob; ux = [], uy = [], uz = [], bx = [], by = [], bz = [])
   T = typeof(prob).parameters[1]
-  put(s, A) = A == [] ? nothing :
-    check(prob.h, ccall((:mhdf_set_real, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, fieldid(prob, s), Array{T,3}(A)))
+  function put(s, A)
+    A == [] && return nothing
+    B = _fieldarg(T, A)
+    GC.@preserve B check(prob.h, ccall((:mhdf_set_real, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, fieldid(prob, s), _fieldptr(B)))
+  end
   if !prob.flag.e; put(:ux, ux); put(:uy, uy); put(:uz, uz); end
   if prob.flag.b;  put(:bx, bx); put(:by, by); put(:bz, bz); end
   return nothing
@@ -263,10 +275,68 @@ end
 increment!(d::Diagnostic) = (d.prob.clock.step % d.freq == 0 && update!(d, d.i + 1); nothing)
 increment!(ds::AbstractVector) = (foreach(increment!, ds); nothing)
 
-"TimeIntegrator!(prob, t₀, N₀; usr_dt, CFL_Coef, diags, ...)   (integrator.jl:31-156, loop + CFL; HDF5 output not on this path)"
+# ---- checkpoints in the reference's on-disk format (integrator.jl:208-288, utils/IC.jl:245-257) ----------------------------
+# HDF5.jl is the reference's own dependency (Project.toml); it is loaded lazily so that the shim itself needs no package.
+_h5() = (isdefined(Main, :HDF5) ? getfield(Main, :HDF5) : Base.require(Base.PkgId(Base.UUID("f67ccb44-e63f-5c2f-98bd-6dc0ccc4ba2f"), "HDF5")))
+const _UNAMES = ((:ux, "i_velocity"), (:uy, "j_velocity"), (:uz, "k_velocity"))
+const _BNAMES = ((:bx, "i_mag_field"), (:by, "j_mag_field"), (:bz, "k_mag_field"))
+"savefile(prob, file_number; file_path_and_name)   (integrator.jl:259-288): the stale vars and the time"
+function savefile(prob, file_number; file_path_and_name = "")
+  H = _h5()
+  name = file_path_and_name * "_t_" * lpad(string(file_number), 4, "0") * ".h5"
+  H.h5open(name, "w") do fw
+    if !prob.flag.e; for (s, ds) in _UNAMES; write(fw, ds, realfield(prob, s)); end; end
+    if prob.flag.b;  for (s, ds) in _BNAMES; write(fw, ds, realfield(prob, s)); end; end
+    write(fw, "time", prob.clock.t)
+  end
+  name
+end
+"readMHDFlows(FileName)   (utils/IC.jl:245-257)"
+function readMHDFlows(FileName)
+  H = _h5()
+  H.h5open(FileName, "r") do f
+    Dict(k => read(f, k) for k in keys(f))
+  end
+end
+"Restart!(prob, file_path_and_name)   (integrator.jl:208-257): fields into vars / sol, clock.t restored"
+function Restart!(prob, file_path_and_name)
+  d = readMHDFlows(file_path_and_name)
+  if !prob.flag.e; SetUpProblemIC!(prob; ux = d["i_velocity"], uy = d["j_velocity"], uz = d["k_velocity"]); end
+  if prob.flag.b;  SetUpProblemIC!(prob; bx = d["i_mag_field"], by = d["j_mag_field"], bz = d["k_mag_field"]); end
+  prob.clock.t = d["time"]
+  nothing
+end
+
+"SetUpRandomPhaseIC!(prob; seed_u, seed_b, k_peak, P, k0): DivFreeSpectraMap + SetUpProblemIC! without leaving the device"
+function SetUpRandomPhaseIC!(prob; seed_u = nothing, seed_b = nothing, k_peak = 0.0, P = 1, k0 = -5/3/2)
+  rp(g, seed) = check(prob.h, ccall((:mhdf_set_random_phase, lib), Cint, (Ptr{Cvoid}, Cint, Culonglong, Cdouble, Cdouble, Cdouble),
+                                    prob.h, g, seed, k0, P, k_peak))
+  seed_u !== nothing && !prob.flag.e && rp(0, seed_u)
+  seed_b !== nothing && prob.flag.b && rp(1, seed_b)
+  nothing
+end
+"DivFreeSpectraMap(Nx, Ny, Nz; Lx, P, k0, b, T, k_peak, seed) -> Fx, Fy, Fz   (utils/IC.jl:122-179), built on the device"
+function DivFreeSpectraMap(Nx::Int, Ny::Int, Nz::Int; Lx = 2π, dev = GPU(), P = 1, k0 = -5/3/2, b = 1, T = Float32, k_peak = 0.0, seed = 0)
+  p = Problem(dev; nx = Nx, ny = Ny, nz = Nz, Lx = Lx, T = T)
+  SetUpRandomPhaseIC!(p; seed_u = seed, k_peak = k_peak, P = P, k0 = k0)
+  F = (realfield(p, :ux; stale = false), realfield(p, :uy; stale = false), realfield(p, :uz; stale = false))
+  finalize(p)
+  F
+end
+
+"TimeIntegrator!(prob, t₀, N₀; usr_dt, CFL_Coef, diags, save, save_loc, filename, file_number, dump_dt, ...)   (integrator.jl:31-156)"
 function TimeIntegrator!(prob, t₀::Number, N₀::Int; usr_dt = 0.0, CFL_Coef = 0.25, CFL_function = nothingfunction,
-                         diags = [], dynamic_dashboard = true, loop_number = 100, save = false, kwargs...)
-  save && error("HDF5 output is outside the B200 hot path")
+                         diags = [], dynamic_dashboard = true, loop_number = 100, save = false,
+                         save_loc = "", filename = "", file_number = 0, dump_dt = 0, kwargs...)
+  file_path_and_name = ""
+  if save                                           # integrator.jl:44-51
+    (length(save_loc) == 0 || length(filename) == 0 || dump_dt == 0) &&
+      error("Save Function Turned ON but save_loc/filename/dump_dt is not declared!\n")
+    file_path_and_name = save_loc * filename
+    savefile(prob, file_number; file_path_and_name = file_path_and_name)
+    file_number += 1
+  end
+  t_next_save = prob.clock.t + dump_dt              # integrator.jl:75
   updateCFL! = CFL_function === nothingfunction ? getCFL! : CFL_function
   p = prob.params
   vi = prob.flag.b ? (prob.flag.e ? p.η : max(p.ν, p.η)) : p.ν
@@ -286,6 +356,12 @@ function TimeIntegrator!(prob, t₀::Number, N₀::Int; usr_dt = 0.0, CFL_Coef =
       DivVCorrection!(prob); prob.flag.b && DivBCorrection!(prob)
     end
     for foo! in prob.usr_func; foo!(prob); end
+    if save && prob.clock.t >= t_next_save          # integrator.jl:136-141
+      ProbDiagnostic(prob)
+      savefile(prob, file_number; file_path_and_name = file_path_and_name)
+      t_next_save += dump_dt
+      file_number += 1
+    end
   end
   n = prob.grid.nx * prob.grid.ny * prob.grid.nz
   print("Total CPU/GPU time run = $(round(time, digits = 3)) s, zone update per second = $(round(prob.clock.step * n / time, digits = 3)) \n")

@@ -102,6 +102,12 @@ int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls) {
 }
 int mhdf_set_vp_field(mhdf_handle* h, int which, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_vp_field(which, p); }); }
 int mhdf_div_correction(mhdf_handle* h, int group) { return guard(h, [&] { h->div_correction(group); }); }
+int mhdf_scale_decomposition(mhdf_handle* h, int group, int which, double k1, double k2, void* out3) {
+  return guard(h, [&] { if (!out3) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->analysis(0, group, which, k1, k2, out3); });
+}
+int mhdf_vector_potential(mhdf_handle* h, int which, void* out3) {
+  return guard(h, [&] { if (!out3) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->analysis(1, 1, which, 0, 0, out3); });
+}
 int mhdf_set_random_phase(mhdf_handle* h, int group, unsigned long long seed, double k0, double P, double k_peak) {
   return guard(h, [&] { h->set_random_phase(group, seed, k0, P, k_peak); });
 }

@@ -1336,6 +1336,41 @@ __global__ void __launch_bounds__(256) k_dfsm_fill(SpecGeom<T> g, DfsmArgs<T> q,
   }
 }
 
+// ---- on-device analysis of the state (utils/MHDAnalysis.jl) ------------------------------------------------------------
+// mode 0: ScaleDecomposition (MHDAnalysis.jl:24-82): f^_c <- f^_c where k1 <= |k| <= k2, else 0  (|k| = sqrt(kr^2 + l^2 + m^2) in T)
+// mode 1: VectorPotential (MHDAnalysis.jl:129-174): a^ = i (k x b^) / k^2 (Coulomb gauge; the k = 0 mode gives 0)
+// in: three consecutive fields of a compact state; out: three compact fields (inverse-transformed by the caller).
+template <typename T>
+__global__ void __launch_bounds__(256) k_analysis(SpecGeom<T> g, const Cx<T>* __restrict__ S, Cx<T>* __restrict__ out, int mode, T k1, T k2) {
+  using C = Cx<T>;
+  const int Ky = g.Kyl, Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    const long long rowi = e / g.Kxp;
+    const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+    C f[3], o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { f[c] = S[c * g.field + e]; o[c] = mk<C>(0, 0); }
+    if (ix < g.Kx && g.ky0 + jc < g.by.count()) {
+      const T k[3] = {g.kx[ix], g.ky[jc], g.kz[kc]};
+      const T kk2 = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
+      if (mode == 0) {
+        const T kr = sqrt(kk2);
+        if (k2 >= kr && kr >= k1) { o[0] = f[0]; o[1] = f[1]; o[2] = f[2]; }
+      } else {
+        const T ik2 = (kk2 > (T)0) ? (T)1 / kk2 : (T)0;
+        const C c0 = mk<C>(k[1] * f[2].x - k[2] * f[1].x, k[1] * f[2].y - k[2] * f[1].y);
+        const C c1 = mk<C>(k[2] * f[0].x - k[0] * f[2].x, k[2] * f[0].y - k[0] * f[2].y);
+        const C c2 = mk<C>(k[0] * f[1].x - k[1] * f[0].x, k[0] * f[1].y - k[1] * f[0].y);
+        o[0] = cscale(cmuli(c0), ik2); o[1] = cscale(cmuli(c1), ik2); o[2] = cscale(cmuli(c2), ik2);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c * g.field + e] = o[c];
+  }
+}
+
 // full (nkr, ny, nz) spectral array <-> compact field.  dir = 0: full -> compact (drop dealiased modes),
 // dir = 1: compact -> full (dealiased modes written as zero).
 template <typename T>

@@ -122,6 +122,7 @@ struct mhdf_handle {
   virtual void set_forcing_a99(const mhdf_a99* p) = 0;
   virtual unsigned long long a99_calls() const = 0;
   virtual void div_correction(int group) = 0;
+  virtual void analysis(int mode, int group, int which, double k1, double k2, void* out3) = 0;
   virtual void set_random_phase(int group, unsigned long long seed, double k0, double P, double k_peak) = 0;
   virtual void set_vp_field(int which, const void* p) = 0;
   virtual void ipc_export(void* blob) = 0;
@@ -1364,6 +1365,33 @@ struct Solver : mhdf_handle {
       const int slot = (phys == MHDF_EMHD) ? 3 + i : f0 + i;
       st_sum[slot] = red_h->sumsq[0];
       st_max[slot] = red_max(0);
+    }
+  }
+  // ScaleDecomposition (mode 0) / VectorPotential (mode 1) of a vector field of the state (utils/MHDAnalysis.jl:24-82, 129-174),
+  // on the device: spectral mask / curl into a dead register, three inverse transforms, three real fields to `out3`.
+  void analysis(int mode, int group, int which, double k1, double k2, void* out3) override {
+    CK(cudaSetDevice(cfg.device));
+    int f0;
+    if (group == 0) { if (phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "the EMHD state has no velocity"}; f0 = 0; }
+    else if (group == 1) { if (phys == MHDF_HD) throw Err{MHDF_ERR_INVALID, "the HD state has no magnetic field"}; f0 = (phys == MHDF_EMHD) ? 0 : 3; }
+    else throw Err{MHDF_ERR_INVALID, "group must be 0 (velocity) or 1 (magnetic field)"};
+    if (mode != 0 && mode != 1) throw Err{MHDF_ERR_INVALID, "analysis mode must be 0 (scale decomposition) or 1 (vector potential)"};
+    int o = -1;
+    const int nreg = (cfg.stepper == MHDF_RK4) ? 4 : 3;
+    for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
+    rank_barrier();
+    MHDF_LAUNCH((k_analysis<T>), spec_grid(), 256, 0, st, geom(), source(which) + (size_t)f0 * cf, reg[o], mode, (T)k1, (T)k2);
+    ++launches;
+    CK(cudaGetLastError());
+    T* re = reinterpret_cast<T*>(R);
+    const size_t n = (size_t)nx * ny * nzl;
+    for (int i = 0; i < 3; ++i) {
+      to_xlayout(reg[o] + (size_t)i * cf, 1);
+      XArgs<T> xa = xargs();
+      xa.real_io = re; xa.in = Q; xa.out = nullptr;
+      launch_xplain<+1>(xa);
+      CK(cudaMemcpyAsync(reinterpret_cast<T*>(out3) + (size_t)i * n, re, n * sizeof(T), cudaMemcpyDefault, st));
+      sync_all();
     }
   }
   // DivFreeSpectraMap (utils/IC.jl:130-179) followed by SetUpProblemIC! (IC.jl:41-109) for one vector field, on the device:

@@ -731,6 +731,24 @@ def spectralline(prob, field, nbins=None):
     return Pk.astype(prob.T), kr
 
 
+def ScaleDecomposition(prob, group="b", kf=(1, 5), which=L.STALE):
+    """ScaleDecomposition(B1, B2, B3, grid; kf) (utils/MHDAnalysis.jl:54-82) of the problem's velocity (group "u") or magnetic
+    field ("b"), on the device: the three components restricted to kf[0] <= |k| <= kf[1].  `which`: the reference's vars.* (STALE,
+    what a script would pass) or the true state (FRESH)."""
+    out = np.empty((3,) + prob._real_shape, dtype=prob.T)
+    g = {"u": 0, "b": 1}[group] if isinstance(group, str) else int(group)
+    L.check(prob._h, L.lib().mhdf_scale_decomposition(prob._h, g, which, float(min(kf)), float(max(kf)), out.ctypes.data))
+    return out[0], out[1], out[2]
+
+
+def VectorPotential(prob, which=L.STALE):
+    """VectorPotential(B1, B2, B3) (utils/MHDAnalysis.jl:129-174) of the problem's magnetic field, on the device: a with
+    curl a = b, div a = 0."""
+    out = np.empty((3,) + prob._real_shape, dtype=prob.T)
+    L.check(prob._h, L.lib().mhdf_vector_potential(prob._h, which, out.ctypes.data))
+    return out[0], out[1], out[2]
+
+
 DFSM_CALL = 0x7FFFFFFF44465350      # counter tag of the device random-phase stream (csrc/kernels.cuh: DFSM_CALL_HI/LO)
 
 

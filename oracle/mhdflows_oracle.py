@@ -643,6 +643,14 @@ def VectorPotential(B1, B2, B3, grid: Grid):
     return A1, A2, A3
 
 
+def ScaleDecomposition(B1, B2, B3, grid: Grid, kf=(1, 5)):
+    """MHDAnalysis.jl:54-82: rfft, keep k1 <= |k| <= k2 (|k| = sqrt(kr^2 + l^2 + m^2) in T), irfft; no dealias."""
+    k1, k2 = min(kf), max(kf)
+    kr = np.sqrt(grid.kr ** 2 + grid.l ** 2 + grid.m ** 2).astype(grid.T)
+    K = ((k2 >= kr) & (kr >= k1)).astype(grid.T)
+    return tuple(grid.irfft((grid.rfft(B) * K).astype(grid.CT)) for B in (B1, B2, B3))
+
+
 def h_m(ib, jb, kb, grid: Grid):
     """MHDAnalysis.jl:113-117: pointwise A.B (no dV)."""
     A1, A2, A3 = VectorPotential(ib, jb, kb, grid)

@@ -97,6 +97,31 @@ def random_phase_ic_on_device_matches_the_oracle():
 
 
 @case
+def on_device_scale_decomposition_and_vector_potential():
+    """mhdf_scale_decomposition / mhdf_vector_potential against the restatements of MHDAnalysis.jl:54-82, 129-174."""
+    for T, tol in ((np.float32, F32_TOL), (np.float64, F64_TOL)):
+        kw = dict(nx=16, ny=32, nz=16, Ly=3.0, T=T, nu=1e-2, eta=1e-2, dt=2e-3, B_field=True)
+        op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+        g = op.grid
+        u, b = O.random_phase_ic(g, 5), O.random_phase_ic(g, 6)
+        O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+        O.stepforward(op)
+        M.stepforward(gp)
+        vb = (op.vars.bx, op.vars.by, op.vars.bz)          # the stale vars: what a user script passes to the analysis functions
+        vu = (op.vars.ux, op.vars.uy, op.vars.uz)
+        for got, ref in zip(M.VectorPotential(gp), O.VectorPotential(*vb, g)):
+            assert O.rel_l2(got, ref) < tol
+        for grp, v in (("b", vb), ("u", vu)):
+            for got, ref in zip(M.ScaleDecomposition(gp, grp, kf=[2, 4.5]), O.ScaleDecomposition(*v, g, kf=[2, 4.5])):
+                assert np.linalg.norm(ref) > 0 and O.rel_l2(got, ref) < tol
+        fresh = [g.irfft(g.dealias(op.sol[3 + i].copy())) for i in range(3)]
+        for got, ref in zip(M.VectorPotential(gp, which=M.FRESH), O.VectorPotential(*fresh, g)):
+            assert O.rel_l2(got, ref) < tol
+        gp.close()
+
+
+@case
 def a99_host_variant_calcN_steps_counter():
     op, gp = _forced_pair(M, O, FO, "host", np.float32, dims=DIMS)
     g = op.grid

@@ -84,3 +84,43 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_julia_shim_binds_only_declared_entry_points_with_the_declared_arity():
+    """julia/MHDFlowsB200.jl cannot be executed here (no Julia): check statically that every `ccall((:mhdf_x, lib), ...)` names
+    an entry point of include/mhdflows_b200.h and passes as many arguments as the prototype declares, and that the
+    `MhdfConfig` / `MhdfA99` structs list the fields of `mhdf_config` / `mhdf_a99` in order."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "mhdflows_b200.h")).read()
+    jl = open(os.path.join(ROOT, "julia", "MHDFlowsB200.jl")).read()
+    protos = {}
+    for m in re.finditer(r"^(?:int|long long|const char\*)\s+(mhdf_\w+)\(([^;]*)\);", hdr, re.M):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    calls = re.findall(r"ccall\(\(:(mhdf_\w+), lib\),\s*\w+,\s*\(([^()]*(?:\{[^()]*\}[^()]*)*)\)", jl)
+    assert len(calls) >= 20
+    for name, types in calls:
+        assert name in protos, f"{name} is not declared in the header"
+        n = len([t for t in types.split(",") if t.strip()])
+        assert n == protos[name], f"{name}: shim passes {n} arguments, the header declares {protos[name]}"
+    bound = {c[0] for c in calls}
+    for must in ("mhdf_create", "mhdf_destroy", "mhdf_set_real", "mhdf_get_real", "mhdf_step", "mhdf_cfl_dt", "mhdf_energy",
+                 "mhdf_set_random_phase", "mhdf_div_correction", "mhdf_set_forcing_a99", "mhdf_spectrum", "mhdf_helicity"):
+        assert must in bound, must
+
+    def c_fields(struct):
+        end = hdr.index("} " + struct + ";")
+        body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            if decl.strip():
+                names += [x.strip().split()[-1].lstrip("*") for x in decl.split(",")]
+        return names
+
+    def jl_fields(struct):
+        body = re.search(r"struct " + struct + r"\n(.*?)\nend", jl, re.S).group(1)
+        return re.findall(r"(\w+)::", body)
+
+    assert jl_fields("MhdfConfig") == c_fields("mhdf_config")
+    assert jl_fields("MhdfA99") == c_fields("mhdf_a99")

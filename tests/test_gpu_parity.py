@@ -202,6 +202,26 @@ def test_stale_vars_and_spectrum(M, O):
     gp.close()
 
 
+def test_on_device_analysis(M, O):
+    """ScaleDecomposition / VectorPotential of the state on the device (utils/MHDAnalysis.jl:54-82, 129-174)."""
+    for T, tol in ((np.float32, F32_TOL), (np.float64, F64_TOL)):
+        op, gp = _pair(M, O, "mhd", (64, 32, 32), T)
+        g = op.grid
+        for _ in range(2):
+            O.stepforward(op)
+        M.stepforward(gp, 2)
+        vb = (op.vars.bx, op.vars.by, op.vars.bz)
+        for got, ref in zip(M.VectorPotential(gp), O.VectorPotential(*vb, g)):
+            assert O.rel_l2(got, ref) < tol
+        for got, ref in zip(M.ScaleDecomposition(gp, "u", kf=[2, 6]), O.ScaleDecomposition(op.vars.ux, op.vars.uy, op.vars.uz, g, kf=[2, 6])):
+            assert np.linalg.norm(ref) > 0 and O.rel_l2(got, ref) < tol
+        a = M.VectorPotential(gp, which=M.FRESH)            # curl a = b, div a = 0 on the true state
+        b = [gp.get_real(n, M.FRESH) for n in ("bx", "by", "bz")]
+        for got, ref in zip(O.Curl(*a, g), b):
+            assert O.rel_l2(got, ref) < 20 * tol
+        gp.close()
+
+
 def test_diagnostic_wrapper(M, O):
     op, gp = _pair(M, O, "hd", (32, 32, 32), np.float32)
     d = M.Diagnostic(lambda p: p.energy(M.FRESH)[0], gp, freq=2, nsteps=6)

@@ -2,6 +2,8 @@
 DivBCorrection! and the volume-penalisation terms, through the C ABI against oracle/forcing_oracle.py.
 (First green hardware run: round 2, profiles/r02_c1_pytest.log; the kernels are also checked on the CPU emulator,
 tests/cpu_emu: Philox known answers, forcing of every mode, k_divclean.)"""
+import math
+
 import numpy as np
 import pytest
 
@@ -255,6 +257,10 @@ def test_volume_penalisation_time_integrator(M, O):
     for base in (0, 3):
         div = g.kr * sol[base] + g.l * sol[base + 1] + g.m * sol[base + 2]
         assert np.linalg.norm(div.ravel()) / np.linalg.norm(sol[base:base + 3].ravel()) < 1e-5
+    # Documented deviation: after a VP step the reference's vars.* still carry the aliased-band content of the
+    # full sol, the library's do not.  Its effect on what getCFL! computes from those vars is bounded here.
+    dt_ref, dt_gpu = O.getCFL(op, math.inf, Coef=0.25), M.getCFL(gp, math.inf, Coef=0.25)
+    assert abs(dt_gpu - dt_ref) / dt_ref < 2e-2, (dt_gpu, dt_ref)
     gp.close()
     with pytest.raises(ValueError):
         M.Problem(M.GPU(), nx=16, B_field=True, EMHD=True, VP_method=True)

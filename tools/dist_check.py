@@ -87,6 +87,9 @@ if which == "check64":
     run("mhd", 64, "RK4", np.float32, 3)
     run("hd", 64, "LSRK54", np.float32, 2)
     run("emhd", 64, "RK4", np.float64, 2)
+elif which == "check128":      # smallest cubic grid 8 ranks can split (every rank needs >= 2 retained ky rows and a non-empty last slab)
+    run("mhd", 128, "RK4", np.float32, 3)
+    run("emhd", 128, "LSRK54", np.float32, 2)
 elif which == "forcing64":
     run("mhd", 64, "RK4", np.float32, 3, driven=True)
     run("mhd", 64, "LSRK54", np.float64, 2, driven=True)
