@@ -110,14 +110,13 @@ def on_device_scale_decomposition_and_vector_potential():
         M.stepforward(gp)
         vb = (op.vars.bx, op.vars.by, op.vars.bz)          # the stale vars: what a user script passes to the analysis functions
         vu = (op.vars.ux, op.vars.uy, op.vars.uz)
-        for got, ref in zip(M.VectorPotential(gp), O.VectorPotential(*vb, g)):
-            assert O.rel_l2(got, ref) < tol
+        # vectors are compared as a whole: a_z of these fields is 1e-3 of |a| (cancellation), its own relative error means nothing
+        assert O.rel_l2(np.stack(M.VectorPotential(gp)), np.stack(O.VectorPotential(*vb, g))) < tol
         for grp, v in (("b", vb), ("u", vu)):
             for got, ref in zip(M.ScaleDecomposition(gp, grp, kf=[2, 4.5]), O.ScaleDecomposition(*v, g, kf=[2, 4.5])):
                 assert np.linalg.norm(ref) > 0 and O.rel_l2(got, ref) < tol
         fresh = [g.irfft(g.dealias(op.sol[3 + i].copy())) for i in range(3)]
-        for got, ref in zip(M.VectorPotential(gp, which=M.FRESH), O.VectorPotential(*fresh, g)):
-            assert O.rel_l2(got, ref) < tol
+        assert O.rel_l2(np.stack(M.VectorPotential(gp, which=M.FRESH)), np.stack(O.VectorPotential(*fresh, g))) < tol
         gp.close()
 
 
