@@ -181,7 +181,24 @@ def test_time_integrator_cfl_path(M, O):
     assert gp.clock.step == op.clock.step == 6            # N0+1 steps, integrator.jl:104
     assert abs(gp.clock.dt - op.clock.dt) / op.clock.dt < 1e-5
     assert abs(gp.clock.t - op.clock.t) / op.clock.t < 1e-5
+    # Six steps at the CFL-limited dt (0.25 dx / vmax = 0.0245: dt k u ~ 0.8) amplify rounding differences of the state about
+    # tenfold per step-pair, so the ACCUMULATED difference is allowed 5e-5 here; the north_star bar is per step, and the same
+    # path over two steps meets it below.
     assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < 5e-5
+    gp.close()
+    op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float32, turb=False)
+    O.TimeIntegrator(op, 1e9, 1, CFL_Coef=0.25)
+    M.TimeIntegrator(gp, 1e9, 1, CFL_Coef=0.25)
+    assert gp.clock.step == op.clock.step == 2
+    assert abs(gp.clock.dt - op.clock.dt) / op.clock.dt < 1e-6
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < F32_TOL
+    gp.close()
+    # Float64: the CFL maxima are reduced in Float64 (XRed::maxsq holds the bit pattern of a double), so dt agrees to rounding
+    op, gp = _pair(M, O, "mhd", (32, 32, 32), np.float64, turb=False)
+    O.TimeIntegrator(op, 1e9, 2, CFL_Coef=0.25)
+    M.TimeIntegrator(gp, 1e9, 2, CFL_Coef=0.25)
+    assert abs(gp.clock.dt - op.clock.dt) / op.clock.dt < 1e-13
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < F64_TOL
     gp.close()
 
 

@@ -84,3 +84,83 @@ def test_writer_refuses_what_it_cannot_represent(tmp_path):
     p.write_bytes(b"not hdf5" * 100)
     with pytest.raises(H.H5Error):
         H.File(str(p))
+
+
+def _structure(f):
+    """Version / flag / size conventions of every structure kind in an HDF5 file, decoded from the raw bytes: what libhdf5
+    checks when it opens the file and walks the root group (superblock, root symbol entry, B-tree node, local heap,
+    symbol-table node, object headers and their dataspace / datatype / layout messages)."""
+    b, base = f.buf, f.base
+    sb = base   # superblock starts at the base address
+    s = {"sig": bytes(b[sb:sb + 8]), "sb_version": b[sb + 8], "freespace_version": b[sb + 9], "root_group_version": b[sb + 10],
+         "reserved0": b[sb + 11], "shared_header_version": b[sb + 12], "sizes": (b[sb + 13], b[sb + 14]), "reserved1": b[sb + 15],
+         "k_leaf_k_int": struct.unpack_from("<HH", b, sb + 16), "consistency": struct.unpack_from("<I", b, sb + 20)[0],
+         "free_space_addr": struct.unpack_from("<Q", b, sb + 24 + 8)[0], "driver_addr": struct.unpack_from("<Q", b, sb + 24 + 24)[0],
+         "eof_is_file_end": base + struct.unpack_from("<Q", b, sb + 24 + 16)[0] == len(b),
+         "root_cache_type": f.root["cache"]}
+    bt, hp = base + f.root["btree"], base + f.root["heap"]
+    ntype, level, used = struct.unpack_from("<BBH", b, bt + 4)
+    s["btree"] = {"sig": bytes(b[bt:bt + 4]), "type": ntype, "level": level, "siblings": struct.unpack_from("<QQ", b, bt + 8)}
+    s["heap"] = {"sig": bytes(b[hp:hp + 4]), "version": b[hp + 4], "reserved": bytes(b[hp + 5:hp + 8])}
+    seg_size, free_off, seg_addr = struct.unpack_from("<QQQ", b, hp + 8)
+    s["heap"]["segment_in_file"] = base + seg_addr + seg_size <= len(b)
+    s["heap"]["segment_aligned"] = seg_size % 8 == 0
+    child = base + struct.unpack_from("<Q", b, bt + 24 + 8)[0]
+    s["snod"] = {"sig": bytes(b[child:child + 4]), "version": b[child + 4], "reserved": b[child + 5]}
+    links = f._group_links(f.root["btree"], f.root["heap"])
+    names = list(links)
+    s["names_sorted"] = names == sorted(names)
+    objs = []
+    for name, e in links.items():
+        h = base + e["header"]
+        nmsg, refs, size = struct.unpack_from("<HII", b, h + 2)
+        o = {"version": b[h], "reserved": b[h + 1], "refcount": refs, "header_aligned": h % 8 == 0, "entry_cache_type": e["cache"]}
+        for mtype, data in f._messages(e["header"]):
+            if mtype == 0x0001:
+                o["dataspace"] = {"version": data[0], "rank": data[1], "flags": data[2]}
+            elif mtype == 0x0003:
+                o["datatype"] = {"class_version": data[0], "bits": bytes(data[1:4]), "size": struct.unpack_from("<I", data, 4)[0], "props": bytes(data[8:])}
+            elif mtype == 0x0008:
+                # version 3: (version, class, ...); versions 1 / 2: (version, dimensionality, class, ...)
+                o["layout"] = {"version": data[0], "class": data[1] if data[0] >= 3 else data[2]}
+                if data[0] >= 3 and data[1] == 1:
+                    addr, nbytes = struct.unpack_from("<QQ", data, 2)
+                    o["layout"]["data_in_file"] = base + addr + nbytes <= len(b)
+        objs.append(o)
+    s["objects"] = objs
+    return s
+
+
+def test_written_file_follows_the_conventions_of_a_libhdf5_written_file(tmp_path):
+    """No HDF5 library can be installed here, so the writer is validated structurally: every structure kind our file contains
+    (superblock, root symbol entry, B-tree node, local heap, symbol-table node, version-1 object headers, dataspace /
+    datatype / contiguous-layout messages) must carry the same versions, reserved bytes, flag and size conventions as the
+    same structure in a file written by the real library -- the fields libhdf5 validates when HDF5.jl opens a dump."""
+    path = os.path.join(DATA, "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(path):
+        pytest.skip("SciPy's MATLAB fixtures are not installed")
+    real = _structure(H.File(path))
+    rng = np.random.default_rng(1)
+    ds = {n: rng.standard_normal((4, 6, 8)) for n in ("i_velocity", "j_velocity", "k_velocity", "i_mag_field", "j_mag_field", "k_mag_field")}
+    ds["time"] = np.float64(1.5)
+    ours = _structure(H.File(H.write(str(tmp_path / "run_t_0000.h5"), ds)))
+    for key in ("sig", "sb_version", "freespace_version", "root_group_version", "reserved0", "shared_header_version", "sizes", "reserved1",
+                "k_leaf_k_int", "free_space_addr", "driver_addr", "root_cache_type", "names_sorted"):
+        assert ours[key] == real[key], (key, ours[key], real[key])
+    # file consistency flags: "unused" in superblock versions 0 / 1 (spec II.A); MATLAB's old library left 3 behind, a cleanly
+    # closed file has 0
+    assert ours["consistency"] == 0 and ours["eof_is_file_end"]
+    for blk in ("btree", "heap", "snod"):
+        assert ours[blk] == real[blk], (blk, ours[blk], real[blk])
+    ref = real["objects"][0]                              # the genuine Float64 dataset
+    assert len(ours["objects"]) == 7
+    for o in ours["objects"]:
+        for key in ("version", "reserved", "refcount", "header_aligned", "entry_cache_type"):
+            assert o[key] == ref[key], (key, o[key], ref[key])
+        assert o["datatype"] == ref["datatype"]           # IEEE Float64 LE, byte for byte as libhdf5 encodes it
+        # layout message: version 3 (what libhdf5 >= 1.8, i.e. HDF5.jl, writes for contiguous data; MATLAB's older library wrote 2)
+        assert o["layout"]["version"] == 3 and ref["layout"]["version"] in (2, 3) and o["layout"]["class"] == ref["layout"]["class"] == 1
+        assert o["layout"].get("data_in_file", True)
+        assert o["dataspace"]["version"] == ref["dataspace"]["version"]
+    ranks = sorted(o["dataspace"]["rank"] for o in ours["objects"])
+    assert ranks == [0, 3, 3, 3, 3, 3, 3]                 # `time` is a scalar dataspace, the fields are (nz, ny, nx)
