@@ -18,8 +18,13 @@ import torch
 
 
 class TorchV0:
-    def __init__(self, n, kind="mhd", nu=0.0, eta=0.0, dt=0.0, device="cuda", L=2 * math.pi):
-        self.n, self.kind, self.nu, self.eta, self.dt = n, kind, float(nu), float(eta), float(dt)
+    LSRK_A = (0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0, -3550918686646.0 / 2091501179385.0,
+              -1275806237668.0 / 842570457699.0)
+    LSRK_B = (1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1720146321549.0 / 2090206949498.0,
+              3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0)
+
+    def __init__(self, n, kind="mhd", nu=0.0, eta=0.0, dt=0.0, device="cuda", L=2 * math.pi, stepper="RK4"):
+        self.n, self.kind, self.nu, self.eta, self.dt, self.stepper = n, kind, float(nu), float(eta), float(dt), stepper
         self.dev = torch.device(device)
         f32, dev = torch.float32, self.dev
         self.nkr = n // 2 + 1
@@ -42,8 +47,12 @@ class TorchV0:
         self.vars = [z() for _ in range(self.Nl)]                      # ux,uy,uz[,bx,by,bz]
         self.nonlin1, self.nonlinh1 = z(), zc()
         self.sol = zc(self.Nl)
-        self.sol1 = zc(self.Nl)
-        self.RHS = [zc(self.Nl) for _ in range(4)]
+        if stepper == "RK4":
+            self.sol1 = zc(self.Nl)
+            self.RHS = [zc(self.Nl) for _ in range(4)]
+        else:                                                          # FourierFlows LSRK54TimeStepper: S2 and RHS
+            self.S2 = zc(self.Nl)
+            self.RHS = [zc(self.Nl)]
         self.t, self.step = 0.0, 0
 
     # mul!(yh, rfftplan, y) / ldiv!(y, rfftplan, deepcopy(yh))
@@ -109,6 +118,15 @@ class TorchV0:
                 self._bi_update(N, a)
 
     def stepforward(self):                                             # FourierFlows RK4 (mirror DyeModule.jl:62-91)
+        if self.stepper != "RK4":                                      # LSRK54 (Carpenter & Kennedy 1994)
+            self.S2.mul_(0)
+            for a, b in zip(self.LSRK_A, self.LSRK_B):
+                self.calcN(self.RHS[0], self.sol)
+                self.S2.copy_(a * self.S2 + self.dt * self.RHS[0])
+                self.sol.add_(b * self.S2)
+            self.t += self.dt
+            self.step += 1
+            return
         dt, sol, R = self.dt, self.sol, self.RHS
         self.calcN(R[0], sol)
         self.sol1.copy_(sol + (dt / 2) * R[0])

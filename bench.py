@@ -311,7 +311,7 @@ def cufft_reference_point(kind, dims, reps=3):
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
-def gpu_baseline_point(kind, n, nu, eta, dt, steps=3, warm=1):
+def gpu_baseline_point(kind, n, nu, eta, dt, stepper="RK4", steps=3, warm=1):
     """`gpu_baseline`: the reference's own GPU formulation (CUDA.jl path: 36-FFT literal op sequence, cuFFT + one unfused kernel
     per broadcast, FourierFlows RK4 with sol1 + 4 RHS arrays) restated in torch eager mode (baseline/torch_v0.py), timed on
     this GPU beside the product.  Its layout (36 S + 7 R of state and scratch) does not fit 1024^3 in 180 GB -- the reference
@@ -322,7 +322,7 @@ def gpu_baseline_point(kind, n, nu, eta, dt, steps=3, warm=1):
         if kind == "emhd":
             return {"unavailable": "the torch stand-in covers the HD / MHD RHS only"}
         nb = min(n, 512)
-        b = TorchV0(nb, kind=kind, nu=nu, eta=eta, dt=dt)
+        b = TorchV0(nb, kind=kind, nu=nu, eta=eta, dt=dt, stepper=stepper)
         for i in range(b.Nl):       # IC field by field on the device
             f = tg_field_device(nb, (nb, nb, nb), i, "cuda")
             b.vars[i].copy_(f)
@@ -344,7 +344,7 @@ def gpu_baseline_point(kind, n, nu, eta, dt, steps=3, warm=1):
         return {"value": nb ** 3 / (ms * 1e-3), "unit": "pts*steps/s", "ms_per_step": ms, "grid": [nb, nb, nb], "steps": steps, "warmup": warm,
                 "kind": "port", "peak_bytes": int(mem),
                 "what": "reference op sequence (MHDSolver.jl:330-351: 36 cuFFT transforms per RHS + one eager kernel per broadcast, "
-                        "FourierFlows RK4) in torch on this GPU; stand-in for the CUDA.jl path, which cannot be installed offline"}
+                        f"FourierFlows {stepper}) in torch on this GPU; stand-in for the CUDA.jl path, which cannot be installed offline"}
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
@@ -650,7 +650,7 @@ def main():
             cf["ours_ms_per_rhs_everything_included"] = ms_per_step / stages
         line["cufft_ref"] = cf
         if not args.no_gpu_baseline:
-            gb = gpu_baseline_point(kind, n, nu, eta, dt)
+            gb = gpu_baseline_point(kind, n, nu, eta, dt, stepper=stepper)
             if "value" in gb:
                 gb["ours_over_gpu_baseline"] = value / gb["value"]
             line["gpu_baseline"] = gb

@@ -289,7 +289,9 @@ __device__ __forceinline__ C r2c_post(C z1, C z2, C w) {
 // dkx != nullptr: the row is differentiated along x on the way in -- X[k] -> i kx[k] X[k] with the kr table of the grid
 // (the EMHD kernels get d/dx B_i and d/dx A_i from the rows of B_i and A_i themselves instead of from separately
 // transformed derivative fields: 6 of the 24 inverse-transformed fields of the gradient form disappear)
-template <typename T, int N, int E, typename SYNC>
+// DX is a compile-time switch: with a run-time one the compiler if-converts the derivative arithmetic into EVERY transform of a
+// rolled loop (measured: the EMHD x pass went from 32.6 to 37.7 ms per 512^3 step, profiles/r02_c7_bench_emhd512.json).
+template <typename T, int N, int E, typename SYNC, bool DX = false>
 __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__ X, int Kx, T scale, int t,
                                         RowSmem<Cx<T>>& sm, const Cx<T>* __restrict__ tw, const T* __restrict__ dkx = nullptr) {
   using C = Cx<T>;
@@ -301,7 +303,7 @@ __device__ __forceinline__ void row_c2r(Cx<T> (&v)[E], const Cx<T>* __restrict__
     const int k2 = M - k;
     C x1 = ldg_pred(X + (unsigned)k, k < Kx);
     C x2 = ldg_pred(X + (unsigned)(k2 < Kx ? k2 : 0), k2 < Kx);
-    if (dkx != nullptr) {   // same expression as k_emhd_derive: i * (k_x * f)
+    if constexpr (DX) {   // same expression as k_emhd_derive: i * (k_x * f)
       x1 = cmuli(cscale(x1, k < Kx ? __ldg(dkx + k) : (T)0));
       x2 = cmuli(cscale(x2, k2 < Kx ? __ldg(dkx + k2) : (T)0));
     }
@@ -608,10 +610,12 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           C g[E];
-          row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? 15 + i : 3 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, j == 0 ? a.kxv : nullptr);
+          if (j == 0) row_c2r<T, N, E, SYNC, true>(g, in + (15 + i) * a.in_field, a.Kx, a.scale, t, sm, twt, a.kxv);
+          else row_c2r<T, N, E, SYNC>(g, in + (3 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
           for (int m = 0; m < E; ++m) acc[m] = lfma(A[j][m], g[m], acc[m]);
-          row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? i : 9 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, j == 0 ? a.kxv : nullptr);
+          if (j == 0) row_c2r<T, N, E, SYNC, true>(g, in + i * a.in_field, a.Kx, a.scale, t, sm, twt, a.kxv);
+          else row_c2r<T, N, E, SYNC>(g, in + (9 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
           for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(bs[j][m]), g[m], acc[m]);
         }
@@ -722,14 +726,22 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
       C acc[E];
 #pragma unroll
       for (int m = 0; m < E; ++m) acc[m] = mk<C>(0, 0);
-#pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
+      {   // j = x: the rows of B_i / A_i themselves, differentiated on the way in (its own two inlined transforms)
         C g[E];
-        const T* dk = (j == 0) ? a.kxv : nullptr;     // j = x: differentiate the rows of B_i / A_i on the way in
-        row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? 15 + i : 3 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, dk);
+        row_c2r<T, N, E, SYNC, true>(g, in + (15 + i) * a.in_field, a.Kx, a.scale, t, sm, twt, a.kxv);
+#pragma unroll
+        for (int m = 0; m < E; ++m) acc[m] = lfma(mult[m * Tm], g[m], acc[m]);
+        row_c2r<T, N, E, SYNC, true>(g, in + i * a.in_field, a.Kx, a.scale, t, sm, twt, a.kxv);
+#pragma unroll
+        for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(mult[(3 * E + m) * Tm]), g[m], acc[m]);
+      }
+#pragma unroll 1
+      for (int j = 1; j < 3; ++j) {
+        C g[E];
+        row_c2r<T, N, E, SYNC>(g, in + (3 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
         for (int m = 0; m < E; ++m) acc[m] = lfma(mult[(j * E + m) * Tm], g[m], acc[m]);
-        row_c2r<T, N, E, SYNC>(g, in + (j == 0 ? i : 9 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt, dk);
+        row_c2r<T, N, E, SYNC>(g, in + (9 + 2 * i + (j - 1)) * a.in_field, a.Kx, a.scale, t, sm, twt);
 #pragma unroll
         for (int m = 0; m < E; ++m) acc[m] = lfma(lneg(mult[((3 + j) * E + m) * Tm]), g[m], acc[m]);
       }

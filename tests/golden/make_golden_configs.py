@@ -26,6 +26,7 @@ from oracle import mhdflows_oracle as O  # noqa: E402
 
 DFSM_CALL = 0x7FFFFFFF44465350      # counter tag of the device random-phase stream (mhdflows_jl_b200.DFSM_CALL)
 NSAMPLE = 20000
+NPEAK = 256
 
 
 def sample_index(g, nfields, seed=0):
@@ -41,6 +42,16 @@ def digest(g, arr, idx, prefix, out):
     out[prefix + "_samples"] = np.stack([a[f].ravel()[idx[f]] for f in range(a.shape[0])])
     out[prefix + "_norms"] = np.array([float(np.linalg.norm(a[f].astype(np.complex128).ravel())) for f in range(a.shape[0])])
     out[prefix + "_spectra"] = np.stack([O.spectralline(g.irfft(a[f].copy()), g)[0].astype(np.float64) for f in range(a.shape[0])])
+    # the NPEAK largest modes of every field: on sparse (Taylor-Green) spectra they ARE the signal, the rest is rounding noise
+    pk_i, pk_v = [], []
+    for f in range(a.shape[0]):
+        flat = a[f].ravel()
+        i = np.argpartition(np.abs(flat), -NPEAK)[-NPEAK:]
+        i = i[np.argsort(-np.abs(flat[i]))]
+        pk_i.append(i)
+        pk_v.append(flat[i])
+    out[prefix + "_peak_index"] = np.stack(pk_i)
+    out[prefix + "_peak_values"] = np.stack(pk_v)
 
 
 def cfg3():

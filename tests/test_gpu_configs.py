@@ -54,6 +54,24 @@ def _nretained(shape):
     return (math.floor((1 - 1 / 3) / 2 * nx)) * keep(ny) * keep(nz)
 
 
+def _check_peaks(fields, gold, prefix, groups, tol=F32_TOL, noise=3e-3):
+    """Sparse (Taylor-Green) spectra: the 256 largest modes of every field carry the signal -- compared at `tol` -- and everything
+    else is rounding noise, which second derivatives amplify by k^2 in Float32 (the Float32 oracle's own EMHD calcN! carries
+    7e-4 of ||N|| of it at 512^3): the noise norm of the CUDA path must stay below `noise` ||N||."""
+    pi, pv = gold[prefix + "_peak_index"], gold[prefix + "_peak_values"]
+    for grp in groups:
+        got = np.stack([fields[f].ravel()[pi[f]] for f in grp]).astype(np.complex128)
+        want = pv[grp].astype(np.complex128)
+        keep = np.abs(want) >= 1e-3 * np.abs(want).max()          # below that the "peaks" of a sparse field are noise themselves
+        assert keep.sum() >= 8
+        got, want = np.where(keep, got, 0), np.where(keep, want, 0)
+        sig = np.linalg.norm(want.ravel())
+        assert np.linalg.norm((got - want).ravel()) / sig < tol, (prefix, grp, "peaks")
+        total = np.sqrt(sum(np.linalg.norm(fields[f].astype(np.complex128).ravel()) ** 2 for f in grp))
+        rest = np.sqrt(max(total ** 2 - np.linalg.norm(got.ravel()) ** 2, 0.0))
+        assert rest < noise * total, (prefix, grp, "noise", rest / total)
+
+
 def _check_spectra(M, prob, gold, prefix, nfields):
     for f in range(nfields):
         Pk, _ = M.spectralline(prob, f)
@@ -95,7 +113,7 @@ def test_config5_emhd512_rk4(M):
     gp = M.Problem(M.GPU(), nx=n, dt=float(g["dt"]), stepper="RK4", B_field=True, EMHD=True)
     fields = bench.tg_fields(n)
     bench.set_ic(M, gp, "emhd", fields)
-    _check(gp.calcN(), g, "N", [[0, 1, 2]])
+    _check_peaks(gp.calcN(), g, "N", [[0, 1, 2]])
     bench.set_ic(M, gp, "emhd", fields)          # calcN! refreshed the stale b: start the step from the IC state again
     M.stepforward(gp, 1)
     _check(gp.sol, g, "sol1", [[0, 1, 2]])

@@ -55,4 +55,13 @@ def vp_setup(p):
 
 run("mhd 32^3 volume penalisation + div corrections", setup=vp_setup, nx=32, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, VP_method=True)
 run("mhd f64 32^3", nx=32, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, T=np.float64)
+
+
+def ic_and_analysis(p):      # device-side DivFreeSpectraMap, ScaleDecomposition, VectorPotential
+    M.SetUpRandomPhaseIC(p, seed_u=3, seed_b=4, k0=-5 / 6)
+    M.ScaleDecomposition(p, "u", kf=[1, 4])
+    M.VectorPotential(p, which=M.FRESH)
+
+
+run("mhd 32x64x32 random-phase IC + on-device analysis", setup=ic_and_analysis, nx=32, ny=64, nz=32, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True)
 print("sanitize-target done")
