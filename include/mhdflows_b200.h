@@ -59,6 +59,7 @@ typedef struct {
   int rank, nranks;
   const void* nccl_id;     /* 128-byte ncclUniqueId from mhdf_nccl_unique_id on rank 0, shared by the host; NULL if nranks == 1 */
   int vp;                  /* VP_method (pgen.jl:84): volume-penalisation terms in the HD / MHD right-hand side (VPSolver.jl:21-59) */
+  int nd;                  /* calcF = NDForceDriving! (pgen/NegativeDamping.jl): negative-damping forcing, set with mhdf_set_forcing_nd */
 } mhdf_config;
 
 /* Problem(...) constructor / finaliser (pgen.jl:64-127, Problems.jl:118-140). */
@@ -108,6 +109,13 @@ typedef struct {
 } mhdf_a99;
 int mhdf_set_forcing_a99(mhdf_handle* h, const mhdf_a99* p);
 int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls);
+
+/* Negative-damping forcing: the reference's `calcF!` = NDForceDriving! with SetUpND!(prob, P, fx, fy, fz)
+ * (pgen/NegativeDamping.jl:14-45).  Every RHS evaluation adds  N_ui += A rfft(f_i u_i),  A = P / (sum_i sum |u_i^2 f_i| dV),  with the
+ * u of that evaluation: the products ride along the forward transforms of the fused x kernel, the sum is a reduction of the same
+ * kernel (all-reduced over the ranks of a slab run).  Needs mhdf_config.nd at creation; acts on the MHD path only, like every
+ * forcing of the reference; a NULL profile pointer keeps the previous profile; P = 0 switches the forcing off. */
+int mhdf_set_forcing_nd(mhdf_handle* h, double P, const void* fx, const void* fy, const void* fz);
 
 /* Volume penalisation (Problem(...; VP_method = true)): the real fields params.χ (which = 0), params.U₀x,U₀y,U₀z (1..3) and, for
  * MHD, params.B₀x,B₀y,B₀z (4..6) (datastructure.jl:80-81,94-95; SetUpProblemIC! keywords U₀x ..., IC.jl:93-106).  Every RHS

@@ -12,7 +12,8 @@ export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDia
        increment!, CPU, GPU, nothingfunction, spectralline, h_k_sum, h_m_sum,
        N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!,
        A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!, setvpfield!,
-       savefile, Restart!, readMHDFlows, DivFreeSpectraMap, SetUpRandomPhaseIC!
+       savefile, Restart!, readMHDFlows, DivFreeSpectraMap, SetUpRandomPhaseIC!,
+       NDForceDriving!, GetNDvars_And_function, SetUpND!
 
 const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
 
@@ -32,6 +33,7 @@ struct MhdfConfig
   rank::Cint; nranks::Cint
   nccl_id::Ptr{Cvoid}
   vp::Cint
+  nd::Cint
 end
 
 const MHDF_HD, MHDF_MHD, MHDF_EMHD = 0, 1, 2
@@ -92,12 +94,14 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   Shear && error("Shear haven't fully implemented yet!")
   (Compressibility || Dye_Module) && error("outside the B200 hot path")
   VP_method && EMHD && error("VP_method: the EMHD equation has no volume-penalisation terms")
-  (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! || calcF === A99GPU.A99ForceDriving!) ||
+  (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! || calcF === A99GPU.A99ForceDriving! ||
+   calcF === NDForceDriving!) ||
     error("arbitrary forcing callbacks cannot run on the device; constant forcings go through setforcing! / N97ForceDriving!")
   stepper in ("RK4", "LSRK54") || error("stepper must be \"RK4\" or \"LSRK54\" on the B200 path")
   physics = EMHD ? MHDF_EMHD : (B_field ? MHDF_MHD : MHDF_HD)
   cfg = MhdfConfig(nx, ny, nz, Lx, Ly, Lz, Î½, Î·, nÎ½, dt, physics, stepper == "RK4" ? 0 : 1,
-                   T === Float32 ? 0 : 1, dev.device, 0, 1, C_NULL, VP_method ? 1 : 0)
+                   T === Float32 ? 0 : 1, dev.device, 0, 1, C_NULL, VP_method ? 1 : 0,
+                   calcF === NDForceDriving! ? 1 : 0)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   code = ccall((:mhdf_create, lib), Cint, (Ref{MhdfConfig}, Ref{Ptr{Cvoid}}), cfg, h)
   code == 0 || check(C_NULL, code)
@@ -222,6 +226,19 @@ module A99GPU
     uv.Fk_A = Float64(uv.A)    # the kernel multiplies A twice (:89, :106)
     _push_a99(prob, uv)
   end
+end
+
+"ND_vars / NDForceDriving! / SetUpND! (pgen/NegativeDamping.jl:8-51): negative-damping forcing F_i = f_i u_i, applied inside the library"
+mutable struct ND_vars; P::Float64; end
+NDForceDriving!(args...) = error("NDForceDriving! is applied inside the library")
+GetNDvars_And_function(dev, nx, ny, nz; T = Float32) = (ND_vars(0.0), NDForceDriving!)
+function SetUpND!(prob, P, fx, fy, fz)
+  T = typeof(prob).parameters[1]
+  a, b, c = _fieldarg(T, fx), _fieldarg(T, fy), _fieldarg(T, fz)
+  GC.@preserve a b c check(prob.h, ccall((:mhdf_set_forcing_nd, lib), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                                         prob.h, P, _fieldptr(a), _fieldptr(b), _fieldptr(c)))
+  prob.vars.usr_vars.P = P
+  nothing
 end
 
 "params.Ï‡, Uâ‚€x â€¦ Bâ‚€z of a VP_method problem: setvpfield!(prob, :Ï‡, mask)   (datastructure.jl:80-81,94-95; IC.jl:93-106)"

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mhdf_step_timed", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
     "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
     "mhdf_set_forcing_a99", "mhdf_forcing_a99_calls", "mhdf_div_correction", "mhdf_set_vp_field",
-    "mhdf_set_random_phase", "mhdf_scale_decomposition", "mhdf_vector_potential",
+    "mhdf_set_random_phase", "mhdf_scale_decomposition", "mhdf_vector_potential", "mhdf_set_forcing_nd",
 ]
 A99_HOST, A99_GPU = 1, 2
 
@@ -32,7 +32,7 @@ class Config(C.Structure):
                 ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
                 ("nu", C.c_double), ("eta", C.c_double), ("n_nu", C.c_int), ("dt", C.c_double),
                 ("physics", C.c_int), ("stepper", C.c_int), ("dtype", C.c_int), ("device", C.c_int),
-                ("rank", C.c_int), ("nranks", C.c_int), ("nccl_id", C.c_void_p), ("vp", C.c_int)]
+                ("rank", C.c_int), ("nranks", C.c_int), ("nccl_id", C.c_void_p), ("vp", C.c_int), ("nd", C.c_int)]
 
 
 class A99(C.Structure):   # mhdf_a99
@@ -94,6 +94,7 @@ def lib():
         "mhdf_set_random_phase": (i, [vp, i, C.c_ulonglong, d, d, d]),
         "mhdf_scale_decomposition": (i, [vp, i, i, d, d, vp]),
         "mhdf_vector_potential": (i, [vp, i, vp]),
+        "mhdf_set_forcing_nd": (i, [vp, d, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(L, name) and os.environ.get("MHDF_LIB"):

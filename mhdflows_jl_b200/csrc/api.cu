@@ -101,6 +101,7 @@ int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls) {
   return MHDF_OK;
 }
 int mhdf_set_vp_field(mhdf_handle* h, int which, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_vp_field(which, p); }); }
+int mhdf_set_forcing_nd(mhdf_handle* h, double P, const void* fx, const void* fy, const void* fz) { return guard(h, [&] { h->set_forcing_nd(P, fx, fy, fz); }); }
 int mhdf_div_correction(mhdf_handle* h, int group) { return guard(h, [&] { h->div_correction(group); }); }
 int mhdf_scale_decomposition(mhdf_handle* h, int group, int which, double k1, double k2, void* out3) {
   return guard(h, [&] { if (!out3) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->analysis(0, group, which, k1, k2, out3); });

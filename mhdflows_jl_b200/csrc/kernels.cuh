@@ -365,6 +365,7 @@ template <> struct XSync<false, 1> { using type = SyncBlock; };
 struct XRed {
   double sumsq[6];   // sum f^2 per input field (ux,uy,uz,bx,by,bz | EMHD: Ax,Ay,Az,bx,by,bz)
   double cross;      // sum u.b
+  double nd;         // sum |u_i^2 f_i| over i = x, y, z (NDForceDriving!: the normalisation of the negative-damping force)
   unsigned long long maxsq[6]; // max f^2 per field as the bit pattern of a non-negative T (orders like an unsigned integer):
                                // Float32 in the low word, Float64 in the whole word -- getCFL!'s maximum in the problem's precision
 };
@@ -449,7 +450,9 @@ enum { PHYS_HD = 0, PHYS_MHD = 1, PHYS_EMHD = 2 };
 //   VP  : HD / MHD with the volume-penalisation method: additionally out V_j = chi/eta (f_j - W_j), W = U0 (and B0 for the
 //         magnetic field), j = x,y,z, appended after the tensor / E fields (reference: VPSolver.jl:21-59); its own
 //         instantiation, the plain kernels are unchanged
-template <typename T, int N, int E, int RB, int PHYS, bool RED, bool VP = false>
+//   ND  : MHD with NDForceDriving! (pgen/NegativeDamping.jl:23-45): additionally out F_i = f_i u_i (i = x, y, z) after the E fields and
+//         the reduction sum |u_i^2 f_i| that normalises the force; VP = 2 selects it (VP = 1: volume penalisation)
+template <typename T, int N, int E, int RB, int PHYS, bool RED, int VP = 0>
 __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   using C = Cx<T>;
   constexpr int M = N / 2, Tm = M / E, R1 = imin(E, M);
@@ -465,10 +468,10 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
   const C* twt = a.tw;
   MHDF_KEEP_PTR(twt);
 
-  double rs[7];
+  double rs[8];
   T rm[6];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) rs[i] = 0.0;
+  for (int i = 0; i < 8; ++i) rs[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) rm[i] = 0.f;
 
@@ -551,7 +554,25 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
           row_r2c<T, N, E, SYNC>(v, out + (6 + i) * a.out_field, a.Kx, t, sm, twt);
         }
       }
-      if constexpr (VP) {
+      if constexpr (VP == 2) {
+        static_assert(PHYS == PHYS_MHD && RED, "NDForceDriving! acts on the MHD path; its normalisation needs the reduction epilogue");
+        const T* frow = a.vp + row * (long long)N;
+        T s = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          C v[E];
+#pragma unroll
+          for (int m = 0; m < E; ++m) {
+            const C fi = reinterpret_cast<const C*>(frow + i * a.vp_field)[t + Tm * m];
+            v[m] = lmul(fi, f[i][m]);                                           // F_i = f_i u_i   (NegativeDamping.jl:38)
+            const C w = lmul(lmul(f[i][m], f[i][m]), fi);                       // u_i^2 f_i        (:32-33)
+            s += fabs(w.x) + fabs(w.y);
+          }
+          row_r2c<T, N, E, SYNC>(v, out + (9 + i) * a.out_field, a.Kx, t, sm, twt);
+        }
+        rs[7] += (double)s;
+      }
+      if constexpr (VP == 1) {
         constexpr int NT = (PHYS == PHYS_MHD) ? 9 : 6;
         const T* vrow = a.vp + row * (long long)N;
         C ce[E];
@@ -643,7 +664,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
     }
   }
   if constexpr (RED) {
-    if (a.red != nullptr) block_reduce_commit<7, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
+    if (a.red != nullptr) block_reduce_commit<8, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
   }
 }
 
@@ -671,10 +692,10 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
   C* mult = reinterpret_cast<C*>(smem_raw) + (size_t)2 * RB * RS + (size_t)r * 6 * M + t;
   const C* twt = a.tw;
   MHDF_KEEP_PTR(twt);
-  double rs[7];
+  double rs[8];
   T rm[6];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) rs[i] = 0.0;
+  for (int i = 0; i < 8; ++i) rs[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) rm[i] = 0.f;
   // reductions with a run-time slot: predicated adds keep rs / rm in registers
@@ -766,7 +787,7 @@ __global__ void __launch_bounds__((N / 2 / E) * RB, (N / 2 / E) * RB * MHDF_EMHD
     }
   }
   if constexpr (RED) {
-    if (a.red != nullptr) block_reduce_commit<7, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
+    if (a.red != nullptr) block_reduce_commit<8, 6>(rs, rm, a.red->sumsq, a.red->maxsq);
   }
 }
 
@@ -1013,6 +1034,8 @@ struct SpecArgs {
   const Cx<T>* force;    // constant spectral forcing [F][compact] (calcF! hook), or null
   unsigned fmask;        // bit f set: field f is forced
   A99Args<T> a99;        // random driving (variant = A99_OFF: none)
+  const double* nd_sum;  // NDForceDriving!: sum |u_i^2 f_i| of this evaluation (device, complete when the kernel starts)
+  double nd_P;           // its P / dV
 };
 // Volume penalisation in the spectral kernel (VP instantiations): the penalisation spectra V^_j follow the tensor / E fields
 // in P;  N_a += -sum_j (delta_aj - k_j k_a / k^2) V^_j  for the velocity and, in MHD, the same with the B0 set for the
@@ -1065,7 +1088,7 @@ __device__ __forceinline__ Cx<T> sym_apply(const SymSrc<T>& r, int fi, Cx<T> v) 
 
 // RHS of one retained mode e = (ix, jc, kc): N[] and the stage input sin[] at that mode.  The mirror operand of the kr = 0
 // symmetrisation is resolved once for all fields and the stage input is loaded once.
-template <typename T, int PHYS, bool A99, bool VP, typename IDX>
+template <typename T, int PHYS, bool A99, int VP, typename IDX>
 __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, int jc, int kc,
                                          Cx<T> (&N)[PHYS == PHYS_MHD ? 6 : 3], Cx<T> (&sin)[PHYS == PHYS_MHD ? 6 : 3]) {
   using C = Cx<T>;
@@ -1115,7 +1138,7 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
         N[3 + c] = mk<C>(-Cv[c].y + dc * bsym.x, Cv[c].x + dc * bsym.y);
       }
     }
-    if constexpr (VP) {
+    if constexpr (VP == 1) {
       constexpr int NT = (PHYS == PHYS_MHD) ? 9 : 6, NG = (PHYS == PHYS_MHD) ? 2 : 1;
 #pragma unroll
       for (int gp = 0; gp < NG; ++gp) {
@@ -1131,6 +1154,11 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
       }
     }
     if constexpr (PHYS == PHYS_MHD) {   // addforcing! after the advection (pgen.jl:159); HD / EMHD: no effect, like the reference
+      if constexpr (VP == 2) {   // NDForceDriving!: N_ui += A F^_i, A = P / (sum |u_i^2 f_i| dV)   (NegativeDamping.jl:34-41)
+        const T A = (T)(a.nd_P / *a.nd_sum);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const C w = a.P[(9 + c) * g.field + e]; N[c].x += A * w.x; N[c].y += A * w.y; }
+      }
       if (a.force != nullptr) {
 #pragma unroll
         for (int f = 0; f < F; ++f)
@@ -1157,7 +1185,7 @@ __device__ __forceinline__ void spec_rhs(const SpecArgs<T>& a, IDX e, int ix, in
 // is 23 % faster -- 0.713 -> 0.550 ms at 256^3, 36.0 -> 27.6 ms per step at 1024^3, profiles/README.md -- and replaced it.
 // The stage updates are written with explicit fused multiply-adds so the result does not depend on the compiler's
 // contraction choices.)  Needs n_fields * field < 2^32 elements (true up to 1024^3 with 15 product fields).
-template <typename T, int PHYS, int MODE, bool A99 = false, bool VP = false>
+template <typename T, int PHYS, int MODE, bool A99 = false, int VP = 0>
 __global__ void __launch_bounds__(256, MHDF_SPEC_MINB) k_spectral(SpecArgs<T> a) {
   using C = Cx<T>;
   const SpecGeom<T>& g = a.g;

@@ -125,6 +125,7 @@ struct mhdf_handle {
   virtual void analysis(int mode, int group, int which, double k1, double k2, void* out3) = 0;
   virtual void set_random_phase(int group, unsigned long long seed, double k0, double P, double k_peak) = 0;
   virtual void set_vp_field(int which, const void* p) = 0;
+  virtual void set_forcing_nd(double P, const void* fx, const void* fy, const void* fz) = 0;
   virtual void ipc_export(void* blob) = 0;
   virtual void ipc_import(const void* blobs) = 0;
 };
@@ -186,6 +187,9 @@ struct Solver : mhdf_handle {
   unsigned fmask = 0;
   bool vp_on = false;  // volume-penalisation method (Problem(...; VP_method = true))
   T* vp_d = nullptr;   // [1 + F][nzl][ny][nx] real: chi, U0x, U0y, U0z[, B0x, B0y, B0z]  (params.χ, params.U₀x ...)
+  bool nd_on = false;  // NDForceDriving! (pgen/NegativeDamping.jl): calcF of an MHD problem created with cfg.nd
+  T* nd_d = nullptr;   // [3][nzl][ny][nx] real: usr_vars.fx, fy, fz
+  double nd_P = 0;     // usr_vars.P
   A99Args<T> a99{};   // random driving (A99ForceDriving!), variant = A99_OFF: none
   unsigned long long a99_call = 0;   // forcing evaluations so far = the Philox counter word
   C *twx = nullptr, *twy = nullptr, *twz = nullptr;
@@ -256,6 +260,10 @@ struct Solver : mhdf_handle {
     vp_on = c.vp != 0;
     if (vp_on && phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "VP_method: the EMHD equation has no volume-penalisation terms (MHDSolver.jl:183-270)"};
     if (vp_on) nout += F;   // the penalisation products chi/eta (f_j - W_j) ride along the forward transforms
+    // NDForceDriving! acts on the MHD path only (HDcalcN! loses its forcing, EMHDcalcN! never calls it: pgen.jl:164-181)
+    nd_on = c.nd != 0 && phys == MHDF_MHD;
+    if (nd_on && vp_on) throw Err{MHDF_ERR_INVALID, "NDForceDriving! together with VP_method is not supported on this path"};
+    if (nd_on) nout += 3;   // the products f_i u_i ride along the forward transforms
     cf = (long long)Kxp * Kyl * Kz;
     t_ = (T)0; dt_ = (T)c.dt;
     for (int i = 0; i < KC_COUNT; ++i) { prof_ms[i] = 0; prof_cnt[i] = 0; }
@@ -296,6 +304,7 @@ struct Solver : mhdf_handle {
       bst = dalloc<T>((size_t)3 * nx * ny * nzl);
     }
     if (vp_on) vp_d = dalloc<T>((size_t)(1 + F) * nx * ny * nzl);   // zero: chi = 0 means "no solid anywhere"
+    if (nd_on) nd_d = dalloc<T>((size_t)3 * nx * ny * nzl);
     twx = make_tw(nx); twy = make_tw(ny); twz = make_tw(nz);
     // wavenumbers: built in Float64 then converted to T (FourierFlows ThreeDGrid; mirror utils/utils.jl:60-64)
     std::vector<T> hx(Kx), hy(Kyl), hz(Kz);
@@ -352,7 +361,7 @@ struct Solver : mhdf_handle {
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
-    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(vp_d); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
+    cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(vp_d); cudaFree(nd_d); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
     cudaFree(plane_loc); cudaFree(plane_all);
@@ -363,7 +372,7 @@ struct Solver : mhdf_handle {
     if (st) cudaStreamDestroy(st);
     st = sc = nullptr; comm = nullptr; ipc_on = false; red_h = nullptr; diag_h = nullptr;
     for (int i = 0; i < 4; ++i) reg[i] = nullptr;
-    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; vp_d = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
+    P = Q = R = D = nullptr; bst = nullptr; force = nullptr; vp_d = nullptr; nd_d = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
     red_d = nullptr; diag_d = nullptr; spec_d = nullptr; plane_loc = plane_all = nullptr; bar_d = nullptr;
     dep_ev.clear(); evs.clear(); ev_free.clear();
     for (int i = 0; i < NCS_MAX; ++i) cs[i] = nullptr;
@@ -490,6 +499,7 @@ struct Solver : mhdf_handle {
       if (red) MHDF_LAUNCH((k_xfused_emhd2<T, N, E, RB, true>), grid, threads, smem, st, a);
       else MHDF_LAUNCH((k_xfused_emhd2<T, N, E, RB, false>), grid, threads, smem, st, a);
     }
+    else if (nd_on && a.vp != nullptr) MHDF_LAUNCH((k_xfused<T, N, E, RB, PHYS_MHD, true, 2>), grid, threads, x_smem<N>(), st, a);
     else if (vp_on && a.vp != nullptr) {   // penalised runs: one instantiation per physics (reductions always compiled in)
       if (phys == MHDF_MHD) MHDF_LAUNCH((k_xfused<T, N, E, RB, PHYS_MHD, true, true>), grid, threads, x_smem<N>(), st, a);
       else MHDF_LAUNCH((k_xfused<T, N, E, RB, PHYS_HD, true, true>), grid, threads, x_smem<N>(), st, a);
@@ -555,6 +565,7 @@ struct Solver : mhdf_handle {
     if (smem > 48 * 1024) {
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_HD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CK(cudaFuncSetAttribute(k_xfused<T, N, E, RB, PHYS_MHD, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CK(cudaFuncSetAttribute(k_xplain<T, N, E, RB, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
@@ -811,7 +822,7 @@ struct Solver : mhdf_handle {
   void finish_red() {
     if (P_ == 1) { CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, st)); return; }
     order(st, sc);
-    NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 7, ncclFloat64, ncclSum, comm, sc));
+    NK(g_nccl.AllReduce(red_d->sumsq, red_d->sumsq, 8, ncclFloat64, ncclSum, comm, sc));
     NK(g_nccl.AllReduce(red_d->maxsq, red_d->maxsq, 6, ncclUint64, ncclMax, comm, sc));
     CK(cudaMemcpyAsync(red_h, red_d, sizeof(XRed), cudaMemcpyDeviceToHost, sc));
     CK(cudaEventRecord(red_own, sc));
@@ -838,6 +849,11 @@ struct Solver : mhdf_handle {
   }
   // penalised RHS evaluations: the x kernel reads chi, U0 (B0) next to the row set; eta = clock.dt * 13/7 (VPSolver.jl:23)
   void set_vp(XArgs<T>& xa, size_t real_off) const {
+    if (nd_on) {   // the negative-damping profiles f_i take the place of the penalisation fields
+      xa.vp = (nd_P != 0) ? nd_d + real_off : nullptr;
+      xa.vp_field = (long long)nx * ny * nzl;
+      return;
+    }
     if (!vp_on) return;
     xa.vp = vp_d + real_off;
     xa.vp_field = (long long)nx * ny * nzl;
@@ -944,6 +960,7 @@ struct Solver : mhdf_handle {
   }
   void rhs_pipe(const C* Sin, SpecArgs<T> sa, bool want_red) {
     pipe_alloc();
+    want_red = want_red || (nd_on && nd_P != 0);   // the negative-damping force is normalised by a reduction of every evaluation
     const int NZC = zchunks, zc = nzl / NZC;
     const size_t Bi = (size_t)nin * zc * Kyl * Kxp, Bo = (size_t)nout * zc * Kyl * Kxp;   // one (chunk, peer) piece
     const long long fld = (long long)zc * Kyl * Kxp;                                      // field stride inside a piece
@@ -1087,6 +1104,7 @@ struct Solver : mhdf_handle {
   // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
   void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
     if (pipe_ok()) { rhs_pipe(Sin, sa, want_red); return; }
+    want_red = want_red || (nd_on && nd_P != 0);
     const C* zin = Sin;
     if (phys != MHDF_EMHD) gather_mirror(Sin);
     if (phys == MHDF_EMHD) {
@@ -1118,7 +1136,7 @@ struct Solver : mhdf_handle {
     wait_mirror();
     launch_spectral(sa);
   }
-  template <int PHYS, bool A99, bool VP> void launch_spectral_m(const SpecArgs<T>& sa) {
+  template <int PHYS, bool A99, int VP> void launch_spectral_m(const SpecArgs<T>& sa) {
     const unsigned plane = (unsigned)Kxp * (unsigned)Kyl;
     const dim3 grid((plane + 255u) / 256u, (unsigned)Kz);
     switch (sa.mode) {
@@ -1133,7 +1151,12 @@ struct Solver : mhdf_handle {
   void launch_spectral(SpecArgs<T>& sa) {
     prof_begin(KC_SPEC);
     const bool driven = (phys == MHDF_MHD) && sa.a99.variant != A99_OFF;   // A99ForceDriving! acts on the MHD path only
-    if (vp_on) {   // penalised runs: the product buffer carries the penalisation spectra as well
+    if (nd_on && nd_P != 0) {   // NDForceDriving!: the normalisation sum of this evaluation is complete (and all-reduced) by now
+      if (P_ > 1 && red_ev) CK(cudaStreamWaitEvent(st, red_ev, 0));
+      sa.nd_sum = &red_d->nd;
+      sa.nd_P = nd_P / ((cfg.Lx / nx) * (cfg.Ly / ny) * (cfg.Lz / nz));
+      launch_spectral_m<PHYS_MHD, false, 2>(sa);
+    } else if (vp_on) {   // penalised runs: the product buffer carries the penalisation spectra as well
       if (driven) launch_spectral_m<PHYS_MHD, true, true>(sa);
       else if (phys == MHDF_MHD) launch_spectral_m<PHYS_MHD, false, true>(sa);
       else launch_spectral_m<PHYS_HD, false, true>(sa);
@@ -1329,6 +1352,21 @@ struct Solver : mhdf_handle {
     const size_t n = (size_t)nx * ny * nzl;
     CK(cudaMemcpyAsync(vp_d + (size_t)which * n, p, n * sizeof(T), cudaMemcpyDefault, st));
     sync_all();
+  }
+  // SetUpND!(prob, P, fx, fy, fz) (pgen/NegativeDamping.jl:14-21): the power P and the three real profiles f_i
+  void set_forcing_nd(double Pw, const void* fx, const void* fy, const void* fz) override {
+    if (!nd_on) {
+      if (cfg.nd != 0) return;   // HD / EMHD problem created with NDForceDriving!: the forcing never reaches N, like the reference
+      throw Err{MHDF_ERR_STATE, "the problem was created without NDForceDriving! (mhdf_config.nd)"};
+    }
+    if (a99.variant != A99_OFF || fmask) throw Err{MHDF_ERR_STATE, "one calcF! per problem: NDForceDriving! cannot be combined with another forcing"};
+    CK(cudaSetDevice(cfg.device));
+    const size_t n = (size_t)nx * ny * nzl;
+    const void* f[3] = {fx, fy, fz};
+    for (int i = 0; i < 3; ++i)
+      if (f[i]) CK(cudaMemcpyAsync(nd_d + (size_t)i * n, f[i], n * sizeof(T), cudaMemcpyDefault, st));
+    sync_all();
+    nd_P = Pw;
   }
   // DivVCorrection! (group 0) / DivBCorrection! (group 1), Solver/VPSolver.jl:61-137: project sol, then refresh the
   // real-space vars of that group (ldiv!(vars.bx, rfftplan, deepcopy(bxh)) ...) = the stale view and its statistics.

@@ -58,6 +58,40 @@ def SetUpN97(prob, F0=1, kf=2):
     prob.set_forcing("uy", -F0 * np.cos(kf * X) * np.sin(kf * Y) * np.cos(kf * Z))
 
 
+class ND_vars:
+    """ND_vars (pgen/NegativeDamping.jl:8-13): the power P and the three real profiles fx, fy, fz of the negative-damping force
+    F_i = f_i u_i.  The profiles live on the device (mhdf_set_forcing_nd); this object mirrors what the user set."""
+
+    def __init__(self, T):
+        self.T = np.dtype(T).type
+        self.P, self.fx, self.fy, self.fz = 0.0, None, None, None
+
+
+def NDForceDriving(*args, **kw):
+    """NDForceDriving! (pgen/NegativeDamping.jl:23-45): pass as `calcF` to Problem together with the `usr_vars` of
+    GetNDvars_And_function, then call SetUpND(prob, P, fx, fy, fz).  Applied inside the CUDA library (mhdf_set_forcing_nd)."""
+    raise RuntimeError("NDForceDriving is applied by the library; it is not called from the host")
+
+
+def GetNDvars_And_function(dev=None, nx=None, ny=None, nz=None, T=np.float32):
+    """GetNDvars_And_function(dev, nx, ny, nz; T) (pgen/NegativeDamping.jl:47-51) -> (usr_vars, calcF)."""
+    return ND_vars(T), NDForceDriving
+
+
+def SetUpND(prob, P, fx, fy, fz):
+    """SetUpND!(prob, P, fx, fy, fz) (pgen/NegativeDamping.jl:14-21)."""
+    uv = prob.vars.usr_vars
+    if not isinstance(uv, ND_vars) or prob.params.calcF is not NDForceDriving:
+        raise ValueError("construct the problem with the usr_vars and calcF of GetNDvars_And_function")
+    ptrs, keep = [], []
+    for f in (fx, fy, fz):
+        ptr, k = prob._real_ptr(f)
+        ptrs.append(ptr)
+        keep.append(k)
+    L.check(prob._h, L.lib().mhdf_set_forcing_nd(prob._h, float(P), *ptrs))
+    uv.P, uv.fx, uv.fy, uv.fz = float(P), fx, fy, fz
+
+
 class A99_vars:
     """A99_vars (pgen/A99ForceDriving.jl:5-16; module A99GPU: pgen/A99ForceDriving_GPU.jl:7-12): `A` and `b` are the
     user-visible knobs; the spectral tables of the reference (Fk, e1x ... e2z) are not stored -- the spectral kernel
@@ -290,9 +324,14 @@ class Problem:
             raise ValueError("VP_method: the EMHD equation has no volume-penalisation terms (MHDSolver.jl:183-270)")
         if calcF is None:
             calcF = nothingfunction
-        if calcF not in (nothingfunction, N97ForceDriving, A99ForceDriving, A99GPU.A99ForceDriving):
+        if calcF not in (nothingfunction, N97ForceDriving, A99ForceDriving, A99GPU.A99ForceDriving, NDForceDriving):
             raise NotImplementedError("arbitrary forcing callbacks cannot run on the device; the built-in forcings are "
-                                      "set_forcing / N97ForceDriving (constant) and A99ForceDriving (random driving)")
+                                      "set_forcing / N97ForceDriving (constant), A99ForceDriving (random driving) and "
+                                      "NDForceDriving (negative damping)")
+        if calcF is NDForceDriving and not isinstance(usr_vars, ND_vars):
+            raise ValueError("NDForceDriving needs usr_vars = the ND_vars of GetNDvars_And_function")
+        if calcF is NDForceDriving and VP_method:
+            raise NotImplementedError("NDForceDriving together with VP_method is not supported on this path")
         if calcF in (A99ForceDriving, A99GPU.A99ForceDriving) and not isinstance(usr_vars, A99_vars):
             raise ValueError("A99ForceDriving needs usr_vars = the A99_vars of GetA99vars_And_function")
         if EMHD and not B_field:
@@ -354,7 +393,7 @@ class Problem:
                        dtype=L.F32 if T is np.float32 else L.F64,
                        device=dev.device if isinstance(dev, GPU) else 0, rank=self.rank, nranks=self.nranks,
                        nccl_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None,
-                       vp=1 if VP_method else 0)
+                       vp=1 if VP_method else 0, nd=1 if calcF is NDForceDriving else 0)
         h = C.c_void_p()
         code = L.lib().mhdf_create(C.byref(cfg), C.byref(h))
         if code != L.OK:

@@ -67,6 +67,36 @@ class PhiloxField:
         return out
 
 
+class NDVars:
+    """ND_vars (NegativeDamping.jl:8-13): P and the real profiles fx, fy, fz."""
+
+    def __init__(self, grid):
+        z = lambda: np.zeros((grid.nz, grid.ny, grid.nx), dtype=grid.T)
+        self.P, self.fx, self.fy, self.fz = 0.0, z(), z(), z()
+
+
+def SetUpND(prob, P, fx, fy, fz):
+    """SetUpND!(prob, P, fx, fy, fz) (NegativeDamping.jl:14-21)."""
+    uv = prob.vars.usr_vars
+    uv.P = P
+    uv.fx[...], uv.fy[...], uv.fz[...] = fx, fy, fz
+
+
+def NDForceDriving(N, sol, t, clock, vars, params, grid):
+    """NDForceDriving! (NegativeDamping.jl:23-45): N_ui += A rfft(f_i u_i), A = P / ((sum|ux^2 fx| + sum|uy^2 fy| + sum|uz^2 fz|) dx dy dz)
+    with the vars.u* the advection of this evaluation just refreshed."""
+    uv = vars.usr_vars
+    u = (vars.ux, vars.uy, vars.uz)
+    f = (uv.fx, uv.fy, uv.fz)
+    integral = sum(float(np.sum(np.abs(ui ** 2 * fi))) for ui, fi in zip(u, f)) * grid.dx * grid.dy * grid.dz
+    A = uv.P / integral
+    for fi, ui, ind in zip(f, u, (params.ux_ind, params.uy_ind, params.uz_ind)):
+        vars.nonlinh1[...] = 0
+        vars.nonlin1[...] = fi * ui
+        vars.nonlinh1[...] = grid.rfft(vars.nonlin1)
+        N[ind] += (A * vars.nonlinh1).astype(grid.CT)
+
+
 class A99Vars:
     """A99_vars{Atrans,T} (A99ForceDriving.jl:5-16): A, b scalars of type T; Fk, e1x, e1y, e2x, e2y, e2z, gi, e^{iθ}
     Complex{T} arrays (nkr, nl, nm)."""

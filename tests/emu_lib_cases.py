@@ -20,7 +20,7 @@ import mhdflows_jl_b200 as M  # noqa: E402
 from oracle import forcing_oracle as FO  # noqa: E402
 from oracle import mhdflows_oracle as O  # noqa: E402
 from tests.test_gpu_parity import _pair  # noqa: E402
-from tests.test_gpu_zforcing import _forced_pair, _vp_pair  # noqa: E402
+from tests.test_gpu_zforcing import _forced_pair, _nd_pair, _vp_pair  # noqa: E402
 
 F32_TOL, F64_TOL = 1e-5, 1e-12
 DIMS = (16, 16, 32)
@@ -118,6 +118,34 @@ def on_device_scale_decomposition_and_vector_potential():
         fresh = [g.irfft(g.dealias(op.sol[3 + i].copy())) for i in range(3)]
         assert O.rel_l2(np.stack(M.VectorPotential(gp, which=M.FRESH)), np.stack(O.VectorPotential(*fresh, g))) < tol
         gp.close()
+
+
+@case
+def negative_damping_forcing_calcN_and_steps():
+    """NDForceDriving! (pgen/NegativeDamping.jl): products in the x kernel, normalisation by its reduction, added in the spectral kernel."""
+    for T, tol, stepper in ((np.float32, F32_TOL, "RK4"), (np.float64, F64_TOL, "LSRK54")):
+        op, gp = _nd_pair(M, O, FO, T, dims=DIMS, stepper=stepper)
+        g = op.grid
+        N = np.zeros_like(op.sol)
+        op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+        ref = g.dealias(N.copy())
+        err = O.rel_l2(gp.calcN(), ref)
+        assert err < tol, err
+        q = O.Problem(nx=g.nx, ny=g.ny, nz=g.nz, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+        q.sol[...] = op.sol
+        N0 = np.zeros_like(op.sol)
+        q.calcN(N0, q.sol.copy(), 0.0, q.clock, q.vars, q.params, g)
+        assert O.rel_l2(ref[:3], g.dealias(N0.copy())[:3]) > 1e-3
+        for _ in range(2):
+            O.stepforward(op)
+        M.stepforward(gp, 2)
+        assert O.rel_l2(gp.sol, _dealiased(op)) < tol
+        gp.close()
+    op, gp = _nd_pair(M, O, FO, np.float32, dims=(16, 16, 16), B_field=False)      # lost in HD, like the reference
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
+    gp.close()
 
 
 @case

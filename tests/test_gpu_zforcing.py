@@ -264,3 +264,64 @@ def test_volume_penalisation_time_integrator(M, O):
     gp.close()
     with pytest.raises(ValueError):
         M.Problem(M.GPU(), nx=16, B_field=True, EMHD=True, VP_method=True)
+
+
+def _nd_pair(M, O, FO, T, dims=(32, 32, 32), stepper="RK4", B_field=True):
+    nx, ny, nz = dims
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, nu=2e-2, dt=4e-3, stepper=stepper)
+    if B_field:
+        kw.update(eta=3e-2, B_field=True)
+    op = O.Problem(calcF=FO.NDForceDriving, **kw)
+    op.vars.usr_vars = FO.NDVars(op.grid)
+    uv, fn = M.GetNDvars_And_function(M.GPU(), nx, ny, nz, T=T)
+    gp = M.Problem(M.GPU(), calcF=fn, usr_vars=uv, **kw)
+    g = op.grid
+    x, y, z = g.x.astype(np.float64).reshape(1, 1, -1), g.y.astype(np.float64).reshape(1, -1, 1), g.z.astype(np.float64).reshape(-1, 1, 1)
+    fx = (1.0 + 0.5 * np.sin(x) * np.cos(2 * y) + 0 * z).astype(T)
+    fy = (0.7 * np.cos(x + z) + 0 * y).astype(T)
+    fz = (np.sin(y) * np.sin(z) - 0.2 + 0 * x).astype(T)
+    FO.SetUpND(op, 0.35, fx, fy, fz)
+    M.SetUpND(gp, 0.35, fx, fy, fz)
+    u, b = O.random_phase_ic(g, 41), O.random_phase_ic(g, 42)
+    if B_field:
+        O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+    else:
+        O.SetUpProblemIC(op, *u)
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2])
+    return op, gp
+
+
+@pytest.mark.parametrize("T,tol,stepper", [(np.float32, F32_TOL, "RK4"), (np.float64, F64_TOL, "RK4"), (np.float32, F32_TOL, "LSRK54")])
+def test_negative_damping_forcing(M, O, FO, T, tol, stepper):
+    """NDForceDriving! + SetUpND! (pgen/NegativeDamping.jl:14-45): N_ui += P rfft(f_i u_i) / (sum |u_i^2 f_i| dV) on every RHS
+    evaluation of an MHD problem, formed inside the fused x kernel and normalised by its own reduction."""
+    op, gp = _nd_pair(M, O, FO, T, dims=(32, 16, 64), stepper=stepper)
+    g = op.grid
+    N = np.zeros_like(op.sol)
+    op.calcN(N, op.sol.copy(), 0.0, op.clock, op.vars, op.params, g)
+    ref = g.dealias(N.copy())
+    assert O.rel_l2(gp.calcN(), ref) < tol
+    q = O.Problem(nx=g.nx, ny=g.ny, nz=g.nz, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)      # the forcing really acts
+    q.sol[...] = op.sol
+    N0 = np.zeros_like(op.sol)
+    q.calcN(N0, q.sol.copy(), 0.0, q.clock, q.vars, q.params, g)
+    assert O.rel_l2(ref[:3], g.dealias(N0.copy())[:3]) > 1e-3 and O.rel_l2(ref[3:], g.dealias(N0.copy())[3:]) == 0.0
+    for _ in range(3):
+        O.stepforward(op)
+    M.stepforward(gp, 3)
+    assert O.rel_l2(gp.sol, g.dealias(op.sol.copy())) < tol
+    gp.close()
+
+
+def test_negative_damping_is_lost_in_hd_and_refused_with_vp(M, O, FO):
+    op, gp = _nd_pair(M, O, FO, np.float32, dims=(32, 32, 32), B_field=False)     # HDcalcN! clobbers the forcing (pgen.jl:176-178)
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < F32_TOL
+    gp.close()
+    uv, fn = M.GetNDvars_And_function(M.GPU(), 32, 32, 32)
+    with pytest.raises(NotImplementedError):
+        M.Problem(M.GPU(), nx=32, B_field=True, calcF=fn, usr_vars=uv, VP_method=True)
+    with pytest.raises(ValueError):
+        M.Problem(M.GPU(), nx=32, B_field=True, calcF=fn)
