@@ -73,6 +73,7 @@ class _FakeFieldProb:
         from mhdflows_jl_b200.problem import _Flag
         self.flag = _Flag(b, e)
         self.clock = _FakeClock()
+        self.rank, self.nranks, self._real_shape = 0, 1, (4, 4, 4)
         rng = np.random.default_rng(0)
         names = ["bx", "by", "bz"] if e else ["ux", "uy", "uz"] + (["bx", "by", "bz"] if b else [])
         self.fields = {n: rng.standard_normal((4, 4, 4)).astype(np.float32) for n in names}
