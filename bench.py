@@ -93,7 +93,10 @@ def tg_fields(n, T=np.float32, pinned=False, dims=None, zrange=None):
     for plane, line in _tg_factors(n, (nx, ny, nz), (z0, z1)):
         if pinned:
             import torch
-            t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            try:
+                t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+            except RuntimeError:      # a host that cannot pin this much memory: pageable buffers (slower e2e copies, same result)
+                t = torch.empty(shape, dtype=torch.float32)
             a = t.numpy()
         else:
             t, a = None, np.empty(shape, dtype=T)

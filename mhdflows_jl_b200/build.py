@@ -38,9 +38,8 @@ def needs_build() -> bool:
 # Tuning variants: built next to the default library as libmhdflows_b200_<name>.so and selected at run time with MHDF_LIB
 # (tools/ab.sh runs the same-box A/B).  f32x2 = Float32 butterflies / products on the packed sm_100 instructions
 # (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2), see csrc/fft_core.cuh.
-VARIANTS = {"f32x2": ["-DMHDF_F32X2"],
-            # the round-1 code shape of the EMHD x kernel (component loop fully unrolled, 194 KB of SASS): A/B partner of the default
-            "emhd_unroll": ["-DMHDF_EMHD_UNROLL_I=1"]}
+# Measured in round 2 (profiles/r02_c1_ab_f32x2.log): strided passes -3...5 %, x pass -3 % at 256^3 but +4 % at 512^3 -- stays opt-in.
+VARIANTS = {"f32x2": ["-DMHDF_F32X2"]}
 
 
 def _compile_and_link(out: str, extra: list, tag: str, verbose: bool) -> str:

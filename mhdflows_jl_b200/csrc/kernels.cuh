@@ -20,10 +20,6 @@
 #define MHDF_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
-#ifndef MHDF_EMHD_UNROLL_I
-#define MHDF_EMHD_UNROLL_I 0   // 1: fully unrolled EMHD component loop in k_xfused (the round-1 code shape)
-#endif
-
 namespace mhdf {
 
 // Retained-band descriptor of one axis: full index n -> compact row, or -1 if dealiased.
@@ -614,16 +610,10 @@ __global__ void __launch_bounds__((N / 2 / E) * RB) k_xfused(XArgs<T> a) {
         rs[i] += (double)s;
         rm[i] = max2(rm[i], mx);
       }
-      // One loop body for the three components (MHDF_EMHD_UNROLL_I = 1 restores the fully unrolled form): unrolled, the kernel
-      // carries 27 inlined row transforms = 194 KB of SASS at 512-point rows against 103 KB for the MHD kernel, and ran 3.4x slower
-      // per row transform than the MHD kernel on B200 (round 1: 60 ms of the 88.6 ms EMHD 512^3 step) at an instruction mix that
-      // is otherwise the same -- the signature of an instruction-cache cliff.  Rolled, 13 transforms remain (~95 KB).  Only
-      // the field offsets depend on i; A[j], bs[j] keep their compile-time indices, the arithmetic and its order are unchanged.
-#if MHDF_EMHD_UNROLL_I
-#pragma unroll
-#else
+      // One rolled loop body for the three components: fully unrolled, the kernel carried 27 inlined row transforms = 194 KB of SASS
+      // at 512-point rows and ran 60.4 ms per 512^3 step of x pass against 45.3 ms rolled (round 2, profiles/r02_c1_emhd.log) -- an
+      // instruction-cache cliff.  Only the field offsets depend on i; A[j], bs[j] keep their compile-time indices.
 #pragma unroll 1
-#endif
       for (int i = 0; i < 3; ++i) {
         C acc[E];
 #pragma unroll
