@@ -79,6 +79,8 @@ __device__ __forceinline__ int blk_off2(int r, const PassArgs<T>& a, int rowstri
 template <typename C> inline C ldg_pred(const C* p, bool ok) { C z; z.x = 0; z.y = 0; return ok ? *p : z; }
 template <typename C> inline void stg_pred(C* p, C v, bool ok) { if (ok) *p = v; }
 #else
+// (L1::no_allocate on these loads was measured and rejected: the x pass re-reads X[M-k] through L1 -- +13 % on the x pass, no
+// change on the strided passes; profiles/r02_c10_time1024.log)
 __device__ __forceinline__ float2 ldg_pred(const float2* p, bool ok) {
   float2 v;
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
@@ -335,6 +337,9 @@ __device__ __forceinline__ void row_r2c(Cx<T> (&v)[E], Cx<T>* __restrict__ Xout,
       stg_pred(Xout + (unsigned)k, r2c_post(z1, z2, XTwSrc<T, N, E>::wn(tw, m, k)), k < Kx);
     }
   } else {
+    // Rows of two warps (1024-point rows): Z[M-k] crosses warps and goes through shared memory.  Measured and rejected on B200
+    // (profiles/r02_c10_time1024.log): an unpadded buffer with stores / loads predicated to the elements a stored column k < Kx
+    // reads -- fewer shared-memory wavefronts, but 1.5 % slower per 1024^3 x pass than this branch-free form.
     RowIdx<M, R1> idx;
 #pragma unroll
     for (int m = 0; m < E; ++m) sm.a[idx(t + Tm * m)] = v[m];
