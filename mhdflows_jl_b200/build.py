@@ -39,7 +39,12 @@ def needs_build() -> bool:
 # (tools/ab.sh runs the same-box A/B).  f32x2 = Float32 butterflies / products on the packed sm_100 instructions
 # (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2), see csrc/fft_core.cuh.
 # Measured in round 2 (profiles/r02_c1_ab_f32x2.log): strided passes -3...5 %, x pass -3 % at 256^3 but +4 % at 512^3 -- stays opt-in.
-VARIANTS = {"f32x2": ["-DMHDF_F32X2"]}
+VARIANTS = {"f32x2": ["-DMHDF_F32X2"],
+            # strided passes on the scalar FP32 forms (the default uses the packed float2p arithmetic there): A/B partner
+            "pass_scalar": ["-DMHDF_PASS_SCALAR"],
+            # 16 columns per block in the 1024-point y passes as well (the z passes have them by default): measured 2 % slower per
+            # 1024^3 step (profiles/r02_c13_time1024.log)
+            "ytx16": ["-DMHDF_Y_TX16"]}
 
 
 def _compile_and_link(out: str, extra: list, tag: str, verbose: bool) -> str:

@@ -61,6 +61,27 @@ inline float2 lfma(float2 a, float2 b, float2 c) { return mk<float2>(std::fmaf(a
 __device__ __forceinline__ float2 lmulsub(float2 a, float2 b, float2 c, float2 d) { return lfma(lneg(c), d, lmul(a, b)); }
 #endif
 
+// ---- float2p: a complex Float32 whose lane-wise arithmetic ALWAYS maps onto the packed sm_100 instructions -----------------
+// Same layout as float2.  The strided axis passes instantiate the FFT building blocks with it (kernels.cuh: PassCx): measured
+// on B200 the packed forms make those passes 3-5 % faster (profiles/r02_c1_ab_f32x2.log: fewer issue slots for a kernel that is
+// co-limited by instruction issue and HBM), while the fused x kernel -- bound by shared-memory latency -- gains nothing from them
+// at 512-point rows and stays on the scalar forms.  add / sub / mul are IEEE-identical per lane; a * b uses one product rounding
+// and one fused multiply-add per lane.
+struct __align__(8) float2p { float x, y; };
+template <> struct RealOf<float2p> { using type = float; };
+__device__ __forceinline__ float2p to_p(float2 a) { float2p r; r.x = a.x; r.y = a.y; return r; }
+__device__ __forceinline__ float2 from_p(float2p a) { float2 r; r.x = a.x; r.y = a.y; return r; }
+#ifndef MHDF_CPU_EMU
+__device__ __forceinline__ unsigned long long pkp_(float2p a) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y)); return r; }
+__device__ __forceinline__ float2p upp_(unsigned long long v) { float2p r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ float2p ladd(float2p a, float2p b) { unsigned long long r; asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pkp_(a)), "l"(pkp_(b))); return upp_(r); }
+__device__ __forceinline__ float2p lsub(float2p a, float2p b) { unsigned long long r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pkp_(a)), "l"(pkp_(b))); return upp_(r); }
+__device__ __forceinline__ float2p lmul(float2p a, float2p b) { unsigned long long r; asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pkp_(a)), "l"(pkp_(b))); return upp_(r); }
+__device__ __forceinline__ float2p lfma(float2p a, float2p b, float2p c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pkp_(a)), "l"(pkp_(b)), "l"(pkp_(c))); return upp_(r); }
+#else
+inline float2p lfma(float2p a, float2p b, float2p c) { return mk<float2p>(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
+#endif
+
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return ladd(a, b); }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { return lsub(a, b); }
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) { return mk<C>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -83,6 +104,16 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
   return lfma(lbc<float2>(a.y), mk<float2>(b.y, b.x), mk<float2>(u.x, -u.y));
 }
 #endif
+
+// a * b = a.x * (b.x, b.y) + (-t.x, t.y),  t = a.y * (b.y, b.x);   a * conj(b) = a.y * (b.y, b.x) + (u.x, -u.y),  u = a.x * b
+__device__ __forceinline__ float2p cmul(float2p a, float2p b) {
+  const float2p t = lmul(lbc<float2p>(a.y), mk<float2p>(b.y, b.x));
+  return lfma(lbc<float2p>(a.x), b, mk<float2p>(-t.x, t.y));
+}
+__device__ __forceinline__ float2p cmulc(float2p a, float2p b) {
+  const float2p u = lmul(lbc<float2p>(a.x), b);
+  return lfma(lbc<float2p>(a.y), mk<float2p>(b.y, b.x), mk<float2p>(u.x, -u.y));
+}
 
 // DIR = -1: forward (exp(-i..)), DIR = +1: inverse (exp(+i..)), both unnormalised.
 
@@ -153,6 +184,10 @@ constexpr __host__ __device__ int imin(int a, int b) { return a < b ? a : b; }
 template <typename C> struct TwGlobal {
   const C* tw;
   __device__ __forceinline__ C get(int, unsigned gi) const { return __ldg(tw + gi); }
+};
+template <> struct TwGlobal<float2p> {
+  const float2* tw;
+  __device__ __forceinline__ float2p get(int, unsigned gi) const { return to_p(__ldg(tw + gi)); }
 };
 
 // One radix-R step on the register file of thread t (no shared memory).  SLOT0 = first twiddle slot of this step.

@@ -8,6 +8,8 @@
 //   real field (API only)   [nz][ny][nx]
 // Kxp = Kx rounded up to 8 elements so every row starts 64-byte aligned; pad columns stay zero.
 #pragma once
+#include <type_traits>
+
 #include "fft_core.cuh"
 
 // MHDF_KEEP_PTR: make the compiler treat a pointer as an opaque 64-bit value from here on (so accesses become
@@ -121,13 +123,27 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
 constexpr int pass_minb(int threads, int tsize) {
   return tsize == 4 ? ((65536 / (threads * 64)) > 16 ? 16 : (65536 / (threads * 64))) : 1;
 }
+// Arithmetic type of the strided passes: Float32 butterflies on the packed instructions (float2p, fft_core.cuh) -- measured on B200
+// against the scalar forms (profiles/r02_c11_*): 256^3 step -2.5 %, 512^3 -0.9 %; at 1024 points the inverse passes gain 5-10 % but
+// the forward passes lose 6 %, so those stay scalar.  MHDF_PASS_SCALAR: scalar everywhere (A/B partner).  Data in memory is plain
+// float2 / double2 either way.
+template <typename T, int N, int DIR> struct PassCx { using type = Cx<T>; };
+#ifndef MHDF_PASS_SCALAR
+template <int N, int DIR> struct PassCx<float, N, DIR> { using type = typename std::conditional<(N >= 1024 && DIR < 0), float2, float2p>::type; };
+#endif
+__device__ __forceinline__ float2p pass_in(float2 v, float2p) { return to_p(v); }
+__device__ __forceinline__ float2 pass_out(float2p v) { return from_p(v); }
+template <typename C> __device__ __forceinline__ C pass_in(C v, C) { return v; }
+template <typename C> __device__ __forceinline__ C pass_out(C v) { return v; }
+
 template <typename T, int N, int E, int TX, int DIR, bool PIN, int BLK, int MINB = pass_minb((N / E) * TX, (int)sizeof(T))>
 __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
-  using C = Cx<T>;
+  using C = Cx<T>;                         // element type in memory
+  using CA = typename PassCx<T, N, DIR>::type;     // element type of the arithmetic
   constexpr int Tn = N / E;
   constexpr int R1 = imin(E, N);
   MHDF_DYN_SMEM(unsigned char, smem_raw);
-  C* sm = reinterpret_cast<C*>(smem_raw);
+  CA* sm = reinterpret_cast<CA*>(smem_raw);
   const int c = threadIdx.x % TX;
   const int t = threadIdx.x / TX;
   const int col = blockIdx.x * TX + c;
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
   const unsigned irow = (unsigned)a.in_row, orow = (unsigned)a.out_row;
   MHDF_KEEP_PTR(ip);
   MHDF_KEEP_PTR(op);
-  C v[E];
+  CA v[E];
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int n = t + Tn * m;
@@ -152,17 +168,17 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
       const unsigned r = (unsigned)(n - (hi ? a.shift : 0));
       const unsigned off = (BLK == 1) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row)
                          : (BLK == 3) ? (unsigned)blk_off2<T>((int)r, a, a.in_row) : r * irow;
-      v[m] = ldg_pred(ip + off, ok);
+      v[m] = pass_in(ldg_pred(ip + off, ok), CA());
     } else {
       const unsigned off = (BLK == 1) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.in_row)
                          : (BLK == 3) ? (unsigned)blk_off2<T>(n, a, a.in_row) : (unsigned)n * irow;
-      v[m] = ldg_pred(ip + off, valid);
+      v[m] = pass_in(ldg_pred(ip + off, valid), CA());
     }
   }
-  PassIdx<N, TX, R1, C> idx{c};
+  PassIdx<N, TX, R1, CA> idx{c};
   // single exchange buffer: two barriers per exchange (scatter | gather | next scatter); twiddles straight from the
   // (L1-resident) global table -- a per-block shared copy does not pay off for one tile per block
-  fft_run_sb<C, N, E, DIR, 1, 1>(v, t, sm, TwGlobal<C>{twp}, idx);
+  fft_run_sb<CA, N, E, DIR, 1, 1>(v, t, sm, TwGlobal<CA>{twp}, idx);
 #pragma unroll
   for (int m = 0; m < E; ++m) {
     const int n = t + Tn * m;
@@ -172,11 +188,11 @@ __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
       const unsigned r = (unsigned)(n - (hi ? a.shift : 0));
       const unsigned off = (BLK == 2) ? (unsigned)blk_off((int)r, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row)
                          : (BLK == 4) ? (unsigned)blk_off2<T>((int)r, a, a.out_row) : r * orow;
-      stg_pred(op + off, v[m], ok);
+      stg_pred(op + off, pass_out(v[m]), ok);
     } else {
       const unsigned off = (BLK == 2) ? (unsigned)blk_off(n, a.blk_rows, a.blk_stride, a.blk_magic, a.out_row)
                          : (BLK == 4) ? (unsigned)blk_off2<T>(n, a, a.out_row) : (unsigned)n * orow;
-      stg_pred(op + off, v[m], valid);
+      stg_pred(op + off, pass_out(v[m]), valid);
     }
   }
 }

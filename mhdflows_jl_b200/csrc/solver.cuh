@@ -440,16 +440,24 @@ struct Solver : mhdf_handle {
 
   // ---- kernel dispatch ------------------------------------------------------------------------
   static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
-  // columns per block: 16 (128-byte row segments); 8 at N = 1024 so two 512-thread blocks fit per SM (16 columns in one
-  // 1024-thread block measured 4 % slower per step on a 256 x 1024 x 1024 grid)
-  static constexpr int passTX(int N) { return sizeof(T) == 4 ? (N >= 1024 ? 8 : 16) : (N >= 1024 ? 4 : 8); }
+  // columns per block: 16 (128-byte row segments); 8 in the 1024-point y passes so that two 512-thread blocks fit per SM.
+  // The 1024-point z passes take 16 columns (one 1024-thread block per SM): their rows are a whole [ky][kx] plane apart, and
+  // 128-byte instead of 64-byte row segments are worth more there than the second resident block -- z inverse 24.3 -> 20.8 ms,
+  // z forward 37.5 -> 28.0 ms per 1024^3 step (profiles/r02_c12_time1024.log); the y passes (rows 2.7 KB apart) keep 8 columns
+  // (MHDF_Y_TX16: 16 there as well -- measured slower, y inverse 26.7 -> 30.6 ms, y forward 39.2 -> 41.9 ms, r02_c13_time1024.log).
+  static constexpr int passTX(int N, bool zpass = false) {
+#ifdef MHDF_Y_TX16
+    zpass = true;
+#endif
+    return sizeof(T) == 4 ? ((N >= 1024 && !zpass) ? 8 : 16) : (N >= 1024 ? 4 : 8);
+  }
   static constexpr int xE(int) { return 8; }
   static constexpr int XNT = 64;   // threads per block of the x kernels: small blocks, rows decoupled per warp
   static constexpr int xRB(int N) { return XNT / (N / 2 / 8) > 0 ? XNT / (N / 2 / 8) : 1; }
 
   bool blk_out = false;
-  template <int N, int DIR> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
-    constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
+  template <int N, int DIR, bool ZP> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
+    constexpr int E = passE(N), TX = passTX(N, ZP), R1 = imin(E, N);
     constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
     dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
     // the blocked side is the z side of the z passes and the ky side of the y passes: output of inverse-z / forward-y,
@@ -461,15 +469,15 @@ struct Solver : mhdf_handle {
     else MHDF_LAUNCH((k_pass<T, N, E, TX, DIR, (DIR > 0), 1>), grid, (N / E) * TX, smem, st, a);
     ++launches;
   }
-  template <int DIR> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
+  template <int DIR, bool ZP = false> void launch_pass(int N, PassArgs<T>& a, int n_outer, int n_fields) {
     switch (N) {
-      case 16: launch_pass_n<16, DIR>(a, n_outer, n_fields); break;
-      case 32: launch_pass_n<32, DIR>(a, n_outer, n_fields); break;
-      case 64: launch_pass_n<64, DIR>(a, n_outer, n_fields); break;
-      case 128: launch_pass_n<128, DIR>(a, n_outer, n_fields); break;
-      case 256: launch_pass_n<256, DIR>(a, n_outer, n_fields); break;
-      case 512: launch_pass_n<512, DIR>(a, n_outer, n_fields); break;
-      case 1024: launch_pass_n<1024, DIR>(a, n_outer, n_fields); break;
+      case 16: launch_pass_n<16, DIR, ZP>(a, n_outer, n_fields); break;
+      case 32: launch_pass_n<32, DIR, ZP>(a, n_outer, n_fields); break;
+      case 64: launch_pass_n<64, DIR, ZP>(a, n_outer, n_fields); break;
+      case 128: launch_pass_n<128, DIR, ZP>(a, n_outer, n_fields); break;
+      case 256: launch_pass_n<256, DIR, ZP>(a, n_outer, n_fields); break;
+      case 512: launch_pass_n<512, DIR, ZP>(a, n_outer, n_fields); break;
+      case 1024: launch_pass_n<1024, DIR, ZP>(a, n_outer, n_fields); break;
       default: throw Err{MHDF_ERR_INVALID, "unsupported axis length"};
     }
     CK(cudaGetLastError());
@@ -571,7 +579,11 @@ struct Solver : mhdf_handle {
     }
   }
   template <int N> void set_pass_attr() {
-    constexpr int E = passE(N), TX = passTX(N), R1 = imin(E, N);
+    set_pass_attr_tx<N, passTX(N, false)>();
+    if constexpr (passTX(N, true) != passTX(N, false)) set_pass_attr_tx<N, passTX(N, true)>();
+  }
+  template <int N, int TX> void set_pass_attr_tx() {
+    constexpr int E = passE(N), R1 = imin(E, N);
     constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
     if (smem > 48 * 1024) {
       CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -600,7 +612,7 @@ struct Solver : mhdf_handle {
     if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
     blk_out = true;
     prof_begin(KC_ZINV);
-    launch_pass<+1>(nz, a, 1, nf);
+    launch_pass<+1, true>(nz, a, 1, nf);
     prof_end();
   }
   void y_inverse(const C* in, C* out, int nf) {
@@ -643,7 +655,7 @@ struct Solver : mhdf_handle {
     if (P_ > 1) { a.blk_rows = nzl; a.blk_stride = (int)blk(nf); a.blk_magic = (unsigned)((0x100000000ULL + nzl - 1) / nzl); }
     blk_out = false;
     prof_begin(KC_ZFWD);
-    launch_pass<-1>(nz, a, 1, nf);
+    launch_pass<-1, true>(nz, a, 1, nf);
     prof_end();
   }
   // all-to-all of the blocked layout: piece q (blk(nf) elements) goes to / comes from rank q; the own piece is a local
@@ -1005,7 +1017,7 @@ struct Solver : mhdf_handle {
       a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bi); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
       blk_out = true;
       prof_begin(KC_ZINV);
-      launch_pass<+1>(nz, a, 1, fgz);
+      launch_pass<+1, true>(nz, a, 1, fgz);
       prof_end();
       zdone[g] = mark(st);
     }
@@ -1086,7 +1098,7 @@ struct Solver : mhdf_handle {
       a.blk2_rows = zc; a.blk2_stride = (int)((size_t)P_ * Bo); a.blk2_magic = (unsigned)((0x100000000ULL + zc - 1) / zc);
       blk_out = false;
       prof_begin(KC_ZFWD);
-      launch_pass<-1>(nz, a, 1, fgf);
+      launch_pass<-1, true>(nz, a, 1, fgf);
       prof_end();
     }
     sa.P = Xin;

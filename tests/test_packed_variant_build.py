@@ -1,4 +1,4 @@
-"""The packed-FP32 build variant (-DMHDF_F32X2) must keep compiling for sm_100a and must really
+"""The packed-FP32 forms (float2p in the strided passes of the default build; everything with -DMHDF_F32X2) must keep compiling for sm_100a and must really
 map the Float32 butterflies onto the packed instructions: cross-compile one small strided pass and one fused x kernel
 and look for FADD2 / FMUL2 / FFMA2 in the SASS (no GPU needed)."""
 import os
@@ -34,16 +34,18 @@ def test_packed_variant_compiles_to_packed_sass(tmp_path):
     cu = tmp_path / "inst.cu"
     cu.write_text(SRC)
     counts = {}
-    for name, flags in (("scalar", []), ("f32x2", ["-DMHDF_F32X2"])):
+    for name, flags in (("scalar", ["-DMHDF_PASS_SCALAR"]), ("default", []), ("f32x2", ["-DMHDF_F32X2"])):
         cubin = str(tmp_path / f"{name}.cubin")
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", *flags,
                "-I", os.path.join(ROOT, "mhdflows_jl_b200", "csrc"), "-o", cubin, str(cu)]
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stderr[-3000:]
         counts[name] = _opcodes(cubin)
-    s, p = counts["scalar"], counts["f32x2"]
-    packed = p.get("FADD2", 0) + p.get("FMUL2", 0) + p.get("FFMA2", 0)
-    assert s.get("FADD2", 0) + s.get("FMUL2", 0) + s.get("FFMA2", 0) == 0          # the default build stays scalar
+    s, d, p = counts["scalar"], counts["default"], counts["f32x2"]
+    npacked = lambda c: c.get("FADD2", 0) + c.get("FMUL2", 0) + c.get("FFMA2", 0)
+    packed = npacked(p)
+    assert npacked(s) == 0                            # -DMHDF_PASS_SCALAR: no packed instruction anywhere
+    assert 30 < npacked(d) < packed                   # default: the strided Float32 passes are packed (float2p), the x kernel is not
     assert packed > 500, p
     # Float64 is untouched by the variant, Float32 scalar FP work almost disappears
     assert p.get("DADD", 0) == s.get("DADD", 0) and p.get("DFMA", 0) == s.get("DFMA", 0)
