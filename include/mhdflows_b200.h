@@ -40,7 +40,7 @@ typedef enum {
 
 enum { MHDF_F32 = 0, MHDF_F64 = 1 };
 enum { MHDF_HD = 0, MHDF_MHD = 1, MHDF_EMHD = 2 };          /* B_field / EMHD flags, pgen.jl:129-150 */
-enum { MHDF_RK4 = 0, MHDF_LSRK54 = 1 };                      /* stepper = "RK4" | "LSRK54", Problems.jl:123-128 */
+enum { MHDF_RK4 = 0, MHDF_LSRK54 = 1, MHDF_HM89 = 2 };       /* stepper = "RK4" | "LSRK54" | "HM89" (EMHD only), Problems.jl:123-128 */
 enum { MHDF_FRESH = 0, MHDF_STALE = 1 };                     /* which real-space view: true state, or the reference's
                                                                `vars.*` = c2r of the last stage input */
 
@@ -52,7 +52,7 @@ typedef struct {
   int n_nu;                /* params.n_nu (hyperviscosity ADDS on top of viscosity when > 1, MHDSolver.jl:94-99) */
   double dt;               /* clock.dt */
   int physics;             /* MHDF_HD | MHDF_MHD | MHDF_EMHD */
-  int stepper;             /* MHDF_RK4 | MHDF_LSRK54 */
+  int stepper;             /* MHDF_RK4 | MHDF_LSRK54 | MHDF_HM89 (HM89TimeStepper, timestepper/HM89.jl; needs physics = MHDF_EMHD) */
   int dtype;               /* MHDF_F32 | MHDF_F64  (T = Float32 default, pgen.jl:90) */
   int device;              /* CUDA device ordinal */
   /* slab decomposition over `nranks` processes (one GPU each); rank 0..nranks-1.  nranks = 1: single GPU. */
@@ -139,6 +139,9 @@ int mhdf_set_random_phase(mhdf_handle* h, int group, unsigned long long seed, do
 
 /* stepforward! (timestepper/timestepper.jl:4-6): nsteps steps of clock.dt. */
 int mhdf_step(mhdf_handle* h, int nsteps);
+/* HM89TimeStepper only (timestepper/HM89.jl:61-84): how many fixed-point iterations the last step took and its last error norm
+ * max |B^n - B^1| (the reference keeps both in locals of HM89substeps!); 0 and 0 for the explicit steppers. */
+int mhdf_stepper_stats(mhdf_handle* h, long long* fixed_point_iters, double* last_error);
 /* eqn.calcN!(N, sol, t, clock, vars, params, grid) (pgen.jl:153-181) on the current sol:
  * writes N as nfields spectral arrays (dealiased modes zero).  Refreshes the stale `vars` like the reference. */
 int mhdf_calcN(mhdf_handle* h, void* host_N);

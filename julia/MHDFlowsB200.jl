@@ -97,9 +97,11 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2œÄ, Ly = Lx, Lz = Lx, c‚Ç
   (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! || calcF === A99GPU.A99ForceDriving! ||
    calcF === NDForceDriving!) ||
     error("arbitrary forcing callbacks cannot run on the device; constant forcings go through setforcing! / N97ForceDriving!")
-  stepper in ("RK4", "LSRK54") || error("stepper must be \"RK4\" or \"LSRK54\" on the B200 path")
+  stepper in ("RK4", "LSRK54", "HM89") || error("stepper must be \"RK4\", \"LSRK54\" or (EMHD) \"HM89\" on the B200 path")
+  stepper == "HM89" && !EMHD && error("stepper \"HM89\" exists for EMHD problems only (Problems.jl:124-126)")
+  stepper == "HM89" && calcF !== nothingfunction && error("HM89 with a forcing function is not supported (HM89.jl:182-196)")
   physics = EMHD ? MHDF_EMHD : (B_field ? MHDF_MHD : MHDF_HD)
-  cfg = MhdfConfig(nx, ny, nz, Lx, Ly, Lz, ŒΩ, Œ∑, nŒΩ, dt, physics, stepper == "RK4" ? 0 : 1,
+  cfg = MhdfConfig(nx, ny, nz, Lx, Ly, Lz, ŒΩ, Œ∑, nŒΩ, dt, physics, stepper == "RK4" ? 0 : (stepper == "LSRK54" ? 1 : 2),
                    T === Float32 ? 0 : 1, dev.device, 0, 1, C_NULL, VP_method ? 1 : 0,
                    calcF === NDForceDriving! ? 1 : 0)
   h = Ref{Ptr{Cvoid}}(C_NULL)
@@ -254,6 +256,13 @@ DivBCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (
 
 "stepforward!(prob) == stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)"
 stepforward!(prob, n::Int = 1) = check(prob.h, ccall((:mhdf_step, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, n))
+
+"HM89TimeStepper: (fixed-point iterations of the last step, its last error norm max |B‚Åø - B¬π|)   (timestepper/HM89.jl:61-84)"
+function stepper_stats(prob)
+  it = Ref{Clonglong}(); Œµ = Ref{Cdouble}()
+  check(prob.h, ccall((:mhdf_stepper_stats, lib), Cint, (Ptr{Cvoid}, Ref{Clonglong}, Ref{Cdouble}), prob.h, it, Œµ))
+  (it[], Œµ[])
+end
 
 "getCFL!(prob, t_diff; Coef)   (integrator.jl:158-198)"
 function getCFL!(prob, t_diff; Coef = 0.3)

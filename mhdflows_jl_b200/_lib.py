@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("MHDF_LIB") or os.path.join(HERE, "libmhdflows_b200.so
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NONFINITE, ERR_STATE = 0, -1, -2, -3, -4, -5
 F32, F64 = 0, 1
 HD, MHD, EMHD = 0, 1, 2
-RK4, LSRK54 = 0, 1
+RK4, LSRK54, HM89 = 0, 1, 2
 FRESH, STALE = 0, 1
 
 # every symbol include/mhdflows_b200.h declares
@@ -19,7 +19,7 @@ SYMBOLS = [
     "mhdf_create", "mhdf_destroy", "mhdf_last_error", "mhdf_nccl_unique_id", "mhdf_set_real", "mhdf_get_real",
     "mhdf_set_spectral", "mhdf_get_spectral", "mhdf_step", "mhdf_calcN", "mhdf_set_dt", "mhdf_set_clock",
     "mhdf_get_clock", "mhdf_cfl_dt", "mhdf_energy", "mhdf_helicity", "mhdf_spectrum", "mhdf_stale_stats",
-    "mhdf_step_timed", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
+    "mhdf_step_timed", "mhdf_stepper_stats", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
     "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
     "mhdf_set_forcing_a99", "mhdf_forcing_a99_calls", "mhdf_div_correction", "mhdf_set_vp_field",
     "mhdf_set_random_phase", "mhdf_scale_decomposition", "mhdf_vector_potential", "mhdf_set_forcing_nd",
@@ -69,6 +69,7 @@ def lib():
         "mhdf_set_spectral": (i, [vp, i, vp]),
         "mhdf_get_spectral": (i, [vp, i, i, vp]),
         "mhdf_step": (i, [vp, i]),
+        "mhdf_stepper_stats": (i, [vp, pll, pd]),
         "mhdf_calcN": (i, [vp, vp]),
         "mhdf_set_dt": (i, [vp, d]),
         "mhdf_set_clock": (i, [vp, d, ll]),

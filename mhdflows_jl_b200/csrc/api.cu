@@ -28,7 +28,8 @@ int mhdf_create(const mhdf_config* c, mhdf_handle** out) {
   if ((long long)c->ny * c->nz < 256) return bad("ny*nz must be at least 256");
   if (!(c->Lx > 0 && c->Ly > 0 && c->Lz > 0)) return bad("Lx, Ly, Lz must be positive");
   if (c->physics < MHDF_HD || c->physics > MHDF_EMHD) return bad("physics must be MHDF_HD, MHDF_MHD or MHDF_EMHD");
-  if (c->stepper != MHDF_RK4 && c->stepper != MHDF_LSRK54) return bad("stepper must be RK4 or LSRK54 (Problems.jl:123-128)");
+  if (c->stepper != MHDF_RK4 && c->stepper != MHDF_LSRK54 && c->stepper != MHDF_HM89) return bad("stepper must be RK4, LSRK54 or HM89 (Problems.jl:123-128)");
+  if (c->stepper == MHDF_HM89 && c->physics != MHDF_EMHD) return bad("the HM89 stepper exists for EMHD problems only (Problems.jl:124)");
   if (c->dtype != MHDF_F32 && c->dtype != MHDF_F64) return bad("dtype must be MHDF_F32 or MHDF_F64");
   if (c->nranks < 1 || c->nranks > 64 || c->rank < 0 || c->rank >= c->nranks) return bad("need 0 <= rank < nranks <= 64");
   int ndev = 0;
@@ -72,6 +73,7 @@ int mhdf_set_real(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { 
 int mhdf_get_real(mhdf_handle* h, int f, int w, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->get_real(f, w, p); }); }
 int mhdf_set_spectral(mhdf_handle* h, int f, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_spectral(f, p); }); }
 int mhdf_get_spectral(mhdf_handle* h, int f, int w, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->get_spectral(f, w, p); }); }
+int mhdf_stepper_stats(mhdf_handle* h, long long* it, double* eps) { return guard(h, [&] { h->stepper_stats(it, eps); }); }
 int mhdf_step(mhdf_handle* h, int n) { return guard(h, [&] { if (n < 0) throw Err{MHDF_ERR_INVALID, "nsteps < 0"}; h->step(n); }); }
 int mhdf_calcN(mhdf_handle* h, void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->calcN(p); }); }
 int mhdf_set_dt(mhdf_handle* h, double dt) { return guard(h, [&] { h->set_dt(dt); }); }

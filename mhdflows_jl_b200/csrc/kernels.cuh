@@ -1517,6 +1517,92 @@ __global__ void __launch_bounds__(256) k_diag(SpecGeom<T> g, const Cx<T>* __rest
   }
 }
 
+// ---- HM89TimeStepper (timestepper/HM89.jl:23-199): the elementwise stages on three compact fields ------------------------
+// HM_STAGE  one stage of LSRK3substeps! / RK3linearterm! (HM89.jl:141-199), in the order of the reference's broadcasts:
+//             [lin: F -= eta k^2 S]   F *= dt   [G: F -= b G]   S += (F c) c2
+//           eta, b are Float64 in the reference (params.eta; the literals 5/9, 153/128): those broadcasts run in Float64 and round on
+//           the store; c = Float32/64 of the rational 1//3, 15//16, 8//15; c2 = dt in the first stage (HM89.jl:158,186), else 1
+// HM_HALF   S = (B0 + B1) 0.5                                                   (HM89.jl:67)
+// HM_FIXED  Bn = B0 + dt F1;  F = Bn - B1;  B1 = Bn                             (HM89.jl:71-82; Bn needs no array of its own,
+//           and dealias!(Bn) is the compact layout itself)
+enum { HM_STAGE = 0, HM_HALF = 1, HM_FIXED = 2 };
+template <typename T>
+struct Hm89Args {
+  int op, lin;
+  Cx<T>* F;          // STAGE: the stage array (F0 / F1); FIXED: out, B^n - B^1
+  const Cx<T>* G;    // STAGE: the other stage array or null; FIXED: F1 = the Hall term of this iteration
+  Cx<T>* S;          // STAGE, HALF: sol
+  const Cx<T>* B0;
+  Cx<T>* B1;
+  double eta, b;
+  T dt, c, c2;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_hm89(SpecGeom<T> g, Hm89Args<T> a) {
+  using C = Cx<T>;
+  const int Ky = g.Kyl, Kz = g.bz.count();
+  const long long total = (long long)g.Kxp * Ky * Kz;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(e % g.Kxp);
+    if (ix >= g.Kx) continue;
+    double ek2 = 0;
+    if (a.op == HM_STAGE && a.lin) {
+      const long long rowi = e / g.Kxp;
+      const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
+      const T kx = g.kx[ix], ky = g.ky[jc], kz = g.kz[kc];
+      ek2 = a.eta * (double)(kx * kx + ky * ky + kz * kz);      // eta * k^2: Float64 * T
+    }
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      const long long i = f * g.field + e;
+      if (a.op == HM_STAGE) {
+        C F = a.F[i];
+        const C S = a.S[i];
+        if (a.lin) F = mk<C>((T)((double)F.x - ek2 * (double)S.x), (T)((double)F.y - ek2 * (double)S.y));
+        F = mk<C>(F.x * a.dt, F.y * a.dt);
+        if (a.G != nullptr) {
+          const C G = a.G[i];
+          F = mk<C>((T)((double)F.x - a.b * (double)G.x), (T)((double)F.y - a.b * (double)G.y));
+        }
+        a.F[i] = F;
+        a.S[i] = mk<C>(S.x + (F.x * a.c) * a.c2, S.y + (F.y * a.c) * a.c2);
+      } else if (a.op == HM_HALF) {
+        const C p = a.B0[i], q = a.B1[i];
+        a.S[i] = mk<C>((p.x + q.x) * (T)0.5, (p.y + q.y) * (T)0.5);
+      } else {
+        const C p = a.B0[i], n = a.G[i], q = a.B1[i];
+        const C bn = mk<C>(p.x + a.dt * n.x, p.y + a.dt * n.y);
+        a.F[i] = mk<C>(bn.x - q.x, bn.y - q.y);
+        a.B1[i] = bn;
+      }
+    }
+  }
+}
+
+// square_mean of HM89substeps! (HM89.jl:45,79): max over the grid points of sqrt(x^2 + y^2 + z^2) of three real fields, in T;
+// the bit pattern of the non-negative result goes to *out with an atomic max (see XRed::maxsq)
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm3_max(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z, long long n,
+                                                   unsigned long long* __restrict__ out) {
+  T mx = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const T a = x[i], b = y[i], c = z[i];
+    T v = sqrt(a * a + b * b + c * c);
+    if (!(v == v)) v = (T)INFINITY;                              // fmax drops NaNs: a NaN counts as +inf, the caller stops on it
+    mx = max2(mx, v);
+  }
+  __shared__ T sh[8];
+  warp_red_max(mx);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T m = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = max2(m, sh[w]);
+    atomic_max_bits(out, m);
+  }
+}
+
 // Shell spectrum of one compact field: Pk[round(|k|)] += |f^|^2 over the HALF spectrum, no weights
 // (reference: MHDAnalysis.jl:237-255 `spectralline`).  kr = 0 plane symmetrised (what rfft of the
 // real field holds).  Shared-memory histogram per block, then one atomic per bin.

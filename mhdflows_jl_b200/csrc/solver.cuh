@@ -105,6 +105,7 @@ struct mhdf_handle {
   virtual void get_spectral(int field, int which, void* p) = 0;
   virtual void step(int n) = 0;
   virtual void calcN(void* p) = 0;
+  virtual void stepper_stats(long long* iters, double* eps) const = 0;
   virtual void set_dt(double dt) = 0;
   virtual void set_clock(double t, long long step) = 0;
   virtual void get_clock(double* t, double* dt, long long* step) const = 0;
@@ -177,7 +178,9 @@ struct Solver : mhdf_handle {
   int* ferr_h = nullptr;   // host-mapped: set by a wait that timed out
   bool use_flags = [] { const char* e = getenv("MHDF_FLAGS"); return !e || atoi(e) != 0; }();
   // state registers (compact, F fields each)
-  C* reg[4] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int NREG_MAX = 5;
+  C* reg[NREG_MAX] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int nreg_() const { return cfg.stepper == MHDF_RK4 ? 4 : (cfg.stepper == MHDF_HM89 ? 5 : 3); }   // HM89: sol, F0, F1, B0, B1
   int iY = 0;       // register holding sol
   int iStale = -1;  // register holding the last stage input (RK4), -1 if none
   C *P = nullptr, *Q = nullptr, *R = nullptr, *D = nullptr;
@@ -285,7 +288,7 @@ struct Solver : mhdf_handle {
       std::memcpy(&id, c.nccl_id, sizeof id);
       NK(g_nccl.CommInitRank(&comm, P_, id, rank_));
     }
-    const int nreg = (c.stepper == MHDF_RK4) ? 4 : 3;
+    const int nreg = nreg_();
     for (int i = 0; i < nreg; ++i) reg[i] = dalloc<C>((size_t)F * cf);
     // work buffers (elements).  P: inverse-z output / forward-y output (send layouts);  Q: inverse-y output (x input)
     // / second exchange target;  R: first exchange target / x output / forward-z output / API staging.
@@ -360,7 +363,7 @@ struct Solver : mhdf_handle {
     if (sc) cudaStreamDestroy(sc);
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    for (int i = 0; i < 4; ++i) cudaFree(reg[i]);
+    for (int i = 0; i < NREG_MAX; ++i) cudaFree(reg[i]);
     cudaFree(P); cudaFree(Q); cudaFree(R); cudaFree(D); cudaFree(bst); cudaFree(force); cudaFree(vp_d); cudaFree(nd_d); cudaFree(Xin); cudaFree(Xout); cudaFree(P2);
     cudaFree(twx); cudaFree(twy); cudaFree(twz);
     cudaFree(kxv); cudaFree(kyv); cudaFree(kzv);
@@ -371,7 +374,7 @@ struct Solver : mhdf_handle {
     if (diag_h) cudaFreeHost(diag_h);
     if (st) cudaStreamDestroy(st);
     st = sc = nullptr; comm = nullptr; ipc_on = false; red_h = nullptr; diag_h = nullptr;
-    for (int i = 0; i < 4; ++i) reg[i] = nullptr;
+    for (int i = 0; i < NREG_MAX; ++i) reg[i] = nullptr;
     P = Q = R = D = nullptr; bst = nullptr; force = nullptr; vp_d = nullptr; nd_d = nullptr; Xin = Xout = P2 = nullptr; twx = twy = twz = nullptr; kxv = kyv = kzv = nullptr;
     red_d = nullptr; diag_d = nullptr; spec_d = nullptr; plane_loc = plane_all = nullptr; bar_d = nullptr;
     dep_ev.clear(); evs.clear(); ev_free.clear();
@@ -1210,6 +1213,7 @@ struct Solver : mhdf_handle {
 
   void one_step() {
     const T dt = dt_;
+    if (cfg.stepper == MHDF_HM89) { hm89_step(); return; }
     if (cfg.stepper == MHDF_RK4) {
       // registers: Y = reg[iY]; two stage buffers and the accumulator are the other three
       int o[3], n = 0;
@@ -1253,6 +1257,107 @@ struct Solver : mhdf_handle {
     step_ += 1;
   }
 
+
+  // ---- HM89TimeStepper (timestepper/HM89.jl:23-199; Problem(...; EMHD = true, stepper = "HM89"), Problems.jl:124-126) ------------
+  // One step = LSRK3 predictor (3 Hall-term evaluations) -> DivFreeCorrection! -> fixed-point iteration of the implicit midpoint
+  // rule (one evaluation + one three-field inverse transform + one max reduction per iteration, until max |B^n - B^1| <= 5e-4) ->
+  // RK3linearterm! (resistive term, three explicit stages that also read what the loop left in F0 / F1, like the reference) ->
+  // DivFreeCorrection! -> vars.b = irfft(sol).  Registers: sol = reg[iY], then F0, F1, B0, B1 (B^n is formed in place).
+  // The reference writes B^n - B^1 in real space INTO vars.bx/by/bz (HM89.jl:49,76-78): the next evaluation of the loop reads that
+  // difference as its stale b -- reproduced (the inverse transforms land in the stale-b array of the EMHD x kernel).
+  // One deviation: the closing ldiv!(vars.b, sol) of the reference sees the aliased band that RK3linearterm! left in sol
+  // (c2 dt N on the modes dealias! removes at the next evaluation); the compact state has no such band, vars.b is the dealiased field.
+  long long hm_iters = 0;   // fixed-point iterations of the last step
+  double hm_eps = 0;        // its last error norm
+  static constexpr int HM_MAX_ITERS = 10000;
+  void hm_launch(const Hm89Args<T>& a) {
+    MHDF_LAUNCH((k_hm89<T>), spec_grid(), 256, 0, st, geom(), a);
+    ++launches;
+    CK(cudaGetLastError());
+  }
+  void hm_eval(C* N, const C* S, bool want_red) {   // N = EMHDcalcN!(S) (no forcing, no resistive term: pgen.jl:164-171)
+    SpecArgs<T> sa = blank_args();
+    sa.mode = STEP_CALCN; sa.Nout = N;
+    rhs(S, sa, want_red);
+  }
+  void hm_stage(C* Fa, const C* G, C* S, double b, double c, bool first, bool lin) {
+    Hm89Args<T> a;
+    std::memset(&a, 0, sizeof a);
+    a.op = HM_STAGE; a.lin = lin ? 1 : 0;
+    a.F = Fa; a.G = G; a.S = S;
+    a.eta = cfg.eta; a.b = b;
+    a.dt = dt_; a.c = (T)c; a.c2 = first ? dt_ : (T)1;
+    hm_launch(a);
+  }
+  void hm_divfree(C* S) {
+    MHDF_LAUNCH((k_divclean<T>), spec_grid(), 256, 0, st, geom(), S);
+    ++launches;
+    CK(cudaGetLastError());
+  }
+  void hm89_step() {
+    C *S = reg[iY];
+    C* o[4];
+    { int n = 0; for (int i = 0; i < 5; ++i) if (i != iY) o[n++] = reg[i]; }
+    C *F0 = o[0], *F1 = o[1], *B0 = o[2], *B1 = o[3];
+    const size_t bytes = (size_t)F * cf * sizeof(C);
+    const double c1 = 1.0 / 3.0, c2 = 15.0 / 16.0, c3 = 8.0 / 15.0;
+    CK(cudaMemcpyAsync(B0, S, bytes, cudaMemcpyDeviceToDevice, st));                    // copyto!(B0, sol)
+    hm_eval(F0, S, false); hm_stage(F0, nullptr, S, 0.0, c1, true, false);              // LSRK3substeps!
+    hm_eval(F1, S, false); hm_stage(F1, F0, S, 5.0 / 9.0, c2, false, false);
+    hm_eval(F0, S, false); hm_stage(F0, F1, S, 153.0 / 128.0, c3, false, false);
+    hm_divfree(S);
+    CK(cudaMemcpyAsync(B1, S, bytes, cudaMemcpyDeviceToDevice, st));                    // copyto!(B1, sol); dealias!(B1)
+    T* re = reinterpret_cast<T*>(R);
+    const size_t n = (size_t)nx * ny * nzl;
+    double eps = 1.0;
+    hm_iters = 0;
+    while (eps > 5e-4) {
+      Hm89Args<T> a;
+      std::memset(&a, 0, sizeof a);
+      a.op = HM_HALF; a.S = S; a.B0 = B0; a.B1 = B1;
+      hm_launch(a);                                                                    // B_half = (B0 + B1) 0.5
+      hm_eval(F1, S, true);                                                            // the Hall term of B_half; its curl B maxima feed getCFL!
+      sync_all();
+      check_flags();
+      absorb_red();
+      a.op = HM_FIXED; a.F = F0; a.G = F1; a.dt = dt_;
+      hm_launch(a);                                                                    // B^n = B0 + dt N; F0 = B^n - B^1; B^1 = B^n
+      for (int i = 0; i < 3; ++i) {                                                    // vars.b <- irfft(B^n - B^1)
+        to_xlayout(F0 + (size_t)i * cf, 1);
+        XArgs<T> xa = xargs();
+        xa.real_io = re; xa.in = Q; xa.out = nullptr;
+        launch_xplain<+1>(xa);
+        CK(cudaMemcpyAsync(bst + (size_t)i * n, re, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      }
+      red_reset();
+      MHDF_LAUNCH((k_norm3_max<T>), spec_grid(), 256, 0, st, bst, bst + n, bst + 2 * n, (long long)n, &red_d->maxsq[0]);
+      ++launches;
+      CK(cudaGetLastError());
+      finish_red();
+      sync_all();
+      check_flags();
+      eps = red_max(0);
+      ++hm_iters;
+      if (!std::isfinite(eps)) break;                                                  // NaN ends the reference's loop too; the caller's NaN check reports it
+      if (hm_iters >= HM_MAX_ITERS) throw Err{MHDF_ERR_STATE, "HM89: the fixed-point iteration did not converge (the reference would loop forever)"};
+    }
+    hm_eps = eps;
+    CK(cudaMemcpyAsync(S, B1, bytes, cudaMemcpyDeviceToDevice, st));                    // copyto!(sol, B1)
+    hm_stage(F0, nullptr, S, 0.0, c1, true, true);                                      // RK3linearterm! with calcF! = nothingfunction
+    hm_stage(F1, F0, S, 5.0 / 9.0, c2, false, true);
+    hm_stage(F0, F1, S, 153.0 / 128.0, c3, false, true);
+    hm_divfree(S);
+    iStale = iY;
+    refresh_vars(0);                                                                   // vars.b = irfft(sol): stale b, maxima, energies
+    if (!std::isfinite(eps)) st_sum[3] = eps;                                          // surfaces as MHDF_ERR_NONFINITE in step()
+    t_ = t_ + dt_;
+    step_ += 1;
+  }
+
+  void stepper_stats(long long* iters, double* eps) const override {
+    if (iters) *iters = hm_iters;
+    if (eps) *eps = hm_eps;
+  }
   void step(int n) override {
     CK(cudaSetDevice(cfg.device));
     rank_barrier();
@@ -1260,7 +1365,7 @@ struct Solver : mhdf_handle {
     sync_all();
     check_flags();
     if (n > 0) {
-      absorb_red();
+      if (cfg.stepper != MHDF_HM89) absorb_red();   // HM89 keeps its own statistics (curl B of the last evaluation, b of the closing ldiv!)
       check_finite();
     }
   }
@@ -1283,14 +1388,14 @@ struct Solver : mhdf_handle {
     CK(cudaEventElapsedTime(&f, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     *ms = f;
-    if (n > 0) { absorb_red(); check_finite(); }
+    if (n > 0) { if (cfg.stepper != MHDF_HM89) absorb_red(); check_finite(); }
   }
 
   void calcN(void* p) override {
     CK(cudaSetDevice(cfg.device));
     // N goes to a register that is dead between steps
     int o = -1;
-    const int nreg = (cfg.stepper == MHDF_RK4) ? 4 : 3;
+    const int nreg = nreg_();
     for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
     SpecArgs<T> sa = blank_args();
     sa.mode = STEP_CALCN; sa.Nout = reg[o];
@@ -1427,7 +1532,7 @@ struct Solver : mhdf_handle {
     else throw Err{MHDF_ERR_INVALID, "group must be 0 (velocity) or 1 (magnetic field)"};
     if (mode != 0 && mode != 1) throw Err{MHDF_ERR_INVALID, "analysis mode must be 0 (scale decomposition) or 1 (vector potential)"};
     int o = -1;
-    const int nreg = (cfg.stepper == MHDF_RK4) ? 4 : 3;
+    const int nreg = nreg_();
     for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
     rank_barrier();
     MHDF_LAUNCH((k_analysis<T>), spec_grid(), 256, 0, st, geom(), source(which) + (size_t)f0 * cf, reg[o], mode, (T)k1, (T)k2);

@@ -336,10 +336,13 @@ class Problem:
             raise ValueError("A99ForceDriving needs usr_vars = the A99_vars of GetA99vars_And_function")
         if EMHD and not B_field:
             raise ValueError("EMHD requires B_field=true (datastructure.jl:78-88)")
-        if stepper == "HM89":
-            raise NotImplementedError("HM89 is outside the hot path (SURVEY 2 #11)")
-        if stepper not in ("RK4", "LSRK54"):
-            raise ValueError(f"stepper {stepper!r}: only \"RK4\" and \"LSRK54\" are on the B200 path")
+        if stepper == "HM89" and not EMHD:
+            # Problems.jl:124-128: without EFlag the name goes to FourierFlows.TimeStepper, which does not know it
+            raise ValueError("stepper \"HM89\" exists for EMHD problems only (Problems.jl:124-126)")
+        if stepper == "HM89" and calcF is not nothingfunction:
+            raise NotImplementedError("HM89 with a forcing function: RK3linearterm! (HM89.jl:182-196) is built for calcF = nothingfunction")
+        if stepper not in ("RK4", "LSRK54", "HM89"):
+            raise ValueError(f"stepper {stepper!r}: \"RK4\", \"LSRK54\" and (EMHD) \"HM89\" are on the B200 path")
         ny = nx if ny is None else ny
         nz = nx if nz is None else nz
         Ly = Lx if Ly is None else Ly
@@ -389,7 +392,7 @@ class Problem:
             self._real_shape = (nz, ny, nx)
             self._spec_shape = (nz, ny, nx // 2 + 1)
         cfg = L.Config(nx=nx, ny=ny, nz=nz, Lx=Lx, Ly=Ly, Lz=Lz, nu=float(nu), eta=float(eta), n_nu=int(n_nu),
-                       dt=float(dt), physics=physics, stepper=L.RK4 if stepper == "RK4" else L.LSRK54,
+                       dt=float(dt), physics=physics, stepper={"RK4": L.RK4, "LSRK54": L.LSRK54, "HM89": L.HM89}[stepper],
                        dtype=L.F32 if T is np.float32 else L.F64,
                        device=dev.device if isinstance(dev, GPU) else 0, rank=self.rank, nranks=self.nranks,
                        nccl_id=C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None,
@@ -560,6 +563,12 @@ class Problem:
 
     def launch_count(self):
         return L.lib().mhdf_launch_count(self._h)
+
+    def stepper_stats(self):
+        """HM89TimeStepper: (fixed-point iterations of the last step, its last error norm max |Bⁿ - B¹|), HM89.jl:61-84."""
+        it, eps = C.c_longlong(), C.c_double()
+        L.check(self._h, L.lib().mhdf_stepper_stats(self._h, C.byref(it), C.byref(eps)))
+        return it.value, eps.value
 
     def __repr__(self):  # Problems.jl:142-159
         b = "ON (EMHD)" if self.flag.e else ("ON (Ideal MHD)" if self.flag.b else "OFF")

@@ -418,6 +418,112 @@ class LSRK54TimeStepper:
         self.C = [T(float(c)) for c in LSRK54_C]
 
 
+class HM89TimeStepper:
+    """timestepper/HM89.jl:7-23: five work arrays F0, F1, B0, B1, Bn and c = (1//3, 15//16, 8//15)."""
+
+    def __init__(self, sol_like, T):
+        self.F0, self.F1, self.B0, self.B1, self.Bn = (np.zeros_like(sol_like) for _ in range(5))
+        self.c = tuple(T(float(c)) for c in (Fraction(1, 3), Fraction(15, 16), Fraction(8, 15)))   # Rational -> T in the broadcasts
+        self.iters = 0          # fixed-point iterations of the last step (bookkeeping of this restatement)
+        self.eps = 0.0          # last error norm
+        self.dealias_vars = False   # True: the closing ldiv! reads a dealiased copy of sol (what a pruned-spectrum
+                                    # implementation holds); False = the reference, literally
+
+
+def DivFreeCorrection(sol, vars, params, grid):
+    """timestepper/HM89.jl:105-139: Phi = -i (k . B^) / k^2, B^_i -= i k_i Phi."""
+    CT = grid.CT
+    ki, kj, kk = grid.kr, grid.l, grid.m
+    vars.nonlin1 *= 0
+    vars.nonlinh1 *= 0
+    S = vars.nonlinh1
+    bxh, byh, bzh = sol[params.bx_ind], sol[params.by_ind], sol[params.bz_ind]
+    S[...] = CT(-1j) * (ki * bxh + kj * byh + kk * bzh)          # :129
+    S[...] = S * grid.invKrsq                                    # :130
+    bxh -= CT(1j) * ki * S                                       # :133-135
+    byh -= CT(1j) * kj * S
+    bzh -= CT(1j) * kk * S
+
+
+def LSRK3substeps(sol, clock, ts, calcN, vars, params, grid):
+    """timestepper/HM89.jl:141-167, literally: the first stage multiplies by dt twice (:157-158), 5/9 and 153/128 are
+    Float64 constants (the broadcast runs in ComplexF64 and rounds on the store)."""
+    T = grid.T
+    t, dt, c = clock.t, T(clock.dt), ts.c
+    calcN(ts.F0, sol, t + dt, clock, vars, params, grid)
+    ts.F0 *= dt
+    sol += ts.F0 * c[0] * dt
+    calcN(ts.F1, sol, t + dt, clock, vars, params, grid)
+    ts.F1 *= dt
+    ts.F1 -= np.float64(5 / 9) * ts.F0
+    sol += c[1] * ts.F1
+    calcN(ts.F0, sol, t + dt, clock, vars, params, grid)
+    ts.F0 *= dt
+    ts.F0 -= np.float64(153 / 128) * ts.F1
+    sol += c[2] * ts.F0
+
+
+def RK3linearterm(sol, ts, clock, vars, params, grid):
+    """timestepper/HM89.jl:169-199: the same three stages on F = calcF!(...) - eta k^2 sol.  params.calcF! = nothingfunction
+    leaves F0 / F1 as the fixed-point loop left them (F0 = the last B^n - B^1, F1 = the last curl(J x B)): they ARE read."""
+    T = grid.T
+    t, dt, c = clock.t, T(clock.dt), ts.c
+    k2, eta = grid.Krsq, np.float64(params.eta)
+    calcF = params.calcF if params.calcF is not None else (lambda *a: None)
+    calcF(ts.F0, sol, t + dt, clock, vars, params, grid)
+    ts.F0 -= eta * k2 * sol
+    ts.F0 *= dt
+    sol += ts.F0 * c[0] * dt
+    calcF(ts.F1, sol, t + dt, clock, vars, params, grid)
+    ts.F1 -= eta * k2 * sol
+    ts.F1 *= dt
+    ts.F1 -= np.float64(5 / 9) * ts.F0
+    sol += c[1] * ts.F1
+    calcF(ts.F0, sol, t + dt, clock, vars, params, grid)
+    ts.F0 -= eta * k2 * sol
+    ts.F0 *= dt
+    ts.F0 -= np.float64(153 / 128) * ts.F1
+    sol += c[2] * ts.F0
+
+
+def HM89substeps(sol, clock, ts, calcN, vars, params, grid):
+    """timestepper/HM89.jl:35-103: LSRK3 predictor, divergence cleaning, fixed-point iteration of the implicit midpoint rule
+    on the Hall term (error = max |B^n - B^1| in real space, threshold 5e-4, written into vars.b*: the NEXT evaluation of
+    the loop reads that difference as its stale b), then the resistive term with the explicit three-stage scheme."""
+    T = grid.T
+    t, dt = clock.t, T(clock.dt)
+    B0, B1, Bn = ts.B0, ts.B1, ts.Bn
+    dBh, NL = ts.F0, ts.F1
+    B0[...] = sol                                                # :54
+    LSRK3substeps(sol, clock, ts, calcN, vars, params, grid)
+    DivFreeCorrection(sol, vars, params, grid)
+    B1[...] = sol
+    grid.dealias(B1)
+    B_half = sol
+    eps, err = 1.0, 5e-4
+    ts.iters = 0
+    while eps > err:
+        B_half[...] = (B0 + B1) * 0.5                            # :67
+        calcN(NL, B_half, t, clock, vars, params, grid)
+        Bn[...] = B0 + dt * NL                                   # :71
+        grid.dealias(Bn)
+        dBh[...] = Bn - B1                                       # :75
+        vars.bx[...] = grid.irfft(dBh[0].copy())                 # :76-78 (dBx, dBy, dBz ARE vars.bx, by, bz)
+        vars.by[...] = grid.irfft(dBh[1].copy())
+        vars.bz[...] = grid.irfft(dBh[2].copy())
+        eps = float(np.max(np.sqrt(vars.bx * vars.bx + vars.by * vars.by + vars.bz * vars.bz)))   # :79
+        B1[...] = Bn
+        ts.iters += 1
+    ts.eps = eps
+    sol[...] = B1                                                # :86
+    RK3linearterm(sol, ts, clock, vars, params, grid)
+    DivFreeCorrection(sol, vars, params, grid)
+    src = grid.dealias(sol.copy()) if ts.dealias_vars else sol
+    vars.bx[...] = grid.irfft(src[params.bx_ind].copy())         # :91-93
+    vars.by[...] = grid.irfft(src[params.by_ind].copy())
+    vars.bz[...] = grid.irfft(src[params.bz_ind].copy())
+
+
 def stepforward(prob):
     """timestepper/timestepper.jl:4-6 -> FourierFlows.stepforward!"""
     sol, clock, ts, vars, params, grid = prob.sol, prob.clock, prob.timestepper, prob.vars, prob.params, prob.grid
@@ -425,7 +531,9 @@ def stepforward(prob):
     T = grid.T
     dt = T(clock.dt)
     t = clock.t
-    if isinstance(ts, RK4TimeStepper):
+    if isinstance(ts, HM89TimeStepper):                            # HM89.jl:25-33: clock.t += clock.dt (in T), step += 1
+        HM89substeps(sol, clock, ts, calcN, vars, params, grid)
+    elif isinstance(ts, RK4TimeStepper):
         R1, R2, R3, R4 = ts.RHS
         calcN(R1, sol, t, clock, vars, params, grid)               # L = 0: addlinearterm! is a no-op
         ts.sol1[...] = sol + (dt / T(2)) * R1
@@ -481,8 +589,10 @@ class Problem:
             self.timestepper = RK4TimeStepper(self.sol)
         elif stepper == "LSRK54":
             self.timestepper = LSRK54TimeStepper(self.sol, g.T)
+        elif stepper == "HM89" and EMHD:                           # Problems.jl:124-126: only with EFlag
+            self.timestepper = HM89TimeStepper(self.sol, g.T)
         else:
-            raise ValueError(f"stepper {stepper!r} not in scope (RK4, LSRK54)")
+            raise ValueError(f"stepper {stepper!r} not in scope (RK4, LSRK54; HM89 with EMHD)")
         self.stepper = stepper
 
 

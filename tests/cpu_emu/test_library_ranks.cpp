@@ -134,6 +134,7 @@ int main(int argc, char** argv) {
   if (!quick) compare<float>("hd lsrk54 16x32x16", P, peer, MHDF_HD, MHDF_LSRK54, 16, 32, 16, false, false);
   compare<double>("emhd rk4 f64 16x16x16", P, peer, MHDF_EMHD, MHDF_RK4, 16, 16, 16, false, false);
   compare<float>("mhd rk4 a99 + vp 16x16x16", P, peer, MHDF_MHD, MHDF_RK4, 16, 16, 16, true, true);
+  compare<double>("emhd hm89 f64 16x16x16", P, peer, MHDF_EMHD, MHDF_HM89, 16, 16, 16, false, false);   // fixed-point loop: max over ranks
   std::printf("library ranks driver done: %d failure(s)\n", g_fail);
   return g_fail ? 1 : 0;
 }

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 import mhdflows_jl_b200 as M  # noqa: E402
 from oracle import forcing_oracle as FO  # noqa: E402
 from oracle import mhdflows_oracle as O  # noqa: E402
-from tests.test_gpu_parity import _pair  # noqa: E402
+from tests.test_gpu_parity import _hm89_check, _pair  # noqa: E402
 from tests.test_gpu_zforcing import _forced_pair, _nd_pair, _vp_pair  # noqa: E402
 
 F32_TOL, F64_TOL = 1e-5, 1e-12
@@ -399,6 +399,13 @@ def second_emhd_kernel_form_is_bit_identical():
         assert np.linalg.norm(a[0]) > 0
         for x, y in zip(a, b):
             assert np.array_equal(x, y), stepper
+
+
+@case
+def hm89_stepper_emhd_both_precisions():
+    """HM89TimeStepper (timestepper/HM89.jl): predictor, fixed-point loop with the stale-b quirk, resistive stages, CFL inputs."""
+    _hm89_check(M, O, np.float64, F64_TOL, (16, 16, 16), steps=2)
+    _hm89_check(M, O, np.float32, F32_TOL, (16, 16, 32), steps=1)
 
 
 @case

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "mhdflows_jl_b200", "csrc")
 
 # case-name filters of the concurrent workers (balanced by measured run time)
-GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5"],
+GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5", "hm89"],
           ["a99_gpu", "a99_lsrk54", "a99_reproducible", "div_b_correction_emhd"],
           ["div_corrections", "volume_penalisation_hd", "random_phase", "on_device"],
           ["volume_penalisation_mhd", "volume_penalisation_time", "second_emhd", "negative_damping"],

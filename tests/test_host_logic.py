@@ -17,8 +17,10 @@ def test_problem_rejects_what_the_reference_rejects_before_touching_the_device()
         M.Problem(M.GPU(), nx=32, Compressibility=True)             # pgen.jl:98-100
     with pytest.raises(ValueError, match="EMHD requires"):
         M.Problem(M.GPU(), nx=32, EMHD=True)
-    with pytest.raises(NotImplementedError):
-        M.Problem(M.GPU(), nx=32, stepper="HM89")
+    with pytest.raises(ValueError, match="EMHD problems only"):
+        M.Problem(M.GPU(), nx=32, stepper="HM89")                   # Problems.jl:124-126: HM89TimeStepper only with EFlag
+    with pytest.raises(NotImplementedError, match="forcing"):
+        M.Problem(M.GPU(), nx=32, B_field=True, EMHD=True, stepper="HM89", calcF=M.N97ForceDriving)
     with pytest.raises(ValueError):
         M.Problem(M.GPU(), nx=32, stepper="ETDRK4")
     with pytest.raises(M.MHDFlowsError):

@@ -190,3 +190,30 @@ def test_divfree_spectra_map_is_solenoidal_and_real():
     # solenoidal up to the Hermitian symmetrisation the c2r applies on the kr=0 plane (zeroed anyway)
     assert np.sqrt(np.sum(np.abs(div) ** 2)) / nrm < 1e-10
     assert np.isfinite(fx).all() and fx.std() > 0
+
+
+def test_hm89_restatement_properties():
+    """timestepper/HM89.jl, as written: the field leaves a step solenoidal (DivFreeCorrection!), the fixed point converges below
+    5e-4, and -- because RK3linearterm! reads the arrays the loop left behind (calcF! = nothingfunction never clears them) -- the
+    resistive stages re-apply the Hall term: with eta = 0 a step advances B by (1 + 15/16 - 8/15 * 153/128) dt N = 1.3 dt N(B_half)."""
+    kw = dict(nx=16, dt=1e-3, eta=0.0, B_field=True, EMHD=True, T=np.float64)
+    p = O.Problem(stepper="HM89", **kw)
+    g = p.grid
+    b = [g.irfft(g.dealias(g.rfft(x))) for x in O.random_phase_ic(g, 3)]
+    O.SetUpProblemIC(p, bx=b[0], by=b[1], bz=b[2])
+    B0 = p.sol.copy()
+    O.stepforward(p)
+    ts = p.timestepper
+    assert 2 <= ts.iters < 20 and ts.eps <= 5e-4
+    assert p.clock.step == 1 and p.clock.t == 1e-3
+    m = g.retained_mask()
+    div = g.kr * p.sol[0] + g.l * p.sol[1] + g.m * p.sol[2]
+    assert np.abs(div[m]).max() < 1e-13 * np.abs(p.sol[:, m]).max()
+    q = O.Problem(stepper="RK4", **kw)            # scratch vars for one more evaluation; stale b = the last (tiny) difference ~ 0
+    N = np.zeros_like(B0)
+    O.EMHDcalcN(N, (B0 + ts.B1) * 0.5, 0, q.clock, q.vars, q.params, g)
+    pred = B0 + (1 + 15 / 16 - 8 / 15 * 153 / 128) * 1e-3 * N
+    O.DivFreeCorrection(pred, q.vars, q.params, g)
+    assert O.rel_l2((p.sol - B0)[:, m], (pred - B0)[:, m]) < 2e-2
+    with pytest.raises(ValueError):
+        O.Problem(nx=16, B_field=True, stepper="HM89")          # Problems.jl:124: only with EFlag
