@@ -66,3 +66,19 @@ def test_driven_slab_run_equals_single_gpu():
     for l in lines:
         m = re.search(r"spectral max rel diff ([0-9.e+-]+)\s+real ([0-9.e+-]+)", l)
         assert m and float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l
+
+
+def test_hm89_slab_run_equals_single_gpu():
+    """HM89TimeStepper on 2 GPUs: the error norm of the fixed-point loop is reduced over the ranks (max), so every rank leaves the
+    loop in the same iteration and the state stays bit-identical to the single-GPU run."""
+    if _ngpu() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29547", os.path.join(ROOT, "tools", "dist_check.py"), "hm89_64"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, MHDF_PEER="1"), cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("dist-vs-single emhd")]
+    assert len(lines) == 2
+    for l in lines:
+        m = re.search(r"spectral max rel diff ([0-9.e+-]+)\s+real ([0-9.e+-]+)", l)
+        assert m and float(m.group(1)) == 0.0 and float(m.group(2)) == 0.0, l

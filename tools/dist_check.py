@@ -90,6 +90,9 @@ if which == "check64":
 elif which == "check128":      # smallest cubic grid 8 ranks can split (every rank needs >= 2 retained ky rows and a non-empty last slab)
     run("mhd", 128, "RK4", np.float32, 3)
     run("emhd", 128, "LSRK54", np.float32, 2)
+elif which == "hm89_64":       # the EMHD HM89 stepper: its fixed-point error norm is a max over the ranks; iteration counts must agree
+    run("emhd", 64, "HM89", np.float32, 2)
+    run("emhd", 64, "HM89", np.float64, 2)
 elif which == "forcing64":
     run("mhd", 64, "RK4", np.float32, 3, driven=True)
     run("mhd", 64, "LSRK54", np.float64, 2, driven=True)
