@@ -127,6 +127,14 @@ __device__ __forceinline__ constexpr double s16(int k) {
        : k == 4 ? 1.0 : k == 5 ? 0.92387953251128673848 : k == 6 ? 0.70710678118654752440 : 0.38268343236508977173;
 }
 
+// cos/sin(2*pi*k/32), k = 0..15 (radix-32 butterflies of the MHDF_PASS_E32 variant)
+__device__ __forceinline__ constexpr double c32(int k) {
+  return k == 0 ? 1.00000000000000000000 : k == 1 ? 0.98078528040323043058 : k == 2 ? 0.92387953251128673848 : k == 3 ? 0.83146961230254523567 : k == 4 ? 0.70710678118654757274 : k == 5 ? 0.55557023301960228867 : k == 6 ? 0.38268343236508983729 : k == 7 ? 0.19509032201612833135 : k == 8 ? 0.00000000000000006123 : k == 9 ? -0.19509032201612819257 : k == 10 ? -0.38268343236508972627 : k == 11 ? -0.55557023301960195560 : k == 12 ? -0.70710678118654746172 : k == 13 ? -0.83146961230254534669 : k == 14 ? -0.92387953251128673848 : -0.98078528040323043058;
+}
+__device__ __forceinline__ constexpr double s32(int k) {
+  return k == 0 ? 0.00000000000000000000 : k == 1 ? 0.19509032201612824808 : k == 2 ? 0.38268343236508978178 : k == 3 ? 0.55557023301960217765 : k == 4 ? 0.70710678118654746172 : k == 5 ? 0.83146961230254523567 : k == 6 ? 0.92387953251128673848 : k == 7 ? 0.98078528040323043058 : k == 8 ? 1.00000000000000000000 : k == 9 ? 0.98078528040323043058 : k == 10 ? 0.92387953251128673848 : k == 11 ? 0.83146961230254545772 : k == 12 ? 0.70710678118654757274 : k == 13 ? 0.55557023301960217765 : k == 14 ? 0.38268343236508989280 : 0.19509032201612860891;
+}
+
 // In-register radix-R DFT, natural order in -> natural order out (decimation in time).
 template <int R, int DIR, typename C> struct Bfly;
 
@@ -152,7 +160,7 @@ template <int DIR, typename C> struct Bfly<4, DIR, C> {
   }
 };
 template <int R, int DIR, typename C> struct Bfly {
-  static_assert(R == 8 || R == 16, "radix must be 2, 4, 8 or 16");
+  static_assert(R == 8 || R == 16 || R == 32, "radix must be 2, 4, 8, 16 or 32");
   using T = typename RealOf<C>::type;
   static __device__ __forceinline__ void run(C (&v)[R]) {
     C e[R / 2], o[R / 2];
@@ -166,8 +174,8 @@ template <int R, int DIR, typename C> struct Bfly {
       if (k == 0) t = o[0];
       else if (k == R / 4) t = (DIR < 0) ? cmulmi(o[k]) : cmuli(o[k]);
       else {
-        const T wc = (T)c16(k * (16 / R));
-        const T ws = (T)(DIR * s16(k * (16 / R)));
+        const T wc = (T)(R == 32 ? c32(k) : c16(k * (16 / (R == 32 ? 16 : R))));
+        const T ws = (T)(DIR * (R == 32 ? s32(k) : s16(k * (16 / (R == 32 ? 16 : R)))));
         t = cmul(o[k], mk<C>(wc, ws));
       }
       v[k] = cadd(e[k], t);

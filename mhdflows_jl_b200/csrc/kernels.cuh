@@ -120,8 +120,9 @@ template <int N, int TX, int R1, typename C> struct PassIdx {
 // BLK: 0 = plain strides, 1 = input side blocked, 2 = output side blocked, 3 / 4 = input / output side two-level blocked
 // Float32: at most 64 registers per thread (launch bound) -- measured 13 % faster per 512^3 step than the 76-80
 // registers the compiler takes otherwise, because one more block fits per SM.
-constexpr int pass_minb(int threads, int tsize) {
-  return tsize == 4 ? ((65536 / (threads * 64)) > 16 ? 16 : (65536 / (threads * 64))) : 1;
+// (32 points per thread -- the MHDF_PASS_E32 variant -- hold 64 data registers: budget 128)
+constexpr int pass_minb(int threads, int tsize, int E = 16) {
+  return tsize == 4 ? ((65536 / (threads * (E >= 32 ? 128 : 64))) > 16 ? 16 : (65536 / (threads * (E >= 32 ? 128 : 64)))) : 1;
 }
 // Arithmetic type of the strided passes: Float32 butterflies on the packed instructions (float2p, fft_core.cuh) -- measured on B200
 // against the scalar forms (profiles/r02_c11_*): 256^3 step -2.5 %, 512^3 -0.9 %; at 1024 points the inverse passes gain 5-10 % but
@@ -129,14 +130,18 @@ constexpr int pass_minb(int threads, int tsize) {
 // float2 / double2 either way.
 template <typename T, int N, int DIR> struct PassCx { using type = Cx<T>; };
 #ifndef MHDF_PASS_SCALAR
+#ifdef MHDF_PASS_FWD_PACKED   // A/B: packed arithmetic in the forward 1024-point passes as well
+template <int N, int DIR> struct PassCx<float, N, DIR> { using type = float2p; };
+#else
 template <int N, int DIR> struct PassCx<float, N, DIR> { using type = typename std::conditional<(N >= 1024 && DIR < 0), float2, float2p>::type; };
+#endif
 #endif
 __device__ __forceinline__ float2p pass_in(float2 v, float2p) { return to_p(v); }
 __device__ __forceinline__ float2 pass_out(float2p v) { return from_p(v); }
 template <typename C> __device__ __forceinline__ C pass_in(C v, C) { return v; }
 template <typename C> __device__ __forceinline__ C pass_out(C v) { return v; }
 
-template <typename T, int N, int E, int TX, int DIR, bool PIN, int BLK, int MINB = pass_minb((N / E) * TX, (int)sizeof(T))>
+template <typename T, int N, int E, int TX, int DIR, bool PIN, int BLK, int MINB = pass_minb((N / E) * TX, (int)sizeof(T), E)>
 __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
   using C = Cx<T>;                         // element type in memory
   using CA = typename PassCx<T, N, DIR>::type;     // element type of the arithmetic

@@ -442,7 +442,19 @@ struct Solver : mhdf_handle {
   }
 
   // ---- kernel dispatch ------------------------------------------------------------------------
-  static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
+  // points per thread of the strided passes: 16 (8, 4 on short axes); 32 in the Float32 1024-point passes -- radix 32 x 32, ONE
+  // shared-memory exchange instead of two, 128 registers, 256 / 512 threads per block.  Measured on B200 (profiles/r02_c16_time1024.log,
+  // 1024^3 step): y inverse 26.4 -> 24.5 ms, y forward 39.0 -> 37.4, z inverse 20.9 -> 19.1, z forward 28.1 -> 24.9; step 222.1 -> 213.9 ms.
+  // MHDF_PASS_E32: 0 = 16 points everywhere (A/B partner), 1 = the 1024-point y passes only, 2 = y and z (default), 3 = the
+  // 512-point passes as well.
+#ifndef MHDF_PASS_E32
+#define MHDF_PASS_E32 2
+#endif
+  static constexpr int passE(int N, bool zpass = false) {
+    if (sizeof(T) == 4 && MHDF_PASS_E32 >= 1 && N >= 1024 && (!zpass || MHDF_PASS_E32 >= 2)) return 32;
+    if (sizeof(T) == 4 && MHDF_PASS_E32 >= 3 && N >= 512) return 32;
+    return N >= 128 ? 16 : (N >= 32 ? 8 : 4);
+  }
   // columns per block: 16 (128-byte row segments); 8 in the 1024-point y passes so that two 512-thread blocks fit per SM.
   // The 1024-point z passes take 16 columns (one 1024-thread block per SM): their rows are a whole [ky][kx] plane apart, and
   // 128-byte instead of 64-byte row segments are worth more there than the second resident block -- z inverse 24.3 -> 20.8 ms,
@@ -460,7 +472,7 @@ struct Solver : mhdf_handle {
 
   bool blk_out = false;
   template <int N, int DIR, bool ZP> void launch_pass_n(PassArgs<T>& a, int n_outer, int n_fields) {
-    constexpr int E = passE(N), TX = passTX(N, ZP), R1 = imin(E, N);
+    constexpr int E = passE(N, ZP), TX = passTX(N, ZP), R1 = imin(E, N);
     constexpr size_t smem = (size_t)PassIdx<N, TX, R1, C>::SIZE * sizeof(C);
     dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
     // the blocked side is the z side of the z passes and the ky side of the y passes: output of inverse-z / forward-y,
@@ -582,11 +594,11 @@ struct Solver : mhdf_handle {
     }
   }
   template <int N> void set_pass_attr() {
-    set_pass_attr_tx<N, passTX(N, false)>();
-    if constexpr (passTX(N, true) != passTX(N, false)) set_pass_attr_tx<N, passTX(N, true)>();
+    set_pass_attr_tx<N, passTX(N, false), false>();
+    if constexpr (passTX(N, true) != passTX(N, false) || passE(N, true) != passE(N, false)) set_pass_attr_tx<N, passTX(N, true), true>();
   }
-  template <int N, int TX> void set_pass_attr_tx() {
-    constexpr int E = passE(N), R1 = imin(E, N);
+  template <int N, int TX, bool ZP> void set_pass_attr_tx() {
+    constexpr int E = passE(N, ZP), R1 = imin(E, N);
     constexpr int smem = (int)(PassIdx<N, TX, R1, C>::SIZE * sizeof(C));
     if (smem > 48 * 1024) {
       CK(cudaFuncSetAttribute(k_pass<T, N, E, TX, -1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
