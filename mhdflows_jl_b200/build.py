@@ -43,11 +43,10 @@ VARIANTS = {"f32x2": ["-DMHDF_F32X2"],
             # strided passes on the scalar FP32 forms (the default uses the packed float2p arithmetic there): A/B partner
             "pass_scalar": ["-DMHDF_PASS_SCALAR"],
             # 16 columns per block in the 1024-point y passes as well (the z passes have them by default): measured 2 % slower per
-            # 1024^3 step with 16 points per thread (profiles/r02_c13_time1024.log); re-tested with 32 points per thread in call 17
+            # 1024^3 step with 16 points per thread (profiles/r02_c13_time1024.log) and with 32 (r02_c17_time1024.log)
             "ytx16": ["-DMHDF_Y_TX16"],
             "e16": ["-DMHDF_PASS_E32=0"],            # 16 points per thread in every strided pass (the default until call 16)
-            "e32_512": ["-DMHDF_PASS_E32=3"],        # 32 points per thread in the 512-point passes as well
-            "fwdp": ["-DMHDF_PASS_FWD_PACKED"]}      # packed arithmetic in the forward 1024-point passes too
+            "fwdp": ["-DMHDF_PASS_FWD_PACKED"]}      # packed arithmetic in the forward 1024-point z passes too (measured 2 % slower there)      # packed arithmetic in the forward 1024-point passes too
 
 
 def _compile_and_link(out: str, extra: list, tag: str, verbose: bool) -> str:

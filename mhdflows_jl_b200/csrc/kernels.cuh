@@ -125,15 +125,16 @@ constexpr int pass_minb(int threads, int tsize, int E = 16) {
   return tsize == 4 ? ((65536 / (threads * (E >= 32 ? 128 : 64))) > 16 ? 16 : (65536 / (threads * (E >= 32 ? 128 : 64)))) : 1;
 }
 // Arithmetic type of the strided passes: Float32 butterflies on the packed instructions (float2p, fft_core.cuh) -- measured on B200
-// against the scalar forms (profiles/r02_c11_*): 256^3 step -2.5 %, 512^3 -0.9 %; at 1024 points the inverse passes gain 5-10 % but
-// the forward passes lose 6 %, so those stay scalar.  MHDF_PASS_SCALAR: scalar everywhere (A/B partner).  Data in memory is plain
-// float2 / double2 either way.
-template <typename T, int N, int DIR> struct PassCx { using type = Cx<T>; };
+// against the scalar forms, per pass: everything below 1024 points gains (256^3 step -2.5 %, 512^3 -0.9 %, profiles/r02_c11_*); at
+// 1024 points the inverse passes gain 5-10 %, the forward y passes (8 columns per block) gain 9 % (37.3 -> 34.0 ms per 1024^3 step)
+// and the forward z passes (16 columns) lose 2 % (profiles/r02_c17_time1024.log), so only those stay scalar.  MHDF_PASS_SCALAR:
+// scalar everywhere, MHDF_PASS_FWD_PACKED: packed everywhere (A/B partners).  Data in memory is plain float2 / double2 either way.
+template <typename T, int N, int DIR, int TX> struct PassCx { using type = Cx<T>; };
 #ifndef MHDF_PASS_SCALAR
-#ifdef MHDF_PASS_FWD_PACKED   // A/B: packed arithmetic in the forward 1024-point passes as well
-template <int N, int DIR> struct PassCx<float, N, DIR> { using type = float2p; };
+#ifdef MHDF_PASS_FWD_PACKED
+template <int N, int DIR, int TX> struct PassCx<float, N, DIR, TX> { using type = float2p; };
 #else
-template <int N, int DIR> struct PassCx<float, N, DIR> { using type = typename std::conditional<(N >= 1024 && DIR < 0), float2, float2p>::type; };
+template <int N, int DIR, int TX> struct PassCx<float, N, DIR, TX> { using type = typename std::conditional<(N >= 1024 && DIR < 0 && TX >= 16), float2, float2p>::type; };
 #endif
 #endif
 __device__ __forceinline__ float2p pass_in(float2 v, float2p) { return to_p(v); }
@@ -144,7 +145,7 @@ template <typename C> __device__ __forceinline__ C pass_out(C v) { return v; }
 template <typename T, int N, int E, int TX, int DIR, bool PIN, int BLK, int MINB = pass_minb((N / E) * TX, (int)sizeof(T), E)>
 __global__ void __launch_bounds__((N / E) * TX, MINB) k_pass(PassArgs<T> a) {
   using C = Cx<T>;                         // element type in memory
-  using CA = typename PassCx<T, N, DIR>::type;     // element type of the arithmetic
+  using CA = typename PassCx<T, N, DIR, TX>::type; // element type of the arithmetic
   constexpr int Tn = N / E;
   constexpr int R1 = imin(E, N);
   MHDF_DYN_SMEM(unsigned char, smem_raw);

@@ -442,13 +442,14 @@ struct Solver : mhdf_handle {
   }
 
   // ---- kernel dispatch ------------------------------------------------------------------------
-  // points per thread of the strided passes: 16 (8, 4 on short axes); 32 in the Float32 1024-point passes -- radix 32 x 32, ONE
-  // shared-memory exchange instead of two, 128 registers, 256 / 512 threads per block.  Measured on B200 (profiles/r02_c16_time1024.log,
-  // 1024^3 step): y inverse 26.4 -> 24.5 ms, y forward 39.0 -> 37.4, z inverse 20.9 -> 19.1, z forward 28.1 -> 24.9; step 222.1 -> 213.9 ms.
-  // MHDF_PASS_E32: 0 = 16 points everywhere (A/B partner), 1 = the 1024-point y passes only, 2 = y and z (default), 3 = the
-  // 512-point passes as well.
+  // points per thread of the strided passes: 16 (8, 4 on short axes); 32 in the Float32 512- and 1024-point passes -- radix 32 x 32
+  // (32 x 16), ONE shared-memory exchange instead of two, 128 registers, 256 / 512 threads per block.  Measured on B200, ms per
+  // 1024^3 step (profiles/r02_c16_time1024.log): y inverse 26.4 -> 24.5, y forward 39.0 -> 37.4, z inverse 20.9 -> 19.1, z forward
+  // 28.1 -> 24.9, step 222.1 -> 213.9; per 512^3 step (r02_c17_time1024.log): the four passes 11.7 -> 10.7, step 24.7 -> 23.6-24.1.
+  // MHDF_PASS_E32: 0 = 16 points everywhere (A/B partner), 1 = the 1024-point y passes only, 2 = 1024-point y and z passes, 3 = the
+  // 512-point passes as well (default).
 #ifndef MHDF_PASS_E32
-#define MHDF_PASS_E32 2
+#define MHDF_PASS_E32 3
 #endif
   static constexpr int passE(int N, bool zpass = false) {
     if (sizeof(T) == 4 && MHDF_PASS_E32 >= 1 && N >= 1024 && (!zpass || MHDF_PASS_E32 >= 2)) return 32;

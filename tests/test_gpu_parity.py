@@ -52,7 +52,7 @@ def _pair(M, O, kind, nxyz, T, stepper="RK4", turb=True, dt=None):
 
 
 @pytest.mark.parametrize("dims", [(16, 16, 16), (32, 32, 32), (64, 32, 16), (16, 64, 128), (128, 128, 128), (256, 256, 256),
-                                  (1024, 16, 16), (16, 1024, 16), (16, 16, 1024), (512, 16, 32)])   # thin grids: every plan length
+                                  (1024, 16, 16), (16, 1024, 16), (16, 16, 1024), (512, 16, 32), (16, 512, 32), (32, 16, 512)])   # thin grids: every plan length, every axis
 def test_fft_r2c_c2r_against_numpy(M, O, dims):
     nx, ny, nz = dims
     p = M.Problem(M.GPU(), nx=nx, ny=ny, nz=nz, B_field=True)
