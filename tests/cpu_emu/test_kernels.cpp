@@ -45,9 +45,9 @@ template <typename T> double rel_err(const std::vector<Cx<T>>& a, const std::vec
 }
 static constexpr int passE(int N) { return N >= 128 ? 16 : (N >= 32 ? 8 : 4); }
 
-template <typename T, int N, int DIR, int BLK>
+template <typename T, int N, int DIR, int BLK, int EO = 0, int TXO = 0>
 void run_pass(PassArgs<T> a, int n_outer, int n_fields) {
-  constexpr int E = passE(N), TX = sizeof(T) == 4 ? 16 : 8;
+  constexpr int E = EO ? EO : passE(N), TX = TXO ? TXO : (sizeof(T) == 4 ? 16 : 8);
   dim3 grid((a.inner + TX - 1) / TX, n_outer, n_fields);
   emu::launch(k_pass<T, N, E, TX, DIR, (DIR > 0), BLK>, grid, (N / E) * TX, a);
 }
@@ -56,7 +56,8 @@ static void zero_blk(PassArgs<double>& a) { a.blk_rows = a.blk_stride = 0; a.blk
 static unsigned magic(int r) { return (unsigned)((0x100000000ULL + r - 1) / r); }
 
 // ---- A. one strided pass against a naive DFT ------------------------------------------------------------------
-template <typename T, int N> void test_pass() {
+template <typename T, int N, int EO = 0, int TXO = 0> void test_pass() {
+  const std::string tag = EO ? " E=" + std::to_string(EO) + " TX=" + std::to_string(TXO) : std::string();
   using C = Cx<T>;
   const Band b = band_of(N);
   const int K = b.count(), inner = 24, outer = 2, nf = 2;
@@ -71,7 +72,7 @@ template <typename T, int N> void test_pass() {
   a.in_field = (long long)outer * N * inner; a.out_field = (long long)outer * K * inner;
   a.inner = inner; a.lo = b.lo; a.hi0 = b.hi0; a.shift = b.hi0 - b.lo;
   zero_blk(a);
-  run_pass<T, N, -1, 0>(a, outer, nf);
+  run_pass<T, N, -1, 0, EO, TXO>(a, outer, nf);
   std::vector<cd> ref(out.size());
   for (int f = 0; f < nf; ++f) for (int o = 0; o < outer; ++o) for (int c = 0; c < inner; ++c)
     for (int kc = 0; kc < K; ++kc) {
@@ -81,14 +82,14 @@ template <typename T, int N> void test_pass() {
       ref[((size_t)(f * outer + o) * K + kc) * inner + c] = s;
     }
   double e = rel_err<T>(out, ref);
-  report("pass forward N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64"), e < (sizeof(T) == 4 ? 2e-6 : 1e-14), e);
+  report("pass forward N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64") + tag, e < (sizeof(T) == 4 ? 2e-6 : 1e-14), e);
   // inverse: retained rows in (others zero), full rows out
   auto in2 = randc<T>((size_t)nf * outer * K * inner, 2);
   std::vector<C> out2((size_t)nf * outer * N * inner);
   a.in = in2.data(); a.out = out2.data();
   a.in_outer = (long long)K * inner; a.out_outer = (long long)N * inner;
   a.in_field = (long long)outer * K * inner; a.out_field = (long long)outer * N * inner;
-  run_pass<T, N, +1, 0>(a, outer, nf);
+  run_pass<T, N, +1, 0, EO, TXO>(a, outer, nf);
   std::vector<cd> ref2(out2.size());
   for (int f = 0; f < nf; ++f) for (int o = 0; o < outer; ++o) for (int c = 0; c < inner; ++c)
     for (int n = 0; n < N; ++n) {
@@ -101,7 +102,7 @@ template <typename T, int N> void test_pass() {
       ref2[((size_t)(f * outer + o) * N + n) * inner + c] = s;
     }
   e = rel_err<T>(out2, ref2);
-  report("pass inverse N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64"), e < (sizeof(T) == 4 ? 2e-6 : 1e-14), e);
+  report("pass inverse N=" + std::to_string(N) + (sizeof(T) == 4 ? " f32" : " f64") + tag, e < (sizeof(T) == 4 ? 2e-6 : 1e-14), e);
 }
 
 // ---- B. slab transposes: blocked (one- and two-level) addressing must reproduce the single-rank passes exactly ----
@@ -804,6 +805,8 @@ static void test_derive_and_pack() {
 int main() {
   test_pass<float, 16>(); test_pass<float, 32>(); test_pass<float, 64>(); test_pass<double, 16>(); test_pass<double, 32>();
   test_pass<float, 128>();
+  // the 32-points-per-thread plans of the long axes (radix 32 x 16, 32 x 32: one exchange), in the library's three block shapes
+  test_pass<float, 512, 32, 16>(); test_pass<float, 1024, 32, 8>(); test_pass<float, 1024, 32, 16>();
   test_slab<1>(); test_slab<2>(); test_slab<4>();
   test_xfused<16>(); test_xfused<32>(); test_xfused<64>(); test_xfused<128>(); test_xfused<256>();
   test_xfused<512>(); test_xfused<1024>();        // Tm = 32 (one warp per row) and Tm = 64 (block barrier, shared-memory post-step)
