@@ -164,11 +164,15 @@ int mhdf_stale_stats(const mhdf_handle* h, double* maxsq6, double* sumsq6);
  * (host or device memory):
  *   ScaleDecomposition(B1, B2, B3, grid; kf = [k1, k2]) (MHDAnalysis.jl:54-82): the part of the velocity (group 0) or of the
  *     magnetic field (group 1) with k1 <= |k| <= k2;
- *   VectorPotential(B1, B2, B3) (MHDAnalysis.jl:129-174): a = curl^-1 b in the Coulomb gauge, a^ = i (k x b^) / k^2.
+ *   VectorPotential(B1, B2, B3) (MHDAnalysis.jl:129-174): a = curl^-1 b in the Coulomb gauge, a^ = i (k x b^) / k^2;
+ *   CF(V) = real(ifft(abs.(fft(V)).^2)) (utils/TurbStatTool.jl:67, WITHOUT its fftshift: zero lag at element 0) of each component of
+ *     the velocity (group 0) or the magnetic field (group 1): the periodic autocorrelation from which the two-point structure
+ *     functions SFC(V) = 2 (mean(V) - CF(V)) and the radial SF_2 1D (TurbStatTool.jl:72, 90-120) follow on the host.
  * which = MHDF_FRESH (sol) or MHDF_STALE (the reference's vars.*, what a user script would pass).  The reference applies these
  * to arbitrary arrays; here the input is the (dealiased) state, i.e. equal whenever the argument is band-limited. */
 int mhdf_scale_decomposition(mhdf_handle* h, int group, int which, double k1, double k2, void* out3);
 int mhdf_vector_potential(mhdf_handle* h, int which, void* out3);
+int mhdf_correlation(mhdf_handle* h, int group, int which, void* out3);
 
 /* Measurement helpers. */
 int mhdf_step_timed(mhdf_handle* h, int nsteps, double* ms_total);   /* CUDA events on the library stream */

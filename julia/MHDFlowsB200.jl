@@ -13,7 +13,7 @@ export Problem, SetUpProblemIC!, stepforward!, TimeIntegrator!, getCFL!, ProbDia
        N97ForceDriving!, GetN97vars_And_function, SetUpN97!, setforcing!,
        A99ForceDriving!, GetA99vars_And_function, SetUpFk, A99GPU, DivVCorrection!, DivBCorrection!, setvpfield!,
        savefile, Restart!, readMHDFlows, DivFreeSpectraMap, SetUpRandomPhaseIC!,
-       NDForceDriving!, GetNDvars_And_function, SetUpND!
+       NDForceDriving!, GetNDvars_And_function, SetUpND!, stepper_stats, ScaleDecomposition, VectorPotential, CF, SFC
 
 const lib = get(ENV, "MHDFLOWS_B200_LIB", "libmhdflows_b200.so")
 
@@ -253,6 +253,41 @@ end
 "DivVCorrection!(prob) / DivBCorrection!(prob)   (Solver/VPSolver.jl:61-137)"
 DivVCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, 0))
 DivBCorrection!(prob) = check(prob.h, ccall((:mhdf_div_correction, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, 1))
+
+# ---- on-device analysis of the state (utils/MHDAnalysis.jl:54-82, 129-174; utils/TurbStatTool.jl:67-120) ----------------------
+# The reference applies these to arrays a script hands over (usually prob.vars.*); here they act on the problem's own fields:
+# which = 1 the stale vars.* (default), 0 the true state.
+_group(g) = g === :u ? Cint(0) : Cint(1)
+function _three(prob::MHDFlowsProblem{T}, f) where T
+  out = Array{T}(undef, prob.grid.nx, prob.grid.ny, prob.grid.nz, 3)
+  check(prob.h, f(out))
+  (out[:, :, :, 1], out[:, :, :, 2], out[:, :, :, 3])
+end
+"ScaleDecomposition(prob; group = :b, kf = [1, 5])   (MHDAnalysis.jl:54-82): the components restricted to kf[1] <= |k| <= kf[2]"
+ScaleDecomposition(prob; group = :b, kf = [1, 5], which = 1) = _three(prob, out ->
+  ccall((:mhdf_scale_decomposition, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cdouble, Ptr{Cvoid}), prob.h, _group(group), which, minimum(kf), maximum(kf), out))
+"VectorPotential(prob)   (MHDAnalysis.jl:129-174): a with curl a = b in the Coulomb gauge"
+VectorPotential(prob; which = 1) = _three(prob, out ->
+  ccall((:mhdf_vector_potential, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, which, out))
+"CF(prob; group)   (TurbStatTool.jl:67): fftshift(real(ifft(abs.(fft(V)).^2))) of the three components"
+function CF(prob; group = :b, which = 1)
+  c = _three(prob, out -> ccall((:mhdf_correlation, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), prob.h, _group(group), which, out))
+  sh = (prob.grid.nx ÷ 2, prob.grid.ny ÷ 2, prob.grid.nz ÷ 2)
+  map(x -> circshift(x, sh), c)                       # fftshift
+end
+"SFC(prob; group)   (TurbStatTool.jl:72): 2 (mean(V) - CF(V)) per component, as written"
+function SFC(prob::MHDFlowsProblem{T}; group = :b, which = 1) where T
+  f0 = (group === :u || prob.flag.e) ? 0 : 3
+  n3 = prob.grid.nx * prob.grid.ny * prob.grid.nz
+  g = prob.grid
+  m = map(1:3) do i                                    # mean(V) = V^(k = 0) / N^3
+    A = Array{Complex{T},3}(undef, g.nx ÷ 2 + 1, g.ny, g.nz)
+    check(prob.h, ccall((:mhdf_get_spectral, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), prob.h, f0 + i - 1, which, A))
+    T(real(A[1, 1, 1]) / n3)
+  end
+  c = CF(prob; group = group, which = which)
+  ntuple(i -> 2 .* (m[i] .- c[i]), 3)
+end
 
 "stepforward!(prob) == stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)"
 stepforward!(prob, n::Int = 1) = check(prob.h, ccall((:mhdf_step, lib), Cint, (Ptr{Cvoid}, Cint), prob.h, n))

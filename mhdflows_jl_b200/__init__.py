@@ -8,12 +8,12 @@ from ._lib import EMHD, F32, F64, FRESH, HD, LSRK54, MHD, RK4, STALE, MHDFlowsEr
 from .problem import (Cylindrical_Mask_Function, A99GPU, A99_vars, A99ForceDriving, DivBCorrection, DivVCorrection, GetA99vars_And_function, SetUpFk,  # noqa: F401
                       CPU, GPU, Diagnostic, DivFreeSpectraMap, GetN97vars_And_function, N97ForceDriving,  # noqa: F401
                       ProbDiagnostic, Problem, SetUpN97, SetUpProblemIC, TimeIntegrator, getCFL, increment,
-                      nothingfunction, spectralline, stepforward, SetUpRandomPhaseIC, DFSM_CALL, ScaleDecomposition, VectorPotential,
+                      nothingfunction, spectralline, stepforward, SetUpRandomPhaseIC, DFSM_CALL, ScaleDecomposition, VectorPotential, CF, SFC, SF2_1D,
                       NDForceDriving, GetNDvars_And_function, SetUpND, ND_vars)
 
 from .io import Restart, readMHDFlows, savefile  # noqa: F401,E402
 
 __all__ = ["savefile", "Restart", "readMHDFlows", "Problem", "SetUpProblemIC", "stepforward", "TimeIntegrator", "getCFL", "ProbDiagnostic", "Diagnostic",
-           "increment", "DivFreeSpectraMap", "SetUpRandomPhaseIC", "ScaleDecomposition", "VectorPotential", "NDForceDriving", "GetNDvars_And_function", "SetUpND", "ND_vars", "spectralline", "N97ForceDriving", "GetN97vars_And_function", "SetUpN97", "A99ForceDriving", "GetA99vars_And_function", "SetUpFk", "A99GPU", "A99_vars",
+           "increment", "DivFreeSpectraMap", "SetUpRandomPhaseIC", "ScaleDecomposition", "VectorPotential", "CF", "SFC", "SF2_1D", "NDForceDriving", "GetNDvars_And_function", "SetUpND", "ND_vars", "spectralline", "N97ForceDriving", "GetN97vars_And_function", "SetUpN97", "A99ForceDriving", "GetA99vars_And_function", "SetUpFk", "A99GPU", "A99_vars",
            "DivVCorrection", "DivBCorrection", "Cylindrical_Mask_Function", "CPU", "GPU", "nothingfunction", "MHDFlowsError",
            "FRESH", "STALE"]

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mhdf_step_timed", "mhdf_stepper_stats", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
     "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
     "mhdf_set_forcing_a99", "mhdf_forcing_a99_calls", "mhdf_div_correction", "mhdf_set_vp_field",
-    "mhdf_set_random_phase", "mhdf_scale_decomposition", "mhdf_vector_potential", "mhdf_set_forcing_nd",
+    "mhdf_set_random_phase", "mhdf_scale_decomposition", "mhdf_vector_potential", "mhdf_correlation", "mhdf_set_forcing_nd",
 ]
 A99_HOST, A99_GPU = 1, 2
 
@@ -95,6 +95,7 @@ def lib():
         "mhdf_set_random_phase": (i, [vp, i, C.c_ulonglong, d, d, d]),
         "mhdf_scale_decomposition": (i, [vp, i, i, d, d, vp]),
         "mhdf_vector_potential": (i, [vp, i, vp]),
+        "mhdf_correlation": (i, [vp, i, i, vp]),
         "mhdf_set_forcing_nd": (i, [vp, d, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -111,6 +111,9 @@ int mhdf_scale_decomposition(mhdf_handle* h, int group, int which, double k1, do
 int mhdf_vector_potential(mhdf_handle* h, int which, void* out3) {
   return guard(h, [&] { if (!out3) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->analysis(1, 1, which, 0, 0, out3); });
 }
+int mhdf_correlation(mhdf_handle* h, int group, int which, void* out3) {
+  return guard(h, [&] { if (!out3) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->analysis(2, group, which, 0, 0, out3); });
+}
 int mhdf_set_random_phase(mhdf_handle* h, int group, unsigned long long seed, double k0, double P, double k_peak) {
   return guard(h, [&] { h->set_random_phase(group, seed, k0, P, k_peak); });
 }

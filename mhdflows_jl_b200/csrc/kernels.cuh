@@ -1396,9 +1396,11 @@ __global__ void __launch_bounds__(256) k_dfsm_fill(SpecGeom<T> g, DfsmArgs<T> q,
 // ---- on-device analysis of the state (utils/MHDAnalysis.jl) ------------------------------------------------------------
 // mode 0: ScaleDecomposition (MHDAnalysis.jl:24-82): f^_c <- f^_c where k1 <= |k| <= k2, else 0  (|k| = sqrt(kr^2 + l^2 + m^2) in T)
 // mode 1: VectorPotential (MHDAnalysis.jl:129-174): a^ = i (k x b^) / k^2 (Coulomb gauge; the k = 0 mode gives 0)
+// mode 2: power spectra |f^_c|^2 (real): their inverse transform is the autocorrelation CF(V) = real(ifft(|fft(V)|^2)) of each
+//         component (utils/TurbStatTool.jl:67), the building block of the two-point structure functions SFC / SF_2 1D (:72, 90-120)
 // in: three consecutive fields of a compact state; out: three compact fields (inverse-transformed by the caller).
 template <typename T>
-__global__ void __launch_bounds__(256) k_analysis(SpecGeom<T> g, const Cx<T>* __restrict__ S, Cx<T>* __restrict__ out, int mode, T k1, T k2) {
+__global__ void __launch_bounds__(256) k_analysis(SpecGeom<T> g, const Cx<T>* __restrict__ S, int f0, Cx<T>* __restrict__ out, int mode, T k1, T k2) {
   using C = Cx<T>;
   const int Ky = g.Kyl, Kz = g.bz.count();
   const long long total = (long long)g.Kxp * Ky * Kz;
@@ -1408,13 +1410,25 @@ __global__ void __launch_bounds__(256) k_analysis(SpecGeom<T> g, const Cx<T>* __
     const int jc = (int)(rowi % Ky), kc = (int)(rowi / Ky);
     C f[3], o[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { f[c] = S[c * g.field + e]; o[c] = mk<C>(0, 0); }
+    for (int c = 0; c < 3; ++c) { f[c] = S[(f0 + c) * g.field + e]; o[c] = mk<C>(0, 0); }
     if (ix < g.Kx && g.ky0 + jc < g.by.count()) {
       const T k[3] = {g.kx[ix], g.ky[jc], g.kz[kc]};
       const T kk2 = k[0] * k[0] + k[1] * k[1] + k[2] * k[2];
       if (mode == 0) {
         const T kr = sqrt(kk2);
         if (k2 >= kr && kr >= k1) { o[0] = f[0]; o[1] = f[1]; o[2] = f[2]; }
+      } else if (mode == 2) {
+        // kr = 0 plane: the power of what rfft of the REAL field holds there (the symmetrised mode); a mode whose mirror is dealiased
+        // away is a real-space wave of half its amplitude on both sides: a quarter of its power each, i.e. 2 |f^sym|^2 = |f^|^2 / 2
+        // here, which the Hermitian part taken by the inverse transform splits over the two
+        bool unpaired = false;
+        if (ix == 0) unpaired = g.by.row_of_wave(-g.by.wave(g.ky0 + jc)) < 0 || g.bz.row_of_wave(-g.bz.wave(kc)) < 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const C v = (ix == 0) ? load_sym<T>(S, f0 + c, g, ix, jc, kc) : f[c];
+          const T p = v.x * v.x + v.y * v.y;
+          o[c] = mk<C>(unpaired ? p + p : p, (T)0);
+        }
       } else {
         const T ik2 = (kk2 > (T)0) ? (T)1 / kk2 : (T)0;
         const C c0 = mk<C>(k[1] * f[2].x - k[2] * f[1].x, k[1] * f[2].y - k[2] * f[1].y);

@@ -1535,7 +1535,8 @@ struct Solver : mhdf_handle {
       st_max[slot] = red_max(0);
     }
   }
-  // ScaleDecomposition (mode 0) / VectorPotential (mode 1) of a vector field of the state (utils/MHDAnalysis.jl:24-82, 129-174),
+  // ScaleDecomposition (mode 0) / VectorPotential (mode 1) of a vector field of the state (utils/MHDAnalysis.jl:24-82, 129-174) and
+  // the autocorrelation functions CF of its components (mode 2, utils/TurbStatTool.jl:67),
   // on the device: spectral mask / curl into a dead register, three inverse transforms, three real fields to `out3`.
   void analysis(int mode, int group, int which, double k1, double k2, void* out3) override {
     CK(cudaSetDevice(cfg.device));
@@ -1543,12 +1544,13 @@ struct Solver : mhdf_handle {
     if (group == 0) { if (phys == MHDF_EMHD) throw Err{MHDF_ERR_INVALID, "the EMHD state has no velocity"}; f0 = 0; }
     else if (group == 1) { if (phys == MHDF_HD) throw Err{MHDF_ERR_INVALID, "the HD state has no magnetic field"}; f0 = (phys == MHDF_EMHD) ? 0 : 3; }
     else throw Err{MHDF_ERR_INVALID, "group must be 0 (velocity) or 1 (magnetic field)"};
-    if (mode != 0 && mode != 1) throw Err{MHDF_ERR_INVALID, "analysis mode must be 0 (scale decomposition) or 1 (vector potential)"};
+    if (mode < 0 || mode > 2) throw Err{MHDF_ERR_INVALID, "analysis mode must be 0 (scale decomposition), 1 (vector potential) or 2 (autocorrelation)"};
     int o = -1;
     const int nreg = nreg_();
     for (int i = 0; i < nreg; ++i) if (i != iY && i != iStale) { o = i; break; }
     rank_barrier();
-    MHDF_LAUNCH((k_analysis<T>), spec_grid(), 256, 0, st, geom(), source(which) + (size_t)f0 * cf, reg[o], mode, (T)k1, (T)k2);
+    if (mode == 2) { gather_mirror(source(which)); wait_mirror(); }   // the power spectrum needs the symmetrised kr = 0 plane
+    MHDF_LAUNCH((k_analysis<T>), spec_grid(), 256, 0, st, geom(), source(which), f0, reg[o], mode, (T)k1, (T)k2);
     ++launches;
     CK(cudaGetLastError());
     T* re = reinterpret_cast<T*>(R);

@@ -797,6 +797,47 @@ def VectorPotential(prob, which=L.STALE):
     return out[0], out[1], out[2]
 
 
+def CF(prob, group="b", which=L.STALE):
+    """CF(V) = fftshift(real(ifft(abs.(fft(V)).^2))) (utils/TurbStatTool.jl:67) of the three components of the problem's velocity
+    ("u") or magnetic field ("b"): periodic autocorrelation functions, transforms on the device (mhdf_correlation), the fftshift
+    here.  The argument is the (dealiased) state, cf. ScaleDecomposition."""
+    if prob.nranks > 1:
+        raise NotImplementedError("CF of a slab-decomposed problem: mhdf_correlation returns this rank's z planes without the fftshift")
+    out = np.empty((3,) + prob._real_shape, dtype=prob.T)
+    g = {"u": 0, "b": 1}[group] if isinstance(group, str) else int(group)
+    L.check(prob._h, L.lib().mhdf_correlation(prob._h, g, which, out.ctypes.data))
+    return tuple(np.fft.fftshift(out[i]) for i in range(3))
+
+
+def SFC(prob, group="b", which=L.STALE):
+    """SFC(V) = 2 (mean(V) - CF(V)) (TurbStatTool.jl:72, as written: the mean of V, not of V^2) per component."""
+    g = {"u": 0, "b": 1}[group] if isinstance(group, str) else int(group)
+    f0 = 0 if (g == 0 or prob.flag.e) else 3
+    cf = CF(prob, group, which)
+    n3 = prob.grid.nx * prob.grid.ny * prob.grid.nz
+    means = [prob.T(prob.get_spectral(f0 + i, which)[0, 0, 0].real / n3) for i in range(3)]      # mean(V) = V^(k = 0) / N^3
+    return tuple((2 * (m - c)).astype(prob.T) for m, c in zip(means, cf))
+
+
+def SF2_1D(prob, group="b", which=L.STALE):
+    """SF₂1D(Vx, Vz, Vy) (TurbStatTool.jl:90-120): radial two-point structure function of a vector field of the problem -- the sum of
+    the three SFC cubes averaged over shells of round(|r|), r measured from element (N/2, N/2, N/2) (1-based) like the reference's
+    loop (one element off the zero lag of the fftshift: reproduced)."""
+    sx, sy, sz = SFC(prob, group, which)
+    sfv = (sx + sy + sz).astype(np.float64)
+    nz, ny, nx = sfv.shape
+    R = int(math.ceil(math.sqrt((nx // 2) ** 2 + (ny // 2) ** 2 + (nz // 2) ** 2)))
+    i = np.arange(1, nx + 1).reshape(1, 1, -1) - nx // 2
+    j = np.arange(1, ny + 1).reshape(1, -1, 1) - ny // 2
+    k = np.arange(1, nz + 1).reshape(-1, 1, 1) - nz // 2
+    kk = np.rint(np.sqrt((i * i + j * j + k * k).astype(np.float64))).astype(np.int64)
+    ok = kk > 0
+    mask = np.bincount(kk[ok], minlength=2 * R + 1)[1:2 * R + 1].astype(np.float64)
+    tot = np.bincount(kk[ok], weights=sfv[ok], minlength=2 * R + 1)[1:2 * R + 1]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return tot / mask
+
+
 DFSM_CALL = 0x7FFFFFFF44465350      # counter tag of the device random-phase stream (csrc/kernels.cuh: DFSM_CALL_HI/LO)
 
 

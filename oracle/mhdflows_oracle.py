@@ -761,6 +761,34 @@ def ScaleDecomposition(B1, B2, B3, grid: Grid, kf=(1, 5)):
     return tuple(grid.irfft((grid.rfft(B) * K).astype(grid.CT)) for B in (B1, B2, B3))
 
 
+def CF(V):
+    """TurbStatTool.jl:67: CF(V) = fftshift(real(ifft(abs.(fft(V)).^2))) -- periodic autocorrelation of a cube."""
+    return np.fft.fftshift(np.real(sfft.ifftn(np.abs(sfft.fftn(V.astype(np.float64))) ** 2))).astype(V.dtype)
+
+
+def SFC(V):
+    """TurbStatTool.jl:72: SFC(V) = 2*(mean(V) .- CF(V)), as written (the mean of V, not of V^2)."""
+    return (2 * (np.mean(V) - CF(V))).astype(V.dtype)
+
+
+def SF2_1D(Vx, Vz, Vy):
+    """TurbStatTool.jl:90-120 (SF_2 1D), literally: 1-based loops, displacement measured from element (N/2, N/2, N/2), shells of
+    round(|r|) (ties to even), 2R output bins (empty shells give 0/0 = NaN)."""
+    nz, ny, nx = Vx.shape
+    SFV = (SFC(Vx) + SFC(Vy) + SFC(Vz)).astype(np.float64)
+    R = int(math.ceil(math.sqrt((nx // 2) ** 2 + (ny // 2) ** 2 + (nz // 2) ** 2)))
+    mask, sfr = np.zeros(2 * R), np.zeros(2 * R)
+    for k in range(1, nz + 1):
+        for j in range(1, ny + 1):
+            for i in range(1, nx + 1):
+                kk = int(np.rint(math.sqrt((i - nx // 2) ** 2 + (j - ny // 2) ** 2 + (k - nz // 2) ** 2)))
+                if kk > 0:
+                    mask[kk - 1] += 1
+                    sfr[kk - 1] += SFV[k - 1, j - 1, i - 1]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return sfr / mask
+
+
 def h_m(ib, jb, kb, grid: Grid):
     """MHDAnalysis.jl:113-117: pointwise A.B (no dV)."""
     A1, A2, A3 = VectorPotential(ib, jb, kb, grid)

@@ -20,7 +20,7 @@ import mhdflows_jl_b200 as M  # noqa: E402
 from oracle import forcing_oracle as FO  # noqa: E402
 from oracle import mhdflows_oracle as O  # noqa: E402
 from tests.test_gpu_parity import _hm89_check, _pair  # noqa: E402
-from tests.test_gpu_zforcing import _forced_pair, _nd_pair, _vp_pair  # noqa: E402
+from tests.test_gpu_zforcing import _forced_pair, _nd_pair, _structure_function_check, _vp_pair  # noqa: E402
 
 F32_TOL, F64_TOL = 1e-5, 1e-12
 DIMS = (16, 16, 32)
@@ -118,6 +118,13 @@ def on_device_scale_decomposition_and_vector_potential():
         fresh = [g.irfft(g.dealias(op.sol[3 + i].copy())) for i in range(3)]
         assert O.rel_l2(np.stack(M.VectorPotential(gp, which=M.FRESH)), np.stack(O.VectorPotential(*fresh, g))) < tol
         gp.close()
+
+
+@case
+def on_device_structure_functions():
+    """mhdf_correlation + the host-side SFC / SF_2 1D of the mirror against the restatements of TurbStatTool.jl:67, 72, 90-120."""
+    _structure_function_check(M, O, np.float64, F64_TOL, (16, 16, 16))
+    _structure_function_check(M, O, np.float32, F32_TOL, (16, 32, 16))
 
 
 @case

@@ -325,3 +325,31 @@ def test_negative_damping_is_lost_in_hd_and_refused_with_vp(M, O, FO):
         M.Problem(M.GPU(), nx=32, B_field=True, calcF=fn, usr_vars=uv, VP_method=True)
     with pytest.raises(ValueError):
         M.Problem(M.GPU(), nx=32, B_field=True, calcF=fn)
+
+
+def _structure_function_check(M, O, T, tol, dims):
+    """CF / SFC / SF₂1D (utils/TurbStatTool.jl:67, 72, 90-120) of the state's fields on the device against the literal restatement
+    applied to the reference's vars.* (the stale real-space fields a script would pass)."""
+    nx, ny, nz = dims
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)
+    op, gp = O.Problem(**kw), M.Problem(M.GPU(), **kw)
+    u, b = O.random_phase_ic(op.grid, 31), O.random_phase_ic(op.grid, 32)
+    O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+    M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+    O.stepforward(op)
+    M.stepforward(gp)
+    for grp, v in (("u", (op.vars.ux, op.vars.uy, op.vars.uz)), ("b", (op.vars.bx, op.vars.by, op.vars.bz))):
+        for got, ref in zip(M.CF(gp, grp), (O.CF(x) for x in v)):
+            assert np.linalg.norm(ref) > 0 and O.rel_l2(got, ref) < 3 * tol      # quadratic in the field: twice its relative error
+        for got, ref in zip(M.SFC(gp, grp), (O.SFC(x) for x in v)):
+            assert O.rel_l2(got, ref) < 3 * tol
+    got, ref = M.SF2_1D(gp, "u"), O.SF2_1D(op.vars.ux, op.vars.uz, op.vars.uy)
+    ok = np.isfinite(ref)
+    assert got.shape == ref.shape and np.array_equal(np.isfinite(got), ok) and ok.sum() > 3
+    assert np.linalg.norm(got[ok] - ref[ok]) < 3 * tol * np.linalg.norm(ref[ok])
+    gp.close()
+
+
+@pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
+def test_structure_functions_on_device(M, O, T, tol):
+    _structure_function_check(M, O, T, tol, (32, 16, 16))

@@ -217,3 +217,25 @@ def test_hm89_restatement_properties():
     assert O.rel_l2((p.sol - B0)[:, m], (pred - B0)[:, m]) < 2e-2
     with pytest.raises(ValueError):
         O.Problem(nx=16, B_field=True, stepper="HM89")          # Problems.jl:124: only with EFlag
+
+
+def test_correlation_and_structure_function_restatements():
+    """TurbStatTool.jl:67-120: CF is the periodic autocorrelation sum_x V(x) V(x + r) with zero lag at the fftshift centre; SFC and
+    SF_2 1D follow it literally (mean of V, shells measured from element N/2 in 1-based counting)."""
+    rng = np.random.default_rng(5)
+    V = rng.standard_normal((8, 8, 8))
+    cf = O.CF(V)
+    for r in ((0, 0, 0), (1, 0, 0), (0, 3, 0), (2, 5, 7)):
+        direct = float(np.sum(V * np.roll(V, shift=tuple(-x for x in r), axis=(0, 1, 2))))
+        assert abs(cf[(4 + r[0]) % 8, (4 + r[1]) % 8, (4 + r[2]) % 8] - direct) < 1e-10 * abs(cf[4, 4, 4])
+    assert np.allclose(O.SFC(V), 2 * (V.mean() - cf))
+    sf = O.SF2_1D(V, V, V)
+    R = math.ceil(math.sqrt(3 * 4 ** 2))
+    assert sf.shape == (2 * R,) and np.isfinite(sf[:6]).all() and np.isnan(sf[R + 1:]).all()
+    # shell 1 of the literal loop: round(|r|) = 1 (distances 1 and sqrt 2: 18 elements) around element (N/2, N/2, N/2) in 1-based
+    # counting = 0-based (3, 3, 3) -- one off the zero lag at (4, 4, 4)
+    s3 = 3 * O.SFC(V).astype(np.float64)
+    ax = np.arange(8) - 3
+    d = np.rint(np.sqrt(ax.reshape(-1, 1, 1) ** 2 + ax.reshape(1, -1, 1) ** 2 + ax.reshape(1, 1, -1) ** 2))
+    assert (d == 1).sum() == 18
+    assert abs(sf[0] - s3[d == 1].mean()) < 1e-9 * abs(s3[d == 1].mean())
