@@ -41,8 +41,9 @@ typedef enum {
 enum { MHDF_F32 = 0, MHDF_F64 = 1 };
 enum { MHDF_HD = 0, MHDF_MHD = 1, MHDF_EMHD = 2 };          /* B_field / EMHD flags, pgen.jl:129-150 */
 enum { MHDF_RK4 = 0, MHDF_LSRK54 = 1, MHDF_HM89 = 2 };       /* stepper = "RK4" | "LSRK54" | "HM89" (EMHD only), Problems.jl:123-128 */
-enum { MHDF_FRESH = 0, MHDF_STALE = 1 };                     /* which real-space view: true state, or the reference's
-                                                               `vars.*` = c2r of the last stage input */
+enum { MHDF_FRESH = 0, MHDF_STALE = 1, MHDF_STAGE = 2 };     /* which view: true state, the reference's `vars.*` = c2r of the
+                                                               last stage input, or -- inside a forcing callback only --
+                                                               the `sol` argument of the evaluation in flight */
 
 /* Keyword arguments of Problem(dev; ...) (pgen.jl:64-95) that reach the hot path. */
 typedef struct {
@@ -90,6 +91,17 @@ int mhdf_get_spectral(mhdf_handle* h, int field, int which, void* host_spec);
  * host_real = NULL removes the forcing of that field.  Like the reference, it acts on the MHD path only: HDcalcN! adds
  * the forcing BEFORE the advection zeroes N (pgen.jl:176-178, HDSolver.jl:55) and EMHDcalcN! never calls it. */
 int mhdf_set_forcing(mhdf_handle* h, int field, const void* host_real);
+/* Arbitrary calcF! closures (pgen.jl:231-234: `params.calcF!(N, sol, t, clock, vars, params, grid)`, any host function): the
+ * library calls `fn(user, t)` on the host thread of mhdf_step / mhdf_calcN at the beginning of EVERY right-hand-side evaluation
+ * (t = the stage time FourierFlows passes).  Inside, the host may read the evaluation's `sol` with mhdf_get_spectral / mhdf_get_real
+ * (which = MHDF_STAGE) and defines what the evaluation adds to N with mhdf_set_forcing_spectral (or mhdf_set_forcing); a non-zero
+ * return aborts the step with MHDF_ERR_STATE.  Additive forcings only (N += F: every forcing the reference ships); `vars.*` seen
+ * by the callback are the stale ones.  Costs a device synchronisation (and, on slabs, two cross-rank barriers) per evaluation: the
+ * compatibility path for user code, not the fast path -- the reference's own forcings are built in.  fn = NULL removes it. */
+typedef int (*mhdf_forcing_fn)(void* user, double t);
+int mhdf_set_forcing_callback(mhdf_handle* h, mhdf_forcing_fn fn, void* user);
+/* forcing of one field as a spectral array in the layout of mhdf_set_spectral (dealiased modes are ignored); NULL removes it */
+int mhdf_set_forcing_spectral(mhdf_handle* h, int field, const void* fhat);
 
 /* Random solenoidal driving (Alvelius 1999): the reference's `calcF!` = A99ForceDriving!.  Every RHS evaluation adds
  *   N_u += amp * Fk(k) * (e^{i th1} g_i e1(k) + e^{i th2} g_j e2(k)),   Fk = sqrt(exp(-(k-kf)^2/sigma2) / 2pi) / k

@@ -73,6 +73,7 @@ mutable struct MHDFlowsProblem{T}
   flag::Flag
   Nl::Int
   usr_func::Vector{Any}
+  calcF::Any            # an arbitrary closure (host-callback path) or nothing
   vars::Vars            # vars.usr_vars as in the reference (datastructure.jl:5-35); the fields are read with realfield()
 end
 
@@ -94,9 +95,8 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   Shear && error("Shear haven't fully implemented yet!")
   (Compressibility || Dye_Module) && error("outside the B200 hot path")
   VP_method && EMHD && error("VP_method: the EMHD equation has no volume-penalisation terms")
-  (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! || calcF === A99GPU.A99ForceDriving! ||
-   calcF === NDForceDriving!) ||
-    error("arbitrary forcing callbacks cannot run on the device; constant forcings go through setforcing! / N97ForceDriving!")
+  builtin = (calcF === nothingfunction || calcF === N97ForceDriving! || calcF === A99ForceDriving! ||
+             calcF === A99GPU.A99ForceDriving! || calcF === NDForceDriving!)
   stepper in ("RK4", "LSRK54", "HM89") || error("stepper must be \"RK4\", \"LSRK54\" or (EMHD) \"HM89\" on the B200 path")
   stepper == "HM89" && !EMHD && error("stepper \"HM89\" exists for EMHD problems only (Problems.jl:124-126)")
   stepper == "HM89" && calcF !== nothingfunction && error("HM89 with a forcing function is not supported (HM89.jl:182-196)")
@@ -110,7 +110,8 @@ function Problem(dev; nx = 64, ny = nx, nz = nx, Lx = 2Ï€, Ly = Lx, Lz = Lx, câ‚
   prob = MHDFlowsProblem{T}(h[], Clock{T}(h[]), Grid{T}(nx, ny, nz, Lx, Ly, Lz, Lx/nx, Ly/ny, Lz/nz),
                             Params(Î½, Î·, nÎ½, 0), Flag(B_field, EMHD, VP_method, false, false),
                             physics == MHDF_MHD ? 6 : 3, isempty(usr_func) ? Any[nothingfunction] : collect(Any, usr_func),
-                            Vars(usr_vars))
+                            builtin ? nothing : calcF, Vars(usr_vars))
+  builtin || installcalcF!(prob)
   finalizer(p -> ccall((:mhdf_destroy, lib), Cint, (Ptr{Cvoid},), p.h), prob)
   return prob
 end
@@ -124,6 +125,37 @@ _fieldarg(::Type{T}, A::Array) where {T} = Array{T,3}(A)
 _fieldarg(::Type{T}, A) where {T} = (eltype(A) === T || error("device fields must already have the problem's element type"); A)
 _fieldptr(A::Array) = Ptr{Cvoid}(pointer(A))
 _fieldptr(A) = Ptr{Cvoid}(UInt(pointer(A)))          # CuArray: CuPtr -> raw address (unified addressing)
+
+# ---- arbitrary calcF! closures (pgen.jl:231-234) through the library's host callback -----------------------------------------
+# The library calls back at the beginning of every right-hand-side evaluation; `sol` of that evaluation is read with which = 2
+# (MHDF_STAGE), what calcF! adds to a zero N is uploaded and added to the right-hand side.  The device-resident forcings of the
+# reference (N97, A99, negative damping) do not take this path.
+function _forcing_trampoline(user::Ptr{Cvoid}, t::Cdouble)::Cint
+  prob = unsafe_pointer_to_objref(user)
+  T = typeof(prob).parameters[1]; g = prob.grid
+  try
+    S = Array{Complex{T},4}(undef, g.nx Ã· 2 + 1, g.ny, g.nz, prob.Nl)
+    for i in 1:prob.Nl
+      A = Array{Complex{T},3}(undef, g.nx Ã· 2 + 1, g.ny, g.nz)
+      check(prob.h, ccall((:mhdf_get_spectral, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}), prob.h, i - 1, 2, A))
+      S[:, :, :, i] .= A
+    end
+    N = zero(S)
+    prob.calcF(N, S, T(t), prob.clock, prob.vars, prob.params, prob.grid)
+    for i in 1:prob.Nl
+      A = N[:, :, :, i]
+      check(prob.h, ccall((:mhdf_set_forcing_spectral, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}), prob.h, i - 1, any(!iszero, A) ? pointer(A) : C_NULL))
+    end
+    return Cint(0)
+  catch err
+    @error "calcF! failed" exception = err
+    return Cint(-1)
+  end
+end
+function installcalcF!(prob)
+  fn = @cfunction(_forcing_trampoline, Cint, (Ptr{Cvoid}, Cdouble))
+  check(prob.h, ccall((:mhdf_set_forcing_callback, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), prob.h, fn, pointer_from_objref(prob)))
+end
 
 "SetUpProblemIC!(prob; ux, uy, uz, bx, by, bz)   (utils/IC.jl:41-109)"
 function SetUpProblemIC!(prob; ux = [], uy = [], uz = [], bx = [], by = [], bz = [])

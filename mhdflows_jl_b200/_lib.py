@@ -12,7 +12,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NONFINITE, ERR_STATE = 0, -1, -2, -3, -
 F32, F64 = 0, 1
 HD, MHD, EMHD = 0, 1, 2
 RK4, LSRK54, HM89 = 0, 1, 2
-FRESH, STALE = 0, 1
+FRESH, STALE, STAGE = 0, 1, 2
+FORCING_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_double)      # mhdf_forcing_fn
 
 # every symbol include/mhdflows_b200.h declares
 SYMBOLS = [
@@ -21,6 +22,7 @@ SYMBOLS = [
     "mhdf_get_clock", "mhdf_cfl_dt", "mhdf_energy", "mhdf_helicity", "mhdf_spectrum", "mhdf_stale_stats",
     "mhdf_step_timed", "mhdf_stepper_stats", "mhdf_profile", "mhdf_profile_get", "mhdf_launch_count", "mhdf_info",
     "mhdf_ipc_blob_size", "mhdf_ipc_export", "mhdf_ipc_import", "mhdf_set_forcing",
+    "mhdf_set_forcing_spectral", "mhdf_set_forcing_callback",
     "mhdf_set_forcing_a99", "mhdf_forcing_a99_calls", "mhdf_div_correction", "mhdf_set_vp_field",
     "mhdf_set_random_phase", "mhdf_scale_decomposition", "mhdf_vector_potential", "mhdf_correlation", "mhdf_set_forcing_nd",
 ]
@@ -88,6 +90,8 @@ def lib():
         "mhdf_ipc_export": (i, [vp, vp]),
         "mhdf_ipc_import": (i, [vp, vp]),
         "mhdf_set_forcing": (i, [vp, i, vp]),
+        "mhdf_set_forcing_spectral": (i, [vp, i, vp]),
+        "mhdf_set_forcing_callback": (i, [vp, FORCING_FN, vp]),
         "mhdf_set_forcing_a99": (i, [vp, C.POINTER(A99)]),
         "mhdf_forcing_a99_calls": (i, [vp, C.POINTER(C.c_ulonglong)]),
         "mhdf_div_correction": (i, [vp, i]),

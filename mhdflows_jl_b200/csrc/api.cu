@@ -102,6 +102,8 @@ int mhdf_forcing_a99_calls(const mhdf_handle* h, unsigned long long* calls) {
   *calls = h->a99_calls();
   return MHDF_OK;
 }
+int mhdf_set_forcing_callback(mhdf_handle* h, mhdf_forcing_fn fn, void* user) { return guard(h, [&] { h->set_forcing_callback(fn, user); }); }
+int mhdf_set_forcing_spectral(mhdf_handle* h, int field, const void* p) { return guard(h, [&] { h->set_forcing_spectral(field, p); }); }
 int mhdf_set_vp_field(mhdf_handle* h, int which, const void* p) { return guard(h, [&] { if (!p) throw Err{MHDF_ERR_INVALID, "null pointer"}; h->set_vp_field(which, p); }); }
 int mhdf_set_forcing_nd(mhdf_handle* h, double P, const void* fx, const void* fy, const void* fz) { return guard(h, [&] { h->set_forcing_nd(P, fx, fy, fz); }); }
 int mhdf_div_correction(mhdf_handle* h, int group) { return guard(h, [&] { h->div_correction(group); }); }

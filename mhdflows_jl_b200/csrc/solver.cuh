@@ -120,6 +120,8 @@ struct mhdf_handle {
   virtual long long launch_count() const = 0;
   virtual void info(int* nf, int* kx, int* kxp, int* ky, int* kz, long long* bytes) const = 0;
   virtual void set_forcing(int field, const void* p) = 0;
+  virtual void set_forcing_spectral(int field, const void* p) = 0;
+  virtual void set_forcing_callback(mhdf_forcing_fn fn, void* user) = 0;
   virtual void set_forcing_a99(const mhdf_a99* p) = 0;
   virtual unsigned long long a99_calls() const = 0;
   virtual void div_correction(int group) = 0;
@@ -1131,6 +1133,7 @@ struct Solver : mhdf_handle {
   }
   // One RHS evaluation of stage input Sin, finished by the spectral kernel in mode sa.mode.
   void rhs(const C* Sin, SpecArgs<T> sa, bool want_red) {
+    forcing_callback(Sin);
     if (pipe_ok()) { rhs_pipe(Sin, sa, want_red); return; }
     want_red = want_red || (nd_on && nd_P != 0);
     const C* zin = Sin;
@@ -1235,11 +1238,14 @@ struct Solver : mhdf_handle {
       SpecArgs<T> sa = blank_args();
       sa.Y = Y; sa.A = A;
       sa.mode = STEP_RK4_1; sa.ca = dt / (T)6; sa.cs = dt / (T)2; sa.Sout = S0;
+      t_eval = (double)t_;                          // the stage times FourierFlows hands to calcN! (clock.t and dt are T)
       rhs(Y, sa, false);
       sa.mode = STEP_RK4_2; sa.ca = dt / (T)3; sa.cs = dt / (T)2; sa.Sout = S1;
+      t_eval = (double)(T)(t_ + dt / (T)2);
       rhs(S0, sa, false);
       sa.mode = STEP_RK4_3; sa.ca = dt / (T)3; sa.cs = dt; sa.Sout = S0;
       rhs(S1, sa, false);
+      t_eval = (double)(T)(t_ + dt);
       sa.mode = STEP_RK4_4; sa.ca = dt / (T)6; sa.cs = 0; sa.Sout = Y;
       rhs(S0, sa, true);
       iStale = o[0];
@@ -1249,6 +1255,8 @@ struct Solver : mhdf_handle {
       static const double LB[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
                                    1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
                                    2277821191437.0 / 14882151754819.0};
+      static const double LC[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                                   2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
       // registers: sol ping-pongs between two buffers, S2 is the third
       int o[2], n = 0;
       for (int i = 0; i < 3; ++i) if (i != iY) o[n++] = i;
@@ -1258,6 +1266,7 @@ struct Solver : mhdf_handle {
         SpecArgs<T> sa = blank_args();
         sa.mode = STEP_LSRK; sa.A = S2; sa.ca = (T)LA[i]; sa.cs = (T)LB[i]; sa.first = (i == 0);
         sa.Sout = reg[oth];
+        t_eval = (double)(T)(t_ + (T)LC[i] * dt);
         rhs(reg[cur], sa, i == 4);
         int tmp = cur; cur = oth; oth = tmp;
       }
@@ -1413,6 +1422,7 @@ struct Solver : mhdf_handle {
     SpecArgs<T> sa = blank_args();
     sa.mode = STEP_CALCN; sa.Nout = reg[o];
     rank_barrier();
+    t_eval = (double)t_;
     rhs(reg[iY], sa, true);
     sync_all();
     check_flags();
@@ -1462,6 +1472,47 @@ struct Solver : mhdf_handle {
     if (!force) force = dalloc<C>((size_t)F * cf);
     real_to_compact(p, force + field * cf, -1);
     fmask |= 1u << field;
+  }
+  void set_forcing_spectral(int field, const void* p) override {
+    check_field(field);
+    CK(cudaSetDevice(cfg.device));
+    if (p == nullptr) { fmask &= ~(1u << field); return; }
+    if (!force) force = dalloc<C>((size_t)F * cf);
+    const int nyh = (P_ > 1) ? Kyl : ny;
+    const size_t n = (size_t)nkr * nyh * nz;
+    CK(cudaMemcpyAsync(R, p, n * sizeof(C), cudaMemcpyDefault, st));
+    MHDF_LAUNCH((k_pack<T>), pack_grid(), 256, 0, st, R, force + field * cf, nkr, nyh, nz, Kx, Kxp, by, bz, 0, P_ > 1);
+    ++launches;
+    CK(cudaGetLastError());
+    sync_all();
+    fmask |= 1u << field;
+  }
+  // ---- calcF! as an arbitrary host function (pgen.jl:231-234) ------------------------------------------------------------------
+  // Called at the beginning of every RHS evaluation, when no transform buffer is live: the callback's own API calls (get_spectral,
+  // set_forcing...) stage through R / Q.  Slab runs: the un-aliased-buffer argument of the pipelined exchange does not cover API
+  // traffic in the middle of a step, so the callback is bracketed by cross-rank barriers with every rank's pushes drained.
+  mhdf_forcing_fn fcb = nullptr;
+  void* fcb_user = nullptr;
+  const C* stage_in = nullptr;   // `sol` of the evaluation in flight (MHDF_STAGE), valid inside the callback only
+  double t_eval = 0;             // its stage time
+  bool in_cb = false;
+  void set_forcing_callback(mhdf_forcing_fn fn, void* user) override {
+    if (fn != nullptr && (a99.variant != A99_OFF || nd_on)) throw Err{MHDF_ERR_STATE, "one calcF! per problem: a forcing callback cannot be combined with the built-in driving"};
+    if (fn != nullptr && cfg.stepper == MHDF_HM89) throw Err{MHDF_ERR_STATE, "HM89 with a forcing function is not supported (HM89.jl:182-196)"};
+    fcb = fn; fcb_user = user;
+  }
+  void forcing_callback(const C* Sin) {
+    if (fcb == nullptr || in_cb) return;
+    sync_all();
+    check_flags();
+    if (P_ > 1) { rank_barrier(); sync_all(); }
+    stage_in = Sin;
+    in_cb = true;
+    const int rc = fcb(fcb_user, t_eval);
+    in_cb = false;
+    stage_in = nullptr;
+    if (P_ > 1) rank_barrier();
+    if (rc != 0) throw Err{MHDF_ERR_STATE, "the forcing callback reported an error"};
   }
   void set_forcing_a99(const mhdf_a99* p) override {
     if (p == nullptr) { a99.variant = A99_OFF; return; }
@@ -1595,6 +1646,7 @@ struct Solver : mhdf_handle {
     refresh_vars(f0);
   }
   const C* source(int which) const {
+    if (which == MHDF_STAGE && stage_in != nullptr) return stage_in;
     if (which == MHDF_STALE && iStale >= 0) return reg[iStale];
     return reg[iY];
   }

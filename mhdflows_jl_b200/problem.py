@@ -324,10 +324,9 @@ class Problem:
             raise ValueError("VP_method: the EMHD equation has no volume-penalisation terms (MHDSolver.jl:183-270)")
         if calcF is None:
             calcF = nothingfunction
-        if calcF not in (nothingfunction, N97ForceDriving, A99ForceDriving, A99GPU.A99ForceDriving, NDForceDriving):
-            raise NotImplementedError("arbitrary forcing callbacks cannot run on the device; the built-in forcings are "
-                                      "set_forcing / N97ForceDriving (constant), A99ForceDriving (random driving) and "
-                                      "NDForceDriving (negative damping)")
+        builtin = calcF in (nothingfunction, N97ForceDriving, A99ForceDriving, A99GPU.A99ForceDriving, NDForceDriving)
+        if not builtin and not callable(calcF):
+            raise TypeError("calcF must be callable: calcF(N, sol, t, clock, vars, params, grid)")
         if calcF is NDForceDriving and not isinstance(usr_vars, ND_vars):
             raise ValueError("NDForceDriving needs usr_vars = the ND_vars of GetNDvars_And_function")
         if calcF is NDForceDriving and VP_method:
@@ -403,6 +402,39 @@ class Problem:
             raise L.MHDFlowsError(code, (L.lib().mhdf_last_error(None) or b"").decode())
         self._h = h
         self.clock = _Clock(self)
+        self._cb = self._cb_error = None
+        if not builtin:
+            self._install_calcF(calcF)
+
+    # -- arbitrary calcF! closures ----------------------------------------------------------------
+    def _install_calcF(self, calcF):
+        """`calcF(N, sol, t, clock, vars, params, grid)` as in the reference (pgen.jl:231-234), any Python callable: the library
+        calls back at the beginning of every right-hand-side evaluation (mhdf_set_forcing_callback).  `sol` is a host copy of the
+        evaluation's input (Nfield, nz, ny, nkr), `N` a zero array of that shape: what the function adds to N is uploaded and
+        added to the right-hand side (additive forcings -- the reference's `N[..., ind] += F` idiom; rows are 0-based here, i.e.
+        `params.ux_ind - 1`).  `vars.*` are the stale fields.  A device round trip per evaluation: the compatibility path for
+        user code; N97 / A99 / negative-damping forcings run on the device."""
+        def cb(_user, t):
+            try:
+                sol = np.stack([self.get_spectral(i, L.STAGE) for i in range(self.Nl)])
+                N = np.zeros_like(sol)
+                calcF(N, sol, t, self.clock, self.vars, self.params, self.grid)
+                for i in range(self.Nl):
+                    a = np.ascontiguousarray(N[i], dtype=self.CT)
+                    L.check(self._h, L.lib().mhdf_set_forcing_spectral(self._h, i, a.ctypes.data if a.any() else None))
+                return 0
+            except BaseException as e:      # never unwind through the C frames: report, re-raise after the call returns
+                self._cb_error = e
+                return -1
+        self._cb = L.FORCING_FN(cb)          # keeps the trampoline alive as long as the problem
+        L.check(self._h, L.lib().mhdf_set_forcing_callback(self._h, self._cb, None))
+
+    def _check(self, code):
+        """L.check that re-raises an exception thrown inside the forcing callback."""
+        err, self._cb_error = getattr(self, "_cb_error", None), None
+        if err is not None:
+            raise err
+        L.check(self._h, code)
 
     # -- lifetime -------------------------------------------------------------------------------
     def close(self):
@@ -519,7 +551,7 @@ class Problem:
         """eqn.calcN!(N, sol, t, clock, vars, params, grid) on the current sol -> N (host copy)."""
         self._sync_forcing()
         out = np.empty((self.Nl,) + self._spec_shape, dtype=self.CT)
-        L.check(self._h, L.lib().mhdf_calcN(self._h, out.ctypes.data))
+        self._check(L.lib().mhdf_calcN(self._h, out.ctypes.data))
         return out
 
     # -- diagnostics ----------------------------------------------------------------------------
@@ -548,7 +580,7 @@ class Problem:
     def step_timed(self, nsteps):
         self._sync_forcing()
         ms = C.c_double()
-        L.check(self._h, L.lib().mhdf_step_timed(self._h, int(nsteps), C.byref(ms)))
+        self._check(L.lib().mhdf_step_timed(self._h, int(nsteps), C.byref(ms)))
         return ms.value
 
     def profile(self, enable=True):
@@ -618,7 +650,7 @@ def stepforward(prob, nsteps=1):
     """stepforward!(prob.sol, prob.clock, prob.timestepper, prob.eqn, prob.vars, prob.params, prob.grid)
     (timestepper/timestepper.jl:4-6)."""
     prob._sync_forcing()
-    L.check(prob._h, L.lib().mhdf_step(prob._h, int(nsteps)))
+    prob._check(L.lib().mhdf_step(prob._h, int(nsteps)))
 
 
 def DivVCorrection(prob):

@@ -23,8 +23,18 @@ static void band(int n, int* lo, int* hi0) {   // FourierFlows.getaliasedwavenum
   *hi0 = (int)std::ceil(R * n);
 }
 
+// calcF! as a host callback (mhdf_set_forcing_callback): the forcing of field 0 is a fixed spectral array scaled by (1 + 10 t); every
+// rank uploads its own ky rows from inside the callback, the library brackets the callback with cross-rank barriers
+template <typename T> struct CbCtx { mhdf_handle* h; std::vector<T> base, scaled; int calls; };
+template <typename T> static int forcing_cb(void* user, double t) {
+  auto* c = static_cast<CbCtx<T>*>(user);
+  for (size_t i = 0; i < c->base.size(); ++i) c->scaled[i] = (T)((1.0 + 10.0 * t) * (double)c->base[i]);
+  ++c->calls;
+  return mhdf_set_forcing_spectral(c->h, 0, c->scaled.data());
+}
+
 template <typename T>
-static std::vector<std::vector<T>> run(int P, bool peer, int physics, int stepper, int nx, int ny, int nz, int steps, bool a99, bool vp) {
+static std::vector<std::vector<T>> run(int P, bool peer, int physics, int stepper, int nx, int ny, int nz, int steps, bool a99, bool vp, bool cbf = false) {
   const int F = physics == MHDF_MHD ? 6 : 3;
   const int nkr = nx / 2 + 1;
   int lo, hi0;
@@ -65,6 +75,23 @@ static std::vector<std::vector<T>> run(int P, bool peer, int physics, int steppe
     for (int f = 0; f < F; ++f) ok(mhdf_set_real(h, f, fields[f].data() + (size_t)r * slab), "set_real");
     if (vp) for (int w = 0; w <= F; ++w) ok(mhdf_set_vp_field(h, w, vpf[w].data() + (size_t)r * slab), "set_vp_field");
     if (a99) { mhdf_a99 q{MHDF_A99_HOST, 0.5, 2.0, 1.0, 1.0, 42ull, 0ull}; ok(mhdf_set_forcing_a99(h, &q), "a99"); }
+    CbCtx<T> ctx{h, {}, {}, 0};
+    if (cbf) {
+      const int nyh = P > 1 ? Kyl : ny;
+      ctx.base.assign(2 * (size_t)nkr * nyh * nz, (T)0);
+      for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < nyh; ++j) {
+          int iy = j;
+          if (P > 1) { const int jg = r * Kyl + j; if (jg >= Ky) continue; iy = jg < lo ? jg : jg + (hi0 - lo); }
+          for (int i = 0; i < nkr; ++i) {
+            const size_t o = 2 * (((size_t)k * nyh + j) * nkr + i);
+            ctx.base[o] = (T)(0.3 * std::sin(0.7 * i + 1.3 * iy + 2.1 * k));
+            ctx.base[o + 1] = (T)(i == 0 ? 0.0 : 0.2 * std::cos(1.1 * i - 0.4 * iy + 0.9 * k));
+          }
+        }
+      ctx.scaled = ctx.base;
+      ok(mhdf_set_forcing_callback(h, forcing_cb<T>, &ctx), "set_forcing_callback");
+    }
     ok(mhdf_step(h, steps), "step");
     if (physics != MHDF_EMHD) ok(mhdf_div_correction(h, 0), "DivVCorrection");
     ok(mhdf_step(h, 1), "step");
@@ -85,6 +112,7 @@ static std::vector<std::vector<T>> run(int P, bool peer, int physics, int steppe
           std::memcpy(&full[f][2 * (((size_t)k * ny + iy) * nkr)], &loc[2 * (((size_t)k * nyh + j) * nkr)], 2 * (size_t)nkr * sizeof(T));
         }
     }
+    if (cbf && ctx.calls != 4 * (steps + 1)) { std::printf("FAIL forcing callback ran %d times\n", ctx.calls); ++g_fail; }
     if (r == 0) g_launches = mhdf_launch_count(h);
     sync.arrive_and_wait();     // nobody tears its buffers down while a peer may still address them
     ok(mhdf_destroy(h), "destroy");
@@ -99,10 +127,10 @@ static std::vector<std::vector<T>> run(int P, bool peer, int physics, int steppe
 }
 
 template <typename T>
-static void compare(const char* label, int P, bool peer, int physics, int stepper, int nx, int ny, int nz, bool a99, bool vp) {
-  auto one = run<T>(1, false, physics, stepper, nx, ny, nz, 1, a99, vp);
+static void compare(const char* label, int P, bool peer, int physics, int stepper, int nx, int ny, int nz, bool a99, bool vp, bool cbf = false) {
+  auto one = run<T>(1, false, physics, stepper, nx, ny, nz, 1, a99, vp, cbf);
   const long long l1 = g_launches;
-  auto many = run<T>(P, peer, physics, stepper, nx, ny, nz, 1, a99, vp);
+  auto many = run<T>(P, peer, physics, stepper, nx, ny, nz, 1, a99, vp, cbf);
   const long long lP = g_launches;
   bool same = one.size() == many.size() && !one.empty();
   double norm = 0;
@@ -135,6 +163,7 @@ int main(int argc, char** argv) {
   compare<double>("emhd rk4 f64 16x16x16", P, peer, MHDF_EMHD, MHDF_RK4, 16, 16, 16, false, false);
   compare<float>("mhd rk4 a99 + vp 16x16x16", P, peer, MHDF_MHD, MHDF_RK4, 16, 16, 16, true, true);
   compare<double>("emhd hm89 f64 16x16x16", P, peer, MHDF_EMHD, MHDF_HM89, 16, 16, 16, false, false);   // fixed-point loop: max over ranks
+  compare<float>("mhd rk4 calcF callback 16x16x16", P, peer, MHDF_MHD, MHDF_RK4, 16, 16, 16, false, false, true);   // API traffic between the stages of a step
   std::printf("library ranks driver done: %d failure(s)\n", g_fail);
   return g_fail ? 1 : 0;
 }

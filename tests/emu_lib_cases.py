@@ -20,7 +20,7 @@ import mhdflows_jl_b200 as M  # noqa: E402
 from oracle import forcing_oracle as FO  # noqa: E402
 from oracle import mhdflows_oracle as O  # noqa: E402
 from tests.test_gpu_parity import _hm89_check, _pair  # noqa: E402
-from tests.test_gpu_zforcing import _forced_pair, _nd_pair, _structure_function_check, _vp_pair  # noqa: E402
+from tests.test_gpu_zforcing import _closure_forcing_check, _forced_pair, _nd_pair, _structure_function_check, _vp_pair  # noqa: E402
 
 F32_TOL, F64_TOL = 1e-5, 1e-12
 DIMS = (16, 16, 32)
@@ -125,6 +125,14 @@ def on_device_structure_functions():
     """mhdf_correlation + the host-side SFC / SF_2 1D of the mirror against the restatements of TurbStatTool.jl:67, 72, 90-120."""
     _structure_function_check(M, O, np.float64, F64_TOL, (16, 16, 16))
     _structure_function_check(M, O, np.float32, F32_TOL, (16, 32, 16))
+
+
+@case
+def closure_forcing_through_the_host_callback():
+    """Arbitrary calcF! closures: mhdf_set_forcing_callback / MHDF_STAGE / mhdf_set_forcing_spectral behind Problem(calcF = f)."""
+    _closure_forcing_check(M, O, np.float64, F64_TOL, (16, 16, 16), "RK4")
+    _closure_forcing_check(M, O, np.float32, F32_TOL, (16, 16, 32), "LSRK54", steps=1)
+    _closure_forcing_check(M, O, np.float32, F32_TOL, (16, 16, 16), "RK4", B_field=False, steps=1)
 
 
 @case

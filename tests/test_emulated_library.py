@@ -23,6 +23,7 @@ CSRC = os.path.join(ROOT, "mhdflows_jl_b200", "csrc")
 # case-name filters of the concurrent workers (balanced by measured run time)
 GROUPS = [["smoke", "a99_host", "a99_float64", "hdf5", "hm89"],
           ["a99_gpu", "a99_lsrk54", "a99_reproducible", "div_b_correction_emhd"],
+          ["closure"],
           ["div_corrections", "volume_penalisation_hd", "random_phase", "on_device"],
           ["volume_penalisation_mhd", "volume_penalisation_time", "second_emhd", "negative_damping"],
           ["regress_"]]
@@ -82,11 +83,12 @@ def test_end_to_end_cases_on_the_emulated_library(emu_results):
 def test_slab_runs_on_the_emulated_library_equal_the_single_rank_run(emu_results, config):
     """Ranks as threads, NCCL / CUDA IPC replaced by in-process stand-ins (cuda_host_emu.h): the spectral state of the P-rank run is
     bit-identical to the single-rank run -- EMHD Float64, MHD with A99 driving + volume penalisation + DivVCorrection! and the EMHD HM89
-    stepper (fixed-point error norm reduced over the ranks), through the copy-push transport with the z-chunk pipelined path and
+    stepper (fixed-point error norm reduced over the ranks) and a calcF! host callback that uploads per-rank forcing slabs between the
+    stages of a step, through the copy-push transport with the z-chunk pipelined path and
     through send/recv on 4 ranks.  Streams are synchronous here: this checks layouts, offsets, slab bounds and reductions, not event ordering."""
     rc, out = emu_results[("ranks", config)]
     lines = [l for l in out.splitlines() if "ranks-vs-single" in l]
-    assert rc == 0 and len(lines) == 3 and all(l.startswith("PASS") for l in lines), out[-4000:]
+    assert rc == 0 and len(lines) == 4 and all(l.startswith("PASS") for l in lines), out[-4000:]
     if "pipeline" in config:     # the pipelined path really ran: it launches its passes once per z chunk
         for l in lines:
             a, b = l.split("launches ")[1].rstrip(")").split(" -> ")

@@ -353,3 +353,68 @@ def _structure_function_check(M, O, T, tol, dims):
 @pytest.mark.parametrize("T,tol", [(np.float32, F32_TOL), (np.float64, F64_TOL)])
 def test_structure_functions_on_device(M, O, T, tol):
     _structure_function_check(M, O, T, tol, (32, 16, 16))
+
+
+def _closure_forcing_check(M, O, T, tol, dims, stepper, B_field=True, steps=2):
+    """An arbitrary calcF! closure (pgen.jl:231-234) -- time dependent and reading sol -- through the host-callback path of the
+    library against the same function handed to the restatement: stage times, the `sol` argument and the upload must all agree."""
+    nx, ny, nz = dims
+    g0 = O.Grid(nx, ny, nz, T=T)
+    X, Y, Z = (g0.x.astype(np.float64).reshape(1, 1, -1), g0.y.astype(np.float64).reshape(1, -1, 1), g0.z.astype(np.float64).reshape(-1, 1, 1))
+    fxh = g0.rfft((0.5 * np.sin(2 * X) * np.cos(2 * Y) * np.cos(Z)).astype(T))
+    fyh = g0.rfft((-0.5 * np.cos(2 * X) * np.sin(2 * Y) * np.cos(Z)).astype(T))
+    seen = {0: [], 1: []}
+
+    def make(off):           # the mirror's params.*_ind are the reference's 1-based numbers, the restatement's are 0-based
+        def calcF(N, sol, t, clock, vars, params, grid):
+            seen[off].append(float(t))
+            N[params.ux_ind - off] += T(math.cos(40 * t)) * fxh - T(0.3) * sol[params.uy_ind - off]
+            N[params.uy_ind - off] += T(1 + 10 * t) * fyh
+            if B_field:
+                N[params.bz_ind - off] += T(0.05) * sol[params.bx_ind - off]
+        return calcF
+
+    kw = dict(nx=nx, ny=ny, nz=nz, T=T, stepper=stepper, nu=2e-2, dt=4e-3, B_field=B_field)
+    if B_field:
+        kw["eta"] = 3e-2
+    op, gp = O.Problem(calcF=make(0), **kw), M.Problem(M.GPU(), calcF=make(1), **kw)
+    u, b = O.random_phase_ic(op.grid, 41), O.random_phase_ic(op.grid, 42)
+    if B_field:
+        O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2], bx=b[0], by=b[1], bz=b[2])
+    else:
+        O.SetUpProblemIC(op, *u)
+        M.SetUpProblemIC(gp, ux=u[0], uy=u[1], uz=u[2])
+    for _ in range(steps):
+        O.stepforward(op)
+    M.stepforward(gp, steps)
+    assert len(seen[1]) == len(seen[0]) == steps * (4 if stepper == "RK4" else 5)
+    assert np.allclose(seen[1], seen[0], rtol=1e-6 if T is np.float32 else 1e-14, atol=0)      # FourierFlows' stage times
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
+    gp.close()
+    return op
+
+
+@pytest.mark.parametrize("T,tol,stepper", [(np.float32, F32_TOL, "RK4"), (np.float64, F64_TOL, "LSRK54")])
+def test_arbitrary_calcF_closure_through_the_host_callback(M, O, T, tol, stepper):
+    op = _closure_forcing_check(M, O, T, tol, (32, 16, 32), stepper)
+    q = O.Problem(nx=32, ny=16, nz=32, T=T, stepper=stepper, nu=2e-2, eta=3e-2, dt=4e-3, B_field=True)     # the forcing really acts
+    u, b = O.random_phase_ic(q.grid, 41), O.random_phase_ic(q.grid, 42)
+    O.SetUpProblemIC(q, *u, bx=b[0], by=b[1], bz=b[2])
+    for _ in range(2):
+        O.stepforward(q)
+    assert O.rel_l2(q.grid.dealias(q.sol.copy()), op.grid.dealias(op.sol.copy())) > 1e-4
+
+
+def test_calcF_closure_lost_in_hd_and_exceptions_propagate(M, O):
+    _closure_forcing_check(M, O, np.float32, F32_TOL, (32, 32, 32), "RK4", B_field=False, steps=1)   # HDcalcN! clobbers it (pgen.jl:176-178)
+
+    def bad(N, sol, t, clock, vars, params, grid):
+        raise KeyError("boom")
+    p = M.Problem(M.GPU(), nx=32, B_field=True, dt=1e-3, calcF=bad)
+    p.set_real("ux", np.ones((32, 32, 32), dtype=np.float32))
+    with pytest.raises(KeyError):
+        M.stepforward(p)
+    p.close()
+    with pytest.raises(NotImplementedError):
+        M.Problem(M.GPU(), nx=32, B_field=True, EMHD=True, stepper="HM89", calcF=bad)
