@@ -20,7 +20,8 @@ import mhdflows_jl_b200 as M  # noqa: E402
 from oracle import forcing_oracle as FO  # noqa: E402
 from oracle import mhdflows_oracle as O  # noqa: E402
 from tests.test_gpu_parity import _hm89_check, _pair  # noqa: E402
-from tests.test_gpu_zforcing import _closure_forcing_check, _forced_pair, _nd_pair, _structure_function_check, _vp_pair  # noqa: E402
+from tests.test_gpu_zforcing import (_closure_forcing_check, _forced_pair, _nd_pair, _random_phase_case,  # noqa: E402
+                                     _structure_function_check, _vp_pair)
 
 F32_TOL, F64_TOL = 1e-5, 1e-12
 DIMS = (16, 16, 32)
@@ -57,37 +58,6 @@ def smoke_mhd_rk4_against_the_oracle():
     M.stepforward(gp)
     assert O.rel_l2(gp.sol, _dealiased(op)) < F32_TOL
     gp.close()
-
-
-def _random_phase_case(M, O, FO, T, tol, dims, nranks_note=""):
-    """mhdf_set_random_phase against oracle.DivFreeSpectraMap with the device's Philox phases injected (IC.jl:130-179)."""
-    nx, ny, nz = dims
-    L3 = dict(Lx=2 * np.pi, Ly=3.0, Lz=5.0)
-    gp = M.Problem(M.GPU(), nx=nx, ny=ny, nz=nz, T=T, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, **L3)
-    M.SetUpRandomPhaseIC(gp, seed_u=1234, seed_b=(5 << 32) + 678, k0=-5 / 6, P=2.0, k_peak=1.5)
-    g = O.Grid(nx, ny, nz, L3["Lx"], L3["Ly"], L3["Lz"], T)
-    worst = 0.0
-    for names, seed in ((("ux", "uy", "uz"), 1234), (("bx", "by", "bz"), (5 << 32) + 678)):
-        theta = FO.PhiloxField(seed, g).uniforms(M.DFSM_CALL)[0]
-        ref = O.DivFreeSpectraMap(g, theta, k_peak=1.5, P=2.0, k0=-5 / 6)
-        for nm, r in zip(names, ref):
-            assert np.linalg.norm(r) > 0
-            worst = max(worst, O.rel_l2(gp.get_real(nm, M.FRESH), r), O.rel_l2(gp.get_real(nm, M.STALE), r))
-    assert worst < tol, worst
-    # SetUpProblemIC! semantics: sol = rfft(F), vars.* = F  ->  the stale statistics are those of F
-    op = O.Problem(nx=nx, ny=ny, nz=nz, T=T, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, **L3)
-    u = O.DivFreeSpectraMap(g, FO.PhiloxField(1234, g).uniforms(M.DFSM_CALL)[0], k_peak=1.5, P=2.0, k0=-5 / 6)
-    b = O.DivFreeSpectraMap(g, FO.PhiloxField((5 << 32) + 678, g).uniforms(M.DFSM_CALL)[0], k_peak=1.5, P=2.0, k0=-5 / 6)
-    O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
-    ke, me = gp.energy(M.STALE)
-    ko, mo = O.ProbDiagnostic(op, rounded=False)
-    assert abs(ke - ko) < 1e-4 * abs(ko) and abs(me - mo) < 1e-4 * abs(mo)
-    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
-    O.stepforward(op)
-    M.stepforward(gp)
-    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
-    gp.close()
-    return worst
 
 
 @case

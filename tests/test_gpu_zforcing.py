@@ -418,3 +418,41 @@ def test_calcF_closure_lost_in_hd_and_exceptions_propagate(M, O):
     p.close()
     with pytest.raises(NotImplementedError):
         M.Problem(M.GPU(), nx=32, B_field=True, EMHD=True, stepper="HM89", calcF=bad)
+
+
+def _random_phase_case(M, O, FO, T, tol, dims, nranks_note=""):
+    """mhdf_set_random_phase against oracle.DivFreeSpectraMap with the device's Philox phases injected (IC.jl:130-179)."""
+    nx, ny, nz = dims
+    L3 = dict(Lx=2 * np.pi, Ly=3.0, Lz=5.0)
+    gp = M.Problem(M.GPU(), nx=nx, ny=ny, nz=nz, T=T, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, **L3)
+    M.SetUpRandomPhaseIC(gp, seed_u=1234, seed_b=(5 << 32) + 678, k0=-5 / 6, P=2.0, k_peak=1.5)
+    g = O.Grid(nx, ny, nz, L3["Lx"], L3["Ly"], L3["Lz"], T)
+    worst = 0.0
+    for names, seed in ((("ux", "uy", "uz"), 1234), (("bx", "by", "bz"), (5 << 32) + 678)):
+        theta = FO.PhiloxField(seed, g).uniforms(M.DFSM_CALL)[0]
+        ref = O.DivFreeSpectraMap(g, theta, k_peak=1.5, P=2.0, k0=-5 / 6)
+        for nm, r in zip(names, ref):
+            assert np.linalg.norm(r) > 0
+            worst = max(worst, O.rel_l2(gp.get_real(nm, M.FRESH), r), O.rel_l2(gp.get_real(nm, M.STALE), r))
+    assert worst < tol, worst
+    # SetUpProblemIC! semantics: sol = rfft(F), vars.* = F  ->  the stale statistics are those of F
+    op = O.Problem(nx=nx, ny=ny, nz=nz, T=T, nu=1e-2, eta=1e-2, dt=1e-3, B_field=True, **L3)
+    u = O.DivFreeSpectraMap(g, FO.PhiloxField(1234, g).uniforms(M.DFSM_CALL)[0], k_peak=1.5, P=2.0, k0=-5 / 6)
+    b = O.DivFreeSpectraMap(g, FO.PhiloxField((5 << 32) + 678, g).uniforms(M.DFSM_CALL)[0], k_peak=1.5, P=2.0, k0=-5 / 6)
+    O.SetUpProblemIC(op, *u, bx=b[0], by=b[1], bz=b[2])
+    ke, me = gp.energy(M.STALE)
+    ko, mo = O.ProbDiagnostic(op, rounded=False)
+    assert abs(ke - ko) < 1e-4 * abs(ko) and abs(me - mo) < 1e-4 * abs(mo)
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
+    O.stepforward(op)
+    M.stepforward(gp)
+    assert O.rel_l2(gp.sol, op.grid.dealias(op.sol.copy())) < tol
+    gp.close()
+    return worst
+
+
+@pytest.mark.parametrize("T,tol,dims", [(np.float32, F32_TOL, (32, 64, 16)), (np.float64, F64_TOL, (32, 16, 32))])
+def test_random_phase_ic_on_device(M, O, FO, T, tol, dims):
+    """DivFreeSpectraMap + SetUpProblemIC! on the device (mhdf_set_random_phase) against the restatement of IC.jl:130-179 fed with the
+    device's Philox phases, on a non-cubic box with three different side lengths."""
+    _random_phase_case(M, O, FO, T, tol, dims)
