@@ -124,4 +124,4 @@ def test_whole_library_under_address_sanitizer(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=7200, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
     assert res.returncode == 0 and "ERROR: AddressSanitizer" not in res.stderr and "runtime error:" not in res.stderr \
         and "LeakSanitizer" not in res.stderr, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count("PASS") == 11 and "0 failure(s)" in res.stdout
+    assert res.stdout.count("PASS") == 15 and "0 failure(s)" in res.stdout
