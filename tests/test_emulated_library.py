@@ -95,8 +95,8 @@ def test_slab_runs_on_the_emulated_library_equal_the_single_rank_run(emu_results
             assert int(b) > int(a), l
 
 
-@pytest.mark.skipif(os.environ.get("MHDF_EMU_SANITIZE_LIB") != "1", reason="18 min: the whole library under ASan + UBSan + LeakSanitizer "
-                    "(set MHDF_EMU_SANITIZE_LIB=1); last result in profiles/r01_emulator_sanitizers.txt")
+@pytest.mark.skipif(os.environ.get("MHDF_EMU_SANITIZE_LIB") != "1", reason="about 2 h: the whole library under ASan + UBSan + LeakSanitizer "
+                    "(set MHDF_EMU_SANITIZE_LIB=1); last result in profiles/r02_emulator_sanitizers.txt")
 def test_whole_library_under_address_sanitizer(tmp_path):
     """api.cu + solver.cuh + kernels + the C-ABI driver tests/cpu_emu/test_library_sanitize.cpp, all with -fsanitize=address,undefined:
     the solver's device buffers are heap blocks of exactly the computed sizes, so any overrun is reported."""
